@@ -1,0 +1,193 @@
+/*
+ * monovo_b200.h -- C ABI of libmonovo_b200.so: the B200-native (sm_100a) implementation of the
+ * ros2_mono_vo per-frame front-end hot path.
+ *
+ * This header is the drop-in boundary.  The reference reaches the hot path only through
+ * OpenCV calls; each entry point below replaces exactly one of those call sites.  A maintainer of the
+ * reference keeps FeatureProcessor / Initializer / Tracker unchanged and binds these functions inside
+ * src/feature_processor.cpp and at the cv:: call sites of src/initializer.cpp / src/tracker.cpp
+ * (see INTEGRATION.md for the binding code).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch/OpenCV types cross this boundary.
+ *   - every function returns MVO_OK (0) or a negative mvo_status; nothing throws.
+ *   - pointers are HOST memory unless the name ends in _dev; calls are synchronous with respect
+ *     to the context's CUDA stream when they return (outputs are valid on return).
+ *   - there is NO CPU fallback: without a CUDA device mvo_create fails with MVO_ERR_CUDA.
+ *   - one context == one "stream group": `batch` independent camera streams processed in lock step
+ *     on one GPU (batch = 1 is the single camera of the reference node).
+ */
+#ifndef MONOVO_B200_H_
+#define MONOVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVO_API __attribute__((visibility("default")))
+
+typedef enum mvo_status {
+  MVO_OK = 0,
+  MVO_ERR_INVALID = -1,     /* bad argument (null pointer, size out of range, ...)         */
+  MVO_ERR_CUDA = -2,        /* CUDA runtime error, see mvo_last_error()                      */
+  MVO_ERR_CAPACITY = -3,    /* an internal or caller-provided capacity was exceeded          */
+  MVO_ERR_UNSUPPORTED = -4, /* valid request that this build does not implement              */
+  MVO_ERR_DEGENERATE = -5   /* input too small / degenerate for the requested model          */
+} mvo_status;
+
+typedef struct mvo_ctx mvo_ctx;
+
+/* Layout-compatible with the fields of cv::KeyPoint that the reference reads (28 bytes). */
+typedef struct mvo_keypoint {
+  float x, y;      /* pt, full-resolution pixel coordinates (level coords * scale)  */
+  float size;      /* 31 * scale                                                     */
+  float angle;     /* degrees in [0,360)                                             */
+  float response;  /* Harris response                                                */
+  int32_t octave;  /* pyramid level                                                  */
+  int32_t class_id;/* always -1                                                      */
+} mvo_keypoint;
+
+/* Layout-compatible with cv::DMatch (16 bytes). */
+typedef struct mvo_dmatch {
+  int32_t query_idx;
+  int32_t train_idx;
+  int32_t img_idx;   /* always 0 */
+  float distance;    /* Hamming distance as float */
+} mvo_dmatch;
+
+typedef struct mvo_config {
+  int32_t device;        /* CUDA device ordinal                                              */
+  int32_t max_width;     /* largest image width the context will see                         */
+  int32_t max_height;
+  int32_t nfeatures;     /* cv::ORB::create(nfeatures); reference: src/mono_vo.cpp:16 (1000) */
+  int32_t batch;         /* camera streams processed in lock step (>=1)                      */
+  int32_t max_points;    /* capacity for LK / RANSAC point sets (0 -> 2*nfeatures)           */
+  uint64_t ransac_seed;  /* 0 -> 0xFFFFFFFFFFFFFFFF == OpenCV's RNG seed inside find*()       */
+  void* cuda_stream;     /* cudaStream_t to run on; NULL -> the context creates its own      */
+} mvo_config;
+
+/* ------------------------------------------------------------------------------------------------
+ * context
+ * replaces: FeatureProcessor::FeatureProcessor (src/feature_processor.cpp:5-10), which builds
+ * cv::ORB::create(num_features) + cv::BFMatcher(NORM_HAMMING).
+ */
+MVO_API int mvo_create(mvo_ctx** out, const mvo_config* cfg);
+MVO_API void mvo_destroy(mvo_ctx* ctx);
+MVO_API const char* mvo_last_error(const mvo_ctx* ctx);   /* ctx may be NULL: last create error */
+MVO_API const char* mvo_version(void);
+MVO_API void* mvo_cuda_stream(mvo_ctx* ctx);               /* the cudaStream_t the ctx launches on */
+MVO_API int mvo_batch(const mvo_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+MVO_API uint64_t mvo_launch_count(const mvo_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB
+ * replaces: detector_->detectAndCompute(image, cv::noArray(), keypoints, descriptors)
+ *           src/feature_processor.cpp:19-23  (callers src/frame.cpp:12)
+ * img: h x w x channels u8, row stride `stride` bytes; channels 1 (gray) or 3 (BGR, as the node feeds).
+ * kps / desc: caller buffers of capacity `cap` keypoints / cap*32 bytes.  *n_out = number written.
+ * Keypoints come in the canonical order (octave, response desc, y, x); the SET equals cv::ORB's.
+ * desc may be NULL (== FeatureProcessor::detect, src/feature_processor.cpp:12-17).
+ */
+MVO_API int mvo_orb_detect_and_compute(mvo_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                                       int channels, mvo_keypoint* kps, uint8_t* desc, int cap,
+                                       int* n_out);
+
+/* Parity hook == cv::ORB::compute(image, keypoints, descriptors): descriptors for GIVEN keypoints
+ * (pt, angle, octave honoured).  valid[i] = 0 for keypoints closer than 31 px (level coords) to the
+ * level border (cv2 silently drops those); their descriptor rows are zeroed. */
+MVO_API int mvo_orb_compute(mvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, int channels,
+                            const mvo_keypoint* kps_in, int n, uint8_t* desc, uint8_t* valid);
+
+/* Debug / parity taps of the last ORB call on stream 0 of the group. */
+MVO_API int mvo_orb_num_levels(void);
+MVO_API int mvo_orb_level_size(mvo_ctx* ctx, int level, int* w, int* h);
+/* copy pyramid level (blurred = 0: INTER_LINEAR_EXACT level; 1: the 7x7 sigma-2 blurred level) */
+MVO_API int mvo_orb_get_level(mvo_ctx* ctx, int level, int blurred, uint8_t* out, int out_stride);
+/* FAST+NMS candidates of a level after the 31-px edge filter: packed (x | y<<16), FAST score */
+MVO_API int mvo_orb_get_fast(mvo_ctx* ctx, int level, uint32_t* xy, int32_t* score, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hamming kNN (k=2) + Lowe ratio
+ * replaces: matcher_.knnMatch(d1, d2, knn, 2) + the ratio loop, src/feature_processor.cpp:25-40
+ * q: nq x 32 u8 (query == descriptors1), t: nt x 32 u8 (train == descriptors2).
+ * out: capacity nq; accepted matches in query order; *n_out = count.
+ */
+MVO_API int mvo_knn_ratio(mvo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                          double ratio, mvo_dmatch* out, int* n_out);
+/* raw top-2 (parity hook): idx/dist are nq x 2, -1 where the train set has fewer than 2 rows */
+MVO_API int mvo_knn2(mvo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                     int32_t* idx, int32_t* dist);
+
+/* ------------------------------------------------------------------------------------------------
+ * pyramidal Lucas-Kanade
+ * replaces: cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err) with all defaults
+ *           (21x21 window, maxLevel 3, 30 iters / eps 0.01, minEigThreshold 1e-4)
+ *           src/tracker.cpp:68-69
+ */
+MVO_API int mvo_lk_track(mvo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h,
+                         int stride, int channels, const float* prev_xy, int n, float* next_xy,
+                         uint8_t* status, float* err);
+
+/* ------------------------------------------------------------------------------------------------
+ * two-view geometry (deterministic parallel RANSAC; OpenCV's RNG stream and adaptive stop replayed)
+ * p1/p2: n x 2 f32 interleaved (std::vector<cv::Point2f>).  mask: n bytes (0/1), may be NULL.
+ */
+/* replaces cv::findHomography(p1, p2, cv::RANSAC, thr, mask): src/initializer.cpp:82, src/tracker.cpp:243 */
+MVO_API int mvo_find_homography(mvo_ctx* ctx, const float* p1, const float* p2, int n, double thr,
+                                double H[9], uint8_t* mask, int* n_inliers);
+/* replaces cv::findFundamentalMat(p1, p2, cv::FM_RANSAC, thr, conf, mask): src/initializer.cpp:87, src/tracker.cpp:248 */
+MVO_API int mvo_find_fundamental(mvo_ctx* ctx, const float* p1, const float* p2, int n, double thr,
+                                 double conf, double F[9], uint8_t* mask, int* n_inliers);
+/* replaces cv::findEssentialMat(p1, p2, K, cv::RANSAC, conf, thr, mask): src/initializer.cpp:228-229 */
+MVO_API int mvo_find_essential(mvo_ctx* ctx, const float* p1, const float* p2, int n,
+                               const double K[9], double conf, double thr, double E[9],
+                               uint8_t* mask, int* n_inliers);
+/* replaces cv::recoverPose(E, p1, p2, K, R, t, mask): src/initializer.cpp:236.  mask_io may be NULL. */
+MVO_API int mvo_recover_pose(mvo_ctx* ctx, const double E[9], const float* p1, const float* p2, int n,
+                             const double K[9], double R[9], double t[3], uint8_t* mask_io, int* n_good);
+/* replaces cv::triangulatePoints(P0, P1, p0, p1, X4): src/initializer.cpp:125, src/tracker.cpp:149.
+ * X4 is 4 x n f32 row-major (the cv::Mat layout).  Each column is a unit vector, sign unspecified. */
+MVO_API int mvo_triangulate(mvo_ctx* ctx, const double P0[12], const double P1[12], const float* p0,
+                            const float* p1, int n, float* X4);
+
+/* model ids for the hypothesis sweep */
+enum { MVO_MODEL_H = 0, MVO_MODEL_F = 1, MVO_MODEL_E = 2 };
+/* C4 sweep: draw m minimal samples with the OpenCV RNG stream (seeded per ctx), solve, and score every
+ * model over all n correspondences with no early exit.  counts: m x max_models ints (-1 = no model),
+ * max_models = 1 (H), 3 (F), 10 (E).  models (optional): m x max_models x 9 doubles. */
+MVO_API int mvo_score_hypotheses(mvo_ctx* ctx, int model, const float* p1, const float* p2, int n,
+                                 const double K[9], double thr, int m, int32_t* sample_idx,
+                                 int32_t* counts, double* models);
+
+/* ------------------------------------------------------------------------------------------------
+ * stream-group front-end step (bench / batched mode; SURVEY.md section 8d "front-end frame"):
+ * for every stream b of the group: ORB(frame_t) -> kNN+ratio(desc_{t-1}, desc_t) -> LK(kps_{t-1} -> t)
+ * -> H + F RANSAC -> E RANSAC -> recoverPose -> triangulate.  Images: batch x h x w u8 gray.
+ */
+typedef struct mvo_frame_result {
+  int32_t n_keypoints;   /* ORB keypoints of frame t                    */
+  int32_t n_matches;     /* accepted ratio-test matches (t-1 -> t)      */
+  int32_t n_tracked;     /* LK points with status && err < 30           */
+  int32_t score_h;       /* findHomography inliers                      */
+  int32_t score_f;       /* findFundamentalMat inliers                  */
+  int32_t n_inliers_e;   /* findEssentialMat inliers                    */
+  int32_t n_pose_good;   /* recoverPose cheirality count                */
+  int32_t n_triangulated;/* points in front of both cameras             */
+  double R[9];
+  double t[3];
+} mvo_frame_result;
+
+MVO_API int mvo_group_step(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride,
+                           int images_on_device, const double K[9], mvo_frame_result* results);
+/* per-stage device time (ms) of the last mvo_group_step, measured with CUDA events on the ctx stream.
+ * names: "orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total" */
+MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOVO_B200_H_ */

@@ -1,0 +1,155 @@
+"""Seeded synthetic inputs for the VO front-end hot path (test + bench infrastructure).
+
+numpy-only so the very same arrays can be regenerated on the GPU box (no cv2 dependence).
+The frames are "KITTI-shaped": smooth multi-scale texture + many grey rectangles (corner
+sources) + mild blur + sensor noise, so that FAST finds more corners per pyramid level than
+the ORB per-level quota and every quota saturates.
+
+THIS IS TEST INFRASTRUCTURE: only tests/, bench.py and __graft_entry__.smoke() import it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _upsample_bilinear(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    sh, sw = a.shape
+    ys = (np.arange(h) + 0.5) * sh / h - 0.5
+    xs = (np.arange(w) + 0.5) * sw / w - 0.5
+    y0 = np.clip(np.floor(ys).astype(int), 0, sh - 2)
+    x0 = np.clip(np.floor(xs).astype(int), 0, sw - 2)
+    fy = np.clip(ys - y0, 0, 1)[:, None]
+    fx = np.clip(xs - x0, 0, 1)[None, :]
+    a00 = a[y0][:, x0]
+    a01 = a[y0][:, x0 + 1]
+    a10 = a[y0 + 1][:, x0]
+    a11 = a[y0 + 1][:, x0 + 1]
+    return (a00 * (1 - fx) + a01 * fx) * (1 - fy) + (a10 * (1 - fx) + a11 * fx) * fy
+
+
+def _gauss_blur(img: np.ndarray, sigma: float) -> np.ndarray:
+    r = max(1, int(np.ceil(3 * sigma)))
+    x = np.arange(-r, r + 1)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    k /= k.sum()
+    p = np.pad(img, r, mode="reflect")
+    t = sum(k[i] * p[:, i:i + img.shape[1]] for i in range(2 * r + 1))
+    return sum(k[i] * t[i:i + img.shape[0], :] for i in range(2 * r + 1))
+
+
+def synth_frame(h: int, w: int, seed: int) -> np.ndarray:
+    """One grayscale u8 frame, deterministic in (h, w, seed)."""
+    rng = np.random.default_rng(seed)
+    img = np.full((h, w), 128.0)
+    for s in (2, 4, 8, 16, 32):
+        coarse = rng.uniform(-1.0, 1.0, size=(h // s + 2, w // s + 2))
+        img += 12.0 * np.sqrt(s) * _upsample_bilinear(coarse, h, w)
+    img = np.clip(img, 0, 255)
+    nrect = h * w // 600
+    ys = rng.integers(0, h, nrect)
+    xs = rng.integers(0, w, nrect)
+    hs = rng.integers(4, 49, nrect)
+    ws = rng.integers(4, 49, nrect)
+    gs = rng.integers(0, 256, nrect)
+    for y, x, rh, rw, g in zip(ys, xs, hs, ws, gs):
+        img[y:y + rh, x:x + rw] = g
+    img = _gauss_blur(img, 0.8)
+    img += rng.normal(0.0, 2.0, size=(h, w))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def warp_similarity(img: np.ndarray, angle_deg: float, tx: float, ty: float) -> np.ndarray:
+    """Bilinear warp of a u8 image by a small rotation about the centre + shift (reflect-101)."""
+    h, w = img.shape
+    a = np.deg2rad(angle_deg)
+    ca, sa = np.cos(a), np.sin(a)
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    # dst -> src (inverse map)
+    xd, yd = xx - cx - tx, yy - cy - ty
+    xs = ca * xd + sa * yd + cx
+    ys = -sa * xd + ca * yd + cy
+    x0 = np.floor(xs).astype(int)
+    y0 = np.floor(ys).astype(int)
+    fx, fy = xs - x0, ys - y0
+
+    def refl(i, n):
+        i = np.abs(i)
+        i = np.where(i >= n, 2 * (n - 1) - i, i)
+        return np.clip(i, 0, n - 1)
+
+    x0r, x1r = refl(x0, w), refl(x0 + 1, w)
+    y0r, y1r = refl(y0, h), refl(y0 + 1, h)
+    f = img.astype(np.float64)
+    out = (f[y0r, x0r] * (1 - fx) + f[y0r, x1r] * fx) * (1 - fy) + \
+          (f[y1r, x0r] * (1 - fx) + f[y1r, x1r] * fx) * fy
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def synth_pair(h: int, w: int, seed: int):
+    """Frame t and frame t+1 = small seeded similarity warp of it (C1/C3 pairs)."""
+    rng = np.random.default_rng(seed + 7919)
+    f0 = synth_frame(h, w, seed)
+    ang = rng.uniform(-0.4, 0.4)
+    tx, ty = rng.uniform(-3, 3, 2)
+    return f0, warp_similarity(f0, ang, tx, ty)
+
+
+def synth_sequence(h: int, w: int, stream: int, nframes: int):
+    """A seeded smooth trajectory of small warps of one base frame (C2/C5 sequences)."""
+    rng = np.random.default_rng(1000 * stream + 17)
+    base = synth_frame(h, w, 1000 * stream)
+    frames = [base]
+    ang = tx = ty = 0.0
+    for _ in range(1, nframes):
+        ang += rng.uniform(-0.15, 0.15)
+        tx += rng.uniform(-1.5, 1.5)
+        ty += rng.uniform(-0.8, 0.8)
+        frames.append(warp_similarity(base, ang, tx, ty))
+    return frames
+
+
+def rodrigues(rvec) -> np.ndarray:
+    rvec = np.asarray(rvec, dtype=np.float64)
+    th = np.linalg.norm(rvec)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rvec / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+KITTI_K = np.array([[718.856, 0.0, 620.5], [0.0, 718.856, 188.0], [0.0, 0.0, 1.0]])
+
+
+def scene_correspondences(n: int, seed: int, outlier_frac: float = 0.3, noise_px: float = 0.3,
+                          planar: bool = False, K: np.ndarray = KITTI_K,
+                          rvec=(0.01, 0.03, -0.005), tvec=(0.1, -0.02, 0.8), w: int = 1241, h: int = 376):
+    """Two-view correspondences of a seeded 3-D scene (C4): returns p1, p2 (n x 2 f32), R, t, inlier flags."""
+    rng = np.random.default_rng(seed)
+    R = rodrigues(rvec)
+    t = np.asarray(tvec, dtype=np.float64)
+    # sample image points in view 1 uniformly, give them a depth, back-project
+    u = rng.uniform(0, w, n)
+    v = rng.uniform(0, h, n)
+    if planar:
+        # a slanted plane n.X = d
+        nrm = np.array([0.1, -0.2, 1.0]); nrm /= np.linalg.norm(nrm)
+        rays = np.linalg.inv(K) @ np.vstack([u, v, np.ones(n)])
+        depth = 12.0 / (nrm @ rays)
+        X = rays * depth
+    else:
+        depth = rng.uniform(5, 40, n)
+        X = (np.linalg.inv(K) @ np.vstack([u, v, np.ones(n)])) * depth
+    x2 = K @ (R @ X + t[:, None])
+    p1 = np.stack([u, v], 1)
+    p2 = (x2[:2] / x2[2]).T
+    p1 = p1 + rng.normal(0, noise_px, p1.shape)
+    p2 = p2 + rng.normal(0, noise_px, p2.shape)
+    nout = int(round(outlier_frac * n))
+    out_idx = rng.permutation(n)[:nout]
+    p2[out_idx, 0] = rng.uniform(0, w, nout)
+    p2[out_idx, 1] = rng.uniform(0, h, nout)
+    inl = np.ones(n, bool)
+    inl[out_idx] = False
+    return p1.astype(np.float32), p2.astype(np.float32), R, t, inl

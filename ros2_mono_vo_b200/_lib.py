@@ -1,0 +1,91 @@
+"""ctypes binding of libmonovo_b200.so (the C ABI in include/monovo_b200.h).
+
+Fails loudly when the CUDA library has not been built: there is no CPU fallback in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmonovo_b200.so")
+
+MVO_OK, MVO_ERR_INVALID, MVO_ERR_CUDA, MVO_ERR_CAPACITY, MVO_ERR_UNSUPPORTED, MVO_ERR_DEGENERATE = 0, -1, -2, -3, -4, -5
+
+
+class MvoKeypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+class MvoDMatch(C.Structure):
+    _fields_ = [("query_idx", C.c_int32), ("train_idx", C.c_int32), ("img_idx", C.c_int32), ("distance", C.c_float)]
+
+
+class MvoConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
+                ("nfeatures", C.c_int32), ("batch", C.c_int32), ("max_points", C.c_int32),
+                ("ransac_seed", C.c_uint64), ("cuda_stream", C.c_void_p)]
+
+
+class MvoFrameResult(C.Structure):
+    _fields_ = [("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_tracked", C.c_int32),
+                ("score_h", C.c_int32), ("score_f", C.c_int32), ("n_inliers_e", C.c_int32),
+                ("n_pose_good", C.c_int32), ("n_triangulated", C.c_int32),
+                ("R", C.c_double * 9), ("t", C.c_double * 3)]
+
+
+_u8p = C.POINTER(C.c_uint8)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in include/monovo_b200.h
+SIGNATURES = {
+    "mvo_create": (C.c_int, [C.POINTER(_vp), C.POINTER(MvoConfig)]),
+    "mvo_destroy": (None, [_vp]),
+    "mvo_last_error": (C.c_char_p, [_vp]),
+    "mvo_version": (C.c_char_p, []),
+    "mvo_cuda_stream": (_vp, [_vp]),
+    "mvo_batch": (C.c_int, [_vp]),
+    "mvo_launch_count": (C.c_uint64, [_vp]),
+    "mvo_orb_detect_and_compute": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _i32p]),
+    "mvo_orb_compute": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "mvo_orb_num_levels": (C.c_int, []),
+    "mvo_orb_level_size": (C.c_int, [_vp, C.c_int, _i32p, _i32p]),
+    "mvo_orb_get_level": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "mvo_orb_get_fast": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i32p]),
+    "mvo_knn_ratio": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _i32p]),
+    "mvo_knn2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "mvo_lk_track": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
+    "mvo_find_homography": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _i32p]),
+    "mvo_find_fundamental": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _i32p]),
+    "mvo_find_essential": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, _i32p]),
+    "mvo_recover_pose": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i32p]),
+    "mvo_triangulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mvo_score_hypotheses": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int, _vp, _vp, _vp]),
+    "mvo_group_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ros2_mono_vo_b200.build` "
+            "(ros2_mono_vo_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

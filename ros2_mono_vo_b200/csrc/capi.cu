@@ -1,0 +1,275 @@
+// capi.cu -- extern "C" entry points of libmonovo_b200.so (context, ORB, kNN).  See include/monovo_b200.h.
+#include "context.cuh"
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+
+static std::string g_create_error;
+static std::mutex g_create_mutex;
+
+using namespace mvo;
+
+#define MVO_CHECK_ARG(ctx, cond, msg)  \
+  do {                                 \
+    if (!(cond)) {                     \
+      (ctx)->set_error(msg);           \
+      return MVO_ERR_INVALID;          \
+    }                                  \
+  } while (0)
+
+static int ensure_stage(mvo_ctx* c, size_t bytes) {
+  if (bytes > c->h_stage.n) MVO_CUDA_TRY(c, c->h_stage.alloc(bytes + bytes / 4 + 4096));
+  return MVO_OK;
+}
+
+extern "C" {
+
+const char* mvo_version(void) { return "monovo_b200 0.1 (sm_100a)"; }
+
+int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
+  std::lock_guard<std::mutex> lock(g_create_mutex);
+  if (!out || !cfg) {
+    g_create_error = "mvo_create: null argument";
+    return MVO_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->max_width < 16 || cfg->max_height < 16 || cfg->nfeatures < 1 || cfg->batch < 1 ||
+      cfg->max_width > 16384 || cfg->max_height > 16384) {
+    g_create_error = "mvo_create: configuration out of range";
+    return MVO_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    g_create_error = std::string("mvo_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); libmonovo_b200 has no CPU fallback";
+    return MVO_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "mvo_create: device ordinal out of range";
+    return MVO_ERR_INVALID;
+  }
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return MVO_ERR_CUDA;
+  }
+  mvo_ctx* c = new mvo_ctx();
+  c->cfg = *cfg;
+  if (c->cfg.max_points <= 0) c->cfg.max_points = 2 * c->cfg.nfeatures;
+  if (c->cfg.ransac_seed == 0) c->cfg.ransac_seed = 0xFFFFFFFFFFFFFFFFull;
+  if (cfg->cuda_stream) {
+    c->stream = (cudaStream_t)cfg->cuda_stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+      delete c;
+      return MVO_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  for (auto& t : c->timers) {
+    cudaEventCreate(&t.beg);
+    cudaEventCreate(&t.end);
+  }
+  *out = c;
+  return MVO_OK;
+}
+
+void mvo_destroy(mvo_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
+  c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->hist.release();
+  c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();
+  c->c2_count.release(); c->kps.release(); c->desc.release(); c->kp_valid.release(); c->kp_count.release();
+  c->flags.release(); c->h_stage.release(); c->prev_kps.release(); c->prev_desc.release();
+  c->prev_kp_count.release(); c->knn_q.release(); c->knn_t.release(); c->knn_best.release();
+  c->knn_matches.release(); c->knn_nmatch.release(); c->knn_counts.release();
+  for (auto& t : c->timers) {
+    if (t.beg) cudaEventDestroy(t.beg);
+    if (t.end) cudaEventDestroy(t.end);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* mvo_last_error(const mvo_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+void* mvo_cuda_stream(mvo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int mvo_batch(const mvo_ctx* c) { return c ? c->cfg.batch : 0; }
+uint64_t mvo_launch_count(const mvo_ctx* c) { return c ? c->launches : 0; }
+int mvo_orb_num_levels(void) { return kLevels; }
+
+// ------------------------------------------------------------------------------------------------
+int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels,
+                               mvo_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_CHECK_ARG(c, img && kps && n_out && cap >= 0, "mvo_orb_detect_and_compute: null argument");
+  MVO_CHECK_ARG(c, channels == 1 || channels == 3, "channels must be 1 or 3");
+  MVO_CHECK_ARG(c, stride >= w * channels, "stride smaller than a row");
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  int rc = orb_prepare(c, w, h);
+  if (rc) return rc;
+  const OrbGeom& g = c->geom;
+  // the single-image API drives stream 0 of the group; replicate the frame for the other streams
+  if (g.batch != 1) {
+    c->set_error("mvo_orb_detect_and_compute needs a batch==1 context (use mvo_group_step for groups)");
+    return MVO_ERR_INVALID;
+  }
+  rc = orb_upload(c, img, w, h, stride, channels, 0);
+  if (rc) return rc;
+  rc = orb_run_detect(c, desc != nullptr);
+  if (rc) return rc;
+  const size_t kb = (size_t)g.kp_cap * sizeof(mvo_keypoint), db = (size_t)g.kp_cap * 32;
+  rc = ensure_stage(c, kb + db + 64);
+  if (rc) return rc;
+  uint8_t* hs = c->h_stage.p;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs, c->kp_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 16, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64, c->kps.p, kb, cudaMemcpyDeviceToHost, c->stream));
+  if (desc) MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64 + kb, c->desc.p, db, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  int n = *reinterpret_cast<int*>(hs);
+  const int flags = *reinterpret_cast<int*>(hs + 16);
+  if (flags & 1) {
+    c->set_error("FAST candidate list overflow");
+    return MVO_ERR_CAPACITY;
+  }
+  if ((flags & 2) || n > cap) {
+    *n_out = n;
+    c->set_error("keypoint capacity exceeded");
+    return MVO_ERR_CAPACITY;
+  }
+  memcpy(kps, hs + 64, (size_t)n * sizeof(mvo_keypoint));
+  if (desc) memcpy(desc, hs + 64 + kb, (size_t)n * 32);
+  *n_out = n;
+  return MVO_OK;
+}
+
+int mvo_orb_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels,
+                    const mvo_keypoint* kps_in, int n, uint8_t* desc, uint8_t* valid) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_CHECK_ARG(c, img && kps_in && desc && n >= 0, "mvo_orb_compute: null argument");
+  MVO_CHECK_ARG(c, channels == 1 || channels == 3, "channels must be 1 or 3");
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  int rc = orb_prepare(c, w, h);
+  if (rc) return rc;
+  const OrbGeom& g = c->geom;
+  MVO_CHECK_ARG(c, g.batch == 1, "mvo_orb_compute needs a batch==1 context");
+  if (n > g.kp_cap) {
+    c->set_error("more keypoints than the context capacity");
+    return MVO_ERR_CAPACITY;
+  }
+  rc = orb_upload(c, img, w, h, stride, channels, 0);
+  if (rc) return rc;
+  rc = orb_run_levels_only(c);
+  if (rc) return rc;
+  if (n == 0) {
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MVO_OK;
+  }
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->kps.p, kps_in, (size_t)n * sizeof(mvo_keypoint), cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->kp_count.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
+  rc = orb_run_brief_given(c, n);
+  if (rc) return rc;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(desc, c->desc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (valid) MVO_CUDA_TRY(c, cudaMemcpyAsync(valid, c->kp_valid.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MVO_OK;
+}
+
+int mvo_orb_level_size(mvo_ctx* c, int level, int* w, int* h) {
+  if (!c || level < 0 || level >= kLevels || c->geom_w < 0) return MVO_ERR_INVALID;
+  if (w) *w = c->geom.lv[level].w;
+  if (h) *h = c->geom.lv[level].h;
+  return MVO_OK;
+}
+
+int mvo_orb_get_level(mvo_ctx* c, int level, int blurred, uint8_t* out, int out_stride) {
+  if (!c || !out || level < 0 || level >= kLevels || c->geom_w < 0) return MVO_ERR_INVALID;
+  const LevelGeom& lv = c->geom.lv[level];
+  if (out_stride < lv.w) return MVO_ERR_INVALID;
+  const uint8_t* src = (blurred ? c->blur.p : c->pyr.p) + lv.off;
+  MVO_CUDA_TRY(c, cudaMemcpy2DAsync(out, out_stride, src, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MVO_OK;
+}
+
+int mvo_orb_get_fast(mvo_ctx* c, int level, uint32_t* xy, int32_t* score, int cap, int* n_out) {
+  if (!c || !xy || !score || !n_out || level < 0 || level >= kLevels || c->geom_w < 0) return MVO_ERR_INVALID;
+  const LevelGeom& lv = c->geom.lv[level];
+  int n = 0;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(&n, c->cand_count.p + level, 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  n = std::min(n, lv.cand_cap);
+  *n_out = n;
+  if (n > cap) return MVO_ERR_CAPACITY;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(xy, c->cand_xy.p + lv.cand_off, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(score, c->cand_score.p + lv.cand_off, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int knn_host(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, double ratio) {
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  MVO_CUDA_TRY(c, c->knn_q.alloc((size_t)std::max(nq, 1) * 32));
+  MVO_CUDA_TRY(c, c->knn_t.alloc((size_t)std::max(nt, 1) * 32));
+  MVO_CUDA_TRY(c, c->knn_counts.alloc(2));
+  if (nq) MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+  if (nt) MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+  int rc = ensure_stage(c, 64);
+  if (rc) return rc;
+  int* hc = reinterpret_cast<int*>(c->h_stage.p);
+  hc[0] = nq;
+  hc[1] = nt;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_counts.p, hc, 8, cudaMemcpyHostToDevice, c->stream));
+  return knn_run(c, c->knn_q.p, c->knn_counts.p, std::max(nq, 1), std::max(nq, 1), c->knn_t.p, c->knn_counts.p + 1,
+                 std::max(nt, 1), std::max(nt, 1), ratio, 1);
+}
+
+int mvo_knn_ratio(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, double ratio, mvo_dmatch* out,
+                  int* n_out) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_CHECK_ARG(c, n_out && nq >= 0 && nt >= 0 && (nq == 0 || (q && out)) && (nt == 0 || t),
+                "mvo_knn_ratio: bad argument");
+  *n_out = 0;
+  if (nq == 0) return MVO_OK;
+  int rc = knn_host(c, q, nq, t, nt, ratio);
+  if (rc) return rc;
+  rc = ensure_stage(c, (size_t)nq * sizeof(mvo_dmatch) + 64);
+  if (rc) return rc;
+  uint8_t* hs = c->h_stage.p;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs, c->knn_nmatch.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64, c->knn_matches.p, (size_t)nq * sizeof(mvo_dmatch), cudaMemcpyDeviceToHost,
+                                  c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const int n = *reinterpret_cast<int*>(hs);
+  memcpy(out, hs + 64, (size_t)n * sizeof(mvo_dmatch));
+  *n_out = n;
+  return MVO_OK;
+}
+
+int mvo_knn2(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_CHECK_ARG(c, nq >= 0 && nt >= 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t), "mvo_knn2: bad argument");
+  if (nq == 0) return MVO_OK;
+  int rc = knn_host(c, q, nq, t, nt, 0.7);
+  if (rc) return rc;
+  rc = ensure_stage(c, (size_t)nq * 8);
+  if (rc) return rc;
+  uint32_t* hb = reinterpret_cast<uint32_t*>(c->h_stage.p);
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hb, c->knn_best.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nq; ++i)
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t key = hb[2 * i + k];
+      idx[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key & 0x3FFFFFu);
+      dist[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key >> 22);
+    }
+  return MVO_OK;
+}
+
+}  // extern "C"

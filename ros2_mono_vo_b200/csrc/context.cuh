@@ -1,0 +1,75 @@
+// context.cuh -- the stream-group context behind the C ABI (one per group of camera streams).
+#pragma once
+#include "common.cuh"
+
+struct StageTimer {
+  cudaEvent_t beg = nullptr, end = nullptr;
+  bool used = false;
+};
+
+struct mvo_ctx {
+  mvo_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  void set_error(const std::string& s) { err = s; }
+
+  // ---------------- ORB ----------------
+  mvo::OrbGeom geom{};
+  int geom_w = -1, geom_h = -1;
+  mvo::DevBuf<uint8_t> img_in;        // batch * h * stride staging for BGR input
+  mvo::DevBuf<uint8_t> pyr, blur;     // batch * frame_stride
+  mvo::DevBuf<uint32_t> xtab, ytab;   // INTER_LINEAR_EXACT coefficient tables (offset | c1 << 16)
+  mvo::DevBuf<uint32_t> cand_xy;      // batch * cand_total : x | y << 16
+  mvo::DevBuf<int32_t> cand_score;    // batch * cand_total : FAST score
+  mvo::DevBuf<int32_t> cand_count;    // batch * 8
+  mvo::DevBuf<uint32_t> hist;         // batch * 8 * 256 : FAST score histogram
+  mvo::DevBuf<unsigned long long> c2_key, c2_key_sorted;  // Harris stage: sort keys
+  mvo::DevBuf<float2> c2_ra, c2_ra_sorted;                // (response, angle)
+  mvo::DevBuf<int32_t> c2_count;      // batch * 8
+  mvo::DevBuf<mvo_keypoint> kps;      // batch * kp_cap
+  mvo::DevBuf<uint8_t> desc;          // batch * kp_cap * 32
+  mvo::DevBuf<uint8_t> kp_valid;      // batch * kp_cap (orb_compute hook)
+  mvo::DevBuf<int32_t> kp_count;      // batch
+  mvo::DevBuf<int32_t> flags;         // batch : bit0 = candidate overflow, bit1 = keypoint overflow
+  mvo::PinBuf<uint8_t> h_stage;       // pinned staging for H2D / D2H
+  size_t h_stage_bytes = 0;
+
+  // previous-frame state for the group step (device resident)
+  mvo::DevBuf<mvo_keypoint> prev_kps;
+  mvo::DevBuf<uint8_t> prev_desc;
+  mvo::DevBuf<int32_t> prev_kp_count;
+  bool have_prev = false;
+
+  // ---------------- kNN ----------------
+  mvo::DevBuf<uint8_t> knn_q, knn_t;          // staging for the host-pointer API
+  mvo::DevBuf<uint32_t> knn_best;             // batch * maxq * 2 packed keys (dist << 22 | idx)
+  mvo::DevBuf<mvo_dmatch> knn_matches;        // batch * maxq
+  mvo::DevBuf<int32_t> knn_nmatch;            // batch
+  mvo::DevBuf<int32_t> knn_counts;            // 2 ints (nq, nt) for the host-pointer API
+
+  // ---------------- stage timing ----------------
+  static constexpr int kNumStages = 9;
+  StageTimer timers[kNumStages];
+};
+
+namespace mvo {
+
+// host-side module entry points (defined in the respective .cu files)
+int orb_prepare(mvo_ctx* c, int w, int h);
+int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels, int on_device);
+int orb_run_detect(mvo_ctx* c, bool want_desc);
+int orb_run_levels_only(mvo_ctx* c);
+int orb_run_brief_given(mvo_ctx* c, int n);
+
+int knn_prepare(mvo_ctx* c, int maxq);
+// batched device-resident kNN: q/t are [batch][stride_rows][32]; counts on device
+int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_stride_rows, int max_nq,
+            const uint8_t* t_dev, const int32_t* nt_dev, int t_stride_rows, int max_nt, double ratio,
+            int batch);
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace mvo

@@ -1,0 +1,200 @@
+// knn.cu -- brute-force Hamming kNN (k = 2) + Lowe ratio test.
+//
+// Replaces matcher_.knnMatch(d1, d2, knn, 2) + the ratio loop at
+// /root/reference/src/feature_processor.cpp:25-40.  Contract: top-2 by
+// (distance, trainIdx) ascending, accepted iff two neighbours exist and d0 < ratio * d1 in double.
+//
+// knn_top2_kernel: a warp owns Q=4 query descriptors in registers; the train set streams through a
+// swizzled shared-memory tile (conflict-free 128-bit reads, one train row per lane); distances are
+// xor + __popc over the two uint4 halves; every lane keeps a private top-2 of packed keys
+// (dist << 22 | trainIdx), merged at the end by a warp-shuffle top-2 reduction.  The train range
+// can be split over blockIdx.y to fill the 148 SMs for a single stream.
+// knn_finish_kernel: merges the splits, applies the ratio test and compacts in query order.
+#include "context.cuh"
+#include <algorithm>
+
+namespace mvo {
+
+constexpr int kKnnQ = 4;             // queries per warp
+constexpr int kKnnWarps = 8;
+constexpr int kKnnThreads = kKnnWarps * 32;
+constexpr int kKnnTile = 256;        // train rows per smem tile (8 KB)
+constexpr int kKnnMaxSplit = 8;
+constexpr uint32_t kInvalidKey = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void top2_insert(uint32_t& k0, uint32_t& k1, uint32_t key) {
+  k1 = min(k1, max(k0, key));
+  k0 = min(k0, key);
+}
+
+__global__ void __launch_bounds__(kKnnThreads)
+knn_top2_kernel(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_dev, int q_stride_rows,
+                const uint8_t* __restrict__ t, const int32_t* __restrict__ nt_dev, int t_stride_rows,
+                uint2* __restrict__ partial, int max_nq, int nsplit) {
+  __shared__ __align__(16) uint4 tile[kKnnTile * 2];
+  const int b = blockIdx.z;
+  const int nq = min(nq_dev[b], max_nq), nt = nt_dev[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = (blockIdx.x * kKnnWarps + warp) * kKnnQ;
+  if (blockIdx.x * kKnnWarps * kKnnQ >= nq) return;
+
+  // this block's slice of the train set, in whole tiles
+  const int tiles_total = (nt + kKnnTile - 1) / kKnnTile;
+  const int tiles_per = (tiles_total + nsplit - 1) / nsplit;
+  const int t_begin = blockIdx.y * tiles_per * kKnnTile;
+  const int t_end = min(nt, t_begin + tiles_per * kKnnTile);
+
+  uint32_t qr[kKnnQ][8];
+  const uint4* qv = reinterpret_cast<const uint4*>(q + (long long)b * q_stride_rows * 32);
+#pragma unroll
+  for (int i = 0; i < kKnnQ; ++i) {
+    const int qi = min(q0 + i, nq - 1);
+    const uint4 a = __ldg(qv + qi * 2), c = __ldg(qv + qi * 2 + 1);
+    qr[i][0] = a.x; qr[i][1] = a.y; qr[i][2] = a.z; qr[i][3] = a.w;
+    qr[i][4] = c.x; qr[i][5] = c.y; qr[i][6] = c.z; qr[i][7] = c.w;
+  }
+  uint32_t k0[kKnnQ], k1[kKnnQ];
+#pragma unroll
+  for (int i = 0; i < kKnnQ; ++i) k0[i] = k1[i] = kInvalidKey;
+
+  const uint4* tv = reinterpret_cast<const uint4*>(t + (long long)b * t_stride_rows * 32);
+  for (int base = t_begin; base < t_end; base += kKnnTile) {
+    __syncthreads();
+    {
+      // 256 threads x 2 chunks: row r = threadIdx.x, chunk c stored at slot 2r + (c ^ ((r >> 2) & 1))
+      const int r = threadIdx.x;
+      const int gr = base + r;
+      uint4 a = make_uint4(0, 0, 0, 0), c = a;
+      if (gr < t_end) {
+        a = __ldg(tv + (long long)gr * 2);
+        c = __ldg(tv + (long long)gr * 2 + 1);
+      }
+      const int sw = (r >> 2) & 1;
+      tile[2 * r + sw] = a;
+      tile[2 * r + (sw ^ 1)] = c;
+    }
+    __syncthreads();
+    const int rows = min(kKnnTile, t_end - base);
+#pragma unroll 2
+    for (int r = lane; r < rows; r += 32) {
+      const int sw = (r >> 2) & 1;
+      const uint4 a = tile[2 * r + sw], c = tile[2 * r + (sw ^ 1)];
+      const uint32_t idx = (uint32_t)(base + r);
+#pragma unroll
+      for (int i = 0; i < kKnnQ; ++i) {
+        const int d = __popc(qr[i][0] ^ a.x) + __popc(qr[i][1] ^ a.y) + __popc(qr[i][2] ^ a.z) +
+                      __popc(qr[i][3] ^ a.w) + __popc(qr[i][4] ^ c.x) + __popc(qr[i][5] ^ c.y) +
+                      __popc(qr[i][6] ^ c.z) + __popc(qr[i][7] ^ c.w);
+        top2_insert(k0[i], k1[i], ((uint32_t)d << 22) | idx);
+      }
+    }
+  }
+  // warp-shuffle top-2 reduction: merge two sorted pairs per step
+#pragma unroll
+  for (int i = 0; i < kKnnQ; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0[i], o);
+      const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1[i], o);
+      const uint32_t n1 = min(max(k0[i], o0), min(k1[i], o1));
+      k0[i] = min(k0[i], o0);
+      k1[i] = n1;
+    }
+    if (lane == 0 && q0 + i < nq)
+      partial[((long long)b * nsplit + blockIdx.y) * max_nq + q0 + i] = make_uint2(k0[i], k1[i]);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+knn_finish_kernel(const uint2* __restrict__ partial, const int32_t* __restrict__ nq_dev, int max_nq, int nsplit,
+                  double ratio, uint2* __restrict__ best, mvo_dmatch* __restrict__ matches,
+                  int32_t* __restrict__ nmatch) {
+  const int b = blockIdx.x;
+  const int nq = min(nq_dev[b], max_nq);
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < nq; q0 += 1024) {
+    const int qi = q0 + tid;
+    uint32_t k0 = kInvalidKey, k1 = kInvalidKey;
+    if (qi < nq) {
+      for (int s = 0; s < nsplit; ++s) {
+        const uint2 p = partial[((long long)b * nsplit + s) * max_nq + qi];
+        const uint32_t n1 = min(max(k0, p.x), min(k1, p.y));
+        k0 = min(k0, p.x);
+        k1 = n1;
+      }
+      best[(long long)b * max_nq + qi] = make_uint2(k0, k1);
+    }
+    int ok = 0;
+    if (qi < nq && k1 != kInvalidKey) {
+      const float d0 = (float)(k0 >> 22), d1 = (float)(k1 >> 22);
+      ok = ((double)d0 < ratio * (double)d1) ? 1 : 0;   // float < double * float, as in the reference
+    }
+    // ordered compaction: block exclusive scan of ok
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int within = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+      }
+      s_warp[lane] = v;  // inclusive
+    }
+    __syncthreads();
+    const int base = s_base + (warp ? s_warp[warp - 1] : 0);
+    if (ok) {
+      mvo_dmatch m;
+      m.query_idx = qi;
+      m.train_idx = (int)(k0 & 0x3FFFFFu);
+      m.img_idx = 0;
+      m.distance = (float)(k0 >> 22);
+      matches[(long long)b * max_nq + base + within] = m;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) nmatch[b] = s_base;
+}
+
+int knn_prepare(mvo_ctx* c, int maxq) {
+  const size_t B = (size_t)c->cfg.batch;
+  MVO_CUDA_TRY(c, c->knn_best.alloc(B * (size_t)maxq * 2 * (kKnnMaxSplit + 1)));
+  MVO_CUDA_TRY(c, c->knn_matches.alloc(B * (size_t)maxq));
+  MVO_CUDA_TRY(c, c->knn_nmatch.alloc(B));
+  return MVO_OK;
+}
+
+int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_stride_rows, int max_nq,
+            const uint8_t* t_dev, const int32_t* nt_dev, int t_stride_rows, int max_nt, double ratio, int batch) {
+  if (max_nt >= (1 << 22)) {
+    c->set_error("train set too large (>= 2^22 rows)");
+    return MVO_ERR_CAPACITY;
+  }
+  int rc = knn_prepare(c, max_nq);
+  if (rc) return rc;
+  uint2* best = reinterpret_cast<uint2*>(c->knn_best.p);
+  uint2* partial = best + (size_t)batch * max_nq;
+  const int qblocks = std::max(1, (max_nq + kKnnWarps * kKnnQ - 1) / (kKnnWarps * kKnnQ));
+  const int tiles = std::max(1, (max_nt + kKnnTile - 1) / kKnnTile);
+  int nsplit = (2 * 148 + qblocks * batch - 1) / (qblocks * batch);
+  nsplit = std::max(1, std::min(std::min(nsplit, kKnnMaxSplit), tiles));
+  dim3 grid(qblocks, nsplit, batch);
+  knn_top2_kernel<<<grid, kKnnThreads, 0, c->stream>>>(q_dev, nq_dev, q_stride_rows, t_dev, nt_dev, t_stride_rows,
+                                                      partial, max_nq, nsplit);
+  c->launches++;
+  knn_finish_kernel<<<batch, 1024, 0, c->stream>>>(partial, nq_dev, max_nq, nsplit, ratio, best, c->knn_matches.p,
+                                                  c->knn_nmatch.p);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+}  // namespace mvo

@@ -1,0 +1,823 @@
+// orb.cu -- cv::ORB::detectAndCompute re-designed for B200 (sm_100a).
+//
+// Replaces the call at /root/reference/src/feature_processor.cpp:22 (detector_->detectAndCompute).
+// Arithmetic contract: SURVEY.md Appendix A.1 (bit-exact keypoint set / response / angle / descriptors
+// against cv2 4.13.0).  Structure (per stream group, batch dimension = blockIdx.z):
+//
+//   K1  orb_level_kernel<RESIZE>   one launch per pyramid level: INTER_LINEAR_EXACT resize of the 64x32
+//                                  tile (+4 halo) from level l-1 staged in smem with 128-bit loads ->
+//                                  level l store + FAST-9/16 (quick-reject + compacted full score) +
+//                                  3x3 NMS + edge filter + score histogram + 7x7 float blur store.
+//   K2  orb_harris_angle_kernel    warp per surviving candidate (score >= histogram cut): 7x7 Harris
+//                                  (int32 sums, non-fused FP32) + intensity-centroid angle.
+//   K3  orb_rank_kernel            per level all-pairs rank on a unique 64-bit key -> sorted scatter.
+//   K4  orb_finalize_kernel        retainBest(n_l) cut with ties, cross-level prefix, mvo_keypoint write.
+//   K5  orb_brief_kernel           warp per keypoint, lane per descriptor byte (16 rotated samples).
+#include "context.cuh"
+#include <math.h>
+#include <algorithm>
+
+namespace mvo {
+
+// ------------------------------------------------------------------------------------------------
+// constants (bit patterns verified against cv2 4.13.0, see oracle/orb_oracle.py)
+__constant__ float c_gauss[7] = {0.07015932351350784f, 0.13107487559318542f, 0.1907128244638443f,
+                                 0.21610593795776367f, 0.1907128244638443f,  0.13107487559318542f,
+                                 0.07015932351350784f};
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__constant__ signed char c_pattern[512][2] = {
+#include "brief_pattern_31.inc"
+};
+
+constexpr int TW = 64, TH = 32, HALO = 4;
+constexpr int TS = 96;    // smem tile row stride in bytes
+constexpr int TX0 = 16;   // smem column of tile-local x = 0 (keeps the interior 16-byte aligned)
+constexpr int SROWS = TH + 2 * HALO;  // 40
+constexpr int SCOLS = TW + 2 * HALO;  // 72
+constexpr int SRC_ROWS_MAX = 56;
+constexpr int SRC_COLS_MAX = 128;
+constexpr int FW = TW + 2, FH = TH + 2;  // FAST score region (1 halo for NMS)
+constexpr int FS = 68;                   // score row stride
+constexpr int kLevelThreads = 256;
+
+struct LevelArgs {
+  const uint8_t* src;
+  uint8_t* dst;
+  uint8_t* blur;
+  long long frame_stride;
+  int sw, sh, spitch;
+  int w, h, pitch;
+  const uint32_t* xtab;
+  const uint32_t* ytab;
+  uint32_t* cand_xy;
+  int32_t* cand_score;
+  int32_t* cand_count;
+  uint32_t* hist;
+  int32_t* flags;
+  int cand_cap, cand_total, cand_off;
+  int level;
+  int do_fast;   // 0: pyramid + blur only (orb_compute hook)
+};
+
+__device__ __forceinline__ int fast_full_score(const uint8_t* t, int idx) {
+  // OpenCV ring order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+  const int off[16] = {3 * TS,      3 * TS + 1,  2 * TS + 2,  TS + 3,  3,        -TS + 3,  -2 * TS + 2, -3 * TS + 1,
+                       -3 * TS,     -3 * TS - 1, -2 * TS - 2, -TS - 3, -3,       TS - 3,   2 * TS - 2,  3 * TS - 1};
+  const int c = t[idx];
+  int d[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) d[k] = c - (int)t[idx + off[k]];
+  int mn2[16], mx2[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mn2[k] = min(d[k], d[(k + 1) & 15]);
+    mx2[k] = max(d[k], d[(k + 1) & 15]);
+  }
+  int mn4[16], mx4[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
+    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+  }
+  int best = -1000;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+    best = max(best, max(mn9, -mx9));
+  }
+  return best;  // corner iff best > threshold; score = best - 1
+}
+
+template <bool RESIZE>
+__global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArgs a) {
+  __shared__ __align__(16) uint8_t tile[SROWS * TS];
+  // scratch: resize staging (src rows + 8.8 horizontal pass) is dead before the blur row buffer is live
+  __shared__ __align__(16) uint8_t scratch[SRC_ROWS_MAX * SRC_COLS_MAX + SRC_ROWS_MAX * SCOLS * 2];
+  __shared__ uint8_t score[FH * FS];
+  __shared__ uint16_t work[FW * FH];
+  __shared__ uint32_t hist_s[256];
+  __shared__ uint32_t emit_xy[TW * TH / 4];
+  __shared__ uint8_t emit_sc[TW * TH / 4];
+  __shared__ uint32_t tab_x[SCOLS], tab_y[SROWS];
+  __shared__ int n_work, n_emit, emit_base;
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+  const int w = a.w, h = a.h;
+  uint8_t* dst = a.dst + (long long)b * a.frame_stride;
+  uint8_t* blur = a.blur + (long long)b * a.frame_stride;
+
+  if (tid == 0) {
+    n_work = 0;
+    n_emit = 0;
+  }
+  hist_s[tid] = 0;  // kLevelThreads == 256
+
+  if (RESIZE) {
+    const uint8_t* src = a.src + (long long)b * a.frame_stride;
+    uint8_t* src_s = scratch;
+    uint16_t* hbuf = reinterpret_cast<uint16_t*>(scratch + SRC_ROWS_MAX * SRC_COLS_MAX);
+    if (tid < SCOLS) tab_x[tid] = __ldg(a.xtab + min(max(tx0 - HALO + tid, 0), w - 1));
+    if (tid >= 128 && tid < 128 + SROWS) tab_y[tid - 128] = __ldg(a.ytab + min(max(ty0 - HALO + tid - 128, 0), h - 1));
+    __syncthreads();
+    const int r0 = tab_y[0] & 0xffff;
+    const int r1 = min((int)(tab_y[SROWS - 1] & 0xffff) + 1, a.sh - 1);
+    const int nrows = min(r1 - r0 + 1, SRC_ROWS_MAX);
+    const int c0a = (int)(tab_x[0] & 0xffff) & ~15;
+    const int c1e = min((int)(tab_x[SCOLS - 1] & 0xffff) + 1, a.sw - 1);
+    const int nch = min((c1e - c0a) / 16 + 1, SRC_COLS_MAX / 16);
+    // stage A: source rows, 128-bit loads
+    for (int i = tid; i < nrows * nch; i += kLevelThreads) {
+      const int r = i / nch, k = i - r * nch;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * a.spitch + c0a + k * 16));
+      *reinterpret_cast<uint4*>(src_s + r * SRC_COLS_MAX + k * 16) = v;
+    }
+    __syncthreads();
+    // stage B: horizontal pass in 8.8 fixed point
+    for (int i = tid; i < nrows * SCOLS; i += kLevelThreads) {
+      const int r = i / SCOLS, xl = i - r * SCOLS;
+      const uint32_t e = tab_x[xl];
+      const int o = e & 0xffff, c1 = e >> 16;
+      const int o1 = min(o + 1, a.sw - 1);
+      const uint8_t* row = src_s + r * SRC_COLS_MAX - c0a;
+      hbuf[i] = (uint16_t)(row[o] * (256 - c1) + row[o1] * c1);
+    }
+    __syncthreads();
+    // stage C: vertical pass, round to u8
+    for (int i = tid; i < SROWS * SCOLS; i += kLevelThreads) {
+      const int yl = i / SCOLS, xl = i - yl * SCOLS;
+      const uint32_t e = tab_y[yl];
+      const int o = e & 0xffff, c1 = e >> 16;
+      const int o1 = min(o + 1, a.sh - 1);
+      const int ra = min(o - r0, nrows - 1), rb = min(o1 - r0, nrows - 1);
+      const int v = ((int)hbuf[ra * SCOLS + xl] * (256 - c1) + (int)hbuf[rb * SCOLS + xl] * c1 + 32768) >> 16;
+      tile[yl * TS + TX0 - HALO + xl] = (uint8_t)v;
+    }
+    __syncthreads();
+    // level store, 128-bit
+    for (int i = tid; i < TH * (TW / 16); i += kLevelThreads) {
+      const int yl = i / (TW / 16), k = i - yl * (TW / 16);
+      const int gy = ty0 + yl;
+      if (gy < h)
+        *reinterpret_cast<uint4*>(dst + (long long)gy * a.pitch + tx0 + k * 16) =
+            *reinterpret_cast<const uint4*>(tile + (yl + HALO) * TS + TX0 + k * 16);
+    }
+  } else {
+    // level 0: the image itself; load tile + halo with 128-bit loads
+    for (int i = tid; i < SROWS * (TS / 16); i += kLevelThreads) {
+      const int yl = i / (TS / 16), k = i - yl * (TS / 16);
+      const int gy = min(max(ty0 - HALO + yl, 0), h - 1);
+      const int gx0 = tx0 - TX0 + k * 16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (gx0 >= 0 && gx0 < a.pitch) v = __ldg(reinterpret_cast<const uint4*>(dst + (long long)gy * a.pitch + gx0));
+      *reinterpret_cast<uint4*>(tile + yl * TS + k * 16) = v;
+    }
+    __syncthreads();
+  }
+
+  // ---- FAST-9/16: quick reject, compact survivors, full score -------------------------------
+  if (a.do_fast) {
+    for (int p = tid; p < FW * FH; p += kLevelThreads) {
+      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
+      const int gx = tx0 + xl, gy = ty0 + yl;
+      score[(yl + 1) * FS + xl + 1] = 0;
+      if (gx >= kEdge - 1 && gx < w - (kEdge - 1) && gy >= kEdge - 1 && gy < h - (kEdge - 1)) {
+        const int idx = (yl + HALO) * TS + TX0 + xl;
+        const int c = tile[idx];
+        const int hi = c + kFastThr, lo = c - kFastThr;
+        // an arc of 9 contains at least one pixel of every antipodal pair
+        const int p0 = tile[idx + 3 * TS], p8 = tile[idx - 3 * TS];
+        int br = (p0 < lo) | (p8 < lo);  // ring darker than centre - thr  (d > thr)
+        int dk = (p0 > hi) | (p8 > hi);
+        if (br | dk) {
+          const int p4 = tile[idx + 3], p12 = tile[idx - 3];
+          br &= (p4 < lo) | (p12 < lo);
+          dk &= (p4 > hi) | (p12 > hi);
+          if (br | dk) {
+            const int p2 = tile[idx + 2 * TS + 2], p10 = tile[idx - 2 * TS - 2];
+            const int p6 = tile[idx - 2 * TS + 2], p14 = tile[idx + 2 * TS - 2];
+            br &= ((p2 < lo) | (p10 < lo)) & ((p6 < lo) | (p14 < lo));
+            dk &= ((p2 > hi) | (p10 > hi)) & ((p6 > hi) | (p14 > hi));
+            if (br | dk) work[atomicAdd(&n_work, 1)] = (uint16_t)p;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int nw = n_work;
+    for (int i = tid; i < nw; i += kLevelThreads) {
+      const int p = work[i];
+      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
+      const int best = fast_full_score(tile, (yl + HALO) * TS + TX0 + xl);
+      if (best > kFastThr) score[(yl + 1) * FS + xl + 1] = (uint8_t)(best - 1);
+    }
+    __syncthreads();
+    // ---- 3x3 non-max suppression + 31 px edge filter + emit --------------------------------
+    for (int p = tid; p < TW * TH; p += kLevelThreads) {
+      const int yl = p / TW, xl = p - yl * TW;
+      const int gx = tx0 + xl, gy = ty0 + yl;
+      const uint8_t* s = score + (yl + 1) * FS + xl + 1;
+      const int v = s[0];
+      if (v > 0 && gx >= kEdge && gx < w - kEdge && gy >= kEdge && gy < h - kEdge) {
+        if (v > s[-1] && v > s[1] && v > s[-FS - 1] && v > s[-FS] && v > s[-FS + 1] && v > s[FS - 1] &&
+            v > s[FS] && v > s[FS + 1]) {
+          const int e = atomicAdd(&n_emit, 1);
+          emit_xy[e] = (uint32_t)gx | ((uint32_t)gy << 16);
+          emit_sc[e] = (uint8_t)v;
+          atomicAdd(&hist_s[v], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    const int ne = n_emit;
+    if (ne > 0) {
+      if (tid == 0) emit_base = atomicAdd(a.cand_count + b * kLevels + a.level, ne);
+      __syncthreads();
+      const int base = emit_base;
+      for (int i = tid; i < ne; i += kLevelThreads) {
+        const int pos = base + i;
+        if (pos < a.cand_cap) {
+          const long long o = (long long)b * a.cand_total + a.cand_off + pos;
+          a.cand_xy[o] = emit_xy[i];
+          a.cand_score[o] = emit_sc[i];
+        } else {
+          atomicOr(a.flags + b, 1);
+        }
+      }
+      if (hist_s[tid]) atomicAdd(a.hist + ((long long)b * kLevels + a.level) * 256 + tid, hist_s[tid]);
+    }
+  }
+
+  // ---- ORB-internal 7x7 sigma-2 blur: float sepFilter, FMA order of OpenCV's AVX2 path -------
+  {
+    float* rowbuf = reinterpret_cast<float*>(scratch);  // (TH + 6) x TW floats = 9728 B
+    __syncthreads();                                     // scratch (resize staging) is dead
+    for (int i = tid; i < (TH + 6) * TW; i += kLevelThreads) {
+      const int yr = i / TW, xl = i - yr * TW;
+      const int gy = reflect101(ty0 + yr - 3, h);
+      const int ly = min(max(gy - ty0 + HALO, 0), SROWS - 1);
+      const uint8_t* trow = tile + ly * TS + TX0 - tx0;  // index with global x
+      const int gx = tx0 + xl;
+      float s;
+      {
+        int xx[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int rx = reflect101(gx + j - 3, w);
+          xx[j] = min(max(rx, tx0 - HALO), tx0 + TW + HALO - 1);
+        }
+        s = __fmul_rn(c_gauss[0], (float)trow[xx[0]]);
+#pragma unroll
+        for (int j = 1; j < 7; ++j) s = __fmaf_rn(c_gauss[j], (float)trow[xx[j]], s);
+      }
+      rowbuf[i] = s;
+    }
+    __syncthreads();
+    uint8_t* outt = tile;  // reuse rows of the tile? no: tile still needed by nobody after this point
+    __shared__ __align__(16) uint8_t blur_s[TH * TW];
+    (void)outt;
+    for (int i = tid; i < TH * TW; i += kLevelThreads) {
+      const int yl = i / TW, xl = i - yl * TW;
+      const float* r = rowbuf + yl * TW + xl;
+      float s = __fmul_rn(c_gauss[3], r[3 * TW]);
+      s = __fmaf_rn(c_gauss[2], __fadd_rn(r[2 * TW], r[4 * TW]), s);
+      s = __fmaf_rn(c_gauss[1], __fadd_rn(r[1 * TW], r[5 * TW]), s);
+      s = __fmaf_rn(c_gauss[0], __fadd_rn(r[0], r[6 * TW]), s);
+      int v = __float2int_rn(s);
+      v = min(max(v, 0), 255);
+      blur_s[i] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * (TW / 16); i += kLevelThreads) {
+      const int yl = i / (TW / 16), k = i - yl * (TW / 16);
+      const int gy = ty0 + yl;
+      if (gy < h)
+        *reinterpret_cast<uint4*>(blur + (long long)gy * a.pitch + tx0 + k * 16) =
+            *reinterpret_cast<const uint4*>(blur_s + yl * TW + k * 16);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BGR -> gray, (B*3735 + G*19235 + R*9798 + 16384) >> 15   (cvtColor BGR2GRAY)
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, int stride, long long in_frame_stride,
+                                   uint8_t* __restrict__ gray, int pitch, long long frame_stride, int w, int h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= w || y >= h) return;
+  const uint8_t* p = bgr + (long long)b * in_frame_stride + (long long)y * stride + 3 * x;
+  gray[(long long)b * frame_stride + (long long)y * pitch + x] =
+      (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: Harris response + IC angle, one warp per candidate that survives retainBest(2 n_l) by FAST score
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float p1 = __uint_as_float(0x4265226fu), p3 = __uint_as_float(0xc19556eeu);
+  const float p5 = __uint_as_float(0x410e9fbfu), p7 = __uint_as_float(0xc0228ad9u);
+  const float eps = __uint_as_float(0x25800000u);  // (float)DBL_EPSILON
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+  const float c = __fdiv_rn(mn, __fadd_rn(mx, eps));
+  const float c2 = __fmul_rn(c, c);
+  float a = __fadd_rn(__fmul_rn(p7, c2), p5);
+  a = __fadd_rn(__fmul_rn(a, c2), p3);
+  a = __fadd_rn(__fmul_rn(a, c2), p1);
+  a = __fmul_rn(a, c);
+  if (ax < ay) a = __fsub_rn(90.f, a);
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+constexpr int kHarrisWarps = 8;
+
+__global__ void __launch_bounds__(kHarrisWarps * 32)
+orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
+                        const int32_t* __restrict__ cand_score, const int32_t* __restrict__ cand_count,
+                        const uint32_t* __restrict__ hist, unsigned long long* __restrict__ c2_key,
+                        float2* __restrict__ c2_ra, int32_t* __restrict__ c2_count) {
+  const int level = blockIdx.y, b = blockIdx.z;
+  const LevelGeom lv = g.lv[level];
+  __shared__ int s_thr;
+  __shared__ uint32_t s_h[256];
+  const int tid = threadIdx.x;
+  const int count = min(cand_count[b * kLevels + level], lv.cand_cap);
+  const int warp = tid >> 5, lane = tid & 31;
+  if (blockIdx.x * kHarrisWarps >= count) return;
+  // FAST-score cut of retainBest(2 n_l): largest r with #(score >= r) >= 2 n_l; keep score >= r
+  s_h[tid] = hist[((long long)b * kLevels + level) * 256 + tid];
+  __syncthreads();
+  if (tid == 0) {
+    int thr = 0;
+    const int k = 2 * lv.quota;
+    if (count > k) {
+      int acc = 0;
+      for (int r = 255; r >= 0; --r) {
+        acc += s_h[r];
+        if (acc >= k) {
+          thr = r;
+          break;
+        }
+      }
+    }
+    s_thr = thr;
+  }
+  __syncthreads();
+  const int ci = blockIdx.x * kHarrisWarps + warp;
+  if (ci >= count) return;
+  const long long co = (long long)b * g.cand_total + lv.cand_off + ci;
+  if (cand_score[co] < s_thr) return;
+  const uint32_t xy = cand_xy[co];
+  const int x = xy & 0xffff, y = xy >> 16;
+  const uint8_t* img = pyr + (long long)b * g.frame_stride + lv.off;
+  const int pitch = lv.pitch;
+
+  // Harris 7x7 block of Sobel-3 gradients: 49 positions over the 32 lanes (2 rounds)
+  int sa = 0, sb = 0, sc = 0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int p = lane + 32 * r;
+    if (p < 49) {
+      const int dy = p / 7 - 3, dx = p - (p / 7) * 7 - 3;
+      const uint8_t* q = img + (long long)(y + dy) * pitch + x + dx;
+      const int a00 = q[-pitch - 1], a01 = q[-pitch], a02 = q[-pitch + 1];
+      const int a10 = q[-1], a12 = q[1];
+      const int a20 = q[pitch - 1], a21 = q[pitch], a22 = q[pitch + 1];
+      const int ix = (a12 - a10) * 2 + (a02 - a00) + (a22 - a20);
+      const int iy = (a21 - a01) * 2 + (a20 - a00) + (a22 - a02);
+      sa += ix * ix;
+      sb += iy * iy;
+      sc += ix * iy;
+    }
+  }
+  sa = warp_sum(sa);
+  sb = warp_sum(sb);
+  sc = warp_sum(sc);
+
+  // intensity centroid over the radius-15 disc: lane = column u + 15
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int u = lane - 15;
+    const int au = abs(u);
+    const uint8_t* q = img + (long long)y * pitch + x + u;
+#pragma unroll 1
+    for (int v = -15; v <= 15; ++v) {
+      if (au <= c_umax[abs(v)]) {
+        const int p = q[(long long)v * pitch];
+        m10 += u * p;
+        m01 += v * p;
+      }
+    }
+  }
+  m10 = warp_sum(m10);
+  m01 = warp_sum(m01);
+
+  if (lane == 0) {
+    const float s4 = __uint_as_float(0x25ddced1u);  // ((1/(4*7*255))^4 accumulated in float
+    const float k = __uint_as_float(0x3d23d70au);   // 0.04f
+    const float fa = (float)sa, fb = (float)sb, fc = (float)sc;
+    const float t1 = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
+    const float apb = __fadd_rn(fa, fb);
+    const float t2 = __fmul_rn(__fmul_rn(k, apb), apb);
+    const float resp = __fmul_rn(__fsub_rn(t1, t2), s4);
+    const float ang = fast_atan2_deg((float)m01, (float)m10);
+    const int pos = atomicAdd(c2_count + b * kLevels + level, 1);
+    const long long o = (long long)b * g.cand_total + lv.cand_off + pos;
+    // ascending key == (response desc, y asc, x asc); -0.f canonicalised so that ties compare equal
+    const uint32_t ro = ~float_orderable(__fadd_rn(resp, 0.f));
+    c2_key[o] = ((unsigned long long)ro << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+    c2_ra[o] = make_float2(resp, ang);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: rank each Harris candidate inside its level by all-pairs comparison of the unique key
+constexpr int kRankThreads = 256;
+__global__ void __launch_bounds__(kRankThreads)
+orb_rank_kernel(const OrbGeom g, const unsigned long long* __restrict__ key, const float2* __restrict__ ra,
+                const int32_t* __restrict__ c2_count, unsigned long long* __restrict__ key_sorted,
+                float2* __restrict__ ra_sorted) {
+  const int level = blockIdx.y, b = blockIdx.z;
+  const LevelGeom lv = g.lv[level];
+  const int m = c2_count[b * kLevels + level];
+  if (blockIdx.x * kRankThreads >= m) return;
+  const long long base = (long long)b * g.cand_total + lv.cand_off;
+  __shared__ unsigned long long s_key[kRankThreads];
+  const int i = blockIdx.x * kRankThreads + threadIdx.x;
+  const unsigned long long mine = (i < m) ? key[base + i] : ~0ull;
+  int rank = 0;
+  for (int j0 = 0; j0 < m; j0 += kRankThreads) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    s_key[threadIdx.x] = (j < m) ? key[base + j] : ~0ull;
+    __syncthreads();
+    const int lim = min(kRankThreads, m - j0);
+#pragma unroll 8
+    for (int t = 0; t < lim; ++t) rank += (s_key[t] < mine) ? 1 : 0;
+  }
+  if (i < m) {
+    key_sorted[base + rank] = mine;
+    ra_sorted[base + rank] = ra[base + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: retainBest(n_l) with ties + cross-level compaction into mvo_keypoint records
+__global__ void __launch_bounds__(1024)
+orb_finalize_kernel(const OrbGeom g, const unsigned long long* __restrict__ key_sorted,
+                    const float2* __restrict__ ra_sorted, const int32_t* __restrict__ c2_count,
+                    mvo_keypoint* __restrict__ kps, int32_t* __restrict__ kp_count, int32_t* __restrict__ flags) {
+  const int b = blockIdx.x;
+  __shared__ int s_keep[kLevels], s_off[kLevels + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp < kLevels) {
+    const LevelGeom lv = g.lv[warp];
+    const int m = c2_count[b * kLevels + warp];
+    const long long base = (long long)b * g.cand_total + lv.cand_off;
+    int keep = m;
+    if (lv.quota <= 0) keep = 0;
+    else if (m > lv.quota) {
+      // keys ascending == response descending; cut = response of element quota-1, ties stay
+      const uint32_t cut = (uint32_t)(key_sorted[base + lv.quota - 1] >> 32);
+      int cnt = 0;
+      for (int i = lv.quota + lane; i < m; i += 32) cnt += ((uint32_t)(key_sorted[base + i] >> 32) == cut) ? 1 : 0;
+      keep = lv.quota + warp_sum(cnt);
+    }
+    if (lane == 0) s_keep[warp] = keep;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int l = 0; l < kLevels; ++l) {
+      s_off[l] = acc;
+      acc += s_keep[l];
+    }
+    s_off[kLevels] = acc;
+    if (acc > g.kp_cap) atomicOr(flags + b, 2);
+    kp_count[b] = min(acc, g.kp_cap);
+  }
+  __syncthreads();
+  for (int l = 0; l < kLevels; ++l) {
+    const LevelGeom lv = g.lv[l];
+    const long long base = (long long)b * g.cand_total + lv.cand_off;
+    for (int i = tid; i < s_keep[l]; i += blockDim.x) {
+      const int o = s_off[l] + i;
+      if (o >= g.kp_cap) break;
+      const unsigned long long k = key_sorted[base + i];
+      const float2 r = ra_sorted[base + i];
+      mvo_keypoint kp;
+      kp.x = __fmul_rn((float)(int)(k & 0xffff), lv.scale);
+      kp.y = __fmul_rn((float)(int)((k >> 16) & 0xffff), lv.scale);
+      kp.size = __fmul_rn(31.f, lv.scale);
+      kp.angle = r.y;
+      kp.response = r.x;
+      kp.octave = l;
+      kp.class_id = -1;
+      kps[(long long)b * g.kp_cap + o] = kp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: rotated BRIEF, warp per keypoint, lane = descriptor byte (16 samples)
+constexpr int kBriefWarps = 8;
+__global__ void __launch_bounds__(kBriefWarps * 32)
+orb_brief_kernel(const OrbGeom g, const uint8_t* __restrict__ blur, const mvo_keypoint* __restrict__ kps,
+                 const int32_t* __restrict__ kp_count, uint8_t* __restrict__ desc, uint8_t* __restrict__ valid) {
+  const int b = blockIdx.y;
+  const int n = kp_count[b];
+  const int i = blockIdx.x * kBriefWarps + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const mvo_keypoint kp = kps[(long long)b * g.kp_cap + i];
+  const int l = min(max(kp.octave, 0), kLevels - 1);
+  const LevelGeom lv = g.lv[l];
+  const int cx = __float2int_rn(__fmul_rn(kp.x, lv.inv_scale));
+  const int cy = __float2int_rn(__fmul_rn(kp.y, lv.inv_scale));
+  uint8_t* out = desc + ((long long)b * g.kp_cap + i) * 32;
+  const bool ok = (kp.octave >= 0 && kp.octave < kLevels && cx >= kEdge && cx < lv.w - kEdge && cy >= kEdge &&
+                   cy < lv.h - kEdge);
+  if (valid && lane == 0) valid[(long long)b * g.kp_cap + i] = ok ? 1 : 0;
+  if (!ok) {
+    out[lane] = 0;
+    return;
+  }
+  const float ang = __fmul_rn(kp.angle, __uint_as_float(0x3c8efa35u));  // (float)(CV_PI/180)
+  const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+  const uint8_t* img = blur + (long long)b * g.frame_stride + lv.off + (long long)cy * lv.pitch + cx;
+  unsigned byte = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int v[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int pi = lane * 16 + 2 * j + s;
+      const float px = (float)c_pattern[pi][0], py = (float)c_pattern[pi][1];
+      const float rx = __fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa));
+      const float ry = __fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca));
+      v[s] = img[(long long)__float2int_rn(ry) * lv.pitch + __float2int_rn(rx)];
+    }
+    byte |= (v[0] < v[1] ? 1u : 0u) << j;
+  }
+  out[lane] = (uint8_t)byte;
+}
+
+// ================================================================================================
+// host side
+static int build_geometry(mvo_ctx* c, int w, int h, std::vector<uint32_t>& xt, std::vector<uint32_t>& yt) {
+  OrbGeom& g = c->geom;
+  const int n = c->cfg.nfeatures;
+  // per-level quotas, all-float arithmetic as in the OpenCV source
+  const double scale_factor = (double)1.2f;
+  const float factor = (float)(1.0 / scale_factor);
+  float nd = n * (1 - factor) / (1 - (float)pow((double)factor, (double)kLevels));
+  int sum = 0;
+  int quotas[kLevels];
+  for (int l = 0; l < kLevels - 1; ++l) {
+    quotas[l] = (int)lrintf(nd);
+    sum += quotas[l];
+    nd *= factor;
+  }
+  quotas[kLevels - 1] = std::max(n - sum, 0);
+
+  long long off = 0;
+  int cand_off = 0, xoff = 0, yoff = 0;
+  xt.clear();
+  yt.clear();
+  for (int l = 0; l < kLevels; ++l) {
+    LevelGeom& lv = g.lv[l];
+    lv.scale = (float)pow(scale_factor, (double)l);
+    lv.inv_scale = 1.f / lv.scale;
+    lv.w = (int)lrintf((float)w * lv.inv_scale);
+    lv.h = (int)lrintf((float)h * lv.inv_scale);
+    if (lv.w < 1 || lv.h < 1 || lv.w > 65535 || lv.h > 65535) return MVO_ERR_INVALID;
+    lv.pitch = (int)align_up((size_t)lv.w, 128);
+    lv.quota = quotas[l];
+    lv.off = off;
+    off += (long long)lv.pitch * align_up((size_t)lv.h, 8);
+    lv.cand_cap = std::max(4096, (lv.w * lv.h) / 16);
+    lv.cand_off = cand_off;
+    cand_off += lv.cand_cap;
+    lv.xtab_off = xoff;
+    lv.ytab_off = yoff;
+    if (l > 0) {
+      const LevelGeom& pv = g.lv[l - 1];
+      auto fill = [](std::vector<uint32_t>& t, int src, int dst) {
+        const double scale = (double)src / (double)dst;
+        for (int v = 0; v < dst; ++v) {
+          const double f = scale * (v + 0.5) - 0.5;
+          int i = (int)floor(f);
+          int c1 = (int)lrint((f - i) * 256.0);
+          if (i < 0) {
+            i = 0;
+            c1 = 0;
+          }
+          if (i >= src - 1) {
+            i = src - 1;
+            c1 = 0;
+          }
+          t.push_back((uint32_t)i | ((uint32_t)c1 << 16));
+        }
+      };
+      fill(xt, pv.w, lv.w);
+      fill(yt, pv.h, lv.h);
+      // staging bounds of orb_level_kernel
+      for (int t0 = 0; t0 < lv.w; t0 += TW) {
+        const int lo = std::max(t0 - HALO, 0), hi = std::min(t0 + TW + HALO - 1, lv.w - 1);
+        const int c0 = (int)(xt[xoff + lo] & 0xffff) & ~15, c1 = std::min((int)(xt[xoff + hi] & 0xffff) + 1, pv.w - 1);
+        if ((c1 - c0) / 16 + 1 > SRC_COLS_MAX / 16) return MVO_ERR_UNSUPPORTED;
+      }
+      for (int t0 = 0; t0 < lv.h; t0 += TH) {
+        const int lo = std::max(t0 - HALO, 0), hi = std::min(t0 + TH + HALO - 1, lv.h - 1);
+        const int r0 = (int)(yt[yoff + lo] & 0xffff), r1 = std::min((int)(yt[yoff + hi] & 0xffff) + 1, pv.h - 1);
+        if (r1 - r0 + 1 > SRC_ROWS_MAX) return MVO_ERR_UNSUPPORTED;
+      }
+      xoff += lv.w;
+      yoff += lv.h;
+    }
+  }
+  g.frame_stride = (long long)align_up((size_t)off + 256, 256);
+  g.cand_total = cand_off;
+  g.nfeatures = n;
+  g.batch = c->cfg.batch;
+  g.kp_cap = n + n / 4 + 64;
+  return MVO_OK;
+}
+
+int orb_prepare(mvo_ctx* c, int w, int h) {
+  if (w == c->geom_w && h == c->geom_h) return MVO_OK;
+  if (w < 16 || h < 16 || w > c->cfg.max_width || h > c->cfg.max_height) {
+    c->set_error("image size out of the range given to mvo_create");
+    return MVO_ERR_INVALID;
+  }
+  std::vector<uint32_t> xt, yt;
+  int rc = build_geometry(c, w, h, xt, yt);
+  if (rc != MVO_OK) {
+    c->set_error("unsupported pyramid geometry");
+    return rc;
+  }
+  const OrbGeom& g = c->geom;
+  const size_t B = (size_t)g.batch;
+  MVO_CUDA_TRY(c, c->pyr.alloc(B * g.frame_stride));
+  MVO_CUDA_TRY(c, c->blur.alloc(B * g.frame_stride));
+  MVO_CUDA_TRY(c, c->xtab.alloc(xt.size()));
+  MVO_CUDA_TRY(c, c->ytab.alloc(yt.size()));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->xtab.p, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->ytab.p, yt.data(), yt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // xt / yt are stack vectors
+  MVO_CUDA_TRY(c, c->cand_xy.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->cand_score.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->cand_count.alloc(B * kLevels));
+  MVO_CUDA_TRY(c, c->hist.alloc(B * kLevels * 256));
+  MVO_CUDA_TRY(c, c->c2_key.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->c2_key_sorted.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->c2_ra.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->c2_ra_sorted.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->c2_count.alloc(B * kLevels));
+  MVO_CUDA_TRY(c, c->kps.alloc(B * g.kp_cap));
+  MVO_CUDA_TRY(c, c->desc.alloc(B * g.kp_cap * 32));
+  MVO_CUDA_TRY(c, c->kp_valid.alloc(B * g.kp_cap));
+  MVO_CUDA_TRY(c, c->kp_count.alloc(B));
+  MVO_CUDA_TRY(c, c->flags.alloc(B));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->pyr.p, 0, B * g.frame_stride, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->blur.p, 0, B * g.frame_stride, c->stream));
+  c->geom_w = w;
+  c->geom_h = h;
+  return MVO_OK;
+}
+
+// images: batch frames, each h x stride bytes (host or device)
+int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels, int on_device) {
+  const OrbGeom& g = c->geom;
+  const LevelGeom& l0 = g.lv[0];
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (channels == 1) {
+    for (int b = 0; b < g.batch; ++b)
+      MVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->pyr.p + (size_t)b * g.frame_stride + l0.off, l0.pitch,
+                                        img + (size_t)b * h * stride, stride, w, h, kind, c->stream));
+    return MVO_OK;
+  }
+  if (channels != 3) return MVO_ERR_INVALID;
+  const size_t fbytes = (size_t)h * stride;
+  const uint8_t* src = img;
+  if (!on_device) {
+    MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * g.batch));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, fbytes * g.batch, cudaMemcpyHostToDevice, c->stream));
+    src = c->img_in.p;
+  }
+  dim3 grid((w + 255) / 256, h, g.batch);
+  bgr_to_gray_kernel<<<grid, 256, 0, c->stream>>>(src, stride, (long long)fbytes, c->pyr.p + l0.off, l0.pitch,
+                                                  g.frame_stride, w, h);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+static int launch_levels(mvo_ctx* c, int do_fast) {
+  const OrbGeom& g = c->geom;
+  for (int l = 0; l < kLevels; ++l) {
+    const LevelGeom& lv = g.lv[l];
+    LevelArgs a{};
+    a.dst = c->pyr.p + lv.off;
+    a.blur = c->blur.p + lv.off;
+    a.frame_stride = g.frame_stride;
+    a.w = lv.w;
+    a.h = lv.h;
+    a.pitch = lv.pitch;
+    a.cand_xy = c->cand_xy.p;
+    a.cand_score = c->cand_score.p;
+    a.cand_count = c->cand_count.p;
+    a.hist = c->hist.p;
+    a.flags = c->flags.p;
+    a.cand_cap = lv.cand_cap;
+    a.cand_total = g.cand_total;
+    a.cand_off = lv.cand_off;
+    a.level = l;
+    a.do_fast = do_fast;
+    dim3 grid((lv.w + TW - 1) / TW, (lv.h + TH - 1) / TH, g.batch);
+    if (l == 0) {
+      orb_level_kernel<false><<<grid, kLevelThreads, 0, c->stream>>>(a);
+    } else {
+      const LevelGeom& pv = g.lv[l - 1];
+      a.src = c->pyr.p + pv.off;
+      a.sw = pv.w;
+      a.sh = pv.h;
+      a.spitch = pv.pitch;
+      a.xtab = c->xtab.p + lv.xtab_off;
+      a.ytab = c->ytab.p + lv.ytab_off;
+      orb_level_kernel<true><<<grid, kLevelThreads, 0, c->stream>>>(a);
+    }
+    c->launches++;
+  }
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+static int clear_counters(mvo_ctx* c) {
+  const size_t B = (size_t)c->geom.batch;
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->cand_count.p, 0, B * kLevels * 4, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->c2_count.p, 0, B * kLevels * 4, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->hist.p, 0, B * kLevels * 256 * 4, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(c->flags.p, 0, B * 4, c->stream));
+  return MVO_OK;
+}
+
+int orb_run_levels_only(mvo_ctx* c) {
+  int rc = clear_counters(c);
+  if (rc) return rc;
+  return launch_levels(c, 0);
+}
+
+int orb_run_detect(mvo_ctx* c, bool want_desc) {
+  const OrbGeom& g = c->geom;
+  int rc = clear_counters(c);
+  if (rc) return rc;
+  rc = launch_levels(c, 1);
+  if (rc) return rc;
+  int max_cap = 0;
+  for (int l = 0; l < kLevels; ++l) max_cap = std::max(max_cap, g.lv[l].cand_cap);
+  {
+    // grid.x covers the largest candidate list; blocks beyond a level's count exit immediately
+    dim3 grid((max_cap + kHarrisWarps - 1) / kHarrisWarps, kLevels, g.batch);
+    orb_harris_angle_kernel<<<grid, kHarrisWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->cand_xy.p, c->cand_score.p,
+                                                                      c->cand_count.p, c->hist.p, c->c2_key.p,
+                                                                      c->c2_ra.p, c->c2_count.p);
+    c->launches++;
+  }
+  {
+    dim3 grid((max_cap + kRankThreads - 1) / kRankThreads, kLevels, g.batch);
+    orb_rank_kernel<<<grid, kRankThreads, 0, c->stream>>>(g, c->c2_key.p, c->c2_ra.p, c->c2_count.p,
+                                                         c->c2_key_sorted.p, c->c2_ra_sorted.p);
+    c->launches++;
+  }
+  orb_finalize_kernel<<<g.batch, 1024, 0, c->stream>>>(g, c->c2_key_sorted.p, c->c2_ra_sorted.p, c->c2_count.p,
+                                                      c->kps.p, c->kp_count.p, c->flags.p);
+  c->launches++;
+  if (want_desc) {
+    dim3 grid((g.kp_cap + kBriefWarps - 1) / kBriefWarps, g.batch);
+    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->blur.p, c->kps.p, c->kp_count.p, c->desc.p,
+                                                              nullptr);
+    c->launches++;
+  }
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+// descriptors for keypoints already uploaded into c->kps (stream 0), count n in c->kp_count
+int orb_run_brief_given(mvo_ctx* c, int n) {
+  const OrbGeom& g = c->geom;
+  dim3 grid((n + kBriefWarps - 1) / kBriefWarps, 1);
+  if (n > 0) {
+    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->blur.p, c->kps.p, c->kp_count.p, c->desc.p,
+                                                              c->kp_valid.p);
+    c->launches++;
+  }
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+}  // namespace mvo

@@ -1,0 +1,85 @@
+"""Generate golden vectors from cv2 (the OpenCV the reference links, via its Python binding).
+
+Run in the build container:  python tests/golden/gen_golden.py
+Every fixture records cv2.__version__.  Inputs come from oracle/synth.py seeds (numpy-only, so they can
+be regenerated anywhere); each fixture stores the sha256 of its input so a drifting generator is caught.
+The calls mirror the reference's call sites:
+  ORB   /root/reference/src/feature_processor.cpp:6,22   cv::ORB::create(n)->detectAndCompute
+  kNN   /root/reference/src/feature_processor.cpp:7,29   BFMatcher(NORM_HAMMING).knnMatch(q, t, 2)
+"""
+import hashlib
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import synth  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def kp_arrays(kps):
+    return dict(x=np.array([k.pt[0] for k in kps], np.float32), y=np.array([k.pt[1] for k in kps], np.float32),
+                size=np.array([k.size for k in kps], np.float32), angle=np.array([k.angle for k in kps], np.float32),
+                response=np.array([k.response for k in kps], np.float32),
+                octave=np.array([k.octave for k in kps], np.int32))
+
+
+def gen_orb(name, h, w, seed, n, store_image):
+    img = synth.synth_frame(h, w, seed)
+    orb = cv2.ORB_create(n)
+    kps, desc = orb.detectAndCompute(img, None)
+    d = kp_arrays(kps)
+    d.update(desc=desc, cv2_version=cv2.__version__, h=h, w=w, seed=seed, nfeatures=n, image_sha=sha(img))
+    # pyramid + per-level FAST from cv2 primitives (sub-stage oracles)
+    scales = [np.float32(float(np.float32(1.2)) ** l) for l in range(8)]
+    lvl = img
+    fast = cv2.FastFeatureDetector_create(20, True)
+    k32 = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    for l in range(8):
+        if l > 0:
+            inv = np.float32(1.0) / scales[l]
+            sz = (int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv)))
+            lvl = cv2.resize(lvl, sz, interpolation=cv2.INTER_LINEAR_EXACT)
+        d[f"level{l}_sha"] = sha(lvl)
+        d[f"blur{l}_sha"] = sha(cv2.sepFilter2D(lvl, -1, k32, k32, borderType=cv2.BORDER_REFLECT_101))
+        fk = fast.detect(lvl)
+        d[f"fast{l}"] = np.array([(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in fk], np.int32).reshape(-1, 3)
+    if store_image:
+        d["image"] = img
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    print(name, len(kps))
+
+
+def gen_knn():
+    rng = np.random.default_rng(5)
+    # low-entropy descriptors -> many first/second ties (tie rule: lowest train index)
+    q = rng.integers(0, 4, (300, 32)).astype(np.uint8)
+    t = rng.integers(0, 4, (400, 32)).astype(np.uint8)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, 2)
+    idx = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    dist = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    # realistic descriptors: ORB of a synthetic pair
+    f0, f1 = synth.synth_pair(240, 320, 11)
+    orb = cv2.ORB_create(300)
+    _, d0 = orb.detectAndCompute(f0, None)
+    _, d1 = orb.detectAndCompute(f1, None)
+    m2 = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d0, d1, 2)
+    idx2 = np.array([[a.trainIdx, b.trainIdx] for a, b in m2], np.int32)
+    dist2 = np.array([[a.distance, b.distance] for a, b in m2], np.float32)
+    good = np.array([(a.queryIdx, a.trainIdx, a.distance) for a, b in m2 if a.distance < 0.7 * b.distance], np.float32)
+    np.savez_compressed(os.path.join(HERE, "knn.npz"), q=q, t=t, idx=idx, dist=dist, d0=d0, d1=d1, idx2=idx2,
+                        dist2=dist2, good=good, cv2_version=cv2.__version__)
+    print("knn", len(m), len(good))
+
+
+if __name__ == "__main__":
+    gen_orb("orb_small.npz", 240, 320, 3, 300, True)
+    gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
+    gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)
+    gen_knn()
