@@ -64,27 +64,34 @@ __device__ __forceinline__ int fast_full_score(const uint8_t* t, int idx) {
   const int off[16] = {3 * TS,      3 * TS + 1,  2 * TS + 2,  TS + 3,  3,        -TS + 3,  -2 * TS + 2, -3 * TS + 1,
                        -3 * TS,     -3 * TS - 1, -2 * TS - 2, -TS - 3, -3,       TS - 3,   2 * TS - 2,  3 * TS - 1};
   const int c = t[idx];
-  int d[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) d[k] = c - (int)t[idx + off[k]];
-  int mn2[16], mx2[16];
+  // d = centre - ring (bright-centre arcs), e = ring - centre (dark-centre arcs).  Both polarities use
+  // min-chains only: ptxas 12.9 for sm_100a drops the negation when it fuses max(a, -max(..)) into
+  // VIMNMX3 (observed on B200: the score came out as max_k d_k), so no min/max result is negated here.
+  int d[16], e[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    mn2[k] = min(d[k], d[(k + 1) & 15]);
-    mx2[k] = max(d[k], d[(k + 1) & 15]);
+    const int r = (int)t[idx + off[k]];
+    d[k] = c - r;
+    e[k] = r - c;
   }
-  int mn4[16], mx4[16];
+  int d2[16], e2[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    mn4[k] = min(mn2[k], mn2[(k + 2) & 15]);
-    mx4[k] = max(mx2[k], mx2[(k + 2) & 15]);
+    d2[k] = min(d[k], d[(k + 1) & 15]);
+    e2[k] = min(e[k], e[(k + 1) & 15]);
+  }
+  int d4[16], e4[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    d4[k] = min(d2[k], d2[(k + 2) & 15]);
+    e4[k] = min(e2[k], e2[(k + 2) & 15]);
   }
   int best = -1000;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-    const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-    best = max(best, max(mn9, -mx9));
+    const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
+    const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
+    best = max(best, max(d9, e9));
   }
   return best;  // corner iff best > threshold; score = best - 1
 }
@@ -288,6 +295,9 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
       int v = __float2int_rn(s);
       v = min(max(v, 0), 255);
       blur_s[i] = (uint8_t)v;
+#ifdef MVO_DEBUG_SCORE
+      blur_s[i] = score[(yl + 1) * FS + xl + 1];
+#endif
     }
     __syncthreads();
     for (int i = tid; i < TH * (TW / 16); i += kLevelThreads) {
