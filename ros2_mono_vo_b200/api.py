@@ -112,6 +112,22 @@ class Context:
         xy, sc = xy[:n.value], sc[:n.value]
         return (xy & 0xffff).astype(np.int32), (xy >> 16).astype(np.int32), sc.copy()
 
+    # ---- LK ----------------------------------------------------------------------------------
+    def lk_track(self, prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
+        prev = np.ascontiguousarray(prev, np.uint8)
+        nxt = np.ascontiguousarray(nxt, np.uint8)
+        assert prev.shape == nxt.shape
+        h, w = prev.shape[:2]
+        ch = 1 if prev.ndim == 2 else prev.shape[2]
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        out = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        self._check(self.lib.mvo_lk_track(self.h, _ptr(prev), _ptr(nxt), w, h, prev.strides[0], ch, _ptr(pts), n,
+                                          _ptr(out), _ptr(status), _ptr(err)))
+        return out, status, err
+
     # ---- kNN ---------------------------------------------------------------------------------
     def knn_ratio(self, q: np.ndarray, t: np.ndarray, ratio: float) -> np.ndarray:
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
@@ -129,6 +145,12 @@ class Context:
         dist = np.full((len(q), 2), -1, np.int32)
         self._check(self.lib.mvo_knn2(self.h, _ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(dist)))
         return idx, dist
+
+
+def calc_optical_flow_pyr_lk(ctx: "Context", prev_img, next_img, prev_pts):
+    """Mirror of cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err) with default arguments
+    (reference call site src/tracker.cpp:68-69)."""
+    return ctx.lk_track(prev_img, next_img, prev_pts)
 
 
 class FeatureProcessor:

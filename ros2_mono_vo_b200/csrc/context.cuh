@@ -50,6 +50,14 @@ struct mvo_ctx {
   mvo::DevBuf<int32_t> knn_nmatch;            // batch
   mvo::DevBuf<int32_t> knn_counts;            // 2 ints (nq, nt) for the host-pointer API
 
+  // ---------------- LK ----------------
+  mvo::DevBuf<uint8_t> lk_pyr[2];             // ping-pong pyramids (levels 0..3) of prev / next frame
+  mvo::DevBuf<float2> lk_pts_in, lk_pts_out;  // batch * lk_max_pts
+  mvo::DevBuf<uint8_t> lk_status;
+  mvo::DevBuf<float> lk_err;
+  mvo::DevBuf<int32_t> lk_npts;               // batch
+  int lk_w = 0, lk_h = 0, lk_max_pts = 0;
+
   // ---------------- stage timing ----------------
   static constexpr int kNumStages = 9;
   StageTimer timers[kNumStages];
@@ -69,6 +77,11 @@ int knn_prepare(mvo_ctx* c, int maxq);
 int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_stride_rows, int max_nq,
             const uint8_t* t_dev, const int32_t* nt_dev, int t_stride_rows, int max_nt, double ratio,
             int batch);
+
+int lk_prepare(mvo_ctx* c, int w, int h, int max_pts);
+int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device);
+int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, const int32_t* npts_dev, int max_pts,
+           float2* out_dev, uint8_t* status_dev, float* err_dev);
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -7,7 +7,6 @@
     return MVO_ERR_UNSUPPORTED;                            \
   } while (0)
 extern "C" {
-int mvo_lk_track(mvo_ctx* c, const uint8_t*, const uint8_t*, int, int, int, int, const float*, int, float*, uint8_t*, float*) { MVO_STUB(c, "mvo_lk_track"); }
 int mvo_find_homography(mvo_ctx* c, const float*, const float*, int, double, double*, uint8_t*, int*) { MVO_STUB(c, "mvo_find_homography"); }
 int mvo_find_fundamental(mvo_ctx* c, const float*, const float*, int, double, double, double*, uint8_t*, int*) { MVO_STUB(c, "mvo_find_fundamental"); }
 int mvo_find_essential(mvo_ctx* c, const float*, const float*, int, const double*, double, double, double*, uint8_t*, int*) { MVO_STUB(c, "mvo_find_essential"); }

@@ -78,7 +78,39 @@ def gen_knn():
     print("knn", len(m), len(good))
 
 
+def lk_points(h, w, f0, n, seed):
+    """ORB keypoints of f0 + border / outside / flat-region points (edge cases of src/tracker.cpp:61-69)."""
+    orb = cv2.ORB_create(n)
+    kps = orb.detect(f0, None)
+    pts = np.array([k.pt for k in kps], np.float32)
+    rng = np.random.default_rng(seed)
+    extra = np.array([[0, 0], [w - 1, h - 1], [2.5, 3.5], [w - 3.2, 10.1], [-5, -5], [w + 30, h + 30],
+                      [w / 2, h - 1.5], [-40, 20], [w + 25.5, h / 2]], np.float32)
+    rnd = np.stack([rng.uniform(-15, w + 15, 64), rng.uniform(-15, h + 15, 64)], 1).astype(np.float32)
+    return np.concatenate([pts, extra, rnd])
+
+
+def gen_lk():
+    out = {}
+    for tag, h, w, seed, n in (("small", 240, 320, 11, 300), ("c2", 376, 1241, 2, 2000)):
+        f0, f1 = synth.synth_pair(h, w, seed)
+        pts = lk_points(h, w, f0, n, seed)
+        nxt, st, err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None)
+        out.update({f"{tag}_pts": pts, f"{tag}_next": nxt, f"{tag}_status": st.ravel(), f"{tag}_err": err.ravel(),
+                    f"{tag}_sha0": sha(f0), f"{tag}_sha1": sha(f1), f"{tag}_hw_seed": np.array([h, w, seed])})
+        print("lk", tag, len(pts), int(st.sum()))
+    # a flat next image: every point must fail the min-eigenvalue / go nowhere consistently
+    f0 = synth.synth_frame(120, 160, 4)
+    flat = np.full_like(f0, 100)
+    pts = lk_points(120, 160, f0, 100, 1)
+    nxt, st, err = cv2.calcOpticalFlowPyrLK(flat, f0, pts, None)
+    out.update(flat_pts=pts, flat_next=nxt, flat_status=st.ravel(), flat_err=err.ravel())
+    out["cv2_version"] = cv2.__version__
+    np.savez_compressed(os.path.join(HERE, "lk.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_lk()
     gen_orb("orb_small.npz", 240, 320, 3, 300, True)
     gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
     gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)

@@ -1,0 +1,71 @@
+"""GPU parity: pyramidal LK through the C ABI vs the oracle and the cv2 golden.  Tolerance 0.01 px (north_star)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, sha
+from oracle import lk_oracle as lo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+POS_TOL = 0.01      # px, BASELINE.json north_star
+ERR_TOL = 0.02      # mean abs patch difference (grey levels)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ros2_mono_vo_b200 import Context
+    c = Context(1920, 1080, nfeatures=5000)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("tag", ["small", "c2"])
+def test_lk_vs_cv2_golden(ctx, tag):
+    g = load_golden("lk.npz")
+    h, w, seed = g[f"{tag}_hw_seed"].tolist()
+    f0, f1 = synth.synth_pair(h, w, seed)
+    assert sha(f0) == str(g[f"{tag}_sha0"])
+    nxt, st, err = ctx.lk_track(f0, f1, g[f"{tag}_pts"])
+    assert np.array_equal(st, g[f"{tag}_status"])
+    m = st == 1
+    assert np.abs(nxt[m] - g[f"{tag}_next"][m]).max() < POS_TOL
+    assert np.abs(err[m] - g[f"{tag}_err"][m]).max() < ERR_TOL
+    assert np.abs(nxt[~m] - g[f"{tag}_next"][~m]).max() < POS_TOL
+    # reference filter (src/tracker.cpp:70-77): status && err < 30 keeps the same set
+    assert np.array_equal(m & (err < 30.0), (g[f"{tag}_status"] == 1) & (g[f"{tag}_err"] < 30.0))
+
+
+@pytest.mark.parametrize("h,w,seed,n", [(480, 640, 41, 1000), (1080, 1920, 43, 5000), (100, 47, 44, 50)])
+def test_lk_vs_oracle(ctx, h, w, seed, n):
+    f0, f1 = synth.synth_pair(h, w, seed)
+    rng = np.random.default_rng(seed)
+    pts = np.stack([rng.uniform(-25, w + 25, n), rng.uniform(-25, h + 25, n)], 1).astype(np.float32)
+    nxt, st, err = ctx.lk_track(f0, f1, pts)
+    onxt, ost, oerr = lo.lk_track(f0, f1, pts)
+    # status may legitimately differ only where the oracle sits within float noise of a threshold
+    assert (st != ost).mean() < 0.002
+    m = (st == 1) & (ost == 1)
+    assert np.abs(nxt[m] - onxt[m]).max() < POS_TOL
+    assert np.abs(err[m] - oerr[m]).max() < ERR_TOL
+
+
+def test_lk_flat_and_empty(ctx):
+    g = load_golden("lk.npz")
+    f0 = synth.synth_frame(120, 160, 4)
+    nxt, st, err = ctx.lk_track(np.full_like(f0, 100), f0, g["flat_pts"])
+    assert np.array_equal(st, g["flat_status"]) and st.sum() == 0
+    assert np.allclose(nxt, g["flat_next"], atol=1e-3)
+    nxt, st, err = ctx.lk_track(f0, f0, np.zeros((0, 2), np.float32))
+    assert nxt.shape == (0, 2)
+
+
+def test_lk_identity_property(ctx):
+    """Size-independent property at full C3 size: tracking an image onto itself returns the input points."""
+    f0 = synth.synth_frame(1080, 1920, 7)
+    rng = np.random.default_rng(7)
+    pts = np.stack([rng.uniform(30, 1890, 5000), rng.uniform(30, 1050, 5000)], 1).astype(np.float32)
+    nxt, st, err = ctx.lk_track(f0, f0, pts)
+    ok = st == 1
+    assert ok.mean() > 0.99
+    assert np.abs(nxt[ok] - pts[ok]).max() < 1e-3
+    assert err[ok].max() < 1e-3
