@@ -109,7 +109,44 @@ def gen_lk():
     np.savez_compressed(os.path.join(HERE, "lk.npz"), **out)
 
 
+def gen_ransac():
+    """cv2 outputs at the reference's RANSAC call sites (src/initializer.cpp:82,87,228,236,125)."""
+    K = synth.KITTI_K
+    out = {"K": K, "cv2_version": cv2.__version__}
+    for tag, seed, planar, n in (("a", 5, True, 2000), ("b", 6, False, 2000), ("c", 7, True, 500), ("d", 8, False, 800)):
+        p1, p2, R, t, inl = synth.scene_correspondences(n, seed, planar=planar, outlier_frac=0.25)
+        H, mh = cv2.findHomography(p1, p2, cv2.RANSAC, 1.0)
+        F, mf = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+        E, me = cv2.findEssentialMat(p1, p2, K, cv2.RANSAC, 0.99, 1.0)
+        mp = me.copy()
+        good, Rr, tr, mp = cv2.recoverPose(E, p1, p2, K, mask=mp)
+        P0 = K @ np.eye(3, 4)
+        P1 = K @ np.column_stack([Rr, tr])
+        X = cv2.triangulatePoints(P0, P1, p1.T.copy(), p2.T.copy())
+        out.update({f"{tag}_args": np.array([n, seed, int(planar)]), f"{tag}_sha": sha(np.concatenate([p1, p2])),
+                    f"{tag}_H": H, f"{tag}_mask_h": mh.ravel(), f"{tag}_F": F, f"{tag}_mask_f": mf.ravel(),
+                    f"{tag}_E": E, f"{tag}_mask_e": me.ravel(), f"{tag}_R": Rr, f"{tag}_t": tr.ravel(),
+                    f"{tag}_mask_pose": mp.ravel(), f"{tag}_good": good, f"{tag}_X": X, f"{tag}_Rgt": R, f"{tag}_tgt": t})
+        print("ransac", tag, int(mh.sum()), int(mf.sum()), int(me.sum()), good)
+    # per-hypothesis solver vectors
+    p1, p2, R, t, inl = synth.scene_correspondences(400, 9, outlier_frac=0.0)
+    rng = np.random.default_rng(0)
+    i4 = np.array([rng.choice(400, 4, replace=False) for _ in range(8)])
+    i7 = np.array([rng.choice(400, 7, replace=False) for _ in range(8)])
+    i5 = np.array([rng.choice(400, 5, replace=False) for _ in range(8)])
+    out["hyp_p1"], out["hyp_p2"], out["hyp_i4"], out["hyp_i7"], out["hyp_i5"] = p1, p2, i4, i7, i5
+    out["hyp_H"] = np.array([cv2.findHomography(p1[i], p2[i], 0)[0] for i in i4])
+    q1 = np.stack([(p1[:, 0] - K[0, 2]) / K[0, 0], (p1[:, 1] - K[1, 2]) / K[1, 1]], 1).astype(np.float64)
+    q2 = np.stack([(p2[:, 0] - K[0, 2]) / K[0, 0], (p2[:, 1] - K[1, 2]) / K[1, 1]], 1).astype(np.float64)
+    for j, i in enumerate(i7):
+        out[f"hyp_F{j}"] = cv2.findFundamentalMat(p1[i], p2[i], cv2.FM_7POINT)[0].reshape(-1, 3, 3)
+    for j, i in enumerate(i5):
+        out[f"hyp_E{j}"] = cv2.findEssentialMat(q1[i], q2[i], np.eye(3))[0].reshape(-1, 3, 3)
+    np.savez_compressed(os.path.join(HERE, "ransac.npz"), **out)
+
+
 if __name__ == "__main__":
+    gen_ransac()
     gen_lk()
     gen_orb("orb_small.npz", 240, 320, 3, 300, True)
     gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
