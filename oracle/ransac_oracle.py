@@ -296,7 +296,8 @@ def h_errors(H, p1, p2) -> np.ndarray:
     M = p1.astype(f32)
     m = p2.astype(f32)
     one = f32(1.0)
-    ww = one / ((Hf[6] * M[:, 0]).astype(f32) + (Hf[7] * M[:, 1]).astype(f32) + one).astype(f32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        ww = one / ((Hf[6] * M[:, 0]).astype(f32) + (Hf[7] * M[:, 1]).astype(f32) + one).astype(f32)
     dx = (((Hf[0] * M[:, 0]).astype(f32) + (Hf[1] * M[:, 1]).astype(f32)).astype(f32) + Hf[2]).astype(f32) * ww - m[:, 0]
     dy = (((Hf[3] * M[:, 0]).astype(f32) + (Hf[4] * M[:, 1]).astype(f32)).astype(f32) + Hf[5]).astype(f32) * ww - m[:, 1]
     dx, dy = dx.astype(f32), dy.astype(f32)

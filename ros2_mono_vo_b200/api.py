@@ -128,6 +128,77 @@ class Context:
                                           _ptr(out), _ptr(status), _ptr(err)))
         return out, status, err
 
+    # ---- two-view geometry -------------------------------------------------------------------
+    @staticmethod
+    def _pts(p):
+        return np.ascontiguousarray(p, np.float32).reshape(-1, 2)
+
+    def find_homography(self, p1, p2, thr: float = 3.0):
+        """cv::findHomography(p1, p2, RANSAC, thr) -> (H 3x3, mask u8, n_inliers)."""
+        p1, p2 = self._pts(p1), self._pts(p2)
+        H = np.zeros(9)
+        mask = np.zeros(len(p1), np.uint8)
+        n = C.c_int32()
+        self._check(self.lib.mvo_find_homography(self.h, _ptr(p1), _ptr(p2), len(p1), float(thr), _ptr(H), _ptr(mask),
+                                                 C.byref(n)))
+        return H.reshape(3, 3), mask, n.value
+
+    def find_fundamental(self, p1, p2, thr: float = 3.0, conf: float = 0.99):
+        """cv::findFundamentalMat(p1, p2, FM_RANSAC, thr, conf) -> (F, mask, n_inliers)."""
+        p1, p2 = self._pts(p1), self._pts(p2)
+        F = np.zeros(9)
+        mask = np.zeros(len(p1), np.uint8)
+        n = C.c_int32()
+        self._check(self.lib.mvo_find_fundamental(self.h, _ptr(p1), _ptr(p2), len(p1), float(thr), float(conf),
+                                                  _ptr(F), _ptr(mask), C.byref(n)))
+        return F.reshape(3, 3), mask, n.value
+
+    def find_essential(self, p1, p2, K, conf: float = 0.999, thr: float = 1.0):
+        """cv::findEssentialMat(p1, p2, K, RANSAC, conf, thr) -> (E, mask, n_inliers)."""
+        p1, p2 = self._pts(p1), self._pts(p2)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        E = np.zeros(9)
+        mask = np.zeros(len(p1), np.uint8)
+        n = C.c_int32()
+        self._check(self.lib.mvo_find_essential(self.h, _ptr(p1), _ptr(p2), len(p1), _ptr(K), float(conf), float(thr),
+                                                _ptr(E), _ptr(mask), C.byref(n)))
+        return E.reshape(3, 3), mask, n.value
+
+    def recover_pose(self, E, p1, p2, K, mask=None):
+        """cv::recoverPose(E, p1, p2, K, R, t, mask) -> (R, t, mask, n_good)."""
+        p1, p2 = self._pts(p1), self._pts(p2)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        R = np.zeros(9)
+        t = np.zeros(3)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).copy()
+        n = C.c_int32()
+        self._check(self.lib.mvo_recover_pose(self.h, _ptr(E), _ptr(p1), _ptr(p2), len(p1), _ptr(K), _ptr(R), _ptr(t),
+                                              _ptr(m) if m is not None else None, C.byref(n)))
+        return R.reshape(3, 3), t, m, n.value
+
+    def triangulate(self, P0, P1, p0, p1):
+        """cv::triangulatePoints(P0, P1, p0, p1) -> 4 x N f32."""
+        p0, p1 = self._pts(p0), self._pts(p1)
+        P0 = np.ascontiguousarray(P0, np.float64).reshape(12)
+        P1 = np.ascontiguousarray(P1, np.float64).reshape(12)
+        X = np.zeros((4, len(p0)), np.float32)
+        self._check(self.lib.mvo_triangulate(self.h, _ptr(P0), _ptr(P1), _ptr(p0), _ptr(p1), len(p0), _ptr(X)))
+        return X
+
+    def score_hypotheses(self, model: int, p1, p2, m: int, thr: float = 1.0, K=None, want_models: bool = False):
+        """C4 sweep: m minimal samples from the OpenCV RNG stream, solved and scored with no early exit."""
+        p1, p2 = self._pts(p1), self._pts(p2)
+        kk, mm = {0: (4, 1), 1: (7, 3), 2: (5, 10)}[model]
+        idx = np.zeros((m, kk), np.int32)
+        counts = np.zeros((m, mm), np.int32)
+        models = np.zeros((m, mm, 9)) if want_models else None
+        Kp = None if K is None else np.ascontiguousarray(K, np.float64).reshape(9)
+        self._check(self.lib.mvo_score_hypotheses(self.h, model, _ptr(p1), _ptr(p2), len(p1),
+                                                  _ptr(Kp) if Kp is not None else None, float(thr), m, _ptr(idx),
+                                                  _ptr(counts), _ptr(models) if want_models else None))
+        return idx, counts, models
+
     # ---- kNN ---------------------------------------------------------------------------------
     def knn_ratio(self, q: np.ndarray, t: np.ndarray, ratio: float) -> np.ndarray:
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)

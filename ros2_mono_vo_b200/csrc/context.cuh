@@ -7,6 +7,40 @@ struct StageTimer {
   bool used = false;
 };
 
+struct RansacBufs {
+  mvo::DevBuf<uint32_t> rng;          // OpenCV MWC stream for the context seed
+  int rng_len = 0;
+  bool rng_ready = false;
+  int max_pts = 0, cap_iters = 0;
+  mvo::DevBuf<float2> p1, p2;         // batch * max_pts pixel correspondences
+  mvo::DevBuf<double2> q1, q2;        // K-normalised (essential matrix)
+  mvo::DevBuf<uint8_t> mask;          // batch * max_pts
+  mvo::DevBuf<int32_t> inl_idx;       // batch * max_pts
+  mvo::DevBuf<int32_t> npts;          // batch
+  mvo::DevBuf<int32_t> state;         // batch * 4 : sampler state
+  mvo::DevBuf<float> thr2;            // batch : squared threshold as float
+  mvo::DevBuf<double> K;              // batch * 9
+  mvo::DevBuf<int32_t> subsets;       // batch * cap_iters * 8
+  mvo::DevBuf<double> models;         // batch * cap_iters * 10 * 9
+  mvo::DevBuf<int32_t> nmodels;       // batch * cap_iters
+  mvo::DevBuf<int32_t> counts;        // batch * cap_iters * 10
+  mvo::DevBuf<double> best_model;     // batch * 9
+  mvo::DevBuf<int32_t> result;        // batch * 8
+  // pose
+  mvo::DevBuf<double> cands;          // batch * 4 * 12 : (R | t) candidates
+  mvo::DevBuf<uint8_t> cand_mask;     // batch * 4 * max_pts
+  mvo::DevBuf<int32_t> cand_good;     // batch * 4
+  mvo::DevBuf<double> pose;           // batch * 12 : R (9) + t (3)
+  mvo::DevBuf<double> proj;           // batch * 24 : P0, P1
+  mvo::DevBuf<float> X4;              // batch * 4 * max_pts
+  void release() {
+    rng.release(); p1.release(); p2.release(); q1.release(); q2.release(); mask.release(); inl_idx.release();
+    npts.release(); state.release(); thr2.release(); K.release(); subsets.release(); models.release();
+    nmodels.release(); counts.release(); best_model.release(); result.release(); cands.release();
+    cand_mask.release(); cand_good.release(); pose.release(); proj.release(); X4.release();
+  }
+};
+
 struct mvo_ctx {
   mvo_config cfg{};
   cudaStream_t stream = nullptr;
@@ -58,6 +92,10 @@ struct mvo_ctx {
   mvo::DevBuf<int32_t> lk_npts;               // batch
   int lk_w = 0, lk_h = 0, lk_max_pts = 0;
 
+  // ---------------- RANSAC / pose ----------------
+  RansacBufs rs;
+  int last_ransac_iters = 0;
+
   // ---------------- stage timing ----------------
   static constexpr int kNumStages = 9;
   StageTimer timers[kNumStages];
@@ -82,6 +120,14 @@ int lk_prepare(mvo_ctx* c, int w, int h, int max_pts);
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device);
 int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, const int32_t* npts_dev, int max_pts,
            float2* out_dev, uint8_t* status_dev, float* err_dev);
+
+int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters);
+int ransac_find(mvo_ctx* c, int model, double conf);
+int ransac_normalize(mvo_ctx* c);
+int ransac_sweep(mvo_ctx* c, int model, int m);
+int pose_prepare(mvo_ctx* c);
+int pose_recover(mvo_ctx* c, bool use_mask);      // E in rs.best_model, points in rs.q1/q2, mask in rs.mask
+int pose_triangulate(mvo_ctx* c);                 // P0/P1 in rs.proj, points in rs.p1/p2 -> rs.X4
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

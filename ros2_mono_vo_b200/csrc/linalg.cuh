@@ -1,0 +1,348 @@
+// linalg.cuh -- small dense FP64 helpers used per thread by the RANSAC / pose kernels.
+#pragma once
+#ifndef __device__
+#include <cuda_runtime.h>
+#endif
+#include <math.h>
+
+namespace mvo {
+
+// Null space of an R x C matrix (R < C, full row rank assumed) by Gauss-Jordan elimination with complete
+// pivoting.  A is destroyed.  basis: (C-R) vectors of length C, orthonormalised (modified Gram-Schmidt).
+template <int R, int C>
+__device__ void null_space(double* A /* R*C row-major */, double* basis /* (C-R)*C */) {
+  int colperm[C];
+#pragma unroll 1
+  for (int j = 0; j < C; ++j) colperm[j] = j;
+#pragma unroll 1
+  for (int k = 0; k < R; ++k) {
+    // complete pivot in the trailing block
+    int pr = k, pc = k;
+    double best = -1.0;
+#pragma unroll 1
+    for (int i = k; i < R; ++i)
+#pragma unroll 1
+      for (int j = k; j < C; ++j) {
+        const double v = fabs(A[i * C + j]);
+        if (v > best) {
+          best = v;
+          pr = i;
+          pc = j;
+        }
+      }
+    if (pr != k)
+#pragma unroll 1
+      for (int j = 0; j < C; ++j) {
+        const double t = A[k * C + j];
+        A[k * C + j] = A[pr * C + j];
+        A[pr * C + j] = t;
+      }
+    if (pc != k) {
+#pragma unroll 1
+      for (int i = 0; i < R; ++i) {
+        const double t = A[i * C + k];
+        A[i * C + k] = A[i * C + pc];
+        A[i * C + pc] = t;
+      }
+      const int t = colperm[k];
+      colperm[k] = colperm[pc];
+      colperm[pc] = t;
+    }
+    const double piv = A[k * C + k];
+    const double inv = (piv != 0.0) ? 1.0 / piv : 0.0;
+#pragma unroll 1
+    for (int j = k; j < C; ++j) A[k * C + j] *= inv;
+#pragma unroll 1
+    for (int i = 0; i < R; ++i) {
+      if (i == k) continue;
+      const double f = A[i * C + k];
+      if (f != 0.0)
+#pragma unroll 1
+        for (int j = k; j < C; ++j) A[i * C + j] -= f * A[k * C + j];
+    }
+  }
+  // A = [I | N] in permuted columns; null vectors: x_pivot = -N[:, f], x_free(f) = 1
+#pragma unroll 1
+  for (int f = 0; f < C - R; ++f) {
+    double* v = basis + f * C;
+#pragma unroll 1
+    for (int j = 0; j < C; ++j) v[j] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < R; ++i) v[colperm[i]] = -A[i * C + R + f];
+    v[colperm[R + f]] = 1.0;
+  }
+  // modified Gram-Schmidt
+#pragma unroll 1
+  for (int f = 0; f < C - R; ++f) {
+    double* v = basis + f * C;
+#pragma unroll 1
+    for (int g = 0; g < f; ++g) {
+      const double* u = basis + g * C;
+      double d = 0.0;
+#pragma unroll 1
+      for (int j = 0; j < C; ++j) d += u[j] * v[j];
+#pragma unroll 1
+      for (int j = 0; j < C; ++j) v[j] -= d * u[j];
+    }
+    double nrm = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < C; ++j) nrm += v[j] * v[j];
+    nrm = (nrm > 0.0) ? 1.0 / sqrt(nrm) : 0.0;
+#pragma unroll 1
+    for (int j = 0; j < C; ++j) v[j] *= nrm;
+  }
+}
+
+// Solve the N x N system A x = b in place (partial pivoting).  Returns false when singular.
+template <int N>
+__device__ bool lu_solve(double* A /* N*N, destroyed */, double* b /* in: rhs, out: x */) {
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double best = fabs(A[k * N + k]);
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(A[i * N + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (best == 0.0) return false;
+    if (p != k) {
+#pragma unroll 1
+      for (int j = 0; j < N; ++j) {
+        const double t = A[k * N + j];
+        A[k * N + j] = A[p * N + j];
+        A[p * N + j] = t;
+      }
+      const double t = b[k];
+      b[k] = b[p];
+      b[p] = t;
+    }
+    const double inv = 1.0 / A[k * N + k];
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const double f = A[i * N + k] * inv;
+      if (f != 0.0) {
+#pragma unroll 1
+        for (int j = k + 1; j < N; ++j) A[i * N + j] -= f * A[k * N + j];
+        b[i] -= f * b[k];
+      }
+    }
+  }
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll 1
+    for (int j = i + 1; j < N; ++j) s -= A[i * N + j] * b[j];
+    b[i] = s / A[i * N + i];
+  }
+  return true;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix.  A is destroyed (diagonal = eigenvalues),
+// V (row-major, columns = eigenvectors).
+template <int N>
+__device__ void jacobi_eig(double* A, double* V) {
+#pragma unroll 1
+  for (int i = 0; i < N; ++i)
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      diag += A[i * N + i] * A[i * N + i];
+#pragma unroll 1
+      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+    }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll 1
+    for (int p = 0; p < N - 1; ++p)
+#pragma unroll 1
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p * N + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+          const double akp = A[k * N + p], akq = A[k * N + q];
+          A[k * N + p] = c * akp - s * akq;
+          A[k * N + q] = s * akp + c * akq;
+        }
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+          const double apk = A[p * N + k], aqk = A[q * N + k];
+          A[p * N + k] = c * apk - s * aqk;
+          A[q * N + k] = s * apk + c * aqk;
+        }
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+          const double vkp = V[k * N + p], vkq = V[k * N + q];
+          V[k * N + p] = c * vkp - s * vkq;
+          V[k * N + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__device__ __forceinline__ double det3(const double* m) {
+  return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[6] * m[5]) + m[2] * (m[3] * m[7] - m[6] * m[4]);
+}
+
+__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+
+// Real roots of a0 x^3 + a1 x^2 + a2 x + a3, following cv::solveCubic's case analysis.  Returns the count.
+__device__ inline int solve_cubic(double a0, double a1, double a2, double a3, double* x) {
+  int n = 0;
+  if (a0 == 0) {
+    if (a1 == 0) {
+      if (a2 == 0) return 0;
+      x[0] = -a3 / a2;
+      return 1;
+    }
+    double d = a2 * a2 - 4 * a1 * a3;
+    if (d >= 0) {
+      d = sqrt(d);
+      const double q1 = (-a2 + d) * 0.5, q2 = (a2 + d) * -0.5;
+      if (fabs(q1) > fabs(q2)) {
+        x[0] = q1 / a1;
+        x[1] = a3 / q1;
+      } else {
+        x[0] = q2 / a1;
+        x[1] = a3 / q2;
+      }
+      n = d > 0 ? 2 : 1;
+    }
+    return n;
+  }
+  a0 = 1. / a0;
+  a1 *= a0;
+  a2 *= a0;
+  a3 *= a0;
+  const double Q = (a1 * a1 - 3 * a2) * (1. / 9);
+  const double R = (2 * a1 * a1 * a1 - 9 * a1 * a2 + 27 * a3) * (1. / 54);
+  const double Qcubed = Q * Q * Q;
+  double d = (a1 * a1 * (a2 * a2 - 4 * a1 * a3) + 2 * a2 * (9 * a1 * a3 - 2 * a2 * a2) - 27 * a3 * a3) * (1. / 108);
+  const double kPi = 3.14159265358979323846;
+  if (d > 0) {
+    const double theta = acos(R / sqrt(Qcubed));
+    const double sqrtQ = sqrt(Q);
+    const double t0 = -2 * sqrtQ, t1 = theta * (1. / 3), t2 = a1 * (1. / 3);
+    x[0] = t0 * cos(t1) - t2;
+    x[1] = t0 * cos(t1 + (2. * kPi / 3)) - t2;
+    x[2] = t0 * cos(t1 + (4. * kPi / 3)) - t2;
+    n = 3;
+  } else if (d == 0) {
+    if (R >= 0) {
+      x[0] = -2 * pow(R, 1. / 3) - a1 / 3;
+      x[1] = pow(R, 1. / 3) - a1 / 3;
+    } else {
+      x[0] = 2 * pow(-R, 1. / 3) - a1 / 3;
+      x[1] = -pow(-R, 1. / 3) - a1 / 3;
+    }
+    n = x[0] == x[1] ? 1 : 2;
+  } else {
+    d = sqrt(-d);
+    double e = pow(d + fabs(R), 1. / 3);
+    if (R > 0) e = -e;
+    x[0] = (e + Q / e) - a1 * (1. / 3);
+    n = 1;
+  }
+  return n;
+}
+
+// All real roots of a polynomial of degree <= DEG (coefficients c[0] + c[1] x + ... + c[DEG] x^DEG) by
+// recursive bracketing: the real roots of p lie between consecutive real roots of p'.  Each bracket is
+// solved by safeguarded Newton (bisection fallback).  Returns the count (ascending order).  Roots of even
+// multiplicity (tangencies) are not reported.
+template <int DEG>
+__device__ int real_roots(const double* c, double* roots) {
+  int deg = DEG;
+  while (deg > 0 && c[deg] == 0.0) --deg;
+  if (deg == 0) return 0;
+  double bound = 0.0;  // Cauchy bound on |root|; by Gauss-Lucas it also bounds the roots of all derivatives
+#pragma unroll 1
+  for (int i = 0; i < deg; ++i) bound = fmax(bound, fabs(c[i] / c[deg]));
+  bound = 1.0 + bound;
+  double crit[DEG + 1], next[DEG + 1], q[DEG + 1];
+  int ncrit = 0;
+#pragma unroll 1
+  for (int lvl = deg - 1; lvl >= 0; --lvl) {
+    const int qd = deg - lvl;  // degree of the lvl-th derivative
+#pragma unroll 1
+    for (int i = 0; i <= qd; ++i) {
+      double w = c[i + lvl];
+#pragma unroll 1
+      for (int t = 0; t < lvl; ++t) w *= (double)(i + lvl - t);
+      q[i] = w;
+    }
+    auto evalq = [&](double x, double& dv) {
+      double v = q[qd];
+      dv = 0.0;
+#pragma unroll 1
+      for (int i = qd - 1; i >= 0; --i) {
+        dv = dv * x + v;
+        v = v * x + q[i];
+      }
+      return v;
+    };
+    int nn = 0;
+    double lo = -bound, dummy;
+    double flo = evalq(lo, dummy);
+#pragma unroll 1
+    for (int k = 0; k <= ncrit; ++k) {
+      const double hi = (k < ncrit) ? crit[k] : bound;
+      const double fhi = evalq(hi, dummy);
+      if (flo == 0.0) {
+        if (nn == 0 || next[nn - 1] != lo) next[nn++] = lo;
+      } else if (fhi != 0.0 && ((flo < 0.0) != (fhi < 0.0))) {
+        // safeguarded Newton (rtsafe): bisect whenever Newton leaves the bracket or fails to halve the step
+        double xl = (flo < 0.0) ? lo : hi, xh = (flo < 0.0) ? hi : lo;  // f(xl) < 0 < f(xh)
+        double x = 0.5 * (lo + hi), dxold = fabs(hi - lo), dx = dxold, dfx;
+        double fx = evalq(x, dfx);
+#pragma unroll 1
+        for (int it = 0; it < 200; ++it) {
+          if (((x - xh) * dfx - fx) * ((x - xl) * dfx - fx) > 0.0 || fabs(2.0 * fx) > fabs(dxold * dfx)) {
+            dxold = dx;
+            dx = 0.5 * (xh - xl);
+            const double xn = xl + dx;
+            if (xn == x) break;
+            x = xn;
+          } else {
+            dxold = dx;
+            dx = fx / dfx;
+            const double xn = x - dx;
+            if (xn == x) break;
+            x = xn;
+          }
+          if (fabs(dx) <= 2e-16 * fabs(x)) break;
+          fx = evalq(x, dfx);
+          if (fx == 0.0) break;
+          if (fx < 0.0) xl = x; else xh = x;
+        }
+        next[nn++] = x;
+      }
+      lo = hi;
+      flo = fhi;
+    }
+    if (flo == 0.0 && (nn == 0 || next[nn - 1] != lo)) next[nn++] = lo;
+    ncrit = nn;
+#pragma unroll 1
+    for (int k = 0; k < nn; ++k) crit[k] = next[k];
+  }
+#pragma unroll 1
+  for (int k = 0; k < ncrit; ++k) roots[k] = crit[k];
+  return ncrit;
+}
+
+}  // namespace mvo

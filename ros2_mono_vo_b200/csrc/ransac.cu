@@ -1,0 +1,1047 @@
+// ransac.cu -- deterministic parallel RANSAC for H / F / E with OpenCV's RNG stream and adaptive stop.
+//
+// Replaces cv::findHomography / findFundamentalMat / findEssentialMat at
+// /root/reference/src/initializer.cpp:82,87,228 and src/tracker.cpp:243,248.  Contract: SURVEY.md A.4.
+//
+// OpenCV's loop is sequential (draw subset -> solve -> score -> maybe shrink niters).  The RNG stream only
+// depends on data-only subset checks, so here (per stream of the group):
+//   1. ransac_sample_kernel   every draw offset simulates one getSubset attempt in parallel; pointer doubling
+//                             in shared memory follows the attempt chain; an ordered compaction yields the
+//                             exact subsets OpenCV would draw for iterations 0 .. maxIters-1.
+//   2. *_solve_kernel         one thread per hypothesis (4-pt H, 7-pt F, 5-pt E; FP64).
+//   3. ransac_score_kernel    one block per hypothesis, warp-reduced inlier counts (FP32 for H, FP64 F/E).
+//   4. ransac_select_kernel   prefix-max scan replays the strict '>' update + shrinking niters exactly,
+//                             then writes the winner's mask.
+//   5. h_refine_kernel        DLT on the inliers + 10 Levenberg-Marquardt iterations + final mask (H only).
+#include "context.cuh"
+#include "solvers.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace mvo {
+
+constexpr int kDraws = 32768;         // RNG draws visible to one sampler launch (uint16 offsets)
+constexpr int kMaxAttempts = 16384;   // getSubset attempts followed per launch
+constexpr int kSegIters = 2048;       // subsets produced per sampler launch
+constexpr unsigned kEndOff = kDraws;  // sentinel: ran out of draws
+
+template <int MODEL> struct MT;
+template <> struct MT<MVO_MODEL_H> { static constexpr int K = 4, MAXIT = 2000, MAXM = 1; };
+template <> struct MT<MVO_MODEL_F> { static constexpr int K = 7, MAXIT = 1000, MAXM = 3; };
+template <> struct MT<MVO_MODEL_E> { static constexpr int K = 5, MAXIT = 1000, MAXM = 10; };
+
+// ---- subset drawing ----------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ unsigned draw_subset(const uint32_t* __restrict__ rng, unsigned o, unsigned n, int* idx) {
+#pragma unroll 1
+  for (int i = 0; i < K; ++i) {
+    for (;;) {
+      if (o >= kDraws) return kEndOff;
+      const int v = (int)(rng[o++] % n);
+      bool dup = false;
+#pragma unroll 1
+      for (int j = 0; j < i; ++j) dup |= (idx[j] == v);
+      if (!dup) {
+        idx[i] = v;
+        break;
+      }
+    }
+  }
+  return o;
+}
+
+template <int K>
+__device__ __forceinline__ bool have_collinear(const float2* p) {
+  const int i = K - 1;
+#pragma unroll 1
+  for (int j = 0; j < i; ++j) {
+    const double dx1 = (double)__fsub_rn(p[j].x, p[i].x), dy1 = (double)__fsub_rn(p[j].y, p[i].y);
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) {
+      const double dx2 = (double)__fsub_rn(p[k].x, p[i].x), dy2 = (double)__fsub_rn(p[k].y, p[i].y);
+      if (fabs(__dsub_rn(__dmul_rn(dx2, dy1), __dmul_rn(dy2, dx1))) <=
+          (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2)))
+        return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ double det3_pts(float2 a, float2 b, float2 c) {
+  // determinant(Matx33d(a.x, a.y, 1, b.x, b.y, 1, c.x, c.y, 1))
+  const double a00 = a.x, a01 = a.y, a10 = b.x, a11 = b.y, a20 = c.x, a21 = c.y;
+  return __dadd_rn(__dsub_rn(__dmul_rn(a00, __dsub_rn(a11, a21)), __dmul_rn(a01, __dsub_rn(a10, a20))),
+                   __dsub_rn(__dmul_rn(a10, a21), __dmul_rn(a20, a11)));
+}
+
+template <int MODEL>
+__device__ __forceinline__ bool check_subset(const float2* s1, const float2* s2) {
+  if (MODEL == MVO_MODEL_E) return true;
+  constexpr int K = MT<MODEL>::K;
+  if (have_collinear<K>(s1) || have_collinear<K>(s2)) return false;
+  if (MODEL == MVO_MODEL_H) {
+    const int tt[4][3] = {{0, 1, 2}, {1, 2, 3}, {0, 2, 3}, {0, 1, 3}};
+    int negative = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double da = det3_pts(s1[tt[i][0]], s1[tt[i][1]], s1[tt[i][2]]);
+      const double db = det3_pts(s2[tt[i][0]], s2[tt[i][1]], s2[tt[i][2]]);
+      negative += (__dmul_rn(da, db) < 0) ? 1 : 0;
+    }
+    if (negative != 0 && negative != 4) return false;
+  }
+  return true;
+}
+
+// state per stream: [0] draw offset into the global RNG table, [1] subsets produced so far, [2] flags
+template <int MODEL>
+__global__ void __launch_bounds__(1024)
+ransac_sample_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const float2* __restrict__ p1,
+                     const float2* __restrict__ p2, const int32_t* __restrict__ npts, int max_pts,
+                     int32_t* __restrict__ subsets, int32_t* __restrict__ state, int want_total) {
+  constexpr int K = MT<MODEL>::K;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* J0 = reinterpret_cast<uint16_t*>(smem_raw);                  // kDraws + 1 (+1 pad)
+  uint16_t* J1 = J0 + (kDraws + 2);
+  uint16_t* pos = J1 + (kDraws + 2);                                     // kMaxAttempts
+  uint16_t* start = pos + kMaxAttempts;                                  // kSegIters
+  uint32_t* okbits = reinterpret_cast<uint32_t*>(start + kSegIters);     // kDraws / 32
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_last_attempt;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = npts[b];
+  int32_t* st = state + b * 4;
+  const int have = st[1];
+  const int draw_base = st[0];
+  if (have >= want_total) return;
+  int32_t* out = subsets + ((long long)b * want_total) * K;
+  if (n <= K) {
+    // count == modelPoints: OpenCV solves the points once; fewer: nothing to do
+    if (tid == 0) {
+      if (n == K && have == 0) {
+        for (int i = 0; i < K; ++i) out[i] = i;
+        st[1] = 1;
+      }
+      st[2] |= 4;  // exhausted
+    }
+    return;
+  }
+  if (draw_base + kDraws > rng_len) {
+    if (tid == 0) st[2] |= 2;  // RNG table exhausted
+    return;
+  }
+  const uint32_t* rng = rng_table + draw_base;
+  const float2* q1 = p1 + (long long)b * max_pts;
+  const float2* q2 = p2 + (long long)b * max_pts;
+
+  for (int i = tid; i < kDraws / 32; i += 1024) okbits[i] = 0;
+  if (tid == 0) {
+    pos[0] = 0;
+    s_base = 0;
+    s_last_attempt = -1;
+  }
+  __syncthreads();
+  // phase 1: one getSubset attempt from every draw offset
+  for (unsigned o = tid; o <= kDraws; o += 1024) {
+    unsigned e = kEndOff;
+    if (o < kDraws) {
+      int idx[K];
+      e = draw_subset<K>(rng, o, (unsigned)n, idx);
+      if (e != kEndOff) {
+        bool ok = true;
+        if (MODEL != MVO_MODEL_E) {
+          float2 s1[K], s2[K];
+#pragma unroll 1
+          for (int i = 0; i < K; ++i) {
+            s1[i] = q1[idx[i]];
+            s2[i] = q2[idx[i]];
+          }
+          ok = check_subset<MODEL>(s1, s2);
+        }
+        if (ok) atomicOr(&okbits[o >> 5], 1u << (o & 31));
+      }
+    }
+    J0[o] = (uint16_t)e;
+  }
+  __syncthreads();
+  // phase 2: attempt chain by pointer doubling: pos[a] = offset where attempt a starts
+  uint16_t* cur = J0;
+  uint16_t* nxt = J1;
+  for (int len = 1; len < kMaxAttempts; len <<= 1) {
+    for (int j = tid; j < len; j += 1024) pos[j + len] = cur[pos[j]];
+    for (int o = tid; o <= kDraws; o += 1024) nxt[o] = cur[cur[o]];
+    __syncthreads();
+    uint16_t* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  // phase 3: ordered compaction of the successful attempts
+  const int want = min(kSegIters, want_total - have);
+  for (int a0 = 0; a0 < kMaxAttempts; a0 += 1024) {
+    if (s_base >= want) break;
+    const int a = a0 + tid;
+    const unsigned o = pos[a];
+    const int ok = (o < kDraws) ? (int)((okbits[o >> 5] >> (o & 31)) & 1u) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int within = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane];
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, s);
+        if (lane >= s) v += t;
+      }
+      s_warp[lane] = v;
+    }
+    __syncthreads();
+    const int rank = s_base + (warp ? s_warp[warp - 1] : 0) + within;
+    if (ok && rank < want) {
+      start[rank] = (uint16_t)o;
+      if (rank == want - 1) s_last_attempt = a;
+    }
+    __syncthreads();
+    if (tid == 0) s_base += s_warp[31];
+    __syncthreads();
+  }
+  const int got = min(s_base, want);
+  // phase 4: materialise the index tuples
+  for (int i = tid; i < got; i += 1024) {
+    int idx[K];
+    draw_subset<K>(rng, start[i], (unsigned)n, idx);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) out[(long long)(have + i) * K + k] = idx[k];
+  }
+  if (tid == 0) {
+    st[1] = have + got;
+    // where does the next launch continue?  right after the last attempt this launch consumed
+    int a_last = (got == want) ? s_last_attempt : kMaxAttempts - 1;
+    while (a_last > 0 && pos[a_last] >= kDraws) --a_last;
+    int idx[K];
+    const unsigned e = draw_subset<K>(rng, pos[a_last], (unsigned)n, idx);
+    if (e != kEndOff) {
+      st[0] = draw_base + (int)e;
+    } else {
+      st[0] = draw_base + pos[a_last];          // unfinished attempt: redo it with a fresh window
+      if (pos[a_last] == 0) st[2] |= 4;         // no progress possible
+    }
+  }
+}
+
+// ---- solve ---------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(64)
+ransac_solve_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
+                    const double2* __restrict__ q2, int max_pts, const int32_t* __restrict__ subsets,
+                    const int32_t* __restrict__ state, int cap_iters, double* __restrict__ models,
+                    int32_t* __restrict__ nmodels) {
+  constexpr int K = MT<MODEL>::K, MAXM = MT<MODEL>::MAXM;
+  const int b = blockIdx.y;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsub = min(state[b * 4 + 1], cap_iters);
+  if (h >= nsub) return;
+  const int32_t* idx = subsets + ((long long)b * cap_iters + h) * K;
+  double* out = models + ((long long)b * cap_iters + h) * MAXM * 9;
+  int nm = 0;
+  if (MODEL == MVO_MODEL_E) {
+    double2 a[K], c[K];
+    for (int i = 0; i < K; ++i) {
+      a[i] = q1[(long long)b * max_pts + idx[i]];
+      c[i] = q2[(long long)b * max_pts + idx[i]];
+    }
+    double E[10 * 9];
+    nm = solve_e5(a, c, E);
+    for (int i = 0; i < nm * 9; ++i) out[i] = E[i];
+  } else {
+    float2 a[K], c[K];
+    for (int i = 0; i < K; ++i) {
+      a[i] = p1[(long long)b * max_pts + idx[i]];
+      c[i] = p2[(long long)b * max_pts + idx[i]];
+    }
+    if (MODEL == MVO_MODEL_H) {
+      double H[9];
+      nm = solve_h4(a, c, H);
+      if (nm)
+        for (int i = 0; i < 9; ++i) out[i] = H[i];
+    } else {
+      double F[27];
+      nm = solve_f7(a, c, F);
+      for (int i = 0; i < nm * 9; ++i) out[i] = F[i];
+    }
+  }
+  nmodels[(long long)b * cap_iters + h] = nm;
+}
+
+// ---- score ---------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ __forceinline__ float model_error(const double* M, const float* Mf, const float2* p1, const float2* p2,
+                                             const double2* q1, const double2* q2, long long i) {
+  if (MODEL == MVO_MODEL_H) return h_error(Mf, p1[i], p2[i]);
+  if (MODEL == MVO_MODEL_F) return f_error(M, p1[i], p2[i]);
+  return e_error(M, q1[i], q2[i]);
+}
+
+constexpr int kScoreThreads = 128;
+template <int MODEL>
+__global__ void __launch_bounds__(kScoreThreads)
+ransac_score_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
+                    const double2* __restrict__ q2, const int32_t* __restrict__ npts, int max_pts,
+                    const int32_t* __restrict__ state, int cap_iters, const double* __restrict__ models,
+                    const int32_t* __restrict__ nmodels, const float* __restrict__ thr2, int32_t* __restrict__ counts) {
+  constexpr int MAXM = MT<MODEL>::MAXM;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int nsub = min(state[b * 4 + 1], cap_iters);
+  if (h >= nsub) return;
+  const int nm = nmodels[(long long)b * cap_iters + h];
+  __shared__ double s_m[MAXM * 9];
+  __shared__ float s_mf[MAXM * 9];
+  __shared__ int s_cnt[MAXM];
+  const int tid = threadIdx.x;
+  if (tid < nm * 9) {
+    const double v = models[((long long)b * cap_iters + h) * MAXM * 9 + tid];
+    s_m[tid] = v;
+    s_mf[tid] = (float)v;
+  }
+  if (tid < MAXM) s_cnt[tid] = 0;
+  __syncthreads();
+  const int n = npts[b];
+  const float t = thr2[b];
+  const long long base = (long long)b * max_pts;
+  for (int m = 0; m < nm; ++m) {
+    int c = 0;
+    for (int i = tid; i < n; i += kScoreThreads)
+      c += (model_error<MODEL>(s_m + m * 9, s_mf + m * 9, p1, p2, q1, q2, base + i) <= t) ? 1 : 0;
+    c = warp_sum(c);
+    if ((tid & 31) == 0) atomicAdd(&s_cnt[m], c);
+  }
+  __syncthreads();
+  if (tid < MAXM) counts[((long long)b * cap_iters + h) * MAXM + tid] = (tid < nm) ? s_cnt[tid] : -1;
+}
+
+// ---- select: replay of the sequential adaptive loop ---------------------------------------------
+__device__ __forceinline__ int update_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmax(p, 0.);
+  p = fmin(p, 1.);
+  ep = fmax(ep, 0.);
+  ep = fmin(ep, 1.);
+  double num = fmax(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
+}
+
+// result per stream: [0] inlier count, [1] iterations run, [2] winning iteration, [3] winning model slot
+template <int MODEL>
+__global__ void __launch_bounds__(1024)
+ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
+                     const double2* __restrict__ q2, const int32_t* __restrict__ npts, int max_pts,
+                     const int32_t* __restrict__ state, int cap_iters, const double* __restrict__ models,
+                     const int32_t* __restrict__ counts, const float* __restrict__ thr2, double conf,
+                     double* __restrict__ best_model, uint8_t* __restrict__ mask, int32_t* __restrict__ result) {
+  constexpr int K = MT<MODEL>::K, MAXM = MT<MODEL>::MAXM, MAXIT = MT<MODEL>::MAXIT;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = npts[b];
+  const int nsub = min(min(state[b * 4 + 1], cap_iters), MAXIT);
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  __shared__ int s_T;
+  __shared__ unsigned long long s_win[2048 / 1024 + 1];
+  __shared__ double s_m[9];
+  __shared__ float s_mf[9];
+  __shared__ int s_cnt;
+  if (tid == 0) {
+    s_carry = 0;
+    s_T = nsub;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  // key: count << 24 | (0xFFF - iteration) << 12 ... first iteration / first model wins ties (strict '>')
+  // pass A: inclusive prefix max over iterations (chunks of 1024), stop index T
+  unsigned long long mykey[2] = {0, 0}, mypre[2] = {0, 0};
+  for (int c = 0; c < 2; ++c) {
+    const int it = c * 1024 + tid;
+    unsigned long long key = 0;
+    if (it < nsub) {
+      int bestc = -1, bestm = 0;
+      for (int m = 0; m < MAXM; ++m) {
+        const int v = counts[((long long)b * cap_iters + it) * MAXM + m];
+        if (v > bestc) {
+          bestc = v;
+          bestm = m;
+        }
+      }
+      if (bestc > K - 1) key = ((unsigned long long)bestc << 32) | ((unsigned long long)(0xFFFF - it) << 8) | (unsigned)(0xFF - bestm);
+    }
+    mykey[c] = key;
+    unsigned long long v = key;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, v, s);
+      if (lane >= s) v = max(v, o);
+    }
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_warp[lane];
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, w, s);
+        if (lane >= s) w = max(w, o);
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    unsigned long long pre = max(v, s_carry);
+    if (warp > 0) pre = max(pre, s_warp[warp - 1]);
+    mypre[c] = pre;
+    __syncthreads();
+    if (tid == 1023) s_carry = pre;
+    __syncthreads();
+  }
+  // niters after iteration `it` = g(best count so far); iteration it+1 runs iff it+1 < that
+  for (int c = 0; c < 2; ++c) {
+    const int it = c * 1024 + tid;
+    if (it < nsub) {
+      int niters = MAXIT;
+      if (mypre[c]) {
+        const int cnt = (int)(mypre[c] >> 32);
+        niters = update_iters(conf, (double)(n - cnt) / n, K, MAXIT);
+      }
+      if (it + 1 >= niters) atomicMin(&s_T, it + 1);
+    }
+  }
+  __syncthreads();
+  const int T = s_T;   // iterations actually run (>= 1 when nsub >= 1)
+  // winner = prefix max at iteration T-1
+  for (int c = 0; c < 2; ++c) {
+    const int it = c * 1024 + tid;
+    if (it == T - 1) s_win[0] = mypre[c];
+  }
+  if (T == 0 && tid == 0) s_win[0] = 0;
+  __syncthreads();
+  const unsigned long long win = s_win[0];
+  int32_t* res = result + b * 8;
+  uint8_t* mk = mask + (long long)b * max_pts;
+  if (win == 0) {
+    for (int i = tid; i < n; i += 1024) mk[i] = 0;
+    if (tid < 9) best_model[b * 9 + tid] = 0.0;
+    if (tid == 0) {
+      res[0] = 0;
+      res[1] = T;
+      res[2] = -1;
+      res[3] = -1;
+    }
+    return;
+  }
+  const int wit = 0xFFFF - (int)((win >> 8) & 0xFFFF), wm = 0xFF - (int)(win & 0xFF);
+  if (tid < 9) {
+    const double v = models[(((long long)b * cap_iters + wit) * MAXM + wm) * 9 + tid];
+    s_m[tid] = v;
+    s_mf[tid] = (float)v;
+    best_model[b * 9 + tid] = v;
+  }
+  __syncthreads();
+  const float t = thr2[b];
+  const long long base = (long long)b * max_pts;
+  int c = 0;
+  for (int i = tid; i < n; i += 1024) {
+    const int in = (model_error<MODEL>(s_m, s_mf, p1, p2, q1, q2, base + i) <= t) ? 1 : 0;
+    mk[i] = (uint8_t)in;
+    c += in;
+  }
+  c = warp_sum(c);
+  if (lane == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (tid == 0) {
+    res[0] = s_cnt;
+    res[1] = T;
+    res[2] = wit;
+    res[3] = wm;
+  }
+}
+
+// ---- homography refinement: DLT on inliers + cv::LMSolver (10 iterations) + mask of the refined H ----
+constexpr int kRefThreads = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double* v, double* s_red /* NV * 8 */, int tid) {
+  // deterministic: fixed per-thread strides, warp tree, then warps summed in order
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum_d(v[k]);
+  __syncthreads();
+  if ((tid & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_red[(tid >> 5) * NV + k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kRefThreads / 32; ++w) s += s_red[w * NV + k];
+    v[k] = s;
+  }
+}
+
+__device__ __forceinline__ void h_residual(const double* h, double Mx, double My, double mx, double my, double& ww,
+                                           double& xi, double& yi, double& ex, double& ey) {
+  ww = h[6] * Mx + h[7] * My + 1.;
+  ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+  xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+  yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+  ex = xi - mx;
+  ey = yi - my;
+}
+
+__global__ void __launch_bounds__(kRefThreads)
+h_refine_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const int32_t* __restrict__ npts,
+                int max_pts, const float* __restrict__ thr2, double* __restrict__ best_model,
+                uint8_t* __restrict__ mask, int32_t* __restrict__ result, int32_t* __restrict__ inl_idx) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = npts[b];
+  int32_t* res = result + b * 8;
+  if (res[0] <= 0) return;   // no model
+  const float2* P1 = p1 + (long long)b * max_pts;
+  const float2* P2 = p2 + (long long)b * max_pts;
+  uint8_t* mk = mask + (long long)b * max_pts;
+  int32_t* idx = inl_idx + (long long)b * max_pts;
+  __shared__ double s_red[(kRefThreads / 32) * 44];
+  __shared__ int s_warp[kRefThreads / 32];
+  __shared__ int s_base;
+  __shared__ double s_x[8], s_xd[8], s_A[64], s_v[8], s_ctl[8];
+  __shared__ float s_hf[9];
+  __shared__ int s_cnt;
+  // ordered compaction of the inlier indices
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += kRefThreads) {
+    const int i = i0 + tid;
+    const int ok = (i < n) ? (mk[i] != 0) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (ok) idx[off + __popc(bal & ((1u << lane) - 1))] = i;
+    __syncthreads();
+    if (tid == 0)
+      for (int w = 0; w < kRefThreads / 32; ++w) s_base += s_warp[w];
+    __syncthreads();
+  }
+  const int ni = s_base;
+  if (ni < 4) return;
+  // ---- DLT (HomographyEstimatorCallback::runKernel on the inliers) ----
+  double v4[4] = {0, 0, 0, 0};
+  for (int k = tid; k < ni; k += kRefThreads) {
+    const float2 M = P1[idx[k]], m = P2[idx[k]];
+    v4[0] += m.x; v4[1] += m.y; v4[2] += M.x; v4[3] += M.y;
+  }
+  block_sum<4>(v4, s_red, tid);
+  const double cmx = v4[0] / ni, cmy = v4[1] / ni, cMx = v4[2] / ni, cMy = v4[3] / ni;
+  double d4[4] = {0, 0, 0, 0};
+  for (int k = tid; k < ni; k += kRefThreads) {
+    const float2 M = P1[idx[k]], m = P2[idx[k]];
+    d4[0] += fabs(m.x - cmx); d4[1] += fabs(m.y - cmy); d4[2] += fabs(M.x - cMx); d4[3] += fabs(M.y - cMy);
+  }
+  block_sum<4>(d4, s_red, tid);
+  if (fabs(d4[0]) < DBL_EPSILON || fabs(d4[1]) < DBL_EPSILON || fabs(d4[2]) < DBL_EPSILON || fabs(d4[3]) < DBL_EPSILON) return;
+  const double smx = ni / d4[0], smy = ni / d4[1], sMx = ni / d4[2], sMy = ni / d4[3];
+  // LtL blocks: S = sum a a^T, Sx = sum x a a^T, Sy = sum y a a^T, Sr = sum (x^2+y^2) a a^T with a = (X, Y, 1)
+  double acc[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) acc[k] = 0;
+  for (int k = tid; k < ni; k += kRefThreads) {
+    const float2 Mp = P1[idx[k]], mp = P2[idx[k]];
+    const double x = (mp.x - cmx) * smx, y = (mp.y - cmy) * smy;
+    const double X = (Mp.x - cMx) * sMx, Y = (Mp.y - cMy) * sMy;
+    const double aa[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};
+    const double r = x * x + y * y;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      acc[j] += aa[j];
+      acc[6 + j] += x * aa[j];
+      acc[12 + j] += y * aa[j];
+      acc[18 + j] += r * aa[j];
+    }
+  }
+  block_sum<24>(acc, s_red, tid);
+  if (tid == 0) {
+    double L[81];
+    for (int i = 0; i < 81; ++i) L[i] = 0;
+    const int sidx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const int s = sidx[i][j];
+        L[i * 9 + j] = acc[s];
+        L[(3 + i) * 9 + 3 + j] = acc[s];
+        L[i * 9 + 6 + j] = -acc[6 + s];
+        L[(6 + j) * 9 + i] = -acc[6 + s];
+        L[(3 + i) * 9 + 6 + j] = -acc[12 + s];
+        L[(6 + j) * 9 + 3 + i] = -acc[12 + s];
+        L[(6 + i) * 9 + 6 + j] = acc[18 + s];
+      }
+    // smallest eigenvector: Jacobi (9x9)
+    double V[81];
+    jacobi_eig<9>(L, V);
+    int kmin = 0;
+    for (int k = 1; k < 9; ++k)
+      if (L[k * 9 + k] < L[kmin * 9 + kmin]) kmin = k;
+    double h0[9];
+    for (int i = 0; i < 9; ++i) h0[i] = V[i * 9 + kmin];
+    const double inv_hn[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+    const double hn2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+    double t[9], H[9];
+    mat3_mul(inv_hn, h0, t);
+    mat3_mul(t, hn2, H);
+    const double s = 1. / H[8];
+    for (int i = 0; i < 8; ++i) s_x[i] = H[i] * s;
+  }
+  __syncthreads();
+  // ---- LM (cv::LMSolverImpl::run, maxIters 10, eps FLT_EPSILON) ----
+  // initial residual / normal equations
+  double lam = 1.0, lc = 0.75, S = 0;
+  double A[36], vv[8];   // thread 0 keeps the reduced normal matrix (upper triangle) and J^T r
+  auto normal_eq = [&](const double* h) {
+    double a44[45];
+#pragma unroll
+    for (int k = 0; k < 45; ++k) a44[k] = 0;
+    for (int k = tid; k < ni; k += kRefThreads) {
+      const float2 Mp = P1[idx[k]], mp = P2[idx[k]];
+      const double Mx = Mp.x, My = Mp.y;
+      double ww, xi, yi, ex, ey;
+      h_residual(h, Mx, My, (double)mp.x, (double)mp.y, ww, xi, yi, ex, ey);
+      const double jx[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
+      const double jy[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
+      int o = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = i; j < 8; ++j) a44[o++] += jx[i] * jx[j] + jy[i] * jy[j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a44[36 + i] += jx[i] * ex + jy[i] * ey;
+      a44[44] += ex * ex + ey * ey;
+    }
+    // 45 values: reduce in two halves to bound registers
+    block_sum<24>(a44, s_red, tid);
+    block_sum<21>(a44 + 24, s_red, tid);
+    if (tid == 0) {
+      for (int k = 0; k < 36; ++k) A[k] = a44[k];
+      for (int k = 0; k < 8; ++k) vv[k] = a44[36 + k];
+      S = a44[44];
+    }
+  };
+  auto residual_only = [&](const double* h, double& Sd, double& rinf) {
+    double two[2] = {0, 0};
+    for (int k = tid; k < ni; k += kRefThreads) {
+      const float2 Mp = P1[idx[k]], mp = P2[idx[k]];
+      double ww, xi, yi, ex, ey;
+      h_residual(h, (double)Mp.x, (double)Mp.y, (double)mp.x, (double)mp.y, ww, xi, yi, ex, ey);
+      two[0] += ex * ex + ey * ey;
+      two[1] = fmax(two[1], fmax(fabs(ex), fabs(ey)));
+    }
+    // sum for [0], max for [1]
+    double mx = two[1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double one[1] = {two[0]};
+    block_sum<1>(one, s_red, tid);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    double m = 0;
+    for (int w = 0; w < kRefThreads / 32; ++w) m = fmax(m, s_red[w]);
+    __syncthreads();
+    Sd = one[0];
+    rinf = m;
+  };
+  normal_eq(s_x);
+  double Dg[8];
+  if (tid == 0) {
+    int o = 0;
+    for (int i = 0; i < 8; ++i) {
+      Dg[i] = A[o];
+      o += 8 - i;
+    }
+  }
+  double rinf_cur;
+  {
+    double tmpS;
+    residual_only(s_x, tmpS, rinf_cur);
+  }
+  for (int iter = 0;;) {
+    // thread 0: solve (A + lam*D) d = v
+    if (tid == 0) {
+      double Ap[64], d[8];
+      int o = 0;
+      for (int i = 0; i < 8; ++i)
+        for (int j = i; j < 8; ++j) {
+          Ap[i * 8 + j] = Ap[j * 8 + i] = A[o++];
+        }
+      for (int i = 0; i < 64; ++i) s_A[i] = Ap[i];
+      for (int i = 0; i < 8; ++i) Ap[i * 9] += lam * Dg[i];
+      for (int i = 0; i < 8; ++i) d[i] = vv[i];
+      if (!lu_solve<8>(Ap, d))
+        for (int i = 0; i < 8; ++i) d[i] = 0;
+      for (int i = 0; i < 8; ++i) {
+        s_v[i] = d[i];
+        s_xd[i] = s_x[i] - d[i];
+      }
+    }
+    __syncthreads();
+    double Sd, rinf_d;
+    residual_only(s_xd, Sd, rinf_d);
+    if (tid == 0) {
+      // dS = d . (2 v - A d);  R = (S - Sd) / dS
+      double dS = 0, tdot = 0, dinf = 0;
+      for (int i = 0; i < 8; ++i) {
+        double ad = 0;
+        for (int j = 0; j < 8; ++j) ad += s_A[i * 8 + j] * s_v[j];
+        dS += s_v[i] * (2 * vv[i] - ad);
+        tdot += s_v[i] * vv[i];
+        dinf = fmax(dinf, fabs(s_v[i]));
+      }
+      const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+      if (R > 0.75) {
+        lam *= 0.5;
+        if (lam < lc) lam = 0;
+      } else if (R < 0.25) {
+        double nu = (Sd - S) / (fabs(tdot) > DBL_EPSILON ? tdot : 1) + 2;
+        nu = fmin(fmax(nu, 2.), 10.);
+        if (lam == 0) {
+          // lc = 1 / max |diag(A^-1)|
+          double maxval = DBL_EPSILON;
+          for (int c = 0; c < 8; ++c) {
+            double Ap[64], e[8];
+            for (int i = 0; i < 64; ++i) Ap[i] = s_A[i];
+            for (int i = 0; i < 8; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+            if (lu_solve<8>(Ap, e)) maxval = fmax(maxval, fabs(e[c]));
+          }
+          lam = lc = 1. / maxval;
+          nu *= 0.5;
+        }
+        lam *= nu;
+      }
+      s_ctl[0] = (Sd < S) ? 1.0 : 0.0;
+      s_ctl[1] = dinf;
+    }
+    __syncthreads();
+    const bool accept = s_ctl[0] != 0.0;
+    const double dinf = s_ctl[1];
+    __syncthreads();
+    if (accept) {
+      if (tid < 8) s_x[tid] = s_xd[tid];
+      __syncthreads();
+      normal_eq(s_x);
+      rinf_cur = rinf_d;
+    }
+    ++iter;
+    const bool proceed = iter < 10 && dinf >= (double)FLT_EPSILON && rinf_cur >= (double)FLT_EPSILON;
+    if (!proceed) break;
+  }
+  __syncthreads();
+  // ---- final model + mask of the refined H ----
+  if (tid < 8) {
+    best_model[b * 9 + tid] = s_x[tid];
+    s_hf[tid] = (float)s_x[tid];
+  }
+  if (tid == 8) {
+    best_model[b * 9 + 8] = 1.0;
+    s_hf[8] = 1.f;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const float t = thr2[b];
+  int c = 0;
+  for (int i = tid; i < n; i += kRefThreads) {
+    const int in = (h_error(s_hf, P1[i], P2[i]) <= t) ? 1 : 0;
+    mk[i] = (uint8_t)in;
+    c += in;
+  }
+  c = warp_sum(c);
+  if (lane == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (tid == 0) res[0] = s_cnt;
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------
+__global__ void normalize_points_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2,
+                                        const int32_t* __restrict__ npts, int max_pts, const double* __restrict__ K,
+                                        double2* __restrict__ q1, double2* __restrict__ q2) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts[b]) return;
+  const double fx = K[b * 9 + 0], fy = K[b * 9 + 4], cx = K[b * 9 + 2], cy = K[b * 9 + 5];
+  const long long o = (long long)b * max_pts + i;
+  q1[o] = make_double2(((double)p1[o].x - cx) / fx, ((double)p1[o].y - cy) / fy);
+  q2[o] = make_double2(((double)p2[o].x - cx) / fx, ((double)p2[o].y - cy) / fy);
+}
+
+// ====================================================================================================
+// host side
+static void fill_rng_table(uint64_t seed, std::vector<uint32_t>& t, size_t count) {
+  t.resize(count);
+  uint64_t s = seed;
+  for (size_t i = 0; i < count; ++i) {
+    s = (uint64_t)(uint32_t)s * 4164903690ull + (s >> 32);
+    t[i] = (uint32_t)s;
+  }
+}
+
+constexpr size_t kSampleSmem = (size_t)(kDraws + 2) * 2 * 2 + (size_t)kMaxAttempts * 2 + (size_t)kSegIters * 2 + kDraws / 8;
+
+int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
+  RansacBufs& r = c->rs;
+  const size_t B = (size_t)c->cfg.batch;
+  if (!r.rng_ready) {
+    std::vector<uint32_t> t;
+    r.rng_len = 1 << 19;   // 524288 draws: enough for 16384-hypothesis sweeps
+    fill_rng_table(c->cfg.ransac_seed, t, (size_t)r.rng_len);
+    MVO_CUDA_TRY(c, r.rng.alloc(t.size()));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.rng.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
+    r.rng_ready = true;
+  }
+  if (max_pts > r.max_pts) {
+    const size_t n = B * (size_t)max_pts;
+    MVO_CUDA_TRY(c, r.p1.alloc(n));
+    MVO_CUDA_TRY(c, r.p2.alloc(n));
+    MVO_CUDA_TRY(c, r.q1.alloc(n));
+    MVO_CUDA_TRY(c, r.q2.alloc(n));
+    MVO_CUDA_TRY(c, r.mask.alloc(n));
+    MVO_CUDA_TRY(c, r.inl_idx.alloc(n));
+    r.max_pts = max_pts;
+  }
+  if (cap_iters > r.cap_iters) {
+    const size_t n = B * (size_t)cap_iters;
+    MVO_CUDA_TRY(c, r.subsets.alloc(n * 8));
+    MVO_CUDA_TRY(c, r.models.alloc(n * kMaxHypModels * 9));
+    MVO_CUDA_TRY(c, r.nmodels.alloc(n));
+    MVO_CUDA_TRY(c, r.counts.alloc(n * kMaxHypModels));
+    r.cap_iters = cap_iters;
+  }
+  MVO_CUDA_TRY(c, r.npts.alloc(B));
+  MVO_CUDA_TRY(c, r.state.alloc(B * 4));
+  MVO_CUDA_TRY(c, r.thr2.alloc(B));
+  MVO_CUDA_TRY(c, r.K.alloc(B * 9));
+  MVO_CUDA_TRY(c, r.best_model.alloc(B * 9));
+  MVO_CUDA_TRY(c, r.result.alloc(B * 8));
+  return MVO_OK;
+}
+
+template <int MODEL>
+static int run_hypotheses(mvo_ctx* c, int want_total) {
+  // sample -> solve -> score for `want_total` iterations (device-resident points / counts in c->rs)
+  RansacBufs& r = c->rs;
+  const int B = c->cfg.batch;
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)B * 16, c->stream));
+  const int launches = (want_total + kSegIters - 1) / kSegIters + (want_total > kSegIters ? 2 : 0);
+  for (int l = 0; l < launches; ++l) {
+    ransac_sample_kernel<MODEL><<<B, 1024, kSampleSmem, c->stream>>>(r.rng.p, r.rng_len, r.p1.p, r.p2.p, r.npts.p,
+                                                                     r.max_pts, r.subsets.p, r.state.p, want_total);
+    c->launches++;
+  }
+  dim3 gs((want_total + 63) / 64, B);
+  ransac_solve_kernel<MODEL><<<gs, 64, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.subsets.p, r.state.p,
+                                                       want_total, r.models.p, r.nmodels.p);
+  c->launches++;
+  dim3 gc(want_total, B);
+  ransac_score_kernel<MODEL><<<gc, kScoreThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
+                                                                 r.state.p, want_total, r.models.p, r.nmodels.p,
+                                                                 r.thr2.p, r.counts.p);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+// full find*: points must already be in r.p1/r.p2 (and r.q1/r.q2 for E), counts in r.npts, thresholds in r.thr2
+int ransac_find(mvo_ctx* c, int model, double conf) {
+  RansacBufs& r = c->rs;
+  const int B = c->cfg.batch;
+  int rc;
+  if (model == MVO_MODEL_H) {
+    rc = run_hypotheses<MVO_MODEL_H>(c, 2000);
+    if (rc) return rc;
+    ransac_select_kernel<MVO_MODEL_H><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
+                                                                 r.state.p, 2000, r.models.p, r.counts.p, r.thr2.p, conf,
+                                                                 r.best_model.p, r.mask.p, r.result.p);
+    c->launches++;
+    h_refine_kernel<<<B, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.thr2.p, r.best_model.p,
+                                                      r.mask.p, r.result.p, r.inl_idx.p);
+    c->launches++;
+  } else if (model == MVO_MODEL_F) {
+    rc = run_hypotheses<MVO_MODEL_F>(c, 1000);
+    if (rc) return rc;
+    ransac_select_kernel<MVO_MODEL_F><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
+                                                                 r.state.p, 1000, r.models.p, r.counts.p, r.thr2.p, conf,
+                                                                 r.best_model.p, r.mask.p, r.result.p);
+    c->launches++;
+  } else {
+    rc = run_hypotheses<MVO_MODEL_E>(c, 1000);
+    if (rc) return rc;
+    ransac_select_kernel<MVO_MODEL_E><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
+                                                                 r.state.p, 1000, r.models.p, r.counts.p, r.thr2.p, conf,
+                                                                 r.best_model.p, r.mask.p, r.result.p);
+    c->launches++;
+  }
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+int ransac_normalize(mvo_ctx* c) {
+  RansacBufs& r = c->rs;
+  dim3 grid((r.max_pts + 255) / 256, c->cfg.batch);
+  normalize_points_kernel<<<grid, 256, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.K.p, r.q1.p, r.q2.p);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+int ransac_sweep(mvo_ctx* c, int model, int m) {
+  if (model == MVO_MODEL_H) return run_hypotheses<MVO_MODEL_H>(c, m);
+  if (model == MVO_MODEL_F) return run_hypotheses<MVO_MODEL_F>(c, m);
+  return run_hypotheses<MVO_MODEL_E>(c, m);
+}
+
+}  // namespace mvo
+
+// ====================================================================================================
+using namespace mvo;
+
+static int upload_points(mvo_ctx* c, const float* p1, const float* p2, int n, double thr2, const double* K, int cap_iters) {
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  if (c->cfg.batch != 1) {
+    c->set_error("the single-call geometry API needs a batch==1 context");
+    return MVO_ERR_INVALID;
+  }
+  int rc = ransac_prepare(c, std::max(n, std::max(c->rs.max_pts, 64)), std::max(cap_iters, std::max(c->rs.cap_iters, 2000)));
+  if (rc) return rc;
+  RansacBufs& r = c->rs;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.p1.p, p1, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.p2.p, p2, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  struct { int n; float t; } h = {n, (float)thr2};
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.npts.p, &h.n, 4, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.thr2.p, &h.t, 4, cudaMemcpyHostToDevice, c->stream));
+  if (K) MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // h lives on this stack frame
+  return MVO_OK;
+}
+
+static int download_result(mvo_ctx* c, int n, double* model, uint8_t* mask, int* n_inl) {
+  RansacBufs& r = c->rs;
+  int res[8];
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, r.result.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  if (model) MVO_CUDA_TRY(c, cudaMemcpyAsync(model, r.best_model.p, 72, cudaMemcpyDeviceToHost, c->stream));
+  if (mask) MVO_CUDA_TRY(c, cudaMemcpyAsync(mask, r.mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (n_inl) *n_inl = res[0];
+  c->last_ransac_iters = res[1];
+  if (res[2] < 0) {
+    c->set_error("RANSAC found no model");
+    return MVO_ERR_DEGENERATE;
+  }
+  return MVO_OK;
+}
+
+extern "C" {
+
+int mvo_find_homography(mvo_ctx* c, const float* p1, const float* p2, int n, double thr, double* H, uint8_t* mask,
+                        int* n_inliers) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!p1 || !p2 || n < 0) {
+    c->set_error("mvo_find_homography: null argument");
+    return MVO_ERR_INVALID;
+  }
+  if (n < 4) {
+    c->set_error("mvo_find_homography: fewer than 4 correspondences");
+    return MVO_ERR_DEGENERATE;
+  }
+  int rc = upload_points(c, p1, p2, n, thr * thr, nullptr, 2000);
+  if (rc) return rc;
+  rc = ransac_find(c, MVO_MODEL_H, 0.995);
+  if (rc) return rc;
+  return download_result(c, n, H, mask, n_inliers);
+}
+
+int mvo_find_fundamental(mvo_ctx* c, const float* p1, const float* p2, int n, double thr, double conf, double* F,
+                         uint8_t* mask, int* n_inliers) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!p1 || !p2 || n < 0) {
+    c->set_error("mvo_find_fundamental: null argument");
+    return MVO_ERR_INVALID;
+  }
+  if (n < 15) {
+    c->set_error("mvo_find_fundamental: N < 15 switches OpenCV to LMedS, which is not implemented");
+    return n < 7 ? MVO_ERR_DEGENERATE : MVO_ERR_UNSUPPORTED;
+  }
+  if (thr <= 0) thr = 3;
+  if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
+  int rc = upload_points(c, p1, p2, n, thr * thr, nullptr, 1000);
+  if (rc) return rc;
+  rc = ransac_find(c, MVO_MODEL_F, conf);
+  if (rc) return rc;
+  return download_result(c, n, F, mask, n_inliers);
+}
+
+int mvo_find_essential(mvo_ctx* c, const float* p1, const float* p2, int n, const double* K, double conf, double thr,
+                       double* E, uint8_t* mask, int* n_inliers) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!p1 || !p2 || !K || n < 0) {
+    c->set_error("mvo_find_essential: null argument");
+    return MVO_ERR_INVALID;
+  }
+  if (n < 5) {
+    c->set_error("mvo_find_essential: fewer than 5 correspondences");
+    return MVO_ERR_DEGENERATE;
+  }
+  const double t = thr / ((K[0] + K[4]) / 2);
+  int rc = upload_points(c, p1, p2, n, t * t, K, 1000);
+  if (rc) return rc;
+  rc = ransac_normalize(c);
+  if (rc) return rc;
+  rc = ransac_find(c, MVO_MODEL_E, conf);
+  if (rc) return rc;
+  return download_result(c, n, E, mask, n_inliers);
+}
+
+int mvo_score_hypotheses(mvo_ctx* c, int model, const float* p1, const float* p2, int n, const double* K, double thr,
+                         int m, int32_t* sample_idx, int32_t* counts, double* models) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!p1 || !p2 || !counts || n < 8 || m < 1 || m > 16384 || model < 0 || model > 2 || (model == MVO_MODEL_E && !K)) {
+    c->set_error("mvo_score_hypotheses: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  double t2 = thr * thr;
+  if (model == MVO_MODEL_E) {
+    const double t = thr / ((K[0] + K[4]) / 2);
+    t2 = t * t;
+  }
+  int rc = upload_points(c, p1, p2, n, t2, K, m);
+  if (rc) return rc;
+  if (model == MVO_MODEL_E) {
+    rc = ransac_normalize(c);
+    if (rc) return rc;
+  }
+  rc = ransac_sweep(c, model, m);
+  if (rc) return rc;
+  RansacBufs& r = c->rs;
+  const int kk = model == MVO_MODEL_H ? 4 : model == MVO_MODEL_F ? 7 : 5;
+  const int mm = model == MVO_MODEL_H ? 1 : model == MVO_MODEL_F ? 3 : 10;
+  int st[4];
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(st, r.state.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(counts, r.counts.p, (size_t)m * mm * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (sample_idx) MVO_CUDA_TRY(c, cudaMemcpyAsync(sample_idx, r.subsets.p, (size_t)m * kk * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (models) MVO_CUDA_TRY(c, cudaMemcpyAsync(models, r.models.p, (size_t)m * mm * 72, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (st[1] < m) {
+    c->set_error("could not draw the requested number of valid minimal samples");
+    return MVO_ERR_DEGENERATE;
+  }
+  return MVO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""GPU parity: RANSAC H / F / E, recoverPose, triangulation through the C ABI vs the oracle and cv2 goldens.
+
+Tolerances (BASELINE.json north_star): rotation within 0.05 deg, translation direction within 0.1 deg under
+identical hypothesis sets.  Here the hypothesis sets are identical by construction (same RNG stream, same
+subset rules), and masks / inlier counts are compared exactly.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, sha
+from oracle import ransac_oracle as ro
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+ROT_TOL_DEG = 0.05
+T_TOL_DEG = 0.1
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ros2_mono_vo_b200 import Context
+    c = Context(1241, 376, nfeatures=2000, max_points=8192)
+    yield c
+    c.close()
+
+
+def _scene(g, tag):
+    n, seed, planar = g[f"{tag}_args"].tolist()
+    p1, p2, R, t, inl = synth.scene_correspondences(n, seed, planar=bool(planar), outlier_frac=0.25)
+    assert sha(np.concatenate([p1, p2])) == str(g[f"{tag}_sha"])
+    return p1, p2
+
+
+def rot_angle_deg(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+def dir_angle_deg(a, b):
+    c = np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+def up_to_scale_sign(a, b):
+    a = a.ravel() / np.linalg.norm(a)
+    b = b.ravel() / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_ransac_vs_cv2_golden(ctx, tag):
+    g = load_golden("ransac.npz")
+    K = g["K"]
+    p1, p2 = _scene(g, tag)
+    H, mh, nh = ctx.find_homography(p1, p2, 1.0)
+    assert np.array_equal(mh, g[f"{tag}_mask_h"]) and nh == int(g[f"{tag}_mask_h"].sum())
+    assert np.abs(H - g[f"{tag}_H"]).max() < 1e-6 * max(1.0, np.abs(g[f"{tag}_H"]).max())
+    F, mf, nf = ctx.find_fundamental(p1, p2, 1.0, 0.99)
+    assert np.array_equal(mf, g[f"{tag}_mask_f"]) and nf == int(mf.sum())
+    assert np.abs(F - g[f"{tag}_F"]).max() < 1e-8
+    E, me, ne = ctx.find_essential(p1, p2, K, 0.99, 1.0)
+    assert np.array_equal(me, g[f"{tag}_mask_e"]) and ne == int(me.sum())
+    assert up_to_scale_sign(E, g[f"{tag}_E"]) < 1e-6
+    R, t, mp, good = ctx.recover_pose(E, p1, p2, K, mask=me)
+    assert rot_angle_deg(R, g[f"{tag}_R"]) < ROT_TOL_DEG
+    assert dir_angle_deg(t, g[f"{tag}_t"]) < T_TOL_DEG
+    assert good == int(g[f"{tag}_good"])
+    assert np.array_equal(mp != 0, g[f"{tag}_mask_pose"] != 0)
+    assert abs(np.linalg.norm(t) - 1) < 1e-9 and abs(np.linalg.det(R) - 1) < 1e-9
+    X = ctx.triangulate(K @ np.eye(3, 4), K @ np.column_stack([g[f"{tag}_R"], g[f"{tag}_t"]]), p1, p2)
+    Xg = g[f"{tag}_X"].astype(np.float64)
+    assert X.dtype == np.float32 and X.shape == Xg.shape
+    ok = np.abs(Xg[3]) > 1e-3
+    a, b = (X[:3].astype(np.float64) / X[3])[:, ok], (Xg[:3] / Xg[3])[:, ok]
+    assert np.abs(a - b).max() / np.abs(b).max() < 1e-4
+    assert np.abs(np.linalg.norm(X.astype(np.float64), axis=0) - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("seed,planar,n,outl", [(31, False, 2000, 0.3), (32, True, 1500, 0.4), (33, False, 300, 0.1),
+                                                (34, False, 5000, 0.3), (35, True, 64, 0.2)])
+def test_ransac_vs_oracle(ctx, seed, planar, n, outl):
+    K = synth.KITTI_K
+    p1, p2, Rgt, tgt, inl = synth.scene_correspondences(n, seed, planar=planar, outlier_frac=outl)
+    H, mh, nh = ctx.find_homography(p1, p2, 1.0)
+    Ho, mho, _ = ro.find_homography(p1, p2, 1.0)
+    assert np.array_equal(mh, mho)
+    F, mf, nf = ctx.find_fundamental(p1, p2, 1.0, 0.99)
+    Fo, mfo, _ = ro.find_fundamental(p1, p2, 1.0, 0.99)
+    assert np.array_equal(mf, mfo)
+    E, me, ne = ctx.find_essential(p1, p2, K, 0.99, 1.0)
+    Eo, meo, _ = ro.find_essential(p1, p2, K, 0.99, 1.0)
+    assert np.array_equal(me, meo)
+    R, t, mp, good = ctx.recover_pose(E, p1, p2, K, mask=me)
+    Ro, to, mpo, goodo = ro.recover_pose(Eo, p1, p2, K, mask=meo)
+    assert rot_angle_deg(R, Ro) < ROT_TOL_DEG and dir_angle_deg(t, to) < T_TOL_DEG
+    assert abs(good - goodo) <= 1
+    if not planar and n >= 1000:
+        # sanity against the ground-truth motion of the synthetic scene
+        assert rot_angle_deg(R, Rgt) < 0.5 and dir_angle_deg(t, tgt) < 8.0
+
+
+def test_recover_pose_without_mask_and_triangulate_edge(ctx):
+    K = synth.KITTI_K
+    p1, p2, Rgt, tgt, inl = synth.scene_correspondences(500, 41, outlier_frac=0.0)
+    E, me, ne = ctx.find_essential(p1, p2, K, 0.99, 1.0)
+    R, t, m, good = ctx.recover_pose(E, p1, p2, K, mask=None)
+    Ro, to, mo, goodo = ro.recover_pose(E, p1, p2, K, mask=None)
+    assert good == goodo and rot_angle_deg(R, Ro) < 1e-6
+    assert ctx.triangulate(np.eye(3, 4), np.eye(3, 4), p1[:0], p2[:0]).shape == (4, 0)
+
+
+def test_hypothesis_sweep_matches_oracle_subsets(ctx):
+    """C4: deterministic seeded sampling -- the subsets are exactly OpenCV's RNG stream; counts match the oracle."""
+    K = synth.KITTI_K
+    p1, p2, *_ = synth.scene_correspondences(5000, 51, outlier_frac=0.3)
+    for model, name in ((0, "H"), (1, "F"), (2, "E")):
+        idx, counts, models = ctx.score_hypotheses(model, p1, p2, 512, thr=1.0, K=K, want_models=True)
+        ref = ro.sample_subsets(name, p1, p2, 512)
+        assert np.array_equal(idx, ref), name
+        # score a few hypotheses with the oracle error functions on the GPU's own models
+        q1, q2 = ro.normalize_points(p1, K), ro.normalize_points(p2, K)
+        for h in (0, 1, 17, 511):
+            for m in range(counts.shape[1]):
+                if counts[h, m] < 0:
+                    continue
+                M = models[h, m].reshape(3, 3)
+                if name == "H":
+                    c = int((ro.h_errors(M, p1, p2) <= np.float32(1.0)).sum())
+                elif name == "F":
+                    c = int((ro.f_errors(M, p1, p2) <= np.float32(1.0)).sum())
+                else:
+                    t = 1.0 / ((K[0, 0] + K[1, 1]) / 2)
+                    c = int((ro.e_errors(M, q1, q2) <= np.float32(t * t)).sum())
+                assert c == counts[h, m], (name, h, m)
+    # a long sweep keeps following the stream across sampler launches
+    idx, counts, _ = ctx.score_hypotheses(1, p1, p2, 4096, thr=1.0)
+    ref = ro.sample_subsets("F", p1, p2, 4096)
+    assert np.array_equal(idx, ref)
+
+
+def test_degenerate_inputs(ctx):
+    from ros2_mono_vo_b200 import MvoError
+    p = np.random.default_rng(0).uniform(0, 300, (3, 2)).astype(np.float32)
+    with pytest.raises(MvoError):
+        ctx.find_homography(p, p, 1.0)
+    with pytest.raises(MvoError):
+        ctx.find_fundamental(p, p, 1.0)
+    # all points identical: no valid sample can be drawn -> no model, reported as an error code
+    same = np.tile(np.array([[10.0, 20.0]], np.float32), (50, 1))
+    with pytest.raises(MvoError):
+        ctx.find_homography(same, same, 1.0)
