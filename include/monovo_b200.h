@@ -183,6 +183,8 @@ typedef struct mvo_frame_result {
 
 MVO_API int mvo_group_step(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride,
                            int images_on_device, const double K[9], mvo_frame_result* results);
+/* forget the previous frame of every stream (the next step only extracts features) */
+MVO_API int mvo_group_reset(mvo_ctx* ctx);
 /* per-stage device time (ms) of the last mvo_group_step, measured with CUDA events on the ctx stream.
  * names: "orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total" */
 MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);

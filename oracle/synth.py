@@ -95,18 +95,63 @@ def synth_pair(h: int, w: int, seed: int):
     return f0, warp_similarity(f0, ang, tx, ty)
 
 
+def _smooth_field(h: int, w: int, rng, scales=(16, 64)) -> np.ndarray:
+    f = np.zeros((h, w))
+    for s in scales:
+        f += _upsample_bilinear(rng.uniform(-1.0, 1.0, size=(h // s + 2, w // s + 2)), h, w)
+    f -= f.min()
+    return f / max(f.max(), 1e-9)
+
+
+def warp_parallax(img: np.ndarray, T, inv_depth: np.ndarray, K: np.ndarray) -> np.ndarray:
+    """View of a rigid scene after the camera translated by T (no rotation): the new frame's pixel p' with
+    inverse depth rho sees the old frame at x = (x' + T_xy rho) / (1 + T_z rho) (normalised coordinates)."""
+    h, w = img.shape
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    xn, yn = (xx - cx) / fx, (yy - cy) / fy
+    den = 1.0 + T[2] * inv_depth
+    xs = (xn + T[0] * inv_depth) / den * fx + cx
+    ys = (yn + T[1] * inv_depth) / den * fy + cy
+    x0 = np.floor(xs).astype(int)
+    y0 = np.floor(ys).astype(int)
+    fxr, fyr = xs - x0, ys - y0
+
+    def refl(i, n):
+        i = np.abs(i)
+        i = np.where(i >= n, 2 * (n - 1) - i, i)
+        return np.clip(i, 0, n - 1)
+
+    x0r, x1r = refl(x0, w), refl(x0 + 1, w)
+    y0r, y1r = refl(y0, h), refl(y0 + 1, h)
+    f = img.astype(np.float64)
+    out = (f[y0r, x0r] * (1 - fxr) + f[y0r, x1r] * fxr) * (1 - fyr) + \
+          (f[y1r, x0r] * (1 - fxr) + f[y1r, x1r] * fxr) * fyr
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def sequence_camera(h: int, w: int) -> np.ndarray:
+    """KITTI-like intrinsics scaled to the frame size."""
+    f = 718.856 * w / 1241.0
+    return np.array([[f, 0.0, (w - 1) / 2.0], [0.0, f, (h - 1) / 2.0], [0.0, 0.0, 1.0]])
+
+
 def synth_sequence(h: int, w: int, stream: int, nframes: int):
-    """A seeded smooth trajectory of small warps of one base frame (C2/C5 sequences)."""
+    """A seeded camera translating through a rigid non-planar scene (C2/C5 sequences): every frame is one
+    resampling of the base frame with a smooth inverse-depth map (depths 6..50, ~0.5 units of forward motion
+    per frame, i.e. KITTI-like depth/baseline ratios of 12..100).
+    Returns (frames, K)."""
     rng = np.random.default_rng(1000 * stream + 17)
     base = synth_frame(h, w, 1000 * stream)
+    K = sequence_camera(h, w)
+    depth = 6.0 + 44.0 * _smooth_field(h, w, rng)
+    inv_depth = 1.0 / depth
     frames = [base]
-    ang = tx = ty = 0.0
+    T = np.zeros(3)
     for _ in range(1, nframes):
-        ang += rng.uniform(-0.15, 0.15)
-        tx += rng.uniform(-1.5, 1.5)
-        ty += rng.uniform(-0.8, 0.8)
-        frames.append(warp_similarity(base, ang, tx, ty))
-    return frames
+        T = T + np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02), rng.uniform(0.4, 0.6)])
+        frames.append(warp_parallax(base, T, inv_depth, K))
+    return frames, K
 
 
 def rodrigues(rvec) -> np.ndarray:

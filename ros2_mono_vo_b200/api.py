@@ -19,6 +19,11 @@ KP_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32),
                      ("response", np.float32), ("octave", np.int32), ("class_id", np.int32)])
 DMATCH_DTYPE = np.dtype([("query_idx", np.int32), ("train_idx", np.int32), ("img_idx", np.int32),
                          ("distance", np.float32)])
+RESULT_DTYPE = np.dtype([("n_keypoints", np.int32), ("n_matches", np.int32), ("n_tracked", np.int32),
+                         ("score_h", np.int32), ("score_f", np.int32), ("n_inliers_e", np.int32),
+                         ("n_pose_good", np.int32), ("n_triangulated", np.int32),
+                         ("R", np.float64, (9,)), ("t", np.float64, (3,))])
+assert RESULT_DTYPE.itemsize == C.sizeof(_lib.MvoFrameResult)
 assert KP_DTYPE.itemsize == C.sizeof(_lib.MvoKeypoint) == 28
 assert DMATCH_DTYPE.itemsize == C.sizeof(_lib.MvoDMatch) == 16
 
@@ -127,6 +132,35 @@ class Context:
         self._check(self.lib.mvo_lk_track(self.h, _ptr(prev), _ptr(nxt), w, h, prev.strides[0], ch, _ptr(pts), n,
                                           _ptr(out), _ptr(status), _ptr(err)))
         return out, status, err
+
+    # ---- stream-group front-end step ---------------------------------------------------------
+    STAGES = ("orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total")
+
+    def group_step(self, images: np.ndarray, K, device_ptr: int | None = None, shape=None):
+        """One front-end frame for every stream of the group.  images: batch x h x w u8 (host), or pass
+        device_ptr (+ shape=(h, w)) for frames already resident in HBM.  Returns a structured array."""
+        Kp = np.ascontiguousarray(K, np.float64).reshape(9)
+        res = np.zeros(self.batch, RESULT_DTYPE)
+        if device_ptr is None:
+            images = np.ascontiguousarray(images, np.uint8)
+            assert images.ndim == 3 and images.shape[0] == self.batch
+            h, w = images.shape[1:]
+            self._check(self.lib.mvo_group_step(self.h, _ptr(images), w, h, images.strides[1], 0, _ptr(Kp), _ptr(res)))
+        else:
+            h, w = shape
+            self._check(self.lib.mvo_group_step(self.h, C.c_void_p(device_ptr), w, h, w, 1, _ptr(Kp), _ptr(res)))
+        return res
+
+    def group_reset(self):
+        self._check(self.lib.mvo_group_reset(self.h))
+
+    def stage_ms(self) -> dict:
+        out = {}
+        v = C.c_float()
+        for s in self.STAGES:
+            self._check(self.lib.mvo_stage_ms(self.h, s.encode(), C.byref(v)))
+            out[s] = float(v.value)
+        return out
 
     # ---- two-view geometry -------------------------------------------------------------------
     @staticmethod

@@ -86,7 +86,7 @@ void mvo_destroy(mvo_ctx* c) {
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();
   c->c2_count.release(); c->kps.release(); c->desc.release(); c->kp_valid.release(); c->kp_count.release();
   c->flags.release(); c->h_stage.release(); c->prev_kps.release(); c->prev_desc.release();
-  c->prev_kp_count.release(); c->knn_q.release(); c->knn_t.release(); c->knn_best.release();
+  c->prev_kp_count.release(); c->kp_xy.release(); c->prev_kp_xy.release(); c->d_results.release(); c->knn_q.release(); c->knn_t.release(); c->knn_best.release();
   c->knn_matches.release(); c->knn_nmatch.release(); c->knn_counts.release();
   c->lk_pyr[0].release(); c->lk_pyr[1].release(); c->lk_pts_in.release(); c->lk_pts_out.release();
   c->lk_status.release(); c->lk_err.release(); c->lk_npts.release();

@@ -64,6 +64,7 @@ struct mvo_ctx {
   mvo::DevBuf<float2> c2_ra, c2_ra_sorted;                // (response, angle)
   mvo::DevBuf<int32_t> c2_count;      // batch * 8
   mvo::DevBuf<mvo_keypoint> kps;      // batch * kp_cap
+  mvo::DevBuf<float2> kp_xy;          // batch * kp_cap : keypoint positions (LK input of the next frame)
   mvo::DevBuf<uint8_t> desc;          // batch * kp_cap * 32
   mvo::DevBuf<uint8_t> kp_valid;      // batch * kp_cap (orb_compute hook)
   mvo::DevBuf<int32_t> kp_count;      // batch
@@ -73,6 +74,9 @@ struct mvo_ctx {
 
   // previous-frame state for the group step (device resident)
   mvo::DevBuf<mvo_keypoint> prev_kps;
+  mvo::DevBuf<float2> prev_kp_xy;
+  mvo::DevBuf<mvo_frame_result> d_results;
+  int lk_cur = 0;                     // which LK pyramid holds the current frame
   mvo::DevBuf<uint8_t> prev_desc;
   mvo::DevBuf<int32_t> prev_kp_count;
   bool have_prev = false;

@@ -1,0 +1,319 @@
+// group.cu -- mvo_group_step: the whole front-end frame for a group of independent camera streams.
+//
+// One "front-end frame"  per stream: ORB(frame t) -> kNN+ratio(desc t-1, desc t) ->
+// LK(keypoints t-1 -> frame t) -> H + F RANSAC -> E RANSAC -> recoverPose -> triangulate.  It chains the same
+// kernels the single-call ABI uses (every kernel carries the stream index in its grid), keeps all
+// intermediate data on the device and returns one small result record per stream.
+// Call sites it stands for: Tracker::update (/root/reference/src/tracker.cpp:274-333) and
+// Initializer::try_initializing (src/initializer.cpp:165-313).
+#include "context.cuh"
+#include <string.h>
+#include <algorithm>
+
+namespace mvo {
+
+enum Stage { ST_ORB = 0, ST_KNN, ST_LK, ST_H, ST_F, ST_E, ST_POSE, ST_TRI, ST_TOTAL };
+static const char* kStageNames[mvo_ctx::kNumStages] = {"orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e",
+                                                       "pose", "triangulate", "total"};
+
+// keep LK tracks with status && err < err_thr (src/tracker.cpp:70-77), ordered compaction into (p1, p2)
+__global__ void __launch_bounds__(1024)
+lk_collect_kernel(const float2* __restrict__ prev_xy, const float2* __restrict__ next_xy,
+                  const uint8_t* __restrict__ status, const float* __restrict__ err, const int32_t* __restrict__ nprev,
+                  int max_pts, float err_thr, float2* __restrict__ p1, float2* __restrict__ p2,
+                  int32_t* __restrict__ npts) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(nprev[b], max_pts);
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const long long o = (long long)b * max_pts + i;
+    const int ok = (i < n) ? (status[o] != 0 && err[o] < err_thr) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (ok) {
+      const long long d = (long long)b * max_pts + off + __popc(bal & ((1u << lane) - 1));
+      p1[d] = prev_xy[o];
+      p2[d] = next_xy[o];
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int w = 0; w < 32; ++w) s_base += s_warp[w];
+    __syncthreads();
+  }
+  if (tid == 0) npts[b] = s_base;
+}
+
+// per-stream squared threshold; optionally replicate the camera matrix of stream 0 to every stream
+__global__ void fill_params_kernel(float* thr2, float v, double* K, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  thr2[b] = v;
+  if (K && b > 0)
+    for (int i = 0; i < 9; ++i) K[b * 9 + i] = K[i];
+}
+
+// P0 = K [I | 0], P1 = K [R | t]   (src/initializer.cpp:119-123)
+__global__ void make_proj_kernel(const double* __restrict__ K, const double* __restrict__ pose, double* __restrict__ proj,
+                                 int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const double* k = K + b * 9;
+  const double* R = pose + b * 12;
+  const double* t = R + 9;
+  double* P0 = proj + b * 24;
+  double* P1 = P0 + 12;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      P0[i * 4 + j] = k[i * 3 + j];
+      P1[i * 4 + j] = k[i * 3] * R[j] + k[i * 3 + 1] * R[3 + j] + k[i * 3 + 2] * R[6 + j];
+    }
+    P0[i * 4 + 3] = 0;
+    P1[i * 4 + 3] = k[i * 3] * t[0] + k[i * 3 + 1] * t[1] + k[i * 3 + 2] * t[2];
+  }
+}
+
+// chirality count of the triangulated points (src/initializer.cpp:134-157): z > 0 in both cameras
+__global__ void __launch_bounds__(256)
+tri_count_kernel(const float* __restrict__ X4, const uint8_t* __restrict__ mask, const double* __restrict__ pose,
+                 const int32_t* __restrict__ npts, int max_pts, int32_t* __restrict__ out) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = npts[b];
+  const double* R = pose + b * 12;
+  const double* t = R + 9;
+  const float* X = X4 + (long long)b * 4 * max_pts;
+  int c = 0;
+  for (int i = tid; i < n; i += 256) {
+    if (!mask[(long long)b * max_pts + i]) continue;
+    const float w = X[3LL * max_pts + i];
+    const float sc = w != 0.f ? 1.f / w : 1.f;        // convertPointsFromHomogeneous
+    const float x = X[i] * sc, y = X[1LL * max_pts + i] * sc, z = X[2LL * max_pts + i] * sc;
+    if (z <= 0) continue;
+    const double z2 = R[6] * (double)x + R[7] * (double)y + R[8] * (double)z + t[2];
+    if (z2 > 0) ++c;
+  }
+  c = warp_sum(c);
+  __shared__ int s;
+  if (tid == 0) s = 0;
+  __syncthreads();
+  if ((tid & 31) == 0 && c) atomicAdd(&s, c);
+  __syncthreads();
+  if (tid == 0) out[b] = s;
+}
+
+__global__ void gather_results_kernel(const int32_t* kp_count, const int32_t* nmatch, const int32_t* ntracked,
+                                      const int32_t* res_h, const int32_t* res_f, const int32_t* res_e,
+                                      const int32_t* ntri, const double* pose, int have_prev,
+                                      mvo_frame_result* out, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  mvo_frame_result r;
+  memset(&r, 0, sizeof(r));
+  r.n_keypoints = kp_count[b];
+  if (have_prev) {
+    r.n_matches = nmatch[b];
+    r.n_tracked = ntracked[b];
+    r.score_h = res_h[b];
+    r.score_f = res_f[b];
+    r.n_inliers_e = res_e[b * 8 + 0];
+    r.n_pose_good = res_e[b * 8 + 4];
+    r.n_triangulated = ntri[b];
+    for (int i = 0; i < 9; ++i) r.R[i] = pose[b * 12 + i];
+    for (int i = 0; i < 3; ++i) r.t[i] = pose[b * 12 + 9 + i];
+  }
+  out[b] = r;
+}
+
+__global__ void copy_i32_strided_kernel(const int32_t* src, int stride, int32_t* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i * stride];
+}
+
+}  // namespace mvo
+
+using namespace mvo;
+
+#define STAGE_BEG(c, s) cudaEventRecord((c)->timers[s].beg, (c)->stream)
+#define STAGE_END(c, s)                               \
+  do {                                                \
+    cudaEventRecord((c)->timers[s].end, (c)->stream); \
+    (c)->timers[s].used = true;                       \
+  } while (0)
+
+extern "C" {
+
+int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
+                   mvo_frame_result* results) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!images || !K || !results || stride < w) {
+    c->set_error("mvo_group_step: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const int B = c->cfg.batch;
+  int rc = orb_prepare(c, w, h);
+  if (rc) return rc;
+  const OrbGeom& g = c->geom;
+  const int cap = g.kp_cap;
+  if (c->prev_kps.n < (size_t)B * cap) {
+    MVO_CUDA_TRY(c, c->prev_kps.alloc((size_t)B * cap));
+    MVO_CUDA_TRY(c, c->prev_kp_xy.alloc((size_t)B * cap));
+    MVO_CUDA_TRY(c, c->prev_desc.alloc((size_t)B * cap * 32));
+    MVO_CUDA_TRY(c, c->prev_kp_count.alloc(B));
+    MVO_CUDA_TRY(c, c->d_results.alloc(B));
+    c->have_prev = false;
+  }
+  if (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap) {
+    rc = lk_prepare(c, w, h, cap);
+    if (rc) return rc;
+    c->have_prev = false;
+  }
+  rc = ransac_prepare(c, cap, 2000);
+  if (rc) return rc;
+  rc = pose_prepare(c);
+  if (rc) return rc;
+  rc = knn_prepare(c, cap);
+  if (rc) return rc;
+  RansacBufs& r = c->rs;
+  for (auto& t : c->timers) t.used = false;
+
+  STAGE_BEG(c, ST_TOTAL);
+  // ---- ORB ----
+  STAGE_BEG(c, ST_ORB);
+  rc = orb_upload(c, images, w, h, stride, 1, images_on_device);
+  if (rc) return rc;
+  rc = orb_run_detect(c, true);
+  if (rc) return rc;
+  STAGE_END(c, ST_ORB);
+
+  const int cur = c->lk_cur, prev = cur ^ 1;
+  // ---- LK pyramid of the new frame (level 0 = ORB level 0, device to device) ----
+  STAGE_BEG(c, ST_LK);
+  rc = lk_build_pyramid(c, cur, c->pyr.p + g.lv[0].off, g.lv[0].pitch, 2);
+  if (rc) return rc;
+  if (c->have_prev) {
+    rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
+    if (rc) return rc;
+    lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
+                                                 c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
+    c->launches++;
+  }
+  STAGE_END(c, ST_LK);
+
+  if (c->have_prev) {
+    // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
+    STAGE_BEG(c, ST_KNN);
+    rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
+    if (rc) return rc;
+    STAGE_END(c, ST_KNN);
+
+    // counts kept per stage (result slots are reused by the next model)
+    MVO_CUDA_TRY(c, c->knn_counts.alloc((size_t)4 * B));
+    int32_t* res_h = c->knn_counts.p;
+    int32_t* res_f = res_h + B;
+    int32_t* ntri = res_f + B;
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+    const int gb = (B + 127) / 128;
+    // ---- H RANSAC (thr 1.0) ----
+    STAGE_BEG(c, ST_H);
+    fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.thr2.p, 1.0f, r.K.p, B);
+    c->launches++;
+    rc = ransac_find(c, MVO_MODEL_H, 0.995);
+    if (rc) return rc;
+    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.result.p, 8, res_h, B);
+    c->launches++;
+    STAGE_END(c, ST_H);
+    // ---- F RANSAC (thr 1.0, conf 0.99) ----
+    STAGE_BEG(c, ST_F);
+    rc = ransac_find(c, MVO_MODEL_F, 0.99);
+    if (rc) return rc;
+    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.result.p, 8, res_f, B);
+    c->launches++;
+    STAGE_END(c, ST_F);
+    // ---- E RANSAC (K, conf 0.99, thr 1.0) ----
+    STAGE_BEG(c, ST_E);
+    {
+      const double t = 1.0 / ((K[0] + K[4]) / 2);
+      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.thr2.p, (float)(t * t), nullptr, B);
+      c->launches++;
+    }
+    rc = ransac_normalize(c);
+    if (rc) return rc;
+    rc = ransac_find(c, MVO_MODEL_E, 0.99);
+    if (rc) return rc;
+    STAGE_END(c, ST_E);
+    // ---- recoverPose ----
+    STAGE_BEG(c, ST_POSE);
+    rc = pose_recover(c, true);
+    if (rc) return rc;
+    STAGE_END(c, ST_POSE);
+    // ---- triangulate + chirality ----
+    STAGE_BEG(c, ST_TRI);
+    make_proj_kernel<<<gb, 128, 0, c->stream>>>(r.K.p, r.pose.p, r.proj.p, B);
+    c->launches++;
+    rc = pose_triangulate(c);
+    if (rc) return rc;
+    tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.mask.p, r.pose.p, r.npts.p, r.max_pts, ntri);
+    c->launches++;
+    STAGE_END(c, ST_TRI);
+    gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f, r.result.p,
+                                                     ntri, r.pose.p, 1, c->d_results.p, B);
+    c->launches++;
+  } else {
+    gather_results_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(c->kp_count.p, nullptr, nullptr, nullptr, nullptr,
+                                                                 nullptr, nullptr, nullptr, 0, c->d_results.p, B);
+    c->launches++;
+  }
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(results, c->d_results.p, (size_t)B * sizeof(mvo_frame_result), cudaMemcpyDeviceToHost,
+                                  c->stream));
+  if (c->h_stage.n < (size_t)B * 4) MVO_CUDA_TRY(c, c->h_stage.alloc((size_t)B * 4 + 4096));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  STAGE_END(c, ST_TOTAL);
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // new frame becomes the previous one
+  std::swap(c->kps, c->prev_kps);
+  std::swap(c->kp_xy, c->prev_kp_xy);
+  std::swap(c->desc, c->prev_desc);
+  std::swap(c->kp_count, c->prev_kp_count);
+  c->lk_cur ^= 1;
+  c->have_prev = true;
+  // capacity / overflow flags
+  int flags0 = 0;
+  for (int b = 0; b < B; ++b) flags0 |= reinterpret_cast<const int*>(c->h_stage.p)[b];
+  if (flags0 & 1) {
+    c->set_error("FAST candidate list overflow");
+    return MVO_ERR_CAPACITY;
+  }
+  return MVO_OK;
+}
+
+int mvo_group_reset(mvo_ctx* c) {
+  if (!c) return MVO_ERR_INVALID;
+  c->have_prev = false;
+  return MVO_OK;
+}
+
+int mvo_stage_ms(mvo_ctx* c, const char* stage, float* ms) {
+  if (!c || !stage || !ms) return MVO_ERR_INVALID;
+  for (int s = 0; s < mvo_ctx::kNumStages; ++s) {
+    if (strcmp(stage, kStageNames[s]) == 0) {
+      if (!c->timers[s].used) {
+        *ms = 0.f;
+        return MVO_OK;
+      }
+      MVO_CUDA_TRY(c, cudaEventElapsedTime(ms, c->timers[s].beg, c->timers[s].end));
+      return MVO_OK;
+    }
+  }
+  c->set_error("mvo_stage_ms: unknown stage");
+  return MVO_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -480,7 +480,8 @@ orb_rank_kernel(const OrbGeom g, const unsigned long long* __restrict__ key, con
 __global__ void __launch_bounds__(1024)
 orb_finalize_kernel(const OrbGeom g, const unsigned long long* __restrict__ key_sorted,
                     const float2* __restrict__ ra_sorted, const int32_t* __restrict__ c2_count,
-                    mvo_keypoint* __restrict__ kps, int32_t* __restrict__ kp_count, int32_t* __restrict__ flags) {
+                    mvo_keypoint* __restrict__ kps, float2* __restrict__ kp_xy, int32_t* __restrict__ kp_count,
+                    int32_t* __restrict__ flags) {
   const int b = blockIdx.x;
   __shared__ int s_keep[kLevels], s_off[kLevels + 1];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -528,6 +529,7 @@ orb_finalize_kernel(const OrbGeom g, const unsigned long long* __restrict__ key_
       kp.octave = l;
       kp.class_id = -1;
       kps[(long long)b * g.kp_cap + o] = kp;
+      kp_xy[(long long)b * g.kp_cap + o] = make_float2(kp.x, kp.y);
     }
   }
 }
@@ -689,6 +691,7 @@ int orb_prepare(mvo_ctx* c, int w, int h) {
   MVO_CUDA_TRY(c, c->c2_ra_sorted.alloc(B * g.cand_total));
   MVO_CUDA_TRY(c, c->c2_count.alloc(B * kLevels));
   MVO_CUDA_TRY(c, c->kps.alloc(B * g.kp_cap));
+  MVO_CUDA_TRY(c, c->kp_xy.alloc(B * g.kp_cap));
   MVO_CUDA_TRY(c, c->desc.alloc(B * g.kp_cap * 32));
   MVO_CUDA_TRY(c, c->kp_valid.alloc(B * g.kp_cap));
   MVO_CUDA_TRY(c, c->kp_count.alloc(B));
@@ -805,7 +808,7 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
     c->launches++;
   }
   orb_finalize_kernel<<<g.batch, 1024, 0, c->stream>>>(g, c->c2_key_sorted.p, c->c2_ra_sorted.p, c->c2_count.p,
-                                                      c->kps.p, c->kp_count.p, c->flags.p);
+                                                      c->kps.p, c->kp_xy.p, c->kp_count.p, c->flags.p);
   c->launches++;
   if (want_desc) {
     dim3 grid((g.kp_cap + kBriefWarps - 1) / kBriefWarps, g.batch);

@@ -1,0 +1,87 @@
+"""GPU: mvo_group_step (batched, device-resident front-end frame) == the chain of single-call ABI functions,
+which are each parity-tested against the oracle / cv2 goldens elsewhere."""
+import numpy as np
+import pytest
+
+from oracle import knn_oracle as ko
+from oracle import orb_oracle as oo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _single_chain(ctx1, prev_img, img, prev_kps, prev_desc, K):
+    kps, desc = ctx1.orb_detect_and_compute(img)
+    out = {"n_keypoints": len(kps)}
+    if prev_kps is not None:
+        out["n_matches"] = len(ctx1.knn_ratio(prev_desc, desc, 0.7))
+        pts = np.stack([prev_kps["x"], prev_kps["y"]], 1)
+        nxt, st, err = ctx1.lk_track(prev_img, img, pts)
+        ok = (st == 1) & (err < 30.0)
+        p1, p2 = pts[ok], nxt[ok]
+        out["n_tracked"] = int(ok.sum())
+        H, mh, nh = ctx1.find_homography(p1, p2, 1.0)
+        F, mf, nf = ctx1.find_fundamental(p1, p2, 1.0, 0.99)
+        E, me, ne = ctx1.find_essential(p1, p2, K, 0.99, 1.0)
+        R, t, mp, good = ctx1.recover_pose(E, p1, p2, K, mask=me)
+        X = ctx1.triangulate(K @ np.eye(3, 4), K @ np.column_stack([R, t]), p1, p2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            X3 = (X[:3] / X[3]).astype(np.float32)
+        z2 = R[2, 0] * X3[0].astype(np.float64) + R[2, 1] * X3[1] + R[2, 2] * X3[2] + t[2]
+        out.update(score_h=nh, score_f=nf, n_inliers_e=ne, n_pose_good=good, R=R, t=t,
+                   n_triangulated=int(((mp != 0) & (X3[2] > 0) & (z2 > 0)).sum()))
+    return out, kps, desc
+
+
+@pytest.mark.parametrize("h,w,n,batch", [(240, 320, 300, 2), (376, 1241, 2000, 3)])
+def test_group_step_equals_single_calls(h, w, n, batch):
+    from ros2_mono_vo_b200 import Context
+    nframes = 4
+    seqs = [synth.synth_sequence(h, w, s, nframes) for s in range(batch)]
+    K = seqs[0][1]
+    grp = Context(w, h, nfeatures=n, batch=batch)
+    singles = [Context(w, h, nfeatures=n, batch=1, max_points=n + n // 4 + 64) for _ in range(batch)]
+    prev = [(None, None, None)] * batch
+    for t in range(nframes):
+        imgs = np.stack([seqs[s][0][t] for s in range(batch)])
+        res = grp.group_step(imgs, K)
+        for s in range(batch):
+            exp, kps, desc = _single_chain(singles[s], prev[s][0], imgs[s], prev[s][1], prev[s][2], K)
+            for key, val in exp.items():
+                if key in ("R", "t"):
+                    assert np.allclose(res[s][key].reshape(np.shape(val)), val, atol=1e-12), (t, s, key)
+                else:
+                    assert int(res[s][key]) == val, (t, s, key, int(res[s][key]), val)
+            prev[s] = (imgs[s], kps, desc)
+        ms = grp.stage_ms()
+        assert ms["total"] > 0 and ms["orb"] > 0
+    # the first stream against the oracle where that is cheap: keypoint and match counts
+    okp, odesc = oo.orb_detect_and_compute(seqs[0][0][nframes - 1], n)
+    okp0, odesc0 = oo.orb_detect_and_compute(seqs[0][0][nframes - 2], n)
+    assert int(res[0]["n_keypoints"]) == len(okp)
+    assert int(res[0]["n_matches"]) == len(ko.find_matches(odesc0, odesc, 0.7)[0])
+    grp.group_reset()
+    res = grp.group_step(imgs, K)
+    assert (res["n_matches"] == 0).all() and (res["n_keypoints"] > 0).all()
+    grp.close()
+    for c in singles:
+        c.close()
+
+
+def test_group_step_device_resident_input():
+    import torch
+    from ros2_mono_vo_b200 import Context
+    h, w, n, batch = 240, 320, 300, 2
+    seqs = [synth.synth_sequence(h, w, s, 3) for s in range(batch)]
+    K = seqs[0][1]
+    a = Context(w, h, nfeatures=n, batch=batch)
+    b = Context(w, h, nfeatures=n, batch=batch)
+    for t in range(3):
+        imgs = np.stack([seqs[s][0][t] for s in range(batch)])
+        ra = a.group_step(imgs, K)
+        dev = torch.from_numpy(imgs).cuda()
+        torch.cuda.synchronize()
+        rb = b.group_step(None, K, device_ptr=dev.data_ptr(), shape=(h, w))
+        assert np.array_equal(ra, rb)
+    a.close()
+    b.close()
