@@ -186,7 +186,8 @@ MVO_API int mvo_group_step(mvo_ctx* ctx, const uint8_t* images, int w, int h, in
 /* forget the previous frame of every stream (the next step only extracts features) */
 MVO_API int mvo_group_reset(mvo_ctx* ctx);
 /* per-stage device time (ms) of the last mvo_group_step, measured with CUDA events on the ctx stream.
- * names: "orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total" */
+ * names: "orb", "orb_dense" (the fused per-level kernels inside "orb"), "knn", "lk", "ransac_h", "ransac_f",
+ * "ransac_e", "pose", "triangulate", "total" */
 MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);
 
 #ifdef __cplusplus

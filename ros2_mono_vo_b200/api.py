@@ -134,7 +134,7 @@ class Context:
         return out, status, err
 
     # ---- stream-group front-end step ---------------------------------------------------------
-    STAGES = ("orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total")
+    STAGES = ("orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total", "orb_dense")
 
     def group_step(self, images: np.ndarray, K, device_ptr: int | None = None, shape=None):
         """One front-end frame for every stream of the group.  images: batch x h x w u8 (host), or pass

@@ -101,7 +101,7 @@ struct mvo_ctx {
   int last_ransac_iters = 0;
 
   // ---------------- stage timing ----------------
-  static constexpr int kNumStages = 9;
+  static constexpr int kNumStages = 10;
   StageTimer timers[kNumStages];
 };
 

@@ -12,9 +12,9 @@
 
 namespace mvo {
 
-enum Stage { ST_ORB = 0, ST_KNN, ST_LK, ST_H, ST_F, ST_E, ST_POSE, ST_TRI, ST_TOTAL };
+enum Stage { ST_ORB = 0, ST_KNN, ST_LK, ST_H, ST_F, ST_E, ST_POSE, ST_TRI, ST_TOTAL, ST_ORB_DENSE };
 static const char* kStageNames[mvo_ctx::kNumStages] = {"orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e",
-                                                       "pose", "triangulate", "total"};
+                                                       "pose", "triangulate", "total", "orb_dense"};
 
 // keep LK tracks with status && err < err_thr (src/tracker.cpp:70-77), ordered compaction into (p1, p2)
 __global__ void __launch_bounds__(1024)
