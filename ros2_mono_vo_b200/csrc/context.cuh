@@ -20,8 +20,11 @@ struct RansacBufs {
   mvo::DevBuf<int32_t> state;         // batch * 4 : sampler state
   mvo::DevBuf<float> thr2;            // batch : squared threshold as float
   mvo::DevBuf<double> K;              // batch * 9
+  mvo::DevBuf<uint16_t> att_next;     // batch * 32768 : end offset of the getSubset attempt starting at each draw
+  mvo::DevBuf<uint8_t> att_ok;        // batch * 32768 : did that attempt pass checkSubset
   mvo::DevBuf<int32_t> subsets;       // batch * cap_iters * 8
   mvo::DevBuf<double> models;         // batch * cap_iters * 10 * 9
+  mvo::DevBuf<double> e5_scratch;     // batch * cap_iters * 86 : 5-point solver intermediates
   mvo::DevBuf<int32_t> nmodels;       // batch * cap_iters
   mvo::DevBuf<int32_t> counts;        // batch * cap_iters * 10
   mvo::DevBuf<double> best_model;     // batch * 9
@@ -34,9 +37,9 @@ struct RansacBufs {
   mvo::DevBuf<double> proj;           // batch * 24 : P0, P1
   mvo::DevBuf<float> X4;              // batch * 4 * max_pts
   void release() {
-    rng.release(); p1.release(); p2.release(); q1.release(); q2.release(); mask.release(); inl_idx.release();
+    rng.release(); att_next.release(); att_ok.release(); p1.release(); p2.release(); q1.release(); q2.release(); mask.release(); inl_idx.release();
     npts.release(); state.release(); thr2.release(); K.release(); subsets.release(); models.release();
-    nmodels.release(); counts.release(); best_model.release(); result.release(); cands.release();
+    nmodels.release(); counts.release(); e5_scratch.release(); best_model.release(); result.release(); cands.release();
     cand_mask.release(); cand_good.release(); pose.release(); proj.release(); X4.release();
   }
 };

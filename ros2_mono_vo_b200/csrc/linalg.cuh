@@ -141,6 +141,78 @@ __device__ bool lu_solve(double* A /* N*N, destroyed */, double* b /* in: rhs, o
   return true;
 }
 
+// Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite N x N matrix by inverse
+// iteration on (A + delta I): one LU factorisation with partial pivoting + a few triangular solves.  The
+// smallest eigenvalue of the matrices used here (DLT normal matrices) is separated from the next by many
+// orders of magnitude, so three iterations reach machine precision.  A is destroyed.
+template <int N>
+__device__ void smallest_eigvec_spd(double* A, double* x) {
+  double tr = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) tr += A[i * N + i];
+  const double delta = 1e-15 * tr + 1e-300;
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) A[i * N + i] += delta;
+  int piv[N];
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double best = fabs(A[k * N + k]);
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(A[i * N + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    piv[k] = p;
+    if (p != k)
+#pragma unroll 1
+      for (int j = 0; j < N; ++j) {
+        const double t = A[k * N + j];
+        A[k * N + j] = A[p * N + j];
+        A[p * N + j] = t;
+      }
+    const double d = A[k * N + k];
+    const double inv = d != 0.0 ? 1.0 / d : 0.0;
+#pragma unroll 1
+    for (int i = k + 1; i < N; ++i) {
+      const double f = A[i * N + k] * inv;
+      A[i * N + k] = f;
+#pragma unroll 1
+      for (int j = k + 1; j < N; ++j) A[i * N + j] -= f * A[k * N + j];
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) x[i] = 1.0 / sqrt((double)N) * ((i & 1) ? 0.9 : 1.1);
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {   // apply the row permutation, forward substitution (unit lower)
+      const double t = x[k];
+      x[k] = x[piv[k]];
+      x[piv[k]] = t;
+#pragma unroll 1
+      for (int j = 0; j < k; ++j) x[k] -= A[k * N + j] * x[j];
+    }
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; --i) {
+      double sacc = x[i];
+#pragma unroll 1
+      for (int j = i + 1; j < N; ++j) sacc -= A[i * N + j] * x[j];
+      const double d = A[i * N + i];
+      x[i] = d != 0.0 ? sacc / d : sacc;
+    }
+    double nrm = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) nrm += x[i] * x[i];
+    nrm = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) x[i] *= nrm;
+  }
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix.  A is destroyed (diagonal = eigenvalues),
 // V (row-major, columns = eigenvectors).
 template <int N>

@@ -377,14 +377,14 @@ orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const 
     s_thr = thr;
   }
   __syncthreads();
-  const int ci = blockIdx.x * kHarrisWarps + warp;
-  if (ci >= count) return;
-  const long long co = (long long)b * g.cand_total + lv.cand_off + ci;
-  if (cand_score[co] < s_thr) return;
-  const uint32_t xy = cand_xy[co];
-  const int x = xy & 0xffff, y = xy >> 16;
   const uint8_t* img = pyr + (long long)b * g.frame_stride + lv.off;
   const int pitch = lv.pitch;
+  // grid-stride over this level's candidates: the grid is sized for a typical frame, not for the capacity
+  for (int ci = blockIdx.x * kHarrisWarps + warp; ci < count; ci += gridDim.x * kHarrisWarps) {
+  const long long co = (long long)b * g.cand_total + lv.cand_off + ci;
+  if (cand_score[co] < s_thr) continue;
+  const uint32_t xy = cand_xy[co];
+  const int x = xy & 0xffff, y = xy >> 16;
 
   // Harris 7x7 block of Sobel-3 gradients: 49 positions over the 32 lanes (2 rounds)
   int sa = 0, sb = 0, sc = 0;
@@ -442,6 +442,7 @@ orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const 
     c2_key[o] = ((unsigned long long)ro << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
     c2_ra[o] = make_float2(resp, ang);
   }
+  }  // candidate loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -797,8 +798,8 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
   int max_cap = 0;
   for (int l = 0; l < kLevels; ++l) max_cap = std::max(max_cap, g.lv[l].cand_cap);
   {
-    // grid.x covers the largest candidate list; blocks beyond a level's count exit immediately
-    dim3 grid((max_cap + kHarrisWarps - 1) / kHarrisWarps, kLevels, g.batch);
+    // grid-stride kernel: 64 blocks x 8 warps per (level, stream) cover ~512 candidates per pass
+    dim3 grid(std::min(64, (max_cap + kHarrisWarps - 1) / kHarrisWarps), kLevels, g.batch);
     orb_harris_angle_kernel<<<grid, kHarrisWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->cand_xy.p, c->cand_score.p,
                                                                       c->cand_count.p, c->hist.p, c->c2_key.p,
                                                                       c->c2_ra.p, c->c2_count.p);

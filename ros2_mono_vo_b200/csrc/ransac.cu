@@ -5,14 +5,18 @@
 //
 // OpenCV's loop is sequential (draw subset -> solve -> score -> maybe shrink niters).  The RNG stream only
 // depends on data-only subset checks, so here (per stream of the group):
-//   1. ransac_sample_kernel   every draw offset simulates one getSubset attempt in parallel; pointer doubling
-//                             in shared memory follows the attempt chain; an ordered compaction yields the
-//                             exact subsets OpenCV would draw for iterations 0 .. maxIters-1.
+//   1. ransac_attempt_kernel  every draw offset of a window simulates one getSubset attempt (grid-wide);
+//      ransac_chain_kernel    pointer doubling in shared memory follows the attempt chain; an ordered
+//                             compaction yields the exact subsets OpenCV would draw, in iteration order.
 //   2. *_solve_kernel         one thread per hypothesis (4-pt H, 7-pt F, 5-pt E; FP64).
 //   3. ransac_score_kernel    one block per hypothesis, warp-reduced inlier counts (FP32 for H, FP64 F/E).
 //   4. ransac_select_kernel   prefix-max scan replays the strict '>' update + shrinking niters exactly,
 //                             then writes the winner's mask.
 //   5. h_refine_kernel        DLT on the inliers + 10 Levenberg-Marquardt iterations + final mask (H only).
+// The hypotheses are evaluated in two rounds: iterations [0, kRound0) first; the select kernel then knows
+// whether OpenCV's loop would already have stopped (it usually has: 10..150 iterations at the inlier ratios
+// a VO front-end sees) and sets a per-stream `done` flag that turns round 1 (the remaining iterations up to
+// maxIters) into empty launches.  The result is identical to evaluating all maxIters hypotheses.
 #include "context.cuh"
 #include "solvers.cuh"
 #include <algorithm>
@@ -20,10 +24,12 @@
 
 namespace mvo {
 
-constexpr int kDraws = 32768;         // RNG draws visible to one sampler launch (uint16 offsets)
-constexpr int kMaxAttempts = 16384;   // getSubset attempts followed per launch
-constexpr int kSegIters = 2048;       // subsets produced per sampler launch
-constexpr unsigned kEndOff = kDraws;  // sentinel: ran out of draws
+constexpr int kDraws = 32768;         // largest RNG window of one sampler pass (uint16 offsets)
+constexpr int kMaxAttempts = 16384;   // getSubset attempts followed per pass (large window)
+constexpr int kSegIters = 2048;       // subsets produced per sampler pass
+constexpr int kRound0 = 128;          // iterations evaluated before the first early-exit check
+constexpr int kDraws0 = 4096;         // window / attempts of the round-0 sampler pass
+constexpr int kAttempts0 = 1024;
 
 template <int MODEL> struct MT;
 template <> struct MT<MVO_MODEL_H> { static constexpr int K = 4, MAXIT = 2000, MAXM = 1; };
@@ -32,11 +38,12 @@ template <> struct MT<MVO_MODEL_E> { static constexpr int K = 5, MAXIT = 1000, M
 
 // ---- subset drawing ----------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ unsigned draw_subset(const uint32_t* __restrict__ rng, unsigned o, unsigned n, int* idx) {
+__device__ __forceinline__ unsigned draw_subset(const uint32_t* __restrict__ rng, unsigned o, unsigned n, int* idx,
+                                                unsigned window) {
 #pragma unroll 1
   for (int i = 0; i < K; ++i) {
     for (;;) {
-      if (o >= kDraws) return kEndOff;
+      if (o >= window) return window;   // sentinel: ran out of draws
       const int v = (int)(rng[o++] % n);
       bool dup = false;
 #pragma unroll 1
@@ -93,28 +100,69 @@ __device__ __forceinline__ bool check_subset(const float2* s1, const float2* s2)
   return true;
 }
 
-// state per stream: [0] draw offset into the global RNG table, [1] subsets produced so far, [2] flags
+// state per stream (8 ints): [0] draw offset into the global RNG table, [1] subsets produced so far, [2] flags
+// (2: RNG table exhausted, 4: no further subset can be drawn), [3] done (the adaptive loop has terminated inside
+// the evaluated range; later rounds are skipped), [4] hypotheses already solved + scored by earlier rounds
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+ransac_attempt_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const float2* __restrict__ p1,
+                      const float2* __restrict__ p2, const int32_t* __restrict__ npts, int max_pts,
+                      const int32_t* __restrict__ state, int want_total, int window, uint16_t* __restrict__ att_next,
+                      uint8_t* __restrict__ att_ok) {
+  constexpr int K = MT<MODEL>::K;
+  const int b = blockIdx.y;
+  const int32_t* st = state + b * 8;
+  if (st[3] || st[1] >= want_total) return;
+  const int n = npts[b];
+  const int draw_base = st[0];
+  if (n <= K || draw_base + window > rng_len) return;
+  const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (unsigned)window) return;
+  const uint32_t* rng = rng_table + draw_base;
+  int idx[K];
+  const unsigned e = draw_subset<K>(rng, o, (unsigned)n, idx, (unsigned)window);
+  bool ok = false;
+  if (e != (unsigned)window) {
+    ok = true;
+    if (MODEL != MVO_MODEL_E) {
+      const float2* q1 = p1 + (long long)b * max_pts;
+      const float2* q2 = p2 + (long long)b * max_pts;
+      float2 s1[K], s2[K];
+#pragma unroll 1
+      for (int i = 0; i < K; ++i) {
+        s1[i] = q1[idx[i]];
+        s2[i] = q2[idx[i]];
+      }
+      ok = check_subset<MODEL>(s1, s2);
+    }
+  }
+  att_next[(long long)b * kDraws + o] = (uint16_t)e;
+  att_ok[(long long)b * kDraws + o] = ok ? 1 : 0;
+}
+
 template <int MODEL>
 __global__ void __launch_bounds__(1024)
-ransac_sample_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const float2* __restrict__ p1,
-                     const float2* __restrict__ p2, const int32_t* __restrict__ npts, int max_pts,
-                     int32_t* __restrict__ subsets, int32_t* __restrict__ state, int want_total) {
+ransac_chain_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const int32_t* __restrict__ npts,
+                    const uint16_t* __restrict__ att_next, const uint8_t* __restrict__ att_ok,
+                    int32_t* __restrict__ subsets, int32_t* __restrict__ state, int want_total, int cap_iters,
+                    int window, int max_attempts) {
   constexpr int K = MT<MODEL>::K;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t* J0 = reinterpret_cast<uint16_t*>(smem_raw);                  // kDraws + 1 (+1 pad)
-  uint16_t* J1 = J0 + (kDraws + 2);
-  uint16_t* pos = J1 + (kDraws + 2);                                     // kMaxAttempts
-  uint16_t* start = pos + kMaxAttempts;                                  // kSegIters
-  uint32_t* okbits = reinterpret_cast<uint32_t*>(start + kSegIters);     // kDraws / 32
+  uint16_t* J0 = reinterpret_cast<uint16_t*>(smem_raw);                  // window + 1 (+1 pad)
+  uint16_t* J1 = J0 + (window + 2);
+  uint16_t* pos = J1 + (window + 2);                                     // max_attempts
+  uint16_t* start = pos + max_attempts;                                  // kSegIters
+  uint8_t* okb = reinterpret_cast<uint8_t*>(start + kSegIters);          // window
   __shared__ int s_warp[32];
   __shared__ int s_base, s_last_attempt;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = npts[b];
-  int32_t* st = state + b * 4;
+  int32_t* st = state + b * 8;
+  if (st[3]) return;
   const int have = st[1];
   const int draw_base = st[0];
   if (have >= want_total) return;
-  int32_t* out = subsets + ((long long)b * want_total) * K;
+  int32_t* out = subsets + ((long long)b * cap_iters) * K;
   if (n <= K) {
     // count == modelPoints: OpenCV solves the points once; fewer: nothing to do
     if (tid == 0) {
@@ -126,62 +174,40 @@ ransac_sample_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const 
     }
     return;
   }
-  if (draw_base + kDraws > rng_len) {
+  if (draw_base + window > rng_len) {
     if (tid == 0) st[2] |= 2;  // RNG table exhausted
     return;
   }
   const uint32_t* rng = rng_table + draw_base;
-  const float2* q1 = p1 + (long long)b * max_pts;
-  const float2* q2 = p2 + (long long)b * max_pts;
-
-  for (int i = tid; i < kDraws / 32; i += 1024) okbits[i] = 0;
+  const unsigned uw = (unsigned)window;
+  for (int o = tid; o <= window; o += 1024) {
+    J0[o] = (o < window) ? att_next[(long long)b * kDraws + o] : (uint16_t)window;
+    if (o < window) okb[o] = att_ok[(long long)b * kDraws + o];
+  }
   if (tid == 0) {
     pos[0] = 0;
     s_base = 0;
     s_last_attempt = -1;
   }
   __syncthreads();
-  // phase 1: one getSubset attempt from every draw offset
-  for (unsigned o = tid; o <= kDraws; o += 1024) {
-    unsigned e = kEndOff;
-    if (o < kDraws) {
-      int idx[K];
-      e = draw_subset<K>(rng, o, (unsigned)n, idx);
-      if (e != kEndOff) {
-        bool ok = true;
-        if (MODEL != MVO_MODEL_E) {
-          float2 s1[K], s2[K];
-#pragma unroll 1
-          for (int i = 0; i < K; ++i) {
-            s1[i] = q1[idx[i]];
-            s2[i] = q2[idx[i]];
-          }
-          ok = check_subset<MODEL>(s1, s2);
-        }
-        if (ok) atomicOr(&okbits[o >> 5], 1u << (o & 31));
-      }
-    }
-    J0[o] = (uint16_t)e;
-  }
-  __syncthreads();
-  // phase 2: attempt chain by pointer doubling: pos[a] = offset where attempt a starts
+  // attempt chain by pointer doubling: pos[a] = offset where attempt a starts
   uint16_t* cur = J0;
   uint16_t* nxt = J1;
-  for (int len = 1; len < kMaxAttempts; len <<= 1) {
+  for (int len = 1; len < max_attempts; len <<= 1) {
     for (int j = tid; j < len; j += 1024) pos[j + len] = cur[pos[j]];
-    for (int o = tid; o <= kDraws; o += 1024) nxt[o] = cur[cur[o]];
+    for (int o = tid; o <= window; o += 1024) nxt[o] = cur[cur[o]];
     __syncthreads();
     uint16_t* t = cur;
     cur = nxt;
     nxt = t;
   }
-  // phase 3: ordered compaction of the successful attempts
+  // ordered compaction of the successful attempts
   const int want = min(kSegIters, want_total - have);
-  for (int a0 = 0; a0 < kMaxAttempts; a0 += 1024) {
+  for (int a0 = 0; a0 < max_attempts; a0 += 1024) {
     if (s_base >= want) break;
     const int a = a0 + tid;
-    const unsigned o = pos[a];
-    const int ok = (o < kDraws) ? (int)((okbits[o >> 5] >> (o & 31)) & 1u) : 0;
+    const unsigned o = (a < max_attempts) ? pos[a] : uw;
+    const int ok = (o < uw) ? (int)okb[o] : 0;
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     const int within = __popc(bal & ((1u << lane) - 1));
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -206,21 +232,21 @@ ransac_sample_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const 
     __syncthreads();
   }
   const int got = min(s_base, want);
-  // phase 4: materialise the index tuples
+  // materialise the index tuples
   for (int i = tid; i < got; i += 1024) {
     int idx[K];
-    draw_subset<K>(rng, start[i], (unsigned)n, idx);
+    draw_subset<K>(rng, start[i], (unsigned)n, idx, uw);
 #pragma unroll 1
     for (int k = 0; k < K; ++k) out[(long long)(have + i) * K + k] = idx[k];
   }
   if (tid == 0) {
     st[1] = have + got;
-    // where does the next launch continue?  right after the last attempt this launch consumed
-    int a_last = (got == want) ? s_last_attempt : kMaxAttempts - 1;
-    while (a_last > 0 && pos[a_last] >= kDraws) --a_last;
+    // where does the next pass continue?  right after the last attempt this pass consumed
+    int a_last = (got == want) ? s_last_attempt : max_attempts - 1;
+    while (a_last > 0 && pos[a_last] >= uw) --a_last;
     int idx[K];
-    const unsigned e = draw_subset<K>(rng, pos[a_last], (unsigned)n, idx);
-    if (e != kEndOff) {
+    const unsigned e = draw_subset<K>(rng, pos[a_last], (unsigned)n, idx, uw);
+    if (e != uw) {
       st[0] = draw_base + (int)e;
     } else {
       st[0] = draw_base + pos[a_last];          // unfinished attempt: redo it with a fresh window
@@ -234,13 +260,14 @@ template <int MODEL>
 __global__ void __launch_bounds__(64)
 ransac_solve_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
                     const double2* __restrict__ q2, int max_pts, const int32_t* __restrict__ subsets,
-                    const int32_t* __restrict__ state, int cap_iters, double* __restrict__ models,
+                    const int32_t* __restrict__ state, int cap_iters, int h0, int h1, double* __restrict__ models,
                     int32_t* __restrict__ nmodels) {
   constexpr int K = MT<MODEL>::K, MAXM = MT<MODEL>::MAXM;
   const int b = blockIdx.y;
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nsub = min(state[b * 4 + 1], cap_iters);
-  if (h >= nsub) return;
+  if (state[b * 8 + 3]) return;   // done: the adaptive loop ended in an earlier round
+  const int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
+  if (h >= nsub || h < state[b * 8 + 4]) return;
   const int32_t* idx = subsets + ((long long)b * cap_iters + h) * K;
   double* out = models + ((long long)b * cap_iters + h) * MAXM * 9;
   int nm = 0;
@@ -273,6 +300,162 @@ ransac_solve_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2
   nmodels[(long long)b * cap_iters + h] = nm;
 }
 
+// ---- 5-point solver, split for latency: per-thread algebra, then 16 lanes per hypothesis for the roots ----
+constexpr int kE5Scratch = 36 + 39 + 11;   // EE basis, Bm, det polynomial
+
+__global__ void __launch_bounds__(64)
+e5_setup_kernel(const double2* __restrict__ q1, const double2* __restrict__ q2, int max_pts,
+                const int32_t* __restrict__ subsets, const int32_t* __restrict__ state, int cap_iters, int h0, int h1,
+                double* __restrict__ scratch) {
+  const int b = blockIdx.y;
+  if (state[b * 8 + 3]) return;
+  const int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
+  if (h >= nsub || h < state[b * 8 + 4]) return;
+  const int32_t* idx = subsets + ((long long)b * cap_iters + h) * 5;
+  double2 a[5], c[5];
+  for (int i = 0; i < 5; ++i) {
+    a[i] = q1[(long long)b * max_pts + idx[i]];
+    c[i] = q2[(long long)b * max_pts + idx[i]];
+  }
+  double EE[36], Bm[39], detp[11];
+  const bool ok = e5_setup(a, c, EE, Bm, detp);
+  double* out = scratch + ((long long)b * cap_iters + h) * kE5Scratch;
+  for (int i = 0; i < 36; ++i) out[i] = EE[i];
+  for (int i = 0; i < 39; ++i) out[36 + i] = Bm[i];
+  for (int i = 0; i < 11; ++i) out[75 + i] = ok ? detp[i] : 0.0;
+}
+
+// midpoint of [a, b] in the ordered-integer representation of IEEE doubles: at most ~11 steps to pin the
+// binade of a root however wide the bracket is
+__device__ __forceinline__ double mid_key(double a, double b) {
+  long long ka = __double_as_longlong(a), kb = __double_as_longlong(b);
+  ka = ka < 0 ? -(ka & 0x7fffffffffffffffLL) : ka;
+  kb = kb < 0 ? -(kb & 0x7fffffffffffffffLL) : kb;
+  long long km = (ka >> 1) + (kb >> 1) + (ka & kb & 1);
+  if (km < 0) km = (long long)(0x8000000000000000ULL | (unsigned long long)(-km));
+  return __longlong_as_double(km);
+}
+
+__device__ __forceinline__ double poly_eval(const double* q, int qd, double x, double& dv) {
+  double v = q[qd];
+  dv = 0.0;
+#pragma unroll 1
+  for (int i = qd - 1; i >= 0; --i) {
+    dv = dv * x + v;
+    v = v * x + q[i];
+  }
+  return v;
+}
+
+// root of q inside (lo, hi) given a sign change: Newton safeguarded by bisection in key space
+__device__ inline double bracket_root(const double* q, int qd, double lo, double hi, double flo) {
+  double xl = (flo < 0.0) ? lo : hi, xh = (flo < 0.0) ? hi : lo;   // f(xl) < 0 < f(xh)
+  double x = mid_key(lo, hi), dfx;
+  double fx = poly_eval(q, qd, x, dfx);
+  double dxold = fabs(hi - lo);
+#pragma unroll 1
+  for (int it = 0; it < 100; ++it) {
+    if (fx == 0.0) break;
+    if (fx < 0.0) xl = x; else xh = x;
+    double xn = x - fx / dfx;
+    const double a = fmin(xl, xh), bnd = fmax(xl, xh);
+    const double dx = fabs(xn - x);
+    if (!(xn > a && xn < bnd) || 2.0 * dx > dxold) xn = mid_key(xl, xh);   // bisect
+    dxold = fabs(xn - x);
+    if (xn == x) break;
+    const bool conv = dxold <= 4e-16 * fabs(xn);
+    x = xn;
+    if (conv) break;
+    fx = poly_eval(q, qd, x, dfx);
+  }
+  return x;
+}
+
+constexpr int kRootsThreads = 128;   // 8 hypotheses per block, 16 lanes each
+__global__ void __launch_bounds__(kRootsThreads)
+e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1, const double* __restrict__ scratch,
+                double* __restrict__ models, int32_t* __restrict__ nmodels) {
+  const int b = blockIdx.y;
+  if (state[b * 8 + 3]) return;
+  const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+  const int h = h0 + blockIdx.x * (kRootsThreads / 16) + grp;
+  const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
+  const bool live = (h < nsub) && (h >= state[b * 8 + 4]);
+  const unsigned full = 0xffffffffu;
+  const int half = (threadIdx.x >> 4) & 1;          // which 16-lane half of the warp
+  const double* sc = scratch + ((long long)b * cap_iters + (live ? h : 0)) * kE5Scratch;
+  double c[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) c[i] = live ? sc[75 + i] : 0.0;
+  int deg = 10;
+  while (deg > 0 && c[deg] == 0.0) --deg;
+  // Fujiwara bound on |root|: 2 max_k |c[deg-k] / c[deg]|^(1/k); lane k computes term k
+  double bound = 0.0;
+  if (deg > 0 && l16 >= 1 && l16 <= deg) bound = pow(fabs(c[deg - l16] / c[deg]), 1.0 / (double)l16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) bound = fmax(bound, __shfl_xor_sync(full, bound, o, 16));
+  bound = 2.0 * bound + 1e-300;
+  double myroot = 0.0;
+  int ncrit = 0;
+#pragma unroll 1
+  for (int lvl = 9; lvl >= 0; --lvl) {
+    const bool lvl_on = (deg > 0) && (lvl <= deg - 1);
+    const int qd = deg - lvl;
+    double q[11];
+    if (lvl_on) {
+#pragma unroll 1
+      for (int i = 0; i <= qd; ++i) {
+        double w = c[i + lvl];
+#pragma unroll 1
+        for (int t = 0; t < lvl; ++t) w *= (double)(i + lvl - t);
+        q[i] = w;
+      }
+    }
+    // bracket k = (crit[k-1], crit[k]] with crit[-1] = -bound, crit[ncrit] = +bound
+    const double lo_s = __shfl_sync(full, myroot, (l16 > 0 ? l16 - 1 : 0), 16);
+    const double hi_s = __shfl_sync(full, myroot, l16, 16);
+    bool found = false;
+    double root = 0.0;
+    if (lvl_on && l16 <= ncrit) {
+      const double lo = (l16 == 0) ? -bound : lo_s;
+      const double hi = (l16 < ncrit) ? hi_s : bound;
+      double d0;
+      const double flo = poly_eval(q, qd, lo, d0), fhi = poly_eval(q, qd, hi, d0);
+      if (fhi == 0.0) {
+        found = true;
+        root = hi;
+      } else if (flo != 0.0 && ((flo < 0.0) != (fhi < 0.0))) {
+        found = true;
+        root = bracket_root(q, qd, lo, hi, flo);
+      }
+    }
+    const unsigned bal = (__ballot_sync(full, found) >> (16 * half)) & 0xffffu;
+    const int nn = __popc(bal);
+    // lane i takes the i-th found root (found roots are ascending in lane order)
+    const int src = (l16 < nn) ? (int)__fns(bal, 0, l16 + 1) : 0;
+    const double r = __shfl_sync(full, root, src, 16);
+    if (lvl_on) {
+      myroot = (l16 < nn) ? r : 0.0;
+      ncrit = nn;
+    }
+  }
+  // lanes 0 .. ncrit-1 hold the real roots of det B(z): one essential matrix each
+  bool valid = false;
+  double E[9];
+  if (live && l16 < ncrit) valid = e5_model_from_root(myroot, sc, sc + 36, E);
+  const unsigned vb = (__ballot_sync(full, valid) >> (16 * half)) & 0xffffu;
+  if (live) {
+    const int pos = __popc(vb & ((1u << l16) - 1));
+    if (valid && pos < 10) {
+      double* out = models + (((long long)b * cap_iters + h) * 10 + pos) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) out[i] = E[i];
+    }
+    if (l16 == 0) nmodels[(long long)b * cap_iters + h] = min(__popc(vb), 10);
+  }
+}
+
 // ---- score ---------------------------------------------------------------------------------------
 template <int MODEL>
 __device__ __forceinline__ float model_error(const double* M, const float* Mf, const float2* p1, const float2* p2,
@@ -287,12 +470,14 @@ template <int MODEL>
 __global__ void __launch_bounds__(kScoreThreads)
 ransac_score_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
                     const double2* __restrict__ q2, const int32_t* __restrict__ npts, int max_pts,
-                    const int32_t* __restrict__ state, int cap_iters, const double* __restrict__ models,
-                    const int32_t* __restrict__ nmodels, const float* __restrict__ thr2, int32_t* __restrict__ counts) {
+                    const int32_t* __restrict__ state, int cap_iters, int h0, int h1,
+                    const double* __restrict__ models, const int32_t* __restrict__ nmodels,
+                    const float* __restrict__ thr2, int32_t* __restrict__ counts) {
   constexpr int MAXM = MT<MODEL>::MAXM;
-  const int b = blockIdx.y, h = blockIdx.x;
-  const int nsub = min(state[b * 4 + 1], cap_iters);
-  if (h >= nsub) return;
+  const int b = blockIdx.y, h = h0 + blockIdx.x;
+  if (state[b * 8 + 3]) return;
+  const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
+  if (h >= nsub || h < state[b * 8 + 4]) return;
   const int nm = nmodels[(long long)b * cap_iters + h];
   __shared__ double s_m[MAXM * 9];
   __shared__ float s_mf[MAXM * 9];
@@ -338,13 +523,14 @@ template <int MODEL>
 __global__ void __launch_bounds__(1024)
 ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const double2* __restrict__ q1,
                      const double2* __restrict__ q2, const int32_t* __restrict__ npts, int max_pts,
-                     const int32_t* __restrict__ state, int cap_iters, const double* __restrict__ models,
+                     int32_t* __restrict__ state, int cap_iters, int n_eval, const double* __restrict__ models,
                      const int32_t* __restrict__ counts, const float* __restrict__ thr2, double conf,
                      double* __restrict__ best_model, uint8_t* __restrict__ mask, int32_t* __restrict__ result) {
   constexpr int K = MT<MODEL>::K, MAXM = MT<MODEL>::MAXM, MAXIT = MT<MODEL>::MAXIT;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (state[b * 8 + 3]) return;   // an earlier round already produced the final answer
   const int n = npts[b];
-  const int nsub = min(min(state[b * 4 + 1], cap_iters), MAXIT);
+  const int nsub = min(min(min(state[b * 8 + 1], cap_iters), MAXIT), n_eval);
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
   __shared__ int s_T;
@@ -354,7 +540,7 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
   __shared__ int s_cnt;
   if (tid == 0) {
     s_carry = 0;
-    s_T = nsub;
+    s_T = 0x7fffffff;   // "the loop did not stop inside the evaluated range"
     s_cnt = 0;
   }
   __syncthreads();
@@ -414,7 +600,17 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
     }
   }
   __syncthreads();
-  const int T = s_T;   // iterations actually run (>= 1 when nsub >= 1)
+  // the loop stops by itself at s_T, or runs out of evaluated / drawable subsets at nsub
+  const bool stopped = s_T <= nsub;
+  const int T = stopped ? s_T : nsub;   // iterations actually run
+  // final answer iff the loop stopped inside the range, all maxIters were evaluated, or no more subsets exist
+  const bool final_round = stopped || n_eval >= MAXIT || (state[b * 8 + 2] & 6) != 0;
+  __syncthreads();
+  if (tid == 0) {
+    if (final_round) state[b * 8 + 3] = 1;
+    state[b * 8 + 4] = nsub;   // hypotheses [0, nsub) are solved and scored
+  }
+  if (!final_round) return;   // the next round extends the range and selects again
   // winner = prefix max at iteration T-1
   for (int c = 0; c < 2; ++c) {
     const int it = c * 1024 + tid;
@@ -582,14 +778,9 @@ h_refine_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, co
         L[(6 + j) * 9 + 3 + i] = -acc[12 + s];
         L[(6 + i) * 9 + 6 + j] = acc[18 + s];
       }
-    // smallest eigenvector: Jacobi (9x9)
-    double V[81];
-    jacobi_eig<9>(L, V);
-    int kmin = 0;
-    for (int k = 1; k < 9; ++k)
-      if (L[k * 9 + k] < L[kmin * 9 + kmin]) kmin = k;
+    // eigenvector of the smallest eigenvalue (inverse iteration; the DLT null direction)
     double h0[9];
-    for (int i = 0; i < 9; ++i) h0[i] = V[i * 9 + kmin];
+    smallest_eigvec_spd<9>(L, h0);
     const double inv_hn[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
     const double hn2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
     double t[9], H[9];
@@ -789,7 +980,9 @@ static void fill_rng_table(uint64_t seed, std::vector<uint32_t>& t, size_t count
   }
 }
 
-constexpr size_t kSampleSmem = (size_t)(kDraws + 2) * 2 * 2 + (size_t)kMaxAttempts * 2 + (size_t)kSegIters * 2 + kDraws / 8;
+static size_t chain_smem(int window, int attempts) {
+  return (size_t)(window + 2) * 2 * 2 + (size_t)attempts * 2 + (size_t)kSegIters * 2 + (size_t)window + 16;
+}
 
 int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
   RansacBufs& r = c->rs;
@@ -801,9 +994,12 @@ int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
     MVO_CUDA_TRY(c, r.rng.alloc(t.size()));
     MVO_CUDA_TRY(c, cudaMemcpyAsync(r.rng.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, c->stream));
     MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
-    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
-    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_sample_kernel<MVO_MODEL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSampleSmem));
+    const int smem = (int)chain_smem(kDraws, kMaxAttempts);
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MVO_CUDA_TRY(c, r.att_next.alloc(B * kDraws));
+    MVO_CUDA_TRY(c, r.att_ok.alloc(B * kDraws));
     r.rng_ready = true;
   }
   if (max_pts > r.max_pts) {
@@ -822,10 +1018,11 @@ int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
     MVO_CUDA_TRY(c, r.models.alloc(n * kMaxHypModels * 9));
     MVO_CUDA_TRY(c, r.nmodels.alloc(n));
     MVO_CUDA_TRY(c, r.counts.alloc(n * kMaxHypModels));
+    MVO_CUDA_TRY(c, r.e5_scratch.alloc(n * kE5Scratch));
     r.cap_iters = cap_iters;
   }
   MVO_CUDA_TRY(c, r.npts.alloc(B));
-  MVO_CUDA_TRY(c, r.state.alloc(B * 4));
+  MVO_CUDA_TRY(c, r.state.alloc(B * 8));
   MVO_CUDA_TRY(c, r.thr2.alloc(B));
   MVO_CUDA_TRY(c, r.K.alloc(B * 9));
   MVO_CUDA_TRY(c, r.best_model.alloc(B * 9));
@@ -833,61 +1030,98 @@ int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
   return MVO_OK;
 }
 
+// one sampler pass: up to kSegIters more subsets (until `want_total`), from an RNG window of `window` draws
 template <int MODEL>
-static int run_hypotheses(mvo_ctx* c, int want_total) {
-  // sample -> solve -> score for `want_total` iterations (device-resident points / counts in c->rs)
+static void sample_pass(mvo_ctx* c, int want_total, int window, int attempts) {
   RansacBufs& r = c->rs;
   const int B = c->cfg.batch;
-  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)B * 16, c->stream));
-  const int launches = (want_total + kSegIters - 1) / kSegIters + (want_total > kSegIters ? 2 : 0);
-  for (int l = 0; l < launches; ++l) {
-    ransac_sample_kernel<MODEL><<<B, 1024, kSampleSmem, c->stream>>>(r.rng.p, r.rng_len, r.p1.p, r.p2.p, r.npts.p,
-                                                                     r.max_pts, r.subsets.p, r.state.p, want_total);
+  dim3 ga((window + 255) / 256, B);
+  ransac_attempt_kernel<MODEL><<<ga, 256, 0, c->stream>>>(r.rng.p, r.rng_len, r.p1.p, r.p2.p, r.npts.p, r.max_pts,
+                                                          r.state.p, want_total, window, r.att_next.p, r.att_ok.p);
+  ransac_chain_kernel<MODEL><<<B, 1024, chain_smem(window, attempts), c->stream>>>(
+      r.rng.p, r.rng_len, r.npts.p, r.att_next.p, r.att_ok.p, r.subsets.p, r.state.p, want_total, r.cap_iters, window,
+      attempts);
+  c->launches += 2;
+}
+
+template <int MODEL>
+static void solve_score(mvo_ctx* c, int h0, int h1) {
+  RansacBufs& r = c->rs;
+  const int B = c->cfg.batch;
+  const int count = h1 - h0;
+  // the solvers are latency bound (one FP64 thread per hypothesis): few threads per block spreads them over SMs
+  int tpb = 8;
+  while (tpb < 64 && (long long)B * count > 148LL * 4 * tpb) tpb <<= 1;
+  dim3 gs((count + tpb - 1) / tpb, B);
+  if (MODEL == MVO_MODEL_E) {
+    e5_setup_kernel<<<gs, tpb, 0, c->stream>>>(r.q1.p, r.q2.p, r.max_pts, r.subsets.p, r.state.p, r.cap_iters, h0, h1,
+                                               r.e5_scratch.p);
+    dim3 gr((count + kRootsThreads / 16 - 1) / (kRootsThreads / 16), B);
+    e5_roots_kernel<<<gr, kRootsThreads, 0, c->stream>>>(r.state.p, r.cap_iters, h0, h1, r.e5_scratch.p, r.models.p,
+                                                         r.nmodels.p);
     c->launches++;
+  } else {
+    ransac_solve_kernel<MODEL><<<gs, tpb, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.subsets.p,
+                                                          r.state.p, r.cap_iters, h0, h1, r.models.p, r.nmodels.p);
   }
-  dim3 gs((want_total + 63) / 64, B);
-  ransac_solve_kernel<MODEL><<<gs, 64, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.subsets.p, r.state.p,
-                                                       want_total, r.models.p, r.nmodels.p);
-  c->launches++;
-  dim3 gc(want_total, B);
+  dim3 gc(count, B);
   ransac_score_kernel<MODEL><<<gc, kScoreThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                 r.state.p, want_total, r.models.p, r.nmodels.p,
-                                                                 r.thr2.p, r.counts.p);
+                                                                 r.state.p, r.cap_iters, h0, h1, r.models.p,
+                                                                 r.nmodels.p, r.thr2.p, r.counts.p);
+  c->launches += 2;
+}
+
+template <int MODEL>
+static void select_pass(mvo_ctx* c, int n_eval, double conf) {
+  RansacBufs& r = c->rs;
+  ransac_select_kernel<MODEL><<<c->cfg.batch, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
+                                                                  r.state.p, r.cap_iters, n_eval, r.models.p, r.counts.p,
+                                                                  r.thr2.p, conf, r.best_model.p, r.mask.p, r.result.p);
   c->launches++;
+}
+
+// full find*: points must already be in r.p1/r.p2 (and r.q1/r.q2 for E), counts in r.npts, thresholds in r.thr2
+template <int MODEL>
+static int find_model(mvo_ctx* c, double conf) {
+  RansacBufs& r = c->rs;
+  constexpr int MAXIT = MT<MODEL>::MAXIT;
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
+  // round 0: the first kRound0 iterations; usually the adaptive loop has already stopped inside them
+  sample_pass<MODEL>(c, kRound0, kDraws0, kAttempts0);
+  solve_score<MODEL>(c, 0, kRound0);
+  select_pass<MODEL>(c, kRound0, conf);
+  // round 1: everything up to maxIters (empty launches for streams that are done)
+  sample_pass<MODEL>(c, MAXIT, kDraws, kMaxAttempts);
+  solve_score<MODEL>(c, 0, MAXIT);
+  select_pass<MODEL>(c, MAXIT, conf);
   MVO_CUDA_TRY(c, cudaGetLastError());
   return MVO_OK;
 }
 
-// full find*: points must already be in r.p1/r.p2 (and r.q1/r.q2 for E), counts in r.npts, thresholds in r.thr2
 int ransac_find(mvo_ctx* c, int model, double conf) {
   RansacBufs& r = c->rs;
-  const int B = c->cfg.batch;
   int rc;
   if (model == MVO_MODEL_H) {
-    rc = run_hypotheses<MVO_MODEL_H>(c, 2000);
+    rc = find_model<MVO_MODEL_H>(c, conf);
     if (rc) return rc;
-    ransac_select_kernel<MVO_MODEL_H><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                 r.state.p, 2000, r.models.p, r.counts.p, r.thr2.p, conf,
-                                                                 r.best_model.p, r.mask.p, r.result.p);
+    h_refine_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.thr2.p,
+                                                                r.best_model.p, r.mask.p, r.result.p, r.inl_idx.p);
     c->launches++;
-    h_refine_kernel<<<B, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.thr2.p, r.best_model.p,
-                                                      r.mask.p, r.result.p, r.inl_idx.p);
-    c->launches++;
-  } else if (model == MVO_MODEL_F) {
-    rc = run_hypotheses<MVO_MODEL_F>(c, 1000);
-    if (rc) return rc;
-    ransac_select_kernel<MVO_MODEL_F><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                 r.state.p, 1000, r.models.p, r.counts.p, r.thr2.p, conf,
-                                                                 r.best_model.p, r.mask.p, r.result.p);
-    c->launches++;
-  } else {
-    rc = run_hypotheses<MVO_MODEL_E>(c, 1000);
-    if (rc) return rc;
-    ransac_select_kernel<MVO_MODEL_E><<<B, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                 r.state.p, 1000, r.models.p, r.counts.p, r.thr2.p, conf,
-                                                                 r.best_model.p, r.mask.p, r.result.p);
-    c->launches++;
+    MVO_CUDA_TRY(c, cudaGetLastError());
+    return MVO_OK;
   }
+  if (model == MVO_MODEL_F) return find_model<MVO_MODEL_F>(c, conf);
+  return find_model<MVO_MODEL_E>(c, conf);
+}
+
+// C4 sweep: m hypotheses, no early exit
+template <int MODEL>
+static int sweep_model(mvo_ctx* c, int m) {
+  RansacBufs& r = c->rs;
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
+  const int passes = (m + kSegIters - 1) / kSegIters + 2;
+  for (int l = 0; l < passes; ++l) sample_pass<MODEL>(c, m, kDraws, kMaxAttempts);
+  solve_score<MODEL>(c, 0, m);
   MVO_CUDA_TRY(c, cudaGetLastError());
   return MVO_OK;
 }
@@ -902,9 +1136,9 @@ int ransac_normalize(mvo_ctx* c) {
 }
 
 int ransac_sweep(mvo_ctx* c, int model, int m) {
-  if (model == MVO_MODEL_H) return run_hypotheses<MVO_MODEL_H>(c, m);
-  if (model == MVO_MODEL_F) return run_hypotheses<MVO_MODEL_F>(c, m);
-  return run_hypotheses<MVO_MODEL_E>(c, m);
+  if (model == MVO_MODEL_H) return sweep_model<MVO_MODEL_H>(c, m);
+  if (model == MVO_MODEL_F) return sweep_model<MVO_MODEL_F>(c, m);
+  return sweep_model<MVO_MODEL_E>(c, m);
 }
 
 }  // namespace mvo
@@ -1031,8 +1265,8 @@ int mvo_score_hypotheses(mvo_ctx* c, int model, const float* p1, const float* p2
   RansacBufs& r = c->rs;
   const int kk = model == MVO_MODEL_H ? 4 : model == MVO_MODEL_F ? 7 : 5;
   const int mm = model == MVO_MODEL_H ? 1 : model == MVO_MODEL_F ? 3 : 10;
-  int st[4];
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(st, r.state.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  int st[8];
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(st, r.state.p, 32, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(counts, r.counts.p, (size_t)m * mm * 4, cudaMemcpyDeviceToHost, c->stream));
   if (sample_idx) MVO_CUDA_TRY(c, cudaMemcpyAsync(sample_idx, r.subsets.p, (size_t)m * kk * 4, cudaMemcpyDeviceToHost, c->stream));
   if (models) MVO_CUDA_TRY(c, cudaMemcpyAsync(models, r.models.p, (size_t)m * mm * 72, cudaMemcpyDeviceToHost, c->stream));

@@ -144,16 +144,17 @@ __device__ __forceinline__ void pmul_ql(const double* q, const double* l, double
     for (int j = 0; j < 4; ++j) c[c_ql2c[i][j]] += s * q[i] * l[j];
 }
 
-// q1, q2: K-normalised points, constraint q2^T E q1 = 0.  Returns 0..10 models with unit Frobenius norm.
-__device__ inline int solve_e5(const double2* q1, const double2* q2, double* Eout /* 10 x 9 */) {
+// Part 1 of the 5-point solver: null-space basis EE (4 x 9), the z-polynomial matrix Bm (3 x 13, ascending
+// coefficients: bx deg 3, by deg 3, b1 deg 4 per row) and det B(z) (degree 10, ascending).  Returns false when
+// the 10 x 10 elimination is singular.
+__device__ inline bool e5_setup(const double2* q1, const double2* q2, double* EE, double* Bm /* 39 */, double* detp /* 11 */) {
   double A[5 * 9];
   for (int i = 0; i < 5; ++i) {
     const double x1 = q1[i].x, y1 = q1[i].y, x2 = q2[i].x, y2 = q2[i].y;
     double* a = A + i * 9;
     a[0] = x2 * x1; a[1] = x2 * y1; a[2] = x2; a[3] = y2 * x1; a[4] = y2 * y1; a[5] = y2; a[6] = x1; a[7] = y1; a[8] = 1;
   }
-  double EE[4 * 9];  // basis: E = x*EE0 + y*EE1 + z*EE2 + EE3
-  null_space<5, 9>(A, EE);
+  null_space<5, 9>(A, EE);   // E = x*EE0 + y*EE1 + z*EE2 + EE3
   // entries of E as linear polynomials e[rc][4]
   double e[9][4];
   for (int k = 0; k < 9; ++k)
@@ -205,7 +206,7 @@ __device__ inline int solve_e5(const double2* q1, const double2* q2, double* Eou
         p = i;
       }
     }
-    if (best == 0.0) return 0;
+    if (best == 0.0) return false;
     if (p != k)
       for (int j = k; j < 20; ++j) {
         const double t = M[k * 20 + j];
@@ -222,21 +223,17 @@ __device__ inline int solve_e5(const double2* q1, const double2* q2, double* Eou
     }
   }
   // B(z): rows <x2z> - z<x2>, <y2z> - z<y2>, <xyz> - z<xy>; tail = [xz2, xz, x, yz2, yz, y, z3, z2, z, 1]
-  // polynomials stored ascending in z: bx (deg 3), by (deg 3), b1 (deg 4)
-  double Bm[3][13];
   for (int i = 0; i < 3; ++i) {
     const double* ga = M + (4 + 2 * i) * 20 + 10;
     const double* gb = M + (5 + 2 * i) * 20 + 10;
-    double* bx = Bm[i];
-    double* by = Bm[i] + 4;
-    double* b1 = Bm[i] + 8;
-    // ga x-part: ga[0] z^2 + ga[1] z + ga[2];  z * gb x-part: gb[0] z^3 + gb[1] z^2 + gb[2] z
+    double* bx = Bm + i * 13;
+    double* by = bx + 4;
+    double* b1 = bx + 8;
     bx[0] = ga[2];           bx[1] = ga[1] - gb[2]; bx[2] = ga[0] - gb[1]; bx[3] = -gb[0];
     by[0] = ga[5];           by[1] = ga[4] - gb[5]; by[2] = ga[3] - gb[4]; by[3] = -gb[3];
     b1[0] = ga[9];           b1[1] = ga[8] - gb[9]; b1[2] = ga[7] - gb[8]; b1[3] = ga[6] - gb[7]; b1[4] = -gb[6];
   }
   // det B(z): degree 10
-  double detp[11];
   for (int i = 0; i < 11; ++i) detp[i] = 0;
   auto accum = [&](const double* p0, int d0, const double* p1, int d1, const double* p2, int d2, double s) {
     for (int i = 0; i <= d0; ++i)
@@ -245,56 +242,69 @@ __device__ inline int solve_e5(const double2* q1, const double2* q2, double* Eou
         for (int k = 0; k <= d2; ++k) detp[i + j + k] += v * p2[k];
       }
   };
-  // det = bx0 (by1 b12 - b11 by2) - by0 (bx1 b12 - b11 bx2) + b10 (bx1 by2 - by1 bx2)
-  accum(Bm[0], 3, Bm[1] + 4, 3, Bm[2] + 8, 4, 1.0);
-  accum(Bm[0], 3, Bm[1] + 8, 4, Bm[2] + 4, 3, -1.0);
-  accum(Bm[0] + 4, 3, Bm[1], 3, Bm[2] + 8, 4, -1.0);
-  accum(Bm[0] + 4, 3, Bm[1] + 8, 4, Bm[2], 3, 1.0);
-  accum(Bm[0] + 8, 4, Bm[1], 3, Bm[2] + 4, 3, 1.0);
-  accum(Bm[0] + 8, 4, Bm[1] + 4, 3, Bm[2], 3, -1.0);
+  const double* B0 = Bm;
+  const double* B1 = Bm + 13;
+  const double* B2 = Bm + 26;
+  accum(B0, 3, B1 + 4, 3, B2 + 8, 4, 1.0);
+  accum(B0, 3, B1 + 8, 4, B2 + 4, 3, -1.0);
+  accum(B0 + 4, 3, B1, 3, B2 + 8, 4, -1.0);
+  accum(B0 + 4, 3, B1 + 8, 4, B2, 3, 1.0);
+  accum(B0 + 8, 4, B1, 3, B2 + 4, 3, 1.0);
+  accum(B0 + 8, 4, B1 + 4, 3, B2, 3, -1.0);
+  return true;
+}
+
+// Part 2: the essential matrix of one real root z of det B(z).  Returns false for degenerate roots.
+__device__ inline bool e5_model_from_root(double z, const double* EE, const double* Bm, double* E /* 9 */) {
+  double bz[9];
+  for (int i = 0; i < 3; ++i) {
+    const double* bx = Bm + i * 13;
+    const double* by = bx + 4;
+    const double* b1 = bx + 8;
+    bz[i * 3 + 0] = ((bx[3] * z + bx[2]) * z + bx[1]) * z + bx[0];
+    bz[i * 3 + 1] = ((by[3] * z + by[2]) * z + by[1]) * z + by[0];
+    bz[i * 3 + 2] = (((b1[4] * z + b1[3]) * z + b1[2]) * z + b1[1]) * z + b1[0];
+  }
+  // null vector of the (numerically singular) 3x3: the largest of the three row cross products
+  double bestn = -1, xv = 0, yv = 0, wv = 0;
+  for (int a = 0; a < 3; ++a) {
+    const double* r0 = bz + ((a + 1) % 3) * 3;
+    const double* r1 = bz + ((a + 2) % 3) * 3;
+    const double cx = r0[1] * r1[2] - r0[2] * r1[1];
+    const double cy = r0[2] * r1[0] - r0[0] * r1[2];
+    const double cw = r0[0] * r1[1] - r0[1] * r1[0];
+    const double nn = cx * cx + cy * cy + cw * cw;
+    if (nn > bestn) {
+      bestn = nn;
+      xv = cx; yv = cy; wv = cw;
+    }
+  }
+  if (!(bestn > 0.0)) return false;
+  const double inv = 1.0 / sqrt(bestn);
+  if (fabs(wv * inv) < 1e-10) return false;
+  const double x = xv / wv, y = yv / wv;
+  double nrm = 0;
+  for (int i = 0; i < 9; ++i) {
+    E[i] = x * EE[i] + y * EE[9 + i] + z * EE[18 + i] + EE[27 + i];
+    nrm += E[i] * E[i];
+  }
+  if (!(nrm > 0.0) || !isfinite(nrm)) return false;
+  nrm = 1.0 / sqrt(nrm);
+  for (int i = 0; i < 9; ++i) E[i] *= nrm;
+  return true;
+}
+
+// q1, q2: K-normalised points, constraint q2^T E q1 = 0.  Returns 0..10 models with unit Frobenius norm.
+// (sequential driver: used by the host unit test; the CUDA path runs e5_setup per thread and then finds the
+// roots with 16 lanes per hypothesis, see ransac.cu)
+__device__ inline int solve_e5(const double2* q1, const double2* q2, double* Eout /* 10 x 9 */) {
+  double EE[36], Bm[39], detp[11];
+  if (!e5_setup(q1, q2, EE, Bm, detp)) return 0;
   double roots[11];
   const int nr = real_roots<10>(detp, roots);
   int count = 0;
-  for (int k = 0; k < nr && count < 10; ++k) {
-    const double z = roots[k];
-    double bz[9];
-    for (int i = 0; i < 3; ++i) {
-      const double* bx = Bm[i];
-      const double* by = Bm[i] + 4;
-      const double* b1 = Bm[i] + 8;
-      bz[i * 3 + 0] = ((bx[3] * z + bx[2]) * z + bx[1]) * z + bx[0];
-      bz[i * 3 + 1] = ((by[3] * z + by[2]) * z + by[1]) * z + by[0];
-      bz[i * 3 + 2] = (((b1[4] * z + b1[3]) * z + b1[2]) * z + b1[1]) * z + b1[0];
-    }
-    // null vector of the (numerically singular) 3x3: the largest of the three row cross products
-    double bestn = -1, xv = 0, yv = 0, wv = 0;
-    for (int a = 0; a < 3; ++a) {
-      const double* r0 = bz + ((a + 1) % 3) * 3;
-      const double* r1 = bz + ((a + 2) % 3) * 3;
-      const double cx = r0[1] * r1[2] - r0[2] * r1[1];
-      const double cy = r0[2] * r1[0] - r0[0] * r1[2];
-      const double cw = r0[0] * r1[1] - r0[1] * r1[0];
-      const double nn = cx * cx + cy * cy + cw * cw;
-      if (nn > bestn) {
-        bestn = nn;
-        xv = cx; yv = cy; wv = cw;
-      }
-    }
-    if (!(bestn > 0.0)) continue;
-    const double inv = 1.0 / sqrt(bestn);
-    if (fabs(wv * inv) < 1e-10) continue;
-    const double x = xv / wv, y = yv / wv;
-    double* E = Eout + count * 9;
-    double nrm = 0;
-    for (int i = 0; i < 9; ++i) {
-      E[i] = x * EE[i] + y * EE[9 + i] + z * EE[18 + i] + EE[27 + i];
-      nrm += E[i] * E[i];
-    }
-    if (!(nrm > 0.0) || !isfinite(nrm)) continue;
-    nrm = 1.0 / sqrt(nrm);
-    for (int i = 0; i < 9; ++i) E[i] *= nrm;
-    ++count;
-  }
+  for (int k = 0; k < nr && count < 10; ++k)
+    if (e5_model_from_root(roots[k], EE, Bm, Eout + count * 9)) ++count;
   return count;
 }
 

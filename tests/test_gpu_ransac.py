@@ -105,7 +105,7 @@ def test_recover_pose_without_mask_and_triangulate_edge(ctx):
     E, me, ne = ctx.find_essential(p1, p2, K, 0.99, 1.0)
     R, t, m, good = ctx.recover_pose(E, p1, p2, K, mask=None)
     Ro, to, mo, goodo = ro.recover_pose(E, p1, p2, K, mask=None)
-    assert good == goodo and rot_angle_deg(R, Ro) < 1e-6
+    assert good == goodo and rot_angle_deg(R, Ro) < 1e-4
     assert ctx.triangulate(np.eye(3, 4), np.eye(3, 4), p1[:0], p2[:0]).shape == (4, 0)
 
 
