@@ -101,52 +101,79 @@ def cpu_reference_run(frames_by_stream, K, n_frames_budget, seconds_budget):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons of one GPU through NVML from a thread (every ~5 ms), so that
+    even a sub-second timed region gets samples; falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.nv = None
+        self.h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.th = threading.Thread(target=self._loop, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nv is None:
+            return self._smi_once()
+        nv = self.nv
+        self.stop_flag.set()
+        self.th.join(timeout=2)
         try:
-            self.proc.wait(timeout=2)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+            mx = None
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(k for k, b in bits.items() if any(r & b for _, _, r in self.samples))
+        sm = [x[0] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "power_w_max": max((x[1] for x in self.samples), default=None), "samples": len(sm),
+                "reasons": reasons, "source": "nvml, 5 ms period, inside the timed region"}
+
+    def _smi_once(self):
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "power_w_max": float(out[2]), "samples": 1,
+                    "reasons": [n for n, v in zip(names, out[3:7]) if v.strip().lower().startswith("active")],
+                    "source": "nvidia-smi, one query after the timed region"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,7 +215,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=32, help="camera streams per GPU (stream group size)")
@@ -315,7 +342,7 @@ def main():
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": alg_bytes_frame, "frames_per_launch_group": S,
                 "launch_group_ms": dense_ms}
-    prof = os.path.join(ROOT, "profiles", "r01_orb_level_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "orb_level_traffic.json")
     if os.path.exists(prof):
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch_group")

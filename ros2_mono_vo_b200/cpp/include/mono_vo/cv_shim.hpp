@@ -11,6 +11,7 @@
 
 #define MVO_CV_SHIM 1
 #define CV_8U 0
+#define CV_32F 5
 #define CV_64F 6
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << 3))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
@@ -65,7 +66,7 @@ public:
   int type() const { return type_; }
   int depth() const { return type_ & 7; }
   int channels() const { return (type_ >> 3) + 1; }
-  size_t elemSize() const { return (size_t)channels() * (depth() == CV_64F ? 8 : 1); }
+  size_t elemSize() const { return (size_t)channels() * (depth() == CV_64F ? 8 : depth() == CV_32F ? 4 : 1); }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   Mat row(int r) const {
     Mat m = *this;

@@ -50,6 +50,8 @@ public:
 
   /// The stream context (for the geometry / LK entry points in mono_vo/gpu_cv.hpp); created on first use.
   mvo_ctx * context(int width, int height) const;
+  /// The current context (sized for the images seen so far); for call sites that have no image at hand.
+  mvo_ctx * context() const;
 
 private:
   int num_features_;

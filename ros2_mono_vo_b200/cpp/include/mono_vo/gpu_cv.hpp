@@ -119,5 +119,18 @@ inline void triangulatePoints(
   points4d.assign(4 * pts0.size(), 0.f);
   check(c, mvo_triangulate(c, p0, p1, &pts0[0].x, &pts1[0].x, static_cast<int>(pts0.size()), points4d.data()), "triangulatePoints");
 }
+
+/// the cv::Mat form the reference uses (src/initializer.cpp:124-125): points4D becomes 4 x N CV_32F
+inline void triangulatePoints(
+  mvo_ctx * c, const cv::Mat & P0, const cv::Mat & P1, const std::vector<cv::Point2f> & pts0,
+  const std::vector<cv::Point2f> & pts1, cv::Mat & points4d)
+{
+  std::vector<float> x4;
+  triangulatePoints(c, P0, P1, pts0, pts1, x4);
+  const int n = static_cast<int>(pts0.size());
+  points4d.create(4, n, CV_32F);
+  for (int r = 0; r < 4; ++r)
+    for (int i = 0; i < n; ++i) points4d.at<float>(r, i) = x4[static_cast<size_t>(r) * n + i];
+}
 }  // namespace gpu
 }  // namespace mono_vo

@@ -45,6 +45,11 @@ mvo_ctx * FeatureProcessor::context(int width, int height) const
   return ctx_;
 }
 
+mvo_ctx * FeatureProcessor::context() const
+{
+  return context(std::max(ctx_w_, 64), std::max(ctx_h_, 64));
+}
+
 std::vector<cv::KeyPoint> FeatureProcessor::detect(const cv::Mat & image) const
 {
   std::vector<cv::KeyPoint> keypoints;
@@ -85,7 +90,7 @@ void FeatureProcessor::detect_and_compute(
 std::vector<cv::DMatch> FeatureProcessor::find_matches(
   const cv::Mat & descriptors1, const cv::Mat & descriptors2, double lowes_distance_ratio) const
 {
-  mvo_ctx * c = context(std::max(ctx_w_, 64), std::max(ctx_h_, 64));
+  mvo_ctx * c = context();
   const int nq = descriptors1.rows, nt = descriptors2.rows;
   // the ABI wants dense N x 32 rows; Frame::get_descriptors (src/frame.cpp:50-64) produces exactly that
   auto dense = [](const cv::Mat & m) {
