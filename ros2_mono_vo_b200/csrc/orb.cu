@@ -24,8 +24,9 @@ namespace mvo {
 __constant__ float c_gauss[7] = {0.07015932351350784f, 0.13107487559318542f, 0.1907128244638443f,
                                  0.21610593795776367f, 0.1907128244638443f,  0.13107487559318542f,
                                  0.07015932351350784f};
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-__constant__ signed char c_pattern[512][2] = {
+// rBRIEF sampling pattern.  In global memory, not __constant__: every lane reads its own 16 points (a
+// lane-divergent index serialises 32-way on the constant cache); two 128-bit __ldg per lane instead.
+__device__ __align__(16) signed char d_pattern[512][2] = {
 #include "brief_pattern_31.inc"
 };
 
@@ -39,6 +40,10 @@ constexpr int SRC_COLS_MAX = 128;
 constexpr int FW = TW + 2, FH = TH + 2;  // FAST score region (1 halo for NMS)
 constexpr int FS = 68;                   // score row stride
 constexpr int kLevelThreads = 256;
+constexpr int kFastCols = (TW + 8) / 4;  // 18 aligned 4-pixel groups cover x = -4 .. TW+3
+constexpr int kFastLanes = kLevelThreads / kFastCols;  // 14 row lanes
+constexpr int kHSegs = 3;                               // row segments of the horizontal resize pass
+constexpr int kHRows = (SROWS + kHSegs - 1) / kHSegs;   // 14
 
 struct LevelArgs {
   const uint8_t* src;
@@ -59,49 +64,43 @@ struct LevelArgs {
   int do_fast;   // 0: pyramid + blur only (orb_compute hook)
 };
 
+// FAST-9/16 score of one pixel: max over the 16 arcs of 9 contiguous ring pixels of min(d) and of min(-d),
+// d = centre - ring.  Both polarities travel in one register as biased 16-bit lanes (low: d + 256, high:
+// -d + 256, both in [1, 511]) so that every min / max is one VIMNMX3.U16x2.  No min/max result is ever negated
+// (ptxas 12.9 for sm_100a drops the negation when it fuses max(a, -max(b, c)) into VIMNMX3).
 __device__ __forceinline__ int fast_full_score(const uint8_t* t, int idx) {
   // OpenCV ring order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
   const int off[16] = {3 * TS,      3 * TS + 1,  2 * TS + 2,  TS + 3,  3,        -TS + 3,  -2 * TS + 2, -3 * TS + 1,
                        -3 * TS,     -3 * TS - 1, -2 * TS - 2, -TS - 3, -3,       TS - 3,   2 * TS - 2,  3 * TS - 1};
-  const int c = t[idx];
-  // d = centre - ring (bright-centre arcs), e = ring - centre (dark-centre arcs).  Both polarities use
-  // min-chains only: ptxas 12.9 for sm_100a drops the negation when it fuses max(a, -max(..)) into
-  // VIMNMX3 (observed on B200: the score came out as max_k d_k), so no min/max result is negated here.
-  int d[16], e[16];
+  const uint32_t c = t[idx];
+  const uint32_t kc = 0x01000100u - 65535u * c;   // lanes (256 + c, 256 - c) before the ring pixel is applied
+  uint32_t v[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int r = (int)t[idx + off[k]];
-    d[k] = c - r;
-    e[k] = r - c;
-  }
-  int d2[16], e2[16];
+  for (int k = 0; k < 16; ++k) v[k] = kc + 65535u * (uint32_t)t[idx + off[k]];   // (256 + c - r, 256 + r - c)
+  uint32_t m3[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    d2[k] = min(d[k], d[(k + 1) & 15]);
-    e2[k] = min(e[k], e[(k + 1) & 15]);
-  }
-  int d4[16], e4[16];
+  for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+  uint32_t best = 0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    d4[k] = min(d2[k], d2[(k + 2) & 15]);
-    e4[k] = min(e2[k], e2[(k + 2) & 15]);
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t a = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    const uint32_t b = __vimin3_u16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+    best = __vimax3_u16x2(best, a, b);
   }
-  int best = -1000;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
-    const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
-    best = max(best, max(d9, e9));
-  }
-  return best;  // corner iff best > threshold; score = best - 1
+  return (int)max(best & 0xffffu, best >> 16) - 256;  // corner iff > threshold; score = value - 1
+}
+
+// per-byte "d > kFastThr" for four packed absolute differences: bit 7 of every byte
+__device__ __forceinline__ uint32_t bytes_gt_thr(uint32_t d) {
+  return ((d & 0x7f7f7f7fu) + 0x01010101u * (uint32_t)(127 - kFastThr)) | d;
 }
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArgs a) {
+__global__ void __launch_bounds__(kLevelThreads, 4) orb_level_kernel(const LevelArgs a) {
   __shared__ __align__(16) uint8_t tile[SROWS * TS];
-  // scratch: resize staging (src rows + 8.8 horizontal pass) is dead before the blur row buffer is live
-  __shared__ __align__(16) uint8_t scratch[SRC_ROWS_MAX * SRC_COLS_MAX + SRC_ROWS_MAX * SCOLS * 2];
-  __shared__ uint8_t score[FH * FS];
+  // scratch: resize staging (source rows + vertical pass, 8.8 fixed point) is dead before the blur row buffer is live
+  __shared__ __align__(16) uint8_t scratch[SRC_ROWS_MAX * SRC_COLS_MAX + SROWS * SRC_COLS_MAX * 2];
+  __shared__ __align__(16) uint8_t score[(FH * FS + 15) / 16 * 16];
   __shared__ uint16_t work[FW * FH];
   __shared__ uint32_t hist_s[256];
   __shared__ uint32_t emit_xy[TW * TH / 4];
@@ -121,11 +120,15 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
     n_emit = 0;
   }
   hist_s[tid] = 0;  // kLevelThreads == 256
+  if (tid < (int)sizeof(score) / 16) reinterpret_cast<uint4*>(score)[tid] = make_uint4(0, 0, 0, 0);
 
   if (RESIZE) {
+    // INTER_LINEAR_EXACT is exact integer arithmetic up to the final shift: out = (sum wx*wy*src + 2^15) >> 16,
+    // so the two passes commute.  Vertical first: it runs on whole staged words (two pixels per 16-bit lane pair),
+    // the horizontal gather then walks columns with its coefficients in registers.
     const uint8_t* src = a.src + (long long)b * a.frame_stride;
-    uint8_t* src_s = scratch;
-    uint16_t* hbuf = reinterpret_cast<uint16_t*>(scratch + SRC_ROWS_MAX * SRC_COLS_MAX);
+    uint32_t* src_s = reinterpret_cast<uint32_t*>(scratch);                                     // [row][32 words]
+    uint16_t* vbuf = reinterpret_cast<uint16_t*>(scratch + SRC_ROWS_MAX * SRC_COLS_MAX);        // [SROWS][128]
     if (tid < SCOLS) tab_x[tid] = __ldg(a.xtab + min(max(tx0 - HALO + tid, 0), w - 1));
     if (tid >= 128 && tid < 128 + SROWS) tab_y[tid - 128] = __ldg(a.ytab + min(max(ty0 - HALO + tid - 128, 0), h - 1));
     __syncthreads();
@@ -139,28 +142,45 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
     for (int i = tid; i < nrows * nch; i += kLevelThreads) {
       const int r = i / nch, k = i - r * nch;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * a.spitch + c0a + k * 16));
-      *reinterpret_cast<uint4*>(src_s + r * SRC_COLS_MAX + k * 16) = v;
+      *reinterpret_cast<uint4*>(src_s + r * (SRC_COLS_MAX / 4) + k * 4) = v;
     }
     __syncthreads();
-    // stage B: horizontal pass in 8.8 fixed point
-    for (int i = tid; i < nrows * SCOLS; i += kLevelThreads) {
-      const int r = i / SCOLS, xl = i - r * SCOLS;
+    // stage V: vertical pass, one staged word (4 source pixels) per lane, one output row per warp and round
+    {
+      const int wd = tid & 31;
+      if (wd < nch * 4) {
+        for (int yl = tid >> 5; yl < SROWS; yl += kLevelThreads / 32) {
+          const uint32_t e = tab_y[yl];
+          const int o = e & 0xffff;
+          const uint32_t c1 = e >> 16, c0 = 256u - c1;
+          const int ra = min(o - r0, nrows - 1), rb = min(min(o + 1, a.sh - 1) - r0, nrows - 1);
+          const uint32_t pa = src_s[ra * (SRC_COLS_MAX / 4) + wd], pb = src_s[rb * (SRC_COLS_MAX / 4) + wd];
+          const uint32_t te = (pa & 0x00ff00ffu) * c0 + (pb & 0x00ff00ffu) * c1;                // pixels 0, 2
+          const uint32_t to = ((pa >> 8) & 0x00ff00ffu) * c0 + ((pb >> 8) & 0x00ff00ffu) * c1;  // pixels 1, 3
+          uint2 o2;
+          o2.x = __byte_perm(te, to, 0x5410);   // (pixel 0, pixel 1) as u16 pair
+          o2.y = __byte_perm(te, to, 0x7632);   // (pixel 2, pixel 3)
+          *reinterpret_cast<uint2*>(vbuf + yl * SRC_COLS_MAX + wd * 4) = o2;
+        }
+      }
+    }
+    __syncthreads();
+    // stage H: horizontal pass, thread = output column (coefficients in registers) x row segment
+    if (tid < SCOLS * kHSegs) {
+      const int seg = tid / SCOLS, xl = tid - seg * SCOLS;
       const uint32_t e = tab_x[xl];
-      const int o = e & 0xffff, c1 = e >> 16;
-      const int o1 = min(o + 1, a.sw - 1);
-      const uint8_t* row = src_s + r * SRC_COLS_MAX - c0a;
-      hbuf[i] = (uint16_t)(row[o] * (256 - c1) + row[o1] * c1);
-    }
-    __syncthreads();
-    // stage C: vertical pass, round to u8
-    for (int i = tid; i < SROWS * SCOLS; i += kLevelThreads) {
-      const int yl = i / SCOLS, xl = i - yl * SCOLS;
-      const uint32_t e = tab_y[yl];
-      const int o = e & 0xffff, c1 = e >> 16;
-      const int o1 = min(o + 1, a.sh - 1);
-      const int ra = min(o - r0, nrows - 1), rb = min(o1 - r0, nrows - 1);
-      const int v = ((int)hbuf[ra * SCOLS + xl] * (256 - c1) + (int)hbuf[rb * SCOLS + xl] * c1 + 32768) >> 16;
-      tile[yl * TS + TX0 - HALO + xl] = (uint8_t)v;
+      const int o = e & 0xffff;
+      const uint32_t c1 = e >> 16, c0 = 256u - c1;
+      const int oa = o - c0a, ob = min(o + 1, a.sw - 1) - c0a;
+      const uint16_t* va = vbuf + seg * kHRows * SRC_COLS_MAX;
+      uint8_t* tp = tile + seg * kHRows * TS + TX0 - HALO + xl;
+#pragma unroll
+      for (int j = 0; j < kHRows; ++j) {
+        if (seg * kHRows + j < SROWS) {
+          const uint32_t v = ((uint32_t)va[j * SRC_COLS_MAX + oa] * c0 + (uint32_t)va[j * SRC_COLS_MAX + ob] * c1 + 32768u) >> 16;
+          tp[j * TS] = (uint8_t)v;
+        }
+      }
     }
     __syncthreads();
     // level store, 128-bit
@@ -181,38 +201,69 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
       if (gx0 >= 0 && gx0 < a.pitch) v = __ldg(reinterpret_cast<const uint4*>(dst + (long long)gy * a.pitch + gx0));
       *reinterpret_cast<uint4*>(tile + yl * TS + k * 16) = v;
     }
+  }
+  __syncthreads();
+
+  // ---- tiles on the image border: REFLECT_101 halo (only the 7x7 blur looks outside the image) --------
+  if (tx0 == 0 || tx0 + TW + HALO > w || ty0 == 0 || ty0 + TH + HALO > h) {
+    const int xlo = tx0 - HALO, xhi = tx0 + TW + HALO - 1, ylo = ty0 - HALO, yhi = ty0 + TH + HALO - 1;
+    for (int i = tid; i < SROWS * 2 * HALO; i += kLevelThreads) {
+      const int yl = i / (2 * HALO), j = i - yl * (2 * HALO);
+      const int gx = j < HALO ? j - HALO : w + j - HALO;
+      if (gx >= xlo && gx <= xhi) {
+        const int sx = min(max(min(max(reflect101(gx, w), 0), w - 1), xlo), xhi);
+        tile[yl * TS + TX0 + gx - tx0] = tile[yl * TS + TX0 + sx - tx0];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * HALO * SCOLS; i += kLevelThreads) {
+      const int j = i / SCOLS, xc = i - j * SCOLS;
+      const int gy = j < HALO ? j - HALO : h + j - HALO;
+      if (gy >= ylo && gy <= yhi) {
+        const int sy = min(max(min(max(reflect101(gy, h), 0), h - 1), ylo), yhi);
+        tile[(gy - ylo) * TS + TX0 - HALO + xc] = tile[(sy - ylo) * TS + TX0 - HALO + xc];
+      }
+    }
     __syncthreads();
   }
 
-  // ---- FAST-9/16: quick reject, compact survivors, full score -------------------------------
+  // ---- FAST-9/16 ---------------------------------------------------------------------------
   if (a.do_fast) {
-    for (int p = tid; p < FW * FH; p += kLevelThreads) {
-      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
-      const int gx = tx0 + xl, gy = ty0 + yl;
-      score[(yl + 1) * FS + xl + 1] = 0;
-      if (gx >= kEdge - 1 && gx < w - (kEdge - 1) && gy >= kEdge - 1 && gy < h - (kEdge - 1)) {
-        const int idx = (yl + HALO) * TS + TX0 + xl;
-        const int c = tile[idx];
-        const int hi = c + kFastThr, lo = c - kFastThr;
-        // an arc of 9 contains at least one pixel of every antipodal pair
-        const int p0 = tile[idx + 3 * TS], p8 = tile[idx - 3 * TS];
-        int br = (p0 < lo) | (p8 < lo);  // ring darker than centre - thr  (d > thr)
-        int dk = (p0 > hi) | (p8 > hi);
-        if (br | dk) {
-          const int p4 = tile[idx + 3], p12 = tile[idx - 3];
-          br &= (p4 < lo) | (p12 < lo);
-          dk &= (p4 > hi) | (p12 > hi);
-          if (br | dk) {
-            const int p2 = tile[idx + 2 * TS + 2], p10 = tile[idx - 2 * TS - 2];
-            const int p6 = tile[idx - 2 * TS + 2], p14 = tile[idx + 2 * TS - 2];
-            br &= ((p2 < lo) | (p10 < lo)) & ((p6 < lo) | (p14 < lo));
-            dk &= ((p2 > hi) | (p10 > hi)) & ((p6 > hi) | (p14 > hi));
-            if (br | dk) work[atomicAdd(&n_work, 1)] = (uint16_t)p;
+    // phase 1, four pixels per thread: an arc of 9 contains one pixel of every antipodal pair, so a corner needs
+    // |centre - ring| > thr on one of (0, 8) and on one of (4, 12); packed bytes, VABSDIFF4
+    if (tid < kFastCols * kFastLanes) {
+      const int rl = tid / kFastCols, wi = tid - rl * kFastCols;
+      const int xl0 = 4 * wi - 4, gx0 = tx0 + xl0;
+      const int jlo = max(max(-1 - xl0, kEdge - 1 - gx0), 0), jhi = min(min(TW - xl0, w - kEdge - gx0), 3);
+      uint32_t xmask = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j >= jlo && j <= jhi) xmask |= 0x80u << (8 * j);
+      const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+      if (xmask) {
+        for (int yl = rl - 1; yl <= TH; yl += kFastLanes) {
+          const int gy = ty0 + yl;
+          if (gy < kEdge - 1 || gy >= h - (kEdge - 1)) continue;
+          const int wq = ((yl + HALO) * TS + TX0 + xl0) >> 2;
+          const uint32_t c = t32[wq];
+          uint32_t m = bytes_gt_thr(__vabsdiffu4(c, t32[wq + 3 * (TS / 4)])) |
+                       bytes_gt_thr(__vabsdiffu4(c, t32[wq - 3 * (TS / 4)]));
+          m &= xmask;
+          if (!m) continue;
+          const uint32_t l = t32[wq - 1], r = t32[wq + 1];
+          const uint32_t p12 = __byte_perm(l, c, 0x4321);   // pixels x-3 .. x
+          const uint32_t p4 = __byte_perm(c, r, 0x6543);    // pixels x+3 .. x+6
+          m &= bytes_gt_thr(__vabsdiffu4(c, p4)) | bytes_gt_thr(__vabsdiffu4(c, p12));
+          while (m) {
+            const int j = (__ffs(m) - 1) >> 3;
+            m &= m - 1;
+            work[atomicAdd(&n_work, 1)] = (uint16_t)((yl + 1) * FW + xl0 + j + 1);
           }
         }
       }
     }
     __syncthreads();
+    // phase 2: full score of the compacted survivors
     const int nw = n_work;
     for (int i = tid; i < nw; i += kLevelThreads) {
       const int p = work[i];
@@ -221,9 +272,11 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
       if (best > kFastThr) score[(yl + 1) * FS + xl + 1] = (uint8_t)(best - 1);
     }
     __syncthreads();
-    // ---- 3x3 non-max suppression + 31 px edge filter + emit --------------------------------
-    for (int p = tid; p < TW * TH; p += kLevelThreads) {
-      const int yl = p / TW, xl = p - yl * TW;
+    // phase 3: 3x3 non-max suppression + 31 px edge filter, again over the survivor list only
+    for (int i = tid; i < nw; i += kLevelThreads) {
+      const int p = work[i];
+      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
+      if (xl < 0 || xl >= TW || yl < 0 || yl >= TH) continue;
       const int gx = tx0 + xl, gy = ty0 + yl;
       const uint8_t* s = score + (yl + 1) * FS + xl + 1;
       const int v = s[0];
@@ -261,51 +314,65 @@ __global__ void __launch_bounds__(kLevelThreads) orb_level_kernel(const LevelArg
   {
     float* rowbuf = reinterpret_cast<float*>(scratch);  // (TH + 6) x TW floats = 9728 B
     __syncthreads();                                     // scratch (resize staging) is dead
-    for (int i = tid; i < (TH + 6) * TW; i += kLevelThreads) {
-      const int yr = i / TW, xl = i - yr * TW;
-      const int gy = reflect101(ty0 + yr - 3, h);
-      const int ly = min(max(gy - ty0 + HALO, 0), SROWS - 1);
-      const uint8_t* trow = tile + ly * TS + TX0 - tx0;  // index with global x
-      const int gx = tx0 + xl;
-      float s;
-      {
-        int xx[7];
+    const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3];
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+    // row pass: 4 pixels per thread from three aligned words (the halo already holds REFLECT_101 pixels)
+    for (int i = tid; i < (TH + 6) * (TW / 4); i += kLevelThreads) {
+      const int yr = i / (TW / 4), xg = i - yr * (TW / 4);
+      const int wq = ((yr + 1) * TS + TX0 + 4 * xg) >> 2;
+      const uint32_t w0 = t32[wq - 1], w1 = t32[wq], w2 = t32[wq + 1];
+      float f[10];
+      f[0] = (float)((w0 >> 8) & 0xff);
+      f[1] = (float)((w0 >> 16) & 0xff);
+      f[2] = (float)(w0 >> 24);
+      f[3] = (float)(w1 & 0xff);
+      f[4] = (float)((w1 >> 8) & 0xff);
+      f[5] = (float)((w1 >> 16) & 0xff);
+      f[6] = (float)(w1 >> 24);
+      f[7] = (float)(w2 & 0xff);
+      f[8] = (float)((w2 >> 8) & 0xff);
+      f[9] = (float)((w2 >> 16) & 0xff);
+      float o[4];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const int rx = reflect101(gx + j - 3, w);
-          xx[j] = min(max(rx, tx0 - HALO), tx0 + TW + HALO - 1);
-        }
-        s = __fmul_rn(c_gauss[0], (float)trow[xx[0]]);
-#pragma unroll
-        for (int j = 1; j < 7; ++j) s = __fmaf_rn(c_gauss[j], (float)trow[xx[j]], s);
+      for (int j = 0; j < 4; ++j) {
+        float s = __fmul_rn(g0, f[j]);
+        s = __fmaf_rn(g1, f[j + 1], s);
+        s = __fmaf_rn(g2, f[j + 2], s);
+        s = __fmaf_rn(g3, f[j + 3], s);
+        s = __fmaf_rn(g2, f[j + 4], s);
+        s = __fmaf_rn(g1, f[j + 5], s);
+        s = __fmaf_rn(g0, f[j + 6], s);
+        o[j] = s;
       }
-      rowbuf[i] = s;
+      reinterpret_cast<float4*>(rowbuf)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    uint8_t* outt = tile;  // reuse rows of the tile? no: tile still needed by nobody after this point
-    __shared__ __align__(16) uint8_t blur_s[TH * TW];
-    (void)outt;
-    for (int i = tid; i < TH * TW; i += kLevelThreads) {
-      const int yl = i / TW, xl = i - yl * TW;
-      const float* r = rowbuf + yl * TW + xl;
-      float s = __fmul_rn(c_gauss[3], r[3 * TW]);
-      s = __fmaf_rn(c_gauss[2], __fadd_rn(r[2 * TW], r[4 * TW]), s);
-      s = __fmaf_rn(c_gauss[1], __fadd_rn(r[1 * TW], r[5 * TW]), s);
-      s = __fmaf_rn(c_gauss[0], __fadd_rn(r[0], r[6 * TW]), s);
-      int v = __float2int_rn(s);
-      v = min(max(v, 0), 255);
-      blur_s[i] = (uint8_t)v;
-#ifdef MVO_DEBUG_SCORE
-      blur_s[i] = score[(yl + 1) * FS + xl + 1];
-#endif
-    }
-    __syncthreads();
-    for (int i = tid; i < TH * (TW / 16); i += kLevelThreads) {
-      const int yl = i / (TW / 16), k = i - yl * (TW / 16);
-      const int gy = ty0 + yl;
-      if (gy < h)
-        *reinterpret_cast<uint4*>(blur + (long long)gy * a.pitch + tx0 + k * 16) =
-            *reinterpret_cast<const uint4*>(blur_s + yl * TW + k * 16);
+    // column pass: 4 pixels x 4 rows per thread, symmetric taps added first (OpenCV's symmetric column filter)
+    if (tid < (TW / 4) * (TH / 4)) {
+      const int xg = tid & (TW / 4 - 1), yl0 = (tid / (TW / 4)) * 4;
+      const float4* rb = reinterpret_cast<const float4*>(rowbuf) + yl0 * (TW / 4) + xg;
+      float4 r[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) r[k] = rb[k * (TW / 4)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gy = ty0 + yl0 + j;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float m3 = reinterpret_cast<const float*>(&r[j + 3])[q];
+          const float m2 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 2])[q], reinterpret_cast<const float*>(&r[j + 4])[q]);
+          const float m1 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 1])[q], reinterpret_cast<const float*>(&r[j + 5])[q]);
+          const float m0 = __fadd_rn(reinterpret_cast<const float*>(&r[j])[q], reinterpret_cast<const float*>(&r[j + 6])[q]);
+          float s = __fmul_rn(g3, m3);
+          s = __fmaf_rn(g2, m2, s);
+          s = __fmaf_rn(g1, m1, s);
+          s = __fmaf_rn(g0, m0, s);
+          const int v = min(max(__float2int_rn(s), 0), 255);
+          packed |= (uint32_t)v << (8 * q);
+        }
+        if (gy < h) *reinterpret_cast<uint32_t*>(blur + (long long)gy * a.pitch + tx0 + 4 * xg) = packed;
+      }
     }
   }
 }
@@ -408,20 +475,24 @@ orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const 
   sb = warp_sum(sb);
   sc = warp_sum(sc);
 
-  // intensity centroid over the radius-15 disc: lane = column u + 15
+  // intensity centroid over the radius-15 disc: lane = column u + 15; fully unrolled so that the 31 row loads
+  // of a lane are independent and in flight together (disc half-widths fold to constants)
   int m10 = 0, m01 = 0;
   if (lane < 31) {
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     const int u = lane - 15;
     const int au = abs(u);
     const uint8_t* q = img + (long long)y * pitch + x + u;
-#pragma unroll 1
+    int colsum = 0;
+#pragma unroll
     for (int v = -15; v <= 15; ++v) {
-      if (au <= c_umax[abs(v)]) {
-        const int p = q[(long long)v * pitch];
-        m10 += u * p;
+      if (au <= kUmax[v < 0 ? -v : v]) {
+        const int p = q[v * pitch];
+        colsum += p;
         m01 += v * p;
       }
     }
+    m10 = u * colsum;
   }
   m10 = warp_sum(m10);
   m01 = warp_sum(m01);
@@ -560,22 +631,29 @@ orb_brief_kernel(const OrbGeom g, const uint8_t* __restrict__ blur, const mvo_ke
     return;
   }
   const float ang = __fmul_rn(kp.angle, __uint_as_float(0x3c8efa35u));  // (float)(CV_PI/180)
-  const float ca = (float)cos((double)ang), sa = (float)sin((double)ang);
+  double dsa, dca;
+  sincos((double)ang, &dsa, &dca);
+  const float ca = (float)dca, sa = (float)dsa;
   const uint8_t* img = blur + (long long)b * g.frame_stride + lv.off + (long long)cy * lv.pitch + cx;
-  unsigned byte = 0;
+  // this lane's 16 sample points (8 comparisons) = 32 bytes of the pattern
+  const uint4* pp = reinterpret_cast<const uint4*>(&d_pattern[0][0]) + lane * 2;
+  const uint4 pa = __ldg(pp), pb = __ldg(pp + 1);
+  const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+  const int pitch = lv.pitch;
+  int val[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    int v[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int pi = lane * 16 + 2 * j + s;
-      const float px = (float)c_pattern[pi][0], py = (float)c_pattern[pi][1];
+      const float px = (float)(signed char)(pw[j] >> (16 * s)), py = (float)(signed char)(pw[j] >> (16 * s + 8));
       const float rx = __fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa));
       const float ry = __fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca));
-      v[s] = img[(long long)__float2int_rn(ry) * lv.pitch + __float2int_rn(rx)];
+      val[2 * j + s] = img[__float2int_rn(ry) * pitch + __float2int_rn(rx)];
     }
-    byte |= (v[0] < v[1] ? 1u : 0u) << j;
   }
+  unsigned byte = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) byte |= (val[2 * j] < val[2 * j + 1] ? 1u : 0u) << j;
   out[lane] = (uint8_t)byte;
 }
 
