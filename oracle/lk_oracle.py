@@ -25,6 +25,8 @@ FLT_EPSILON = f32(1.1920929e-07)
 
 def pyr_down(img: np.ndarray) -> np.ndarray:
     """cv::pyrDown: [1 4 6 4 1]^2, REFLECT_101, (sum + 128) >> 8, size ((w+1)/2, (h+1)/2)."""
+    if img.ndim == 3:       # cn > 1: every channel on its own
+        return np.stack([pyr_down(img[:, :, c]) for c in range(img.shape[2])], 2)
     h, w = img.shape
     dh, dw = (h + 1) // 2, (w + 1) // 2
     p = np.pad(img.astype(np.int64), 2, mode="reflect")
@@ -41,7 +43,7 @@ def build_pyramid(img: np.ndarray, max_level: int = MAX_LEVEL):
     """Levels exist while the NEXT level stays larger than the window in both dimensions."""
     pyr = [img]
     for _ in range(max_level):
-        h, w = pyr[-1].shape
+        h, w = pyr[-1].shape[:2]
         if (w + 1) // 2 <= WIN or (h + 1) // 2 <= WIN:
             break
         pyr.append(pyr_down(pyr[-1]))
@@ -50,6 +52,9 @@ def build_pyramid(img: np.ndarray, max_level: int = MAX_LEVEL):
 
 def scharr(img: np.ndarray):
     """calcScharrDeriv: int16 dx, dy with REFLECT_101 borders."""
+    if img.ndim == 3:
+        d = [scharr(img[:, :, c]) for c in range(img.shape[2])]
+        return np.stack([a for a, _ in d], 2), np.stack([b for _, b in d], 2)
     p = np.pad(img.astype(np.int32), 1, mode="reflect")
     t0 = (p[:-2, :] + p[2:, :]) * 3 + p[1:-1, :] * 10       # vertical smooth, all padded columns
     t1 = p[2:, :] - p[:-2, :]                                # vertical diff
@@ -73,13 +78,16 @@ def _interp(P, ix, iy, w, shift, pad):
     iw00, iw01, iw10, iw11 = w
     yy = (iy + pad)[:, None, None] + np.arange(WIN)[None, :, None]
     xx = (ix + pad)[:, None, None] + np.arange(WIN)[None, None, :]
-    v = (P[yy, xx] * iw00[:, None, None] + P[yy, xx + 1] * iw01[:, None, None] +
-         P[yy + 1, xx] * iw10[:, None, None] + P[yy + 1, xx + 1] * iw11[:, None, None])
+    e = (slice(None), None, None) + ((None,) if P.ndim == 3 else ())
+    v = (P[yy, xx] * iw00[e] + P[yy, xx + 1] * iw01[e] + P[yy + 1, xx] * iw10[e] + P[yy + 1, xx + 1] * iw11[e])
     return (v + (1 << (shift - 1))) >> shift
 
 
 def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
-    """Returns next_pts (N x 2 f32), status (N u8), err (N f32)."""
+    """Returns next_pts (N x 2 f32), status (N u8), err (N f32).  Images are H x W (cn = 1) or H x W x cn (the node
+    feeds BGR8, /root/reference/src/mono_vo.cpp:94): the window then spans all channels; only err is normalised by cn."""
+    cn = 1 if prev.ndim == 2 else prev.shape[2]
+    sum_axes = (1, 2) if cn == 1 else (1, 2, 3)
     pts = np.asarray(pts, f32).reshape(-1, 2)
     n = len(pts)
     status = np.ones(n, np.uint8)
@@ -94,12 +102,13 @@ def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
     pad = WIN + 1
     for level in range(top, -1, -1):
         I, J = pyr_i[level], pyr_j[level]
-        h, w = I.shape
+        h, w = I.shape[:2]
         dx, dy = scharr(I)
-        Ip = np.pad(I.astype(np.int64), pad, mode="reflect")
-        Jp = np.pad(J.astype(np.int64), pad, mode="reflect")
-        dxp = np.pad(dx.astype(np.int64), pad, mode="constant")
-        dyp = np.pad(dy.astype(np.int64), pad, mode="constant")
+        pw = ((pad, pad), (pad, pad)) + (((0, 0),) if cn > 1 else ())
+        Ip = np.pad(I.astype(np.int64), pw, mode="reflect")
+        Jp = np.pad(J.astype(np.int64), pw, mode="reflect")
+        dxp = np.pad(dx.astype(np.int64), pw, mode="constant")
+        dyp = np.pad(dy.astype(np.int64), pw, mode="constant")
         prev_pt = (pts * f32(1.0 / (1 << level))).astype(f32)
         if level == top:
             next_pt = prev_pt.copy()
@@ -121,9 +130,9 @@ def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
         Iw = _interp(Ip, ip[act, 0], ip[act, 1], wts, W_BITS - 5, pad)
         Ix = _interp(dxp, ip[act, 0], ip[act, 1], wts, W_BITS, pad)
         Iy = _interp(dyp, ip[act, 0], ip[act, 1], wts, W_BITS, pad)
-        A11 = ((Ix * Ix).sum((1, 2)).astype(f32) * FLT_SCALE).astype(f32)
-        A12 = ((Ix * Iy).sum((1, 2)).astype(f32) * FLT_SCALE).astype(f32)
-        A22 = ((Iy * Iy).sum((1, 2)).astype(f32) * FLT_SCALE).astype(f32)
+        A11 = ((Ix * Ix).sum(sum_axes).astype(f32) * FLT_SCALE).astype(f32)
+        A12 = ((Ix * Iy).sum(sum_axes).astype(f32) * FLT_SCALE).astype(f32)
+        A22 = ((Iy * Iy).sum(sum_axes).astype(f32) * FLT_SCALE).astype(f32)
         D = (A11 * A22 - A12 * A12).astype(f32)
         min_eig = ((A22 + A11 - np.sqrt(((A11 - A22) * (A11 - A22) + f32(4.0) * A12 * A12).astype(f32))).astype(f32)
                    / f32(2 * WIN * WIN)).astype(f32)
@@ -156,8 +165,8 @@ def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
             b = (npt[r, 1] - inx[:, 1].astype(f32)).astype(f32)
             Jw = _interp(Jp, inx[:, 0], inx[:, 1], _weights(a, b), W_BITS - 5, pad)
             diff = Jw - Iw[r]
-            b1 = ((diff * Ix[r]).sum((1, 2)).astype(f32) * FLT_SCALE).astype(f32)
-            b2 = ((diff * Iy[r]).sum((1, 2)).astype(f32) * FLT_SCALE).astype(f32)
+            b1 = ((diff * Ix[r]).sum(sum_axes).astype(f32) * FLT_SCALE).astype(f32)
+            b2 = ((diff * Iy[r]).sum(sum_axes).astype(f32) * FLT_SCALE).astype(f32)
             delta = np.stack([((A12[r] * b2 - A22[r] * b1).astype(f32) * Dinv[r]).astype(f32),
                               ((A12[r] * b1 - A11[r] * b2).astype(f32) * Dinv[r]).astype(f32)], 1)
             npt[r] = (npt[r] + delta).astype(f32)
@@ -183,6 +192,6 @@ def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
                     a = (q[:, 0] - iq[:, 0].astype(f32)).astype(f32)
                     b = (q[:, 1] - iq[:, 1].astype(f32)).astype(f32)
                     Jw = _interp(Jp, iq[:, 0], iq[:, 1], _weights(a, b), W_BITS - 5, pad)
-                    e = np.abs(Jw - Iw[ok]).sum((1, 2)).astype(f32)
-                    err[act[ok]] = ((e * f32(1.0)) / f32(32 * WIN * WIN)).astype(f32)   # errval * 1.f/(32*w*cn*h)
+                    e = np.abs(Jw - Iw[ok]).sum(sum_axes).astype(f32)
+                    err[act[ok]] = ((e * f32(1.0)) / f32(32 * WIN * cn * WIN)).astype(f32)   # errval * 1.f/(32*w*cn*h)
     return next_pts, status, err

@@ -17,11 +17,12 @@
 namespace mvo {
 
 constexpr int LKW = 21;
-constexpr int kLkWarps = 8;
+constexpr int kLkWarps = 4;
 constexpr int kRaw = 24;      // raw patch side: 22 interp rows + 1 Scharr ring
-constexpr int kDer = 22;      // derivative patch side
 constexpr int kJReg = 32;     // staged J region side
 constexpr int kJMargin = 5;
+constexpr int kWin = LKW * LKW;          // 441 window pixels
+constexpr int kSlots = (kWin + 31) / 32; // 14 window pixels per lane
 
 struct LkLevel {
   int w, h, pitch;
@@ -67,10 +68,16 @@ lk_pyrdown_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, u
 }
 
 // ---- tracking -------------------------------------------------------------------------------
+// Per-warp scratch.  The two uses never overlap in time: the template patch (I, Ix|Iy) is written by the fused
+// setup and read back into registers before the first J region of the level is staged.
 struct LkWarpSmem {
-  uint8_t raw[kRaw * kRaw];
-  short2 der[kDer * kDer];
-  uint8_t jreg[kJReg * kJReg];
+  union {
+    uint32_t jq[kJReg * kJReg];        // J "quads": (J[y][x], J[y][x+1], J[y+1][x], J[y+1][x+1]) per position
+    struct {
+      uint32_t d[kSlots * 32];         // Ix (low 16, signed) | Iy (high 16, signed)
+      uint16_t i[kSlots * 32];         // I (Q5)
+    } patch;
+  };
 };
 
 __device__ __forceinline__ int safe_reflect(int i, int n) { return min(max(reflect101(i, n), 0), n - 1); }
@@ -84,8 +91,36 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
   w11 = 16384 - w00 - w01 - w10;
 }
 
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (signed 16-bit weights, unsigned pixels): IDP.2A.LO.S16.U8
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// d = c + a.lo16 * b.byte2 + a.hi16 * b.byte3
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_w(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+// Stage the 32x32 J region with top-left (jx0, jy0) as quads: lane = column, 32 independent row loads in flight.
+__device__ __forceinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
+                                           int pitch, int lane) {
+  const int xj = safe_reflect(jx0 + lane, w);
+  uint32_t pprev = 0;
+#pragma unroll
+  for (int r = 0; r < kJReg; ++r) {
+    const uint32_t v = J[(long long)safe_reflect(jy0 + r, h) * pitch + xj];
+    const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
+    if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
+    pprev = pr;
+  }
+}
+
 __global__ void __launch_bounds__(kLkWarps * 32)
-lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
+lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
                 const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
                 float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
   __shared__ LkWarpSmem sm_all[kLkWarps];
@@ -99,6 +134,14 @@ lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t*
   float nx = 0.f, ny = 0.f, e = 0.f;
   int st = 1;
   const float flt_scale = 1.f / (1 << 20);
+  // window pixel k = lane + 32 j  ->  offset of its quad inside the staged J region
+  int qoff[kSlots];
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int k = lane + 32 * j;
+    const int r = k / LKW, c = k - r * LKW;
+    qoff[j] = r * kJReg + c;
+  }
 
   for (int L = g.nlevels - 1; L >= 0; --L) {
     const LkLevel lv = g.lv[L];
@@ -126,50 +169,73 @@ lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t*
     int w00, w01, w10, w11;
     lk_weights(__fsub_rn(qx, (float)ix), __fsub_rn(qy, (float)iy), w00, w01, w10, w11);
 
-    __syncwarp();
-    for (int k = lane; k < kRaw * kRaw; k += 32) {
-      const int r = k / kRaw, c = k - r * kRaw;
-      sm.raw[k] = I[(long long)safe_reflect(iy - 1 + r, h) * pitch + safe_reflect(ix - 1 + c, w)];
-    }
-    __syncwarp();
-    for (int k = lane; k < kDer * kDer; k += 32) {
-      const int r = k / kDer, c = k - r * kDer;
-      const int y = iy + r, x = ix + c;
-      short2 d = make_short2(0, 0);
-      if (x >= 0 && x < w && y >= 0 && y < h) {
-        const uint8_t* q = sm.raw + (r + 1) * kRaw + c + 1;
-        const int a0 = q[-kRaw - 1], a1 = q[-kRaw], a2 = q[-kRaw + 1];
-        const int b0 = q[-1], b1 = q[0], b2 = q[1];
-        const int c0 = q[kRaw - 1], c1 = q[kRaw], c2 = q[kRaw + 1];
-        (void)b1;
-        const int t0l = (a0 + c0) * 3 + b0 * 10, t0r = (a2 + c2) * 3 + b2 * 10;
-        const int t1l = c0 - a0, t1m = c1 - a1, t1r = c2 - a2;
-        d.x = (short)(t0r - t0l);
-        d.y = (short)((t1r + t1l) * 3 + t1m * 10);
+    // ---- fused template setup: lane = raw column (x = ix - 1 + lane, 24 columns), walk the 24 raw rows in
+    //      registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation of
+    //      I / Ix / Iy, normal-matrix sums; the window lands in smem in pixel order k = r * 21 + c.
+    int sA11 = 0, sA12 = 0, sA22 = 0;
+    {
+      const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
+      const int colx = ix - 1 + lane;
+      const int xr = safe_reflect(colx, w);
+      const bool der_col = lane >= 1 && lane <= kRaw - 2 && colx >= 0 && colx < w;  // derivative column inside the image
+      const bool win_col = lane >= 1 && lane <= LKW;                                 // window column c = lane - 1
+      uint32_t v[kRaw];
+#pragma unroll
+      for (int r = 0; r < kRaw; ++r) v[r] = I[(long long)safe_reflect(iy - 1 + r, h) * pitch + xr];
+      __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
+      int dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
+      uint32_t pair0 = 0, pair1 = 0, pd_prev = 0, pdn_prev = 0;
+#pragma unroll
+      for (int r = 0; r < kRaw; ++r) {
+        const int c = (int)v[r];
+        const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
+        const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
+        const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
+        if (r >= 2) {
+          const int rr = r - 2;                                  // derivative row, y = iy + rr
+          const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
+          const bool ok = der_col && (iy + rr >= 0) && (iy + rr < h);
+          const uint32_t pd = ok ? pack_w(gx, gy) : 0u;
+          const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
+          if (rr >= 1) {
+            const int pr = rr - 1;                               // window row
+            const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
+            const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
+            const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
+            const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
+            const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
+            const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
+            if (win_col) {
+              sA11 += vx * vx;
+              sA12 += vx * vy;
+              sA22 += vy * vy;
+              sm.patch.d[pr * LKW + lane - 1] = pack_w(vx, vy);
+              sm.patch.i[pr * LKW + lane - 1] = (uint16_t)iv;
+            }
+          }
+          pd_prev = pd;
+          pdn_prev = pdn;
+        }
+        dx0 = dx1;
+        dx1 = dx2;
+        sm0 = sm1;
+        sm1 = sm2;
+        pair0 = pair1;
+        pair1 = pair2;
       }
-      sm.der[k] = d;
     }
     __syncwarp();
     // window values owned by this lane (pixel k = lane + 32 j)
-    int Iv[14], Ixv[14], Iyv[14];
-    int sA11 = 0, sA12 = 0, sA22 = 0;
+    int Iv[kSlots], Ixv[kSlots], Iyv[kSlots];
 #pragma unroll
-    for (int j = 0; j < 14; ++j) {
+    for (int j = 0; j < kSlots; ++j) {
       const int k = lane + 32 * j;
       Iv[j] = Ixv[j] = Iyv[j] = 0;
-      if (k < LKW * LKW) {
-        const int r = k / LKW, c = k - r * LKW;
-        const uint8_t* q = sm.raw + (r + 1) * kRaw + c + 1;
-        Iv[j] = (q[0] * w00 + q[1] * w01 + q[kRaw] * w10 + q[kRaw + 1] * w11 + (1 << 8)) >> 9;
-        const short2 d00 = sm.der[r * kDer + c], d01 = sm.der[r * kDer + c + 1];
-        const short2 d10 = sm.der[(r + 1) * kDer + c], d11 = sm.der[(r + 1) * kDer + c + 1];
-        const int vx = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
-        const int vy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
-        Ixv[j] = vx;
-        Iyv[j] = vy;
-        sA11 += vx * vx;
-        sA12 += vx * vy;
-        sA22 += vy * vy;
+      if (k < kWin) {
+        const uint32_t d = sm.patch.d[k];
+        Iv[j] = sm.patch.i[k];
+        Ixv[j] = (int)(short)(d & 0xffffu);
+        Iyv[j] = (int)d >> 16;
       }
     }
     const float A11 = __fmul_rn((float)warp_sum_ll(sA11), flt_scale);
@@ -197,21 +263,19 @@ lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t*
         jx0 = inx - kJMargin;
         jy0 = iny - kJMargin;
         __syncwarp();
-        for (int r = 0; r < kJReg; ++r)
-          sm.jreg[r * kJReg + lane] = J[(long long)safe_reflect(jy0 + r, h) * pitch + safe_reflect(jx0 + lane, w)];
+        lk_stage_j(sm.jq, J, jx0, jy0, w, h, pitch, lane);
         __syncwarp();
       }
       int v00, v01, v10, v11;
       lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), v00, v01, v10, v11);
-      const uint8_t* jb = sm.jreg + (iny - jy0) * kJReg + (inx - jx0);
+      const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+      const uint32_t* jb = sm.jq + (iny - jy0) * kJReg + (inx - jx0);
       int sb1 = 0, sb2 = 0;
 #pragma unroll
-      for (int j = 0; j < 14; ++j) {
-        const int k = lane + 32 * j;
-        if (k < LKW * LKW) {
-          const int r = k / LKW, c = k - r * LKW;
-          const uint8_t* q = jb + r * kJReg + c;
-          const int diff = ((q[0] * v00 + q[1] * v01 + q[kJReg] * v10 + q[kJReg + 1] * v11 + (1 << 8)) >> 9) - Iv[j];
+      for (int j = 0; j < kSlots; ++j) {
+        if (lane + 32 * j < kWin) {
+          const uint32_t q = jb[qoff[j]];
+          const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j];
           sb1 += diff * Ixv[j];
           sb2 += diff * Iyv[j];
         }
@@ -243,21 +307,19 @@ lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t*
           jx0 = inx - kJMargin;
           jy0 = iny - kJMargin;
           __syncwarp();
-          for (int r = 0; r < kJReg; ++r)
-            sm.jreg[r * kJReg + lane] = J[(long long)safe_reflect(jy0 + r, h) * pitch + safe_reflect(jx0 + lane, w)];
+          lk_stage_j(sm.jq, J, jx0, jy0, w, h, pitch, lane);
           __syncwarp();
         }
         int v00, v01, v10, v11;
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), v00, v01, v10, v11);
-        const uint8_t* jb = sm.jreg + (iny - jy0) * kJReg + (inx - jx0);
+        const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+        const uint32_t* jb = sm.jq + (iny - jy0) * kJReg + (inx - jx0);
         int se = 0;
 #pragma unroll
-        for (int j = 0; j < 14; ++j) {
-          const int k = lane + 32 * j;
-          if (k < LKW * LKW) {
-            const int r = k / LKW, c = k - r * LKW;
-            const uint8_t* q = jb + r * kJReg + c;
-            se += abs(((q[0] * v00 + q[1] * v01 + q[kJReg] * v10 + q[kJReg + 1] * v11 + (1 << 8)) >> 9) - Iv[j]);
+        for (int j = 0; j < kSlots; ++j) {
+          if (lane + 32 * j < kWin) {
+            const uint32_t q = jb[qoff[j]];
+            se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j]);
           }
         }
         se = warp_sum(se);
@@ -269,7 +331,7 @@ lk_track_kernel(const LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t*
     const long long o = (long long)b * max_pts + i;
     out_pts[o] = make_float2(nx, ny);
     status[o] = (uint8_t)st;
-    err[o] = st ? e : e;
+    err[o] = e;
   }
 }
 

@@ -413,7 +413,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 constexpr int kHarrisWarps = 8;
 
 __global__ void __launch_bounds__(kHarrisWarps * 32)
-orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
+orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
                         const int32_t* __restrict__ cand_score, const int32_t* __restrict__ cand_count,
                         const uint32_t* __restrict__ hist, unsigned long long* __restrict__ c2_key,
                         float2* __restrict__ c2_ra, int32_t* __restrict__ c2_count) {
@@ -520,7 +520,7 @@ orb_harris_angle_kernel(const OrbGeom g, const uint8_t* __restrict__ pyr, const 
 // K3: rank each Harris candidate inside its level by all-pairs comparison of the unique key
 constexpr int kRankThreads = 256;
 __global__ void __launch_bounds__(kRankThreads)
-orb_rank_kernel(const OrbGeom g, const unsigned long long* __restrict__ key, const float2* __restrict__ ra,
+orb_rank_kernel(const __grid_constant__ OrbGeom g, const unsigned long long* __restrict__ key, const float2* __restrict__ ra,
                 const int32_t* __restrict__ c2_count, unsigned long long* __restrict__ key_sorted,
                 float2* __restrict__ ra_sorted) {
   const int level = blockIdx.y, b = blockIdx.z;
@@ -550,7 +550,7 @@ orb_rank_kernel(const OrbGeom g, const unsigned long long* __restrict__ key, con
 // ------------------------------------------------------------------------------------------------
 // K4: retainBest(n_l) with ties + cross-level compaction into mvo_keypoint records
 __global__ void __launch_bounds__(1024)
-orb_finalize_kernel(const OrbGeom g, const unsigned long long* __restrict__ key_sorted,
+orb_finalize_kernel(const __grid_constant__ OrbGeom g, const unsigned long long* __restrict__ key_sorted,
                     const float2* __restrict__ ra_sorted, const int32_t* __restrict__ c2_count,
                     mvo_keypoint* __restrict__ kps, float2* __restrict__ kp_xy, int32_t* __restrict__ kp_count,
                     int32_t* __restrict__ flags) {
@@ -610,7 +610,7 @@ orb_finalize_kernel(const OrbGeom g, const unsigned long long* __restrict__ key_
 // K5: rotated BRIEF, warp per keypoint, lane = descriptor byte (16 samples)
 constexpr int kBriefWarps = 8;
 __global__ void __launch_bounds__(kBriefWarps * 32)
-orb_brief_kernel(const OrbGeom g, const uint8_t* __restrict__ blur, const mvo_keypoint* __restrict__ kps,
+orb_brief_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ blur, const mvo_keypoint* __restrict__ kps,
                  const int32_t* __restrict__ kp_count, uint8_t* __restrict__ desc, uint8_t* __restrict__ valid) {
   const int b = blockIdx.y;
   const int n = kp_count[b];
