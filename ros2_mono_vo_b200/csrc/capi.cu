@@ -69,6 +69,10 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
     }
     c->own_stream = true;
   }
+  c->main_stream = c->stream;
+  for (auto& st : c->aux_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  for (auto& ev : c->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (auto& ev : c->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto& t : c->timers) {
     cudaEventCreate(&t.beg);
     cudaEventCreate(&t.end);
@@ -80,7 +84,17 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
 void mvo_destroy(mvo_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
+  c->stream = c->main_stream;
   cudaStreamSynchronize(c->stream);
+  for (auto& st : c->aux_stream)
+    if (st) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+  for (auto& ev : c->ev_fork)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_join)
+    if (ev) cudaEventDestroy(ev);
   c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
   c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();
@@ -100,7 +114,7 @@ void mvo_destroy(mvo_ctx* c) {
 }
 
 const char* mvo_last_error(const mvo_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
-void* mvo_cuda_stream(mvo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* mvo_cuda_stream(mvo_ctx* c) { return c ? (void*)c->main_stream : nullptr; }
 int mvo_batch(const mvo_ctx* c) { return c ? c->cfg.batch : 0; }
 uint64_t mvo_launch_count(const mvo_ctx* c) { return c ? c->launches : 0; }
 int mvo_orb_num_levels(void) { return kLevels; }

@@ -7,19 +7,13 @@ struct StageTimer {
   bool used = false;
 };
 
-struct RansacBufs {
-  mvo::DevBuf<uint32_t> rng;          // OpenCV MWC stream for the context seed
-  int rng_len = 0;
-  bool rng_ready = false;
-  int max_pts = 0, cap_iters = 0;
-  mvo::DevBuf<float2> p1, p2;         // batch * max_pts pixel correspondences
-  mvo::DevBuf<double2> q1, q2;        // K-normalised (essential matrix)
+// Scratch of one model search.  H, F and E searches of a group step run concurrently on three CUDA streams, each in
+// its own lane; the single-call ABI uses lane 0.
+struct RansacLane {
   mvo::DevBuf<uint8_t> mask;          // batch * max_pts
   mvo::DevBuf<int32_t> inl_idx;       // batch * max_pts
-  mvo::DevBuf<int32_t> npts;          // batch
-  mvo::DevBuf<int32_t> state;         // batch * 4 : sampler state
+  mvo::DevBuf<int32_t> state;         // batch * 8 : sampler state
   mvo::DevBuf<float> thr2;            // batch : squared threshold as float
-  mvo::DevBuf<double> K;              // batch * 9
   mvo::DevBuf<uint16_t> att_next;     // batch * 32768 : end offset of the getSubset attempt starting at each draw
   mvo::DevBuf<uint8_t> att_ok;        // batch * 32768 : did that attempt pass checkSubset
   mvo::DevBuf<int32_t> subsets;       // batch * cap_iters * 8
@@ -29,6 +23,29 @@ struct RansacBufs {
   mvo::DevBuf<int32_t> counts;        // batch * cap_iters * 10
   mvo::DevBuf<double> best_model;     // batch * 9
   mvo::DevBuf<int32_t> result;        // batch * 8
+  int max_pts = 0, cap_iters = 0;
+  bool ready = false;
+  void release() {
+    mask.release(); inl_idx.release(); state.release(); thr2.release(); att_next.release(); att_ok.release();
+    subsets.release(); models.release(); e5_scratch.release(); nmodels.release(); counts.release();
+    best_model.release(); result.release();
+    max_pts = cap_iters = 0; ready = false;
+  }
+};
+
+struct RansacBufs {
+  static constexpr int kLanes = 3;
+  mvo::DevBuf<uint32_t> rng;          // OpenCV MWC stream for the context seed
+  int rng_len = 0;
+  bool rng_ready = false;
+  int max_pts = 0, cap_iters = 0;
+  mvo::DevBuf<float2> p1, p2;         // batch * max_pts pixel correspondences
+  mvo::DevBuf<double2> q1, q2;        // K-normalised (essential matrix)
+  mvo::DevBuf<int32_t> npts;          // batch
+  mvo::DevBuf<double> K;              // batch * 9
+  RansacLane lane[kLanes];
+  int cur = 0;                        // lane the host code is currently issuing work for
+  RansacLane& ln() { return lane[cur]; }
   // pose
   mvo::DevBuf<double> cands;          // batch * 4 * 12 : (R | t) candidates
   mvo::DevBuf<uint8_t> cand_mask;     // batch * 4 * max_pts
@@ -37,16 +54,18 @@ struct RansacBufs {
   mvo::DevBuf<double> proj;           // batch * 24 : P0, P1
   mvo::DevBuf<float> X4;              // batch * 4 * max_pts
   void release() {
-    rng.release(); att_next.release(); att_ok.release(); p1.release(); p2.release(); q1.release(); q2.release(); mask.release(); inl_idx.release();
-    npts.release(); state.release(); thr2.release(); K.release(); subsets.release(); models.release();
-    nmodels.release(); counts.release(); e5_scratch.release(); best_model.release(); result.release(); cands.release();
-    cand_mask.release(); cand_good.release(); pose.release(); proj.release(); X4.release();
+    rng.release(); p1.release(); p2.release(); q1.release(); q2.release(); npts.release(); K.release();
+    for (auto& l : lane) l.release();
+    cands.release(); cand_mask.release(); cand_good.release(); pose.release(); proj.release(); X4.release();
   }
 };
 
 struct mvo_ctx {
   mvo_config cfg{};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // the stream host code currently issues on (main stream, or an aux stream inside a fork)
+  cudaStream_t main_stream = nullptr;
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // group step: F, E(+pose), kNN run beside H
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
   bool own_stream = false;
   std::string err;
   uint64_t launches = 0;
@@ -97,7 +116,7 @@ struct mvo_ctx {
   mvo::DevBuf<uint8_t> lk_status;
   mvo::DevBuf<float> lk_err;
   mvo::DevBuf<int32_t> lk_npts;               // batch
-  int lk_w = 0, lk_h = 0, lk_max_pts = 0;
+  int lk_w = 0, lk_h = 0, lk_max_pts = 0, lk_cn = 1;   // lk_cn: image planes per stream (1 gray, 3 BGR)
 
   // ---------------- RANSAC / pose ----------------
   RansacBufs rs;
@@ -123,12 +142,12 @@ int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_strid
             const uint8_t* t_dev, const int32_t* nt_dev, int t_stride_rows, int max_nt, double ratio,
             int batch);
 
-int lk_prepare(mvo_ctx* c, int w, int h, int max_pts);
+int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn = 1);
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device);
 int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, const int32_t* npts_dev, int max_pts,
            float2* out_dev, uint8_t* status_dev, float* err_dev);
 
-int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters);
+int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters, int lanes = 1);
 int ransac_find(mvo_ctx* c, int model, double conf);
 int ransac_normalize(mvo_ctx* c);
 int ransac_sweep(mvo_ctx* c, int model, int m);

@@ -169,12 +169,12 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
     MVO_CUDA_TRY(c, c->d_results.alloc(B));
     c->have_prev = false;
   }
-  if (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap) {
+  if (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap || c->lk_cn != 1) {
     rc = lk_prepare(c, w, h, cap);
     if (rc) return rc;
     c->have_prev = false;
   }
-  rc = ransac_prepare(c, cap, 2000);
+  rc = ransac_prepare(c, cap, 2000, RansacBufs::kLanes);
   if (rc) return rc;
   rc = pose_prepare(c);
   if (rc) return rc;
@@ -182,6 +182,21 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
   if (rc) return rc;
   RansacBufs& r = c->rs;
   for (auto& t : c->timers) t.used = false;
+
+  // Fork / join: kNN only needs the descriptors, the three model searches only need the LK correspondences, so
+  // they run beside each other on auxiliary CUDA streams (each search in its own RansacLane).
+  struct Fork {
+    mvo_ctx* c;
+    Fork(mvo_ctx* c_, cudaStream_t s, int lane, cudaEvent_t after) : c(c_) {
+      cudaStreamWaitEvent(s, after, 0);
+      c->stream = s;
+      c->rs.cur = lane;
+    }
+    ~Fork() {
+      c->stream = c->main_stream;
+      c->rs.cur = 0;
+    }
+  };
 
   STAGE_BEG(c, ST_TOTAL);
   // ---- ORB ----
@@ -191,8 +206,18 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
   rc = orb_run_detect(c, true);
   if (rc) return rc;
   STAGE_END(c, ST_ORB);
+  cudaEventRecord(c->ev_fork[0], c->main_stream);
 
   const int cur = c->lk_cur, prev = cur ^ 1;
+  if (c->have_prev) {
+    // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
+    Fork f(c, c->aux_stream[2], 0, c->ev_fork[0]);
+    STAGE_BEG(c, ST_KNN);
+    rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
+    if (rc) return rc;
+    STAGE_END(c, ST_KNN);
+    cudaEventRecord(c->ev_join[2], c->stream);
+  }
   // ---- LK pyramid of the new frame (level 0 = ORB level 0, device to device) ----
   STAGE_BEG(c, ST_LK);
   rc = lk_build_pyramid(c, cur, c->pyr.p + g.lv[0].off, g.lv[0].pitch, 2);
@@ -207,63 +232,65 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
   STAGE_END(c, ST_LK);
 
   if (c->have_prev) {
-    // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
-    STAGE_BEG(c, ST_KNN);
-    rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
-    if (rc) return rc;
-    STAGE_END(c, ST_KNN);
-
-    // counts kept per stage (result slots are reused by the next model)
+    // counts kept per stage
     MVO_CUDA_TRY(c, c->knn_counts.alloc((size_t)4 * B));
     int32_t* res_h = c->knn_counts.p;
     int32_t* res_f = res_h + B;
     int32_t* ntri = res_f + B;
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
     const int gb = (B + 127) / 128;
-    // ---- H RANSAC (thr 1.0) ----
-    STAGE_BEG(c, ST_H);
-    fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.thr2.p, 1.0f, r.K.p, B);
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+    fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.lane[0].thr2.p, 1.0f, r.K.p, B);   // + replicate K to every stream
     c->launches++;
+    cudaEventRecord(c->ev_fork[1], c->main_stream);
+    {
+      // ---- F RANSAC (thr 1.0, conf 0.99), lane 1 ----
+      Fork f(c, c->aux_stream[0], 1, c->ev_fork[1]);
+      STAGE_BEG(c, ST_F);
+      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.ln().thr2.p, 1.0f, nullptr, B);
+      c->launches++;
+      rc = ransac_find(c, MVO_MODEL_F, 0.99);
+      if (rc) return rc;
+      copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_f, B);
+      c->launches++;
+      STAGE_END(c, ST_F);
+      cudaEventRecord(c->ev_join[0], c->stream);
+    }
+    {
+      // ---- E RANSAC (K, conf 0.99, thr 1.0) -> recoverPose -> triangulate + chirality, lane 2 ----
+      Fork f(c, c->aux_stream[1], 2, c->ev_fork[1]);
+      STAGE_BEG(c, ST_E);
+      const double t = 1.0 / ((K[0] + K[4]) / 2);
+      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.ln().thr2.p, (float)(t * t), nullptr, B);
+      c->launches++;
+      rc = ransac_normalize(c);
+      if (rc) return rc;
+      rc = ransac_find(c, MVO_MODEL_E, 0.99);
+      if (rc) return rc;
+      STAGE_END(c, ST_E);
+      STAGE_BEG(c, ST_POSE);
+      rc = pose_recover(c, true);
+      if (rc) return rc;
+      STAGE_END(c, ST_POSE);
+      STAGE_BEG(c, ST_TRI);
+      make_proj_kernel<<<gb, 128, 0, c->stream>>>(r.K.p, r.pose.p, r.proj.p, B);
+      c->launches++;
+      rc = pose_triangulate(c);
+      if (rc) return rc;
+      tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.ln().mask.p, r.pose.p, r.npts.p, r.max_pts, ntri);
+      c->launches++;
+      STAGE_END(c, ST_TRI);
+      cudaEventRecord(c->ev_join[1], c->stream);
+    }
+    // ---- H RANSAC (thr 1.0), lane 0, main stream ----
+    STAGE_BEG(c, ST_H);
     rc = ransac_find(c, MVO_MODEL_H, 0.995);
     if (rc) return rc;
-    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.result.p, 8, res_h, B);
+    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_h, B);
     c->launches++;
     STAGE_END(c, ST_H);
-    // ---- F RANSAC (thr 1.0, conf 0.99) ----
-    STAGE_BEG(c, ST_F);
-    rc = ransac_find(c, MVO_MODEL_F, 0.99);
-    if (rc) return rc;
-    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.result.p, 8, res_f, B);
-    c->launches++;
-    STAGE_END(c, ST_F);
-    // ---- E RANSAC (K, conf 0.99, thr 1.0) ----
-    STAGE_BEG(c, ST_E);
-    {
-      const double t = 1.0 / ((K[0] + K[4]) / 2);
-      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.thr2.p, (float)(t * t), nullptr, B);
-      c->launches++;
-    }
-    rc = ransac_normalize(c);
-    if (rc) return rc;
-    rc = ransac_find(c, MVO_MODEL_E, 0.99);
-    if (rc) return rc;
-    STAGE_END(c, ST_E);
-    // ---- recoverPose ----
-    STAGE_BEG(c, ST_POSE);
-    rc = pose_recover(c, true);
-    if (rc) return rc;
-    STAGE_END(c, ST_POSE);
-    // ---- triangulate + chirality ----
-    STAGE_BEG(c, ST_TRI);
-    make_proj_kernel<<<gb, 128, 0, c->stream>>>(r.K.p, r.pose.p, r.proj.p, B);
-    c->launches++;
-    rc = pose_triangulate(c);
-    if (rc) return rc;
-    tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.mask.p, r.pose.p, r.npts.p, r.max_pts, ntri);
-    c->launches++;
-    STAGE_END(c, ST_TRI);
-    gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f, r.result.p,
-                                                     ntri, r.pose.p, 1, c->d_results.p, B);
+    for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(c->main_stream, c->ev_join[k], 0);
+    gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f,
+                                                     r.lane[2].result.p, ntri, r.pose.p, 1, c->d_results.p, B);
     c->launches++;
   } else {
     gather_results_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(c->kp_count.p, nullptr, nullptr, nullptr, nullptr,

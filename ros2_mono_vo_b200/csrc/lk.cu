@@ -108,18 +108,92 @@ __device__ __forceinline__ uint32_t pack_w(int lo, int hi) { return ((uint32_t)l
 // Stage the 32x32 J region with top-left (jx0, jy0) as quads: lane = column, 32 independent row loads in flight.
 __device__ __forceinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
                                            int pitch, int lane) {
-  const int xj = safe_reflect(jx0 + lane, w);
   uint32_t pprev = 0;
+  if (jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h) {
+    // region inside the image (the common case): plain strided rows, no border arithmetic
+    const uint8_t* p = J + jy0 * pitch + jx0 + lane;
 #pragma unroll
-  for (int r = 0; r < kJReg; ++r) {
-    const uint32_t v = J[(long long)safe_reflect(jy0 + r, h) * pitch + xj];
-    const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
-    if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
-    pprev = pr;
+    for (int r = 0; r < kJReg; ++r) {
+      const uint32_t v = p[r * pitch];
+      const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
+      if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
+      pprev = pr;
+    }
+  } else {
+    const int xj = safe_reflect(jx0 + lane, w);
+#pragma unroll 8
+    for (int r = 0; r < kJReg; ++r) {
+      const uint32_t v = J[safe_reflect(jy0 + r, h) * pitch + xj];
+      const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
+      if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
+      pprev = pr;
+    }
   }
 }
 
-__global__ void __launch_bounds__(kLkWarps * 32)
+// Fused template setup of one window on one image plane: lane = raw column (x = ix - 1 + lane, 24 columns), the 24
+// raw rows are walked in registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation
+// of I / Ix / Iy, normal-matrix sums.  Results go to pd (Ix | Iy << 16) and pi (I) in pixel order k = r * 21 + c.
+__device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch,
+                                               int lane, int w00, int w01, int w10, int w11, uint32_t* pd_out,
+                                               uint16_t* pi_out, int& sA11, int& sA12, int& sA22) {
+  const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
+  const int colx = ix - 1 + lane;
+  const int xr = safe_reflect(colx, w);
+  const bool der_col = lane >= 1 && lane <= kRaw - 2 && colx >= 0 && colx < w;  // derivative column inside the image
+  const bool win_col = lane >= 1 && lane <= LKW;                                 // window column c = lane - 1
+  uint32_t v[kRaw];
+  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h) {   // all 32 lanes' columns inside the image
+    const uint8_t* p = I + (iy - 1) * pitch + colx;
+#pragma unroll
+    for (int r = 0; r < kRaw; ++r) v[r] = p[r * pitch];
+  } else {
+#pragma unroll
+    for (int r = 0; r < kRaw; ++r) v[r] = I[safe_reflect(iy - 1 + r, h) * pitch + xr];
+  }
+  int dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
+  uint32_t pair0 = 0, pair1 = 0, pd_prev = 0, pdn_prev = 0;
+#pragma unroll
+  for (int r = 0; r < kRaw; ++r) {
+    const int c = (int)v[r];
+    const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
+    const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
+    const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
+    if (r >= 2) {
+      const int rr = r - 2;                                  // derivative row, y = iy + rr
+      const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
+      const bool ok = der_col && (iy + rr >= 0) && (iy + rr < h);
+      const uint32_t pd = ok ? pack_w(gx, gy) : 0u;
+      const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
+      if (rr >= 1) {
+        const int pr = rr - 1;                               // window row
+        const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
+        const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
+        const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
+        const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
+        const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
+        const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
+        if (win_col) {
+          sA11 += vx * vx;
+          sA12 += vx * vy;
+          sA22 += vy * vy;
+          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
+          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+        }
+      }
+      pd_prev = pd;
+      pdn_prev = pdn;
+    }
+    dx0 = dx1;
+    dx1 = dx2;
+    sm0 = sm1;
+    sm1 = sm2;
+    pair0 = pair1;
+    pair1 = pair2;
+  }
+}
+
+__global__ void __launch_bounds__(kLkWarps * 32, 5)
 lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
                 const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
                 float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
@@ -169,61 +243,10 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
     int w00, w01, w10, w11;
     lk_weights(__fsub_rn(qx, (float)ix), __fsub_rn(qy, (float)iy), w00, w01, w10, w11);
 
-    // ---- fused template setup: lane = raw column (x = ix - 1 + lane, 24 columns), walk the 24 raw rows in
-    //      registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation of
-    //      I / Ix / Iy, normal-matrix sums; the window lands in smem in pixel order k = r * 21 + c.
+    // ---- fused template setup (lk_setup_patch): the window lands in smem in pixel order k = r * 21 + c
     int sA11 = 0, sA12 = 0, sA22 = 0;
-    {
-      const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
-      const int colx = ix - 1 + lane;
-      const int xr = safe_reflect(colx, w);
-      const bool der_col = lane >= 1 && lane <= kRaw - 2 && colx >= 0 && colx < w;  // derivative column inside the image
-      const bool win_col = lane >= 1 && lane <= LKW;                                 // window column c = lane - 1
-      uint32_t v[kRaw];
-#pragma unroll
-      for (int r = 0; r < kRaw; ++r) v[r] = I[(long long)safe_reflect(iy - 1 + r, h) * pitch + xr];
-      __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
-      int dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
-      uint32_t pair0 = 0, pair1 = 0, pd_prev = 0, pdn_prev = 0;
-#pragma unroll
-      for (int r = 0; r < kRaw; ++r) {
-        const int c = (int)v[r];
-        const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
-        const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
-        const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
-        if (r >= 2) {
-          const int rr = r - 2;                                  // derivative row, y = iy + rr
-          const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
-          const bool ok = der_col && (iy + rr >= 0) && (iy + rr < h);
-          const uint32_t pd = ok ? pack_w(gx, gy) : 0u;
-          const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
-          if (rr >= 1) {
-            const int pr = rr - 1;                               // window row
-            const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
-            const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
-            const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
-            const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
-            const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
-            const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
-            if (win_col) {
-              sA11 += vx * vx;
-              sA12 += vx * vy;
-              sA22 += vy * vy;
-              sm.patch.d[pr * LKW + lane - 1] = pack_w(vx, vy);
-              sm.patch.i[pr * LKW + lane - 1] = (uint16_t)iv;
-            }
-          }
-          pd_prev = pd;
-          pdn_prev = pdn;
-        }
-        dx0 = dx1;
-        dx1 = dx2;
-        sm0 = sm1;
-        sm1 = sm2;
-        pair0 = pair1;
-        pair1 = pair2;
-      }
-    }
+    __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
+    lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch.d, sm.patch.i, sA11, sA12, sA22);
     __syncwarp();
     // window values owned by this lane (pixel k = lane + 32 j)
     int Iv[kSlots], Ixv[kSlots], Iyv[kSlots];
@@ -335,6 +358,202 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
   }
 }
 
+// ---- multi-channel windows (the node feeds BGR8: /root/reference/src/mono_vo.cpp:94, src/tracker.cpp:68) -------
+// OpenCV's window then spans all channels: every sum runs over 21 x 21 x cn values, only err is normalised by cn.
+// Planar layout: plane (b * CN + ch) of the pyramid buffer.  The template stays in smem (3 x 441 values do not fit
+// in registers); otherwise the same arithmetic and control flow as lk_track_kernel.
+constexpr int kLkWarpsCn = 2;
+template <int CN>
+struct LkWarpSmemCn {
+  uint32_t jq[CN][kJReg * kJReg];
+  uint32_t d[CN][kSlots * 32];
+  uint16_t i[CN][kSlots * 32];
+};
+
+template <int CN>
+__global__ void __launch_bounds__(kLkWarpsCn * 32)
+lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
+                   const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
+                   float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+  __shared__ LkWarpSmemCn<CN> sm_all[kLkWarpsCn];
+  const int b = blockIdx.y;
+  const int n = min(npts_dev[b], max_pts);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kLkWarpsCn + warp;
+  if (i >= n) return;
+  LkWarpSmemCn<CN>& sm = sm_all[warp];
+  const float2 p0 = pts[(long long)b * max_pts + i];
+  float nx = 0.f, ny = 0.f, e = 0.f;
+  int st = 1;
+  const float flt_scale = 1.f / (1 << 20);
+  int qoff[kSlots];
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int k = lane + 32 * j;
+    const int r = k / LKW, c = k - r * LKW;
+    qoff[j] = r * kJReg + c;
+  }
+  for (int L = g.nlevels - 1; L >= 0; --L) {
+    const LkLevel lv = g.lv[L];
+    const uint8_t* I = pyrI + (long long)b * CN * g.frame_stride + lv.off;
+    const uint8_t* J = pyrJ + (long long)b * CN * g.frame_stride + lv.off;
+    const int w = lv.w, h = lv.h, pitch = lv.pitch;
+    const float s = 1.f / (float)(1 << L);
+    const float ppx = __fmul_rn(p0.x, s), ppy = __fmul_rn(p0.y, s);
+    if (L == g.nlevels - 1) {
+      nx = ppx;
+      ny = ppy;
+    } else {
+      nx = __fmul_rn(nx, 2.f);
+      ny = __fmul_rn(ny, 2.f);
+    }
+    const float qx = __fsub_rn(ppx, 10.f), qy = __fsub_rn(ppy, 10.f);
+    const int ix = (int)floorf(qx), iy = (int)floorf(qy);
+    if (ix < -LKW || ix >= w || iy < -LKW || iy >= h) {
+      if (L == 0) {
+        st = 0;
+        e = 0.f;
+      }
+      continue;
+    }
+    int w00, w01, w10, w11;
+    lk_weights(__fsub_rn(qx, (float)ix), __fsub_rn(qy, (float)iy), w00, w01, w10, w11);
+    long long tA11 = 0, tA12 = 0, tA22 = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int ch = 0; ch < CN; ++ch) {
+      int sA11 = 0, sA12 = 0, sA22 = 0;
+      lk_setup_patch(I + (long long)ch * g.frame_stride, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.d[ch],
+                     sm.i[ch], sA11, sA12, sA22);
+      tA11 += sA11;
+      tA12 += sA12;
+      tA22 += sA22;
+    }
+    __syncwarp();
+    const float A11 = __fmul_rn((float)warp_sum_ll(tA11), flt_scale);
+    const float A12 = __fmul_rn((float)warp_sum_ll(tA12), flt_scale);
+    const float A22 = __fmul_rn((float)warp_sum_ll(tA22), flt_scale);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dA = __fsub_rn(A11, A22);
+    const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * LKW * LKW));
+    if ((double)min_eig < 1e-4 || D < 1.1920929e-07f) {
+      if (L == 0) st = 0;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+    float cx = __fsub_rn(nx, 10.f), cy = __fsub_rn(ny, 10.f);
+    float pdx = 0.f, pdy = 0.f;
+    int jx0 = -100000, jy0 = -100000;
+    for (int it = 0; it < 30; ++it) {
+      const int inx = (int)floorf(cx), iny = (int)floorf(cy);
+      if (inx < -LKW || inx >= w || iny < -LKW || iny >= h) {
+        if (L == 0) st = 0;
+        break;
+      }
+      if (inx < jx0 || inx - jx0 > kJReg - LKW - 1 || iny < jy0 || iny - jy0 > kJReg - LKW - 1) {
+        jx0 = inx - kJMargin;
+        jy0 = iny - kJMargin;
+        __syncwarp();
+#pragma unroll 1
+        for (int ch = 0; ch < CN; ++ch) lk_stage_j(sm.jq[ch], J + (long long)ch * g.frame_stride, jx0, jy0, w, h, pitch, lane);
+        __syncwarp();
+      }
+      int v00, v01, v10, v11;
+      lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), v00, v01, v10, v11);
+      const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+      const int joff = (iny - jy0) * kJReg + (inx - jx0);
+      long long tb1 = 0, tb2 = 0;
+#pragma unroll 1
+      for (int ch = 0; ch < CN; ++ch) {
+        const uint32_t* jb = sm.jq[ch] + joff;
+        int sb1 = 0, sb2 = 0;
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+          const int k = lane + 32 * j;
+          if (k < kWin) {
+            const uint32_t q = jb[qoff[j]];
+            const uint32_t d = sm.d[ch][k];
+            const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)sm.i[ch][k];
+            sb1 += diff * (int)(short)(d & 0xffffu);
+            sb2 += diff * ((int)d >> 16);
+          }
+        }
+        tb1 += sb1;
+        tb2 += sb2;
+      }
+      const float b1 = __fmul_rn((float)warp_sum_ll(tb1), flt_scale);
+      const float b2 = __fmul_rn((float)warp_sum_ll(tb2), flt_scale);
+      const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      cx = __fadd_rn(cx, dx);
+      cy = __fadd_rn(cy, dy);
+      nx = __fadd_rn(cx, 10.f);
+      ny = __fadd_rn(cy, 10.f);
+      if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+      if (it > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+        nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f));
+        ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+    if (L == 0 && st) {
+      const float fx = __fsub_rn(nx, 10.f), fy = __fsub_rn(ny, 10.f);
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -LKW || inx >= w || iny < -LKW || iny >= h) {
+        st = 0;
+      } else {
+        if (inx < jx0 || inx - jx0 > kJReg - LKW - 1 || iny < jy0 || iny - jy0 > kJReg - LKW - 1) {
+          jx0 = inx - kJMargin;
+          jy0 = iny - kJMargin;
+          __syncwarp();
+#pragma unroll 1
+          for (int ch = 0; ch < CN; ++ch) lk_stage_j(sm.jq[ch], J + (long long)ch * g.frame_stride, jx0, jy0, w, h, pitch, lane);
+          __syncwarp();
+        }
+        int v00, v01, v10, v11;
+        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), v00, v01, v10, v11);
+        const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+        const int joff = (iny - jy0) * kJReg + (inx - jx0);
+        int se = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < CN; ++ch) {
+          const uint32_t* jb = sm.jq[ch] + joff;
+#pragma unroll
+          for (int j = 0; j < kSlots; ++j) {
+            const int k = lane + 32 * j;
+            if (k < kWin) {
+              const uint32_t q = jb[qoff[j]];
+              se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)sm.i[ch][k]);
+            }
+          }
+        }
+        se = warp_sum(se);
+        e = __fdiv_rn((float)se, (float)(32 * LKW * CN * LKW));
+      }
+    }
+  }
+  if (lane == 0) {
+    const long long o = (long long)b * max_pts + i;
+    out_pts[o] = make_float2(nx, ny);
+    status[o] = (uint8_t)st;
+    err[o] = e;
+  }
+}
+
+// interleaved BGR rows -> three planes (level 0 of planes b*3 + ch)
+__global__ void lk_split3_kernel(const uint8_t* __restrict__ src, int stride, long long in_frame_stride,
+                                 uint8_t* __restrict__ dst, int pitch, long long frame_stride, int w, int h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= w) return;
+  const uint8_t* p = src + (long long)b * in_frame_stride + (long long)y * stride + 3 * x;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) dst[((long long)b * 3 + ch) * frame_stride + (long long)y * pitch + x] = p[ch];
+}
+
 // ================================================================================================
 static void lk_geometry(int w, int h, LkGeom& g) {
   long long off = 0;
@@ -356,11 +575,11 @@ static void lk_geometry(int w, int h, LkGeom& g) {
   g.frame_stride = (long long)align_up((size_t)off + 256, 256);
 }
 
-int lk_prepare(mvo_ctx* c, int w, int h, int max_pts) {
+int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn) {
   LkGeom g;
   lk_geometry(w, h, g);
   const size_t B = (size_t)c->cfg.batch;
-  for (int k = 0; k < 2; ++k) MVO_CUDA_TRY(c, c->lk_pyr[k].alloc(B * g.frame_stride));
+  for (int k = 0; k < 2; ++k) MVO_CUDA_TRY(c, c->lk_pyr[k].alloc(B * cn * g.frame_stride));
   MVO_CUDA_TRY(c, c->lk_pts_in.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_pts_out.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_status.alloc(B * (size_t)max_pts));
@@ -369,17 +588,32 @@ int lk_prepare(mvo_ctx* c, int w, int h, int max_pts) {
   c->lk_w = w;
   c->lk_h = h;
   c->lk_max_pts = max_pts;
+  c->lk_cn = cn;
   return MVO_OK;
 }
 
 // copy level 0 (batch frames, h x stride each) into LK pyramid buffer `which`, then build levels 1..
+// on_device: 0 host images, 1 device images, 2 the ORB pyramid's level 0 (gray only)
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device) {
   LkGeom g;
   lk_geometry(c->lk_w, c->lk_h, g);
-  const int B = c->cfg.batch;
+  const int B = c->cfg.batch, cn = c->lk_cn;
   uint8_t* base = c->lk_pyr[which].p;
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (on_device == 2) {
+  if (cn == 3) {
+    // interleaved BGR -> staging -> three planes per stream
+    const size_t fbytes = (size_t)c->lk_h * stride;
+    const uint8_t* src = img;
+    if (!on_device) {
+      MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * B));
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, fbytes * B, cudaMemcpyHostToDevice, c->stream));
+      src = c->img_in.p;
+    }
+    dim3 grid((c->lk_w + 255) / 256, c->lk_h, B);
+    lk_split3_kernel<<<grid, 256, 0, c->stream>>>(src, stride, (long long)fbytes, base, g.lv[0].pitch, g.frame_stride,
+                                                  c->lk_w, c->lk_h);
+    c->launches++;
+  } else if (on_device == 2) {
     // source is a batch of pitched device images with frame stride given by `stride` == pitch and
     // frame distance c->geom.frame_stride (ORB pyramid level 0)
     for (int b = 0; b < B; ++b)
@@ -395,7 +629,7 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
   for (int l = 1; l < g.nlevels; ++l) {
     const LkLevel& s = g.lv[l - 1];
     const LkLevel& d = g.lv[l];
-    dim3 grid((d.w + PDW - 1) / PDW, (d.h + PDH - 1) / PDH, B), block(PDW, PDH);
+    dim3 grid((d.w + PDW - 1) / PDW, (d.h + PDH - 1) / PDH, B * cn), block(PDW, PDH);
     lk_pyrdown_kernel<<<grid, block, 0, c->stream>>>(base + s.off, s.w, s.h, s.pitch, base + d.off, d.w, d.h, d.pitch,
                                                      g.frame_stride, g.frame_stride);
     c->launches++;
@@ -409,10 +643,16 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
            float2* out_dev, uint8_t* status_dev, float* err_dev) {
   LkGeom g;
   lk_geometry(c->lk_w, c->lk_h, g);
-  dim3 grid((max_pts + kLkWarps - 1) / kLkWarps, c->cfg.batch);
   if (max_pts > 0) {
-    lk_track_kernel<<<grid, kLkWarps * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev,
-                                                          npts_dev, max_pts, out_dev, status_dev, err_dev);
+    if (c->lk_cn == 3) {
+      dim3 grid((max_pts + kLkWarpsCn - 1) / kLkWarpsCn, c->cfg.batch);
+      lk_track_cn_kernel<3><<<grid, kLkWarpsCn * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p,
+                                                                    pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
+    } else {
+      dim3 grid((max_pts + kLkWarps - 1) / kLkWarps, c->cfg.batch);
+      lk_track_kernel<<<grid, kLkWarps * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev,
+                                                            npts_dev, max_pts, out_dev, status_dev, err_dev);
+    }
     c->launches++;
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
@@ -430,11 +670,11 @@ extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next
     c->set_error("mvo_lk_track: null argument");
     return MVO_ERR_INVALID;
   }
-  if (channels != 1) {
-    c->set_error("mvo_lk_track: only single-channel images are implemented (cn=3 windows are a listed next step)");
+  if (channels != 1 && channels != 3) {
+    c->set_error("mvo_lk_track: images must have 1 (gray) or 3 (BGR) channels");
     return MVO_ERR_UNSUPPORTED;
   }
-  if (w <= LKW || h <= LKW || w > c->cfg.max_width || h > c->cfg.max_height || stride < w) {
+  if (w <= LKW || h <= LKW || w > c->cfg.max_width || h > c->cfg.max_height || stride < w * channels) {
     c->set_error("mvo_lk_track: image size out of range");
     return MVO_ERR_INVALID;
   }
@@ -444,7 +684,7 @@ extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next
   }
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if (n == 0) return MVO_OK;
-  int rc = lk_prepare(c, w, h, std::max(n, c->lk_max_pts));
+  int rc = lk_prepare(c, w, h, std::max(n, c->lk_max_pts), channels);
   if (rc) return rc;
   rc = lk_build_pyramid(c, 0, prev, stride, 0);
   if (rc) return rc;

@@ -198,14 +198,14 @@ int pose_recover(mvo_ctx* c, bool use_mask) {
   RansacBufs& r = c->rs;
   const int B = c->cfg.batch;
   MVO_CUDA_TRY(c, cudaMemsetAsync(r.cand_good.p, 0, (size_t)B * 16, c->stream));
-  pose_decompose_kernel<<<B, 32, 0, c->stream>>>(r.best_model.p, r.cands.p);
+  pose_decompose_kernel<<<B, 32, 0, c->stream>>>(r.ln().best_model.p, r.cands.p);
   c->launches++;
   dim3 grid((r.max_pts + 127) / 128, 4, B);
-  pose_cheirality_kernel<<<grid, 128, 0, c->stream>>>(r.q1.p, r.q2.p, r.npts.p, r.max_pts, r.cands.p, r.mask.p,
+  pose_cheirality_kernel<<<grid, 128, 0, c->stream>>>(r.q1.p, r.q2.p, r.npts.p, r.max_pts, r.cands.p, r.ln().mask.p,
                                                       use_mask ? 1 : 0, r.cand_mask.p, r.cand_good.p, 50.0);
   c->launches++;
   pose_select_kernel<<<B, 256, 0, c->stream>>>(r.npts.p, r.max_pts, r.cands.p, r.cand_mask.p, r.cand_good.p, r.pose.p,
-                                               r.mask.p, r.result.p);
+                                               r.ln().mask.p, r.ln().result.p);
   c->launches++;
   MVO_CUDA_TRY(c, cudaGetLastError());
   return MVO_OK;
@@ -255,8 +255,8 @@ int mvo_recover_pose(mvo_ctx* c, const double* E, const float* p1, const float* 
   int rc = pose_upload(c, p1, p2, n, K);
   if (rc) return rc;
   RansacBufs& r = c->rs;
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.best_model.p, E, 72, cudaMemcpyHostToDevice, c->stream));
-  if (mask_io) MVO_CUDA_TRY(c, cudaMemcpyAsync(r.mask.p, mask_io, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.ln().best_model.p, E, 72, cudaMemcpyHostToDevice, c->stream));
+  if (mask_io) MVO_CUDA_TRY(c, cudaMemcpyAsync(r.ln().mask.p, mask_io, (size_t)n, cudaMemcpyHostToDevice, c->stream));
   rc = ransac_normalize(c);
   if (rc) return rc;
   rc = pose_recover(c, mask_io != nullptr);
@@ -264,8 +264,8 @@ int mvo_recover_pose(mvo_ctx* c, const double* E, const float* p1, const float* 
   double pose[12];
   int res[8];
   MVO_CUDA_TRY(c, cudaMemcpyAsync(pose, r.pose.p, 96, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, r.result.p, 32, cudaMemcpyDeviceToHost, c->stream));
-  if (mask_io) MVO_CUDA_TRY(c, cudaMemcpyAsync(mask_io, r.mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, r.ln().result.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  if (mask_io) MVO_CUDA_TRY(c, cudaMemcpyAsync(mask_io, r.ln().mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < 9; ++i) R[i] = pose[i];
   for (int i = 0; i < 3; ++i) t[i] = pose[9 + i];

@@ -984,7 +984,7 @@ static size_t chain_smem(int window, int attempts) {
   return (size_t)(window + 2) * 2 * 2 + (size_t)attempts * 2 + (size_t)kSegIters * 2 + (size_t)window + 16;
 }
 
-int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
+int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters, int lanes) {
   RansacBufs& r = c->rs;
   const size_t B = (size_t)c->cfg.batch;
   if (!r.rng_ready) {
@@ -998,8 +998,6 @@ int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
     MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MVO_CUDA_TRY(c, cudaFuncSetAttribute(ransac_chain_kernel<MVO_MODEL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MVO_CUDA_TRY(c, r.att_next.alloc(B * kDraws));
-    MVO_CUDA_TRY(c, r.att_ok.alloc(B * kDraws));
     r.rng_ready = true;
   }
   if (max_pts > r.max_pts) {
@@ -1008,25 +1006,38 @@ int ransac_prepare(mvo_ctx* c, int max_pts, int cap_iters) {
     MVO_CUDA_TRY(c, r.p2.alloc(n));
     MVO_CUDA_TRY(c, r.q1.alloc(n));
     MVO_CUDA_TRY(c, r.q2.alloc(n));
-    MVO_CUDA_TRY(c, r.mask.alloc(n));
-    MVO_CUDA_TRY(c, r.inl_idx.alloc(n));
     r.max_pts = max_pts;
   }
-  if (cap_iters > r.cap_iters) {
-    const size_t n = B * (size_t)cap_iters;
-    MVO_CUDA_TRY(c, r.subsets.alloc(n * 8));
-    MVO_CUDA_TRY(c, r.models.alloc(n * kMaxHypModels * 9));
-    MVO_CUDA_TRY(c, r.nmodels.alloc(n));
-    MVO_CUDA_TRY(c, r.counts.alloc(n * kMaxHypModels));
-    MVO_CUDA_TRY(c, r.e5_scratch.alloc(n * kE5Scratch));
-    r.cap_iters = cap_iters;
-  }
+  r.cap_iters = std::max(r.cap_iters, cap_iters);
   MVO_CUDA_TRY(c, r.npts.alloc(B));
-  MVO_CUDA_TRY(c, r.state.alloc(B * 8));
-  MVO_CUDA_TRY(c, r.thr2.alloc(B));
   MVO_CUDA_TRY(c, r.K.alloc(B * 9));
-  MVO_CUDA_TRY(c, r.best_model.alloc(B * 9));
-  MVO_CUDA_TRY(c, r.result.alloc(B * 8));
+  for (int l = 0; l < std::min(std::max(lanes, 1), RansacBufs::kLanes); ++l) {
+    RansacLane& ln = r.lane[l];
+    if (!ln.ready) {
+      MVO_CUDA_TRY(c, ln.att_next.alloc(B * kDraws));
+      MVO_CUDA_TRY(c, ln.att_ok.alloc(B * kDraws));
+      MVO_CUDA_TRY(c, ln.state.alloc(B * 8));
+      MVO_CUDA_TRY(c, ln.thr2.alloc(B));
+      MVO_CUDA_TRY(c, ln.best_model.alloc(B * 9));
+      MVO_CUDA_TRY(c, ln.result.alloc(B * 8));
+      ln.ready = true;
+    }
+    if (r.max_pts > ln.max_pts) {
+      const size_t n = B * (size_t)r.max_pts;
+      MVO_CUDA_TRY(c, ln.mask.alloc(n));
+      MVO_CUDA_TRY(c, ln.inl_idx.alloc(n));
+      ln.max_pts = r.max_pts;
+    }
+    if (r.cap_iters > ln.cap_iters) {
+      const size_t n = B * (size_t)r.cap_iters;
+      MVO_CUDA_TRY(c, ln.subsets.alloc(n * 8));
+      MVO_CUDA_TRY(c, ln.models.alloc(n * kMaxHypModels * 9));
+      MVO_CUDA_TRY(c, ln.nmodels.alloc(n));
+      MVO_CUDA_TRY(c, ln.counts.alloc(n * kMaxHypModels));
+      MVO_CUDA_TRY(c, ln.e5_scratch.alloc(n * kE5Scratch));
+      ln.cap_iters = r.cap_iters;
+    }
+  }
   return MVO_OK;
 }
 
@@ -1037,9 +1048,9 @@ static void sample_pass(mvo_ctx* c, int want_total, int window, int attempts) {
   const int B = c->cfg.batch;
   dim3 ga((window + 255) / 256, B);
   ransac_attempt_kernel<MODEL><<<ga, 256, 0, c->stream>>>(r.rng.p, r.rng_len, r.p1.p, r.p2.p, r.npts.p, r.max_pts,
-                                                          r.state.p, want_total, window, r.att_next.p, r.att_ok.p);
+                                                          r.ln().state.p, want_total, window, r.ln().att_next.p, r.ln().att_ok.p);
   ransac_chain_kernel<MODEL><<<B, 1024, chain_smem(window, attempts), c->stream>>>(
-      r.rng.p, r.rng_len, r.npts.p, r.att_next.p, r.att_ok.p, r.subsets.p, r.state.p, want_total, r.cap_iters, window,
+      r.rng.p, r.rng_len, r.npts.p, r.ln().att_next.p, r.ln().att_ok.p, r.ln().subsets.p, r.ln().state.p, want_total, r.cap_iters, window,
       attempts);
   c->launches += 2;
 }
@@ -1054,20 +1065,20 @@ static void solve_score(mvo_ctx* c, int h0, int h1) {
   while (tpb < 64 && (long long)B * count > 148LL * 4 * tpb) tpb <<= 1;
   dim3 gs((count + tpb - 1) / tpb, B);
   if (MODEL == MVO_MODEL_E) {
-    e5_setup_kernel<<<gs, tpb, 0, c->stream>>>(r.q1.p, r.q2.p, r.max_pts, r.subsets.p, r.state.p, r.cap_iters, h0, h1,
-                                               r.e5_scratch.p);
+    e5_setup_kernel<<<gs, tpb, 0, c->stream>>>(r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p, r.ln().state.p, r.cap_iters, h0, h1,
+                                               r.ln().e5_scratch.p);
     dim3 gr((count + kRootsThreads / 16 - 1) / (kRootsThreads / 16), B);
-    e5_roots_kernel<<<gr, kRootsThreads, 0, c->stream>>>(r.state.p, r.cap_iters, h0, h1, r.e5_scratch.p, r.models.p,
-                                                         r.nmodels.p);
+    e5_roots_kernel<<<gr, kRootsThreads, 0, c->stream>>>(r.ln().state.p, r.cap_iters, h0, h1, r.ln().e5_scratch.p, r.ln().models.p,
+                                                         r.ln().nmodels.p);
     c->launches++;
   } else {
-    ransac_solve_kernel<MODEL><<<gs, tpb, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.subsets.p,
-                                                          r.state.p, r.cap_iters, h0, h1, r.models.p, r.nmodels.p);
+    ransac_solve_kernel<MODEL><<<gs, tpb, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p,
+                                                          r.ln().state.p, r.cap_iters, h0, h1, r.ln().models.p, r.ln().nmodels.p);
   }
   dim3 gc(count, B);
   ransac_score_kernel<MODEL><<<gc, kScoreThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                 r.state.p, r.cap_iters, h0, h1, r.models.p,
-                                                                 r.nmodels.p, r.thr2.p, r.counts.p);
+                                                                 r.ln().state.p, r.cap_iters, h0, h1, r.ln().models.p,
+                                                                 r.ln().nmodels.p, r.ln().thr2.p, r.ln().counts.p);
   c->launches += 2;
 }
 
@@ -1075,17 +1086,17 @@ template <int MODEL>
 static void select_pass(mvo_ctx* c, int n_eval, double conf) {
   RansacBufs& r = c->rs;
   ransac_select_kernel<MODEL><<<c->cfg.batch, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
-                                                                  r.state.p, r.cap_iters, n_eval, r.models.p, r.counts.p,
-                                                                  r.thr2.p, conf, r.best_model.p, r.mask.p, r.result.p);
+                                                                  r.ln().state.p, r.cap_iters, n_eval, r.ln().models.p, r.ln().counts.p,
+                                                                  r.ln().thr2.p, conf, r.ln().best_model.p, r.ln().mask.p, r.ln().result.p);
   c->launches++;
 }
 
-// full find*: points must already be in r.p1/r.p2 (and r.q1/r.q2 for E), counts in r.npts, thresholds in r.thr2
+// full find*: points must already be in r.p1/r.p2 (and r.q1/r.q2 for E), counts in r.npts, thresholds in r.ln().thr2
 template <int MODEL>
 static int find_model(mvo_ctx* c, double conf) {
   RansacBufs& r = c->rs;
   constexpr int MAXIT = MT<MODEL>::MAXIT;
-  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.ln().state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
   // round 0: the first kRound0 iterations; usually the adaptive loop has already stopped inside them
   sample_pass<MODEL>(c, kRound0, kDraws0, kAttempts0);
   solve_score<MODEL>(c, 0, kRound0);
@@ -1104,8 +1115,8 @@ int ransac_find(mvo_ctx* c, int model, double conf) {
   if (model == MVO_MODEL_H) {
     rc = find_model<MVO_MODEL_H>(c, conf);
     if (rc) return rc;
-    h_refine_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.thr2.p,
-                                                                r.best_model.p, r.mask.p, r.result.p, r.inl_idx.p);
+    h_refine_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.ln().thr2.p,
+                                                                r.ln().best_model.p, r.ln().mask.p, r.ln().result.p, r.ln().inl_idx.p);
     c->launches++;
     MVO_CUDA_TRY(c, cudaGetLastError());
     return MVO_OK;
@@ -1118,7 +1129,7 @@ int ransac_find(mvo_ctx* c, int model, double conf) {
 template <int MODEL>
 static int sweep_model(mvo_ctx* c, int m) {
   RansacBufs& r = c->rs;
-  MVO_CUDA_TRY(c, cudaMemsetAsync(r.state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.ln().state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
   const int passes = (m + kSegIters - 1) / kSegIters + 2;
   for (int l = 0; l < passes; ++l) sample_pass<MODEL>(c, m, kDraws, kMaxAttempts);
   solve_score<MODEL>(c, 0, m);
@@ -1159,7 +1170,7 @@ static int upload_points(mvo_ctx* c, const float* p1, const float* p2, int n, do
   MVO_CUDA_TRY(c, cudaMemcpyAsync(r.p2.p, p2, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
   struct { int n; float t; } h = {n, (float)thr2};
   MVO_CUDA_TRY(c, cudaMemcpyAsync(r.npts.p, &h.n, 4, cudaMemcpyHostToDevice, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.thr2.p, &h.t, 4, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(r.ln().thr2.p, &h.t, 4, cudaMemcpyHostToDevice, c->stream));
   if (K) MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // h lives on this stack frame
   return MVO_OK;
@@ -1168,9 +1179,9 @@ static int upload_points(mvo_ctx* c, const float* p1, const float* p2, int n, do
 static int download_result(mvo_ctx* c, int n, double* model, uint8_t* mask, int* n_inl) {
   RansacBufs& r = c->rs;
   int res[8];
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, r.result.p, 32, cudaMemcpyDeviceToHost, c->stream));
-  if (model) MVO_CUDA_TRY(c, cudaMemcpyAsync(model, r.best_model.p, 72, cudaMemcpyDeviceToHost, c->stream));
-  if (mask) MVO_CUDA_TRY(c, cudaMemcpyAsync(mask, r.mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, r.ln().result.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  if (model) MVO_CUDA_TRY(c, cudaMemcpyAsync(model, r.ln().best_model.p, 72, cudaMemcpyDeviceToHost, c->stream));
+  if (mask) MVO_CUDA_TRY(c, cudaMemcpyAsync(mask, r.ln().mask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (n_inl) *n_inl = res[0];
   c->last_ransac_iters = res[1];
@@ -1266,10 +1277,10 @@ int mvo_score_hypotheses(mvo_ctx* c, int model, const float* p1, const float* p2
   const int kk = model == MVO_MODEL_H ? 4 : model == MVO_MODEL_F ? 7 : 5;
   const int mm = model == MVO_MODEL_H ? 1 : model == MVO_MODEL_F ? 3 : 10;
   int st[8];
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(st, r.state.p, 32, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(counts, r.counts.p, (size_t)m * mm * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (sample_idx) MVO_CUDA_TRY(c, cudaMemcpyAsync(sample_idx, r.subsets.p, (size_t)m * kk * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (models) MVO_CUDA_TRY(c, cudaMemcpyAsync(models, r.models.p, (size_t)m * mm * 72, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(st, r.ln().state.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(counts, r.ln().counts.p, (size_t)m * mm * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (sample_idx) MVO_CUDA_TRY(c, cudaMemcpyAsync(sample_idx, r.ln().subsets.p, (size_t)m * kk * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (models) MVO_CUDA_TRY(c, cudaMemcpyAsync(models, r.ln().models.p, (size_t)m * mm * 72, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (st[1] < m) {
     c->set_error("could not draw the requested number of valid minimal samples");
