@@ -95,6 +95,20 @@ def synth_pair(h: int, w: int, seed: int):
     return f0, warp_similarity(f0, ang, tx, ty)
 
 
+def synth_pair_bgr(h: int, w: int, seed: int):
+    """BGR8 version of synth_pair (the node feeds BGR8 images, /root/reference/src/mono_vo.cpp:94): per-channel
+    gain / offset plus independent sensor noise, so the three planes are correlated but not identical."""
+    f0, f1 = synth_pair(h, w, seed)
+    rng = np.random.default_rng(seed + 104729)
+    gains = ((0.9, 10.0), (1.0, 0.0), (0.8, 25.0))
+    out = []
+    for f in (f0, f1):
+        noise = rng.normal(0.0, 1.5, (h, w, 3))
+        out.append(np.stack([np.clip(np.rint(f * g + o + noise[:, :, i]), 0, 255) for i, (g, o) in enumerate(gains)],
+                            2).astype(np.uint8))
+    return out[0], out[1]
+
+
 def _smooth_field(h: int, w: int, rng, scales=(16, 64)) -> np.ndarray:
     f = np.zeros((h, w))
     for s in scales:

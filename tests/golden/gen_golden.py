@@ -109,6 +109,20 @@ def gen_lk():
     np.savez_compressed(os.path.join(HERE, "lk.npz"), **out)
 
 
+def gen_lk_bgr():
+    """cn = 3 windows: the node tracks on BGR8 images (src/mono_vo.cpp:94 -> src/tracker.cpp:68)."""
+    out = {}
+    for tag, h, w, seed, n in (("small", 240, 320, 12, 300), ("c2", 376, 1241, 3, 2000)):
+        f0, f1 = synth.synth_pair_bgr(h, w, seed)
+        pts = lk_points(h, w, cv2.cvtColor(f0, cv2.COLOR_BGR2GRAY), n, seed)
+        nxt, st, err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None)
+        out.update({f"{tag}_pts": pts, f"{tag}_next": nxt, f"{tag}_status": st.ravel(), f"{tag}_err": err.ravel(),
+                    f"{tag}_sha0": sha(f0), f"{tag}_sha1": sha(f1), f"{tag}_hw_seed": np.array([h, w, seed])})
+        print("lk_bgr", tag, len(pts), int(st.sum()))
+    out["cv2_version"] = cv2.__version__
+    np.savez_compressed(os.path.join(HERE, "lk_bgr.npz"), **out)
+
+
 def gen_ransac():
     """cv2 outputs at the reference's RANSAC call sites (src/initializer.cpp:82,87,228,236,125)."""
     K = synth.KITTI_K
@@ -146,8 +160,14 @@ def gen_ransac():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:            # e.g. `python gen_golden.py gen_lk_bgr`: regenerate single fixtures
+        for name in only:
+            globals()[name]()
+        sys.exit(0)
     gen_ransac()
     gen_lk()
+    gen_lk_bgr()
     gen_orb("orb_small.npz", 240, 320, 3, 300, True)
     gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
     gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)

@@ -69,3 +69,27 @@ def test_lk_identity_property(ctx):
     assert ok.mean() > 0.99
     assert np.abs(nxt[ok] - pts[ok]).max() < 1e-3
     assert err[ok].max() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["small", "c2"])
+def test_lk_bgr_vs_cv2_golden(ctx, tag):
+    """BGR8 input (cn = 3), as the reference node feeds it (src/mono_vo.cpp:94 -> src/tracker.cpp:68)."""
+    g = load_golden("lk_bgr.npz")
+    h, w, seed = g[f"{tag}_hw_seed"].tolist()
+    f0, f1 = synth.synth_pair_bgr(h, w, seed)
+    assert sha(f0) == str(g[f"{tag}_sha0"])
+    nxt, st, err = ctx.lk_track(f0, f1, g[f"{tag}_pts"])
+    assert np.array_equal(st, g[f"{tag}_status"])
+    m = st == 1
+    assert np.abs(nxt[m] - g[f"{tag}_next"][m]).max() < POS_TOL
+    assert np.abs(err[m] - g[f"{tag}_err"][m]).max() < ERR_TOL
+    assert np.abs(nxt[~m] - g[f"{tag}_next"][~m]).max() < POS_TOL
+    assert np.array_equal(m & (err < 30.0), (g[f"{tag}_status"] == 1) & (g[f"{tag}_err"] < 30.0))
+    # a gray frame replicated to three channels goes through the same kernel
+    g0, g1 = synth.synth_pair(h, w, seed)
+    pts = g[f"{tag}_pts"]
+    n3, s3, e3 = ctx.lk_track(np.repeat(g0[:, :, None], 3, 2), np.repeat(g1[:, :, None], 3, 2), pts)
+    o3, os3, oe3 = lo.lk_track(np.repeat(g0[:, :, None], 3, 2), np.repeat(g1[:, :, None], 3, 2), pts)
+    assert (s3 != os3).mean() < 0.002
+    mm = (s3 == 1) & (os3 == 1)
+    assert np.abs(n3[mm] - o3[mm]).max() < POS_TOL

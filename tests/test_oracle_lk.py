@@ -43,3 +43,18 @@ def test_pyrdown_and_levels():
     assert len(lo.build_pyramid(synth.synth_frame(376, 1241, 1))) == 4
     p = lo.pyr_down(np.full((9, 11), 77, np.uint8))
     assert p.shape == (5, 6) and (p == 77).all()
+
+
+@pytest.mark.parametrize("tag", ["small", "c2"])
+def test_lk_oracle_bgr_vs_cv2(tag):
+    """cn = 3 windows (the node tracks BGR8 images): every sum spans the three channels."""
+    g = load_golden("lk_bgr.npz")
+    h, w, seed = g[f"{tag}_hw_seed"].tolist()
+    f0, f1 = synth.synth_pair_bgr(h, w, seed)
+    assert sha(f0) == str(g[f"{tag}_sha0"]) and sha(f1) == str(g[f"{tag}_sha1"]), "synthetic generator drifted"
+    nxt, st, err = lo.lk_track(f0, f1, g[f"{tag}_pts"])
+    assert np.array_equal(st, g[f"{tag}_status"])
+    m = st == 1
+    assert np.abs(nxt[m] - g[f"{tag}_next"][m]).max() < 1e-3
+    assert np.abs(err[m] - g[f"{tag}_err"][m]).max() < 5e-3
+    assert np.abs(nxt[~m] - g[f"{tag}_next"][~m]).max() < 1e-3
