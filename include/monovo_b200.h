@@ -154,6 +154,22 @@ MVO_API int mvo_recover_pose(mvo_ctx* ctx, const double E[9], const float* p1, c
 MVO_API int mvo_triangulate(mvo_ctx* ctx, const double P0[12], const double P1[12], const float* p0,
                             const float* p1, int n, float* X4);
 
+/* replaces cv::solvePnPRansac(points_3d, points_2d, K, d, rvec, tvec, false, iterations, reproj_err, confidence,
+ * inliers): src/tracker.cpp:309 (the reference passes 100, 8.0, 0.99; SOLVEPNP_ITERATIVE; no extrinsic guess).
+ * obj_xyz: n x 3 f32 (std::vector<cv::Point3f>), img_xy: n x 2 f32.  dist: n_dist distortion coefficients or NULL --
+ * they must all be zero (rectified images).  inliers: capacity n indices of the winning hypothesis' inliers (may be
+ * NULL), *n_inliers their count.  rvec / tvec: the Levenberg-Marquardt pose on those inliers.
+ * MVO_ERR_DEGENERATE == OpenCV returning false (no model). */
+MVO_API int mvo_solve_pnp_ransac(mvo_ctx* ctx, const float* obj_xyz, const float* img_xy, int n, const double K[9],
+                                 const double* dist, int n_dist, int iterations, double reproj_err,
+                                 double confidence, double rvec[3], double tvec[3], int32_t* inliers,
+                                 int* n_inliers);
+/* parity hook: hypotheses of the last mvo_solve_pnp_ransac call -- subsets: iterations x 5, models: iterations x 12
+ * (R row-major | t), counts: iterations (-1 where the minimal solver failed).  Any pointer may be NULL. */
+MVO_API int mvo_pnp_get_hypotheses(mvo_ctx* ctx, int iterations, int32_t* subsets, double* models, int32_t* counts);
+/* replaces cv::Rodrigues(rvec, R): src/tracker.cpp:315 (host arithmetic; R is 3x3 row-major) */
+MVO_API int mvo_rodrigues(const double rvec[3], double R[9]);
+
 /* model ids for the hypothesis sweep */
 enum { MVO_MODEL_H = 0, MVO_MODEL_F = 1, MVO_MODEL_E = 2 };
 /* C4 sweep: draw m minimal samples with the OpenCV RNG stream (seeded per ctx), solve, and score every

@@ -109,6 +109,29 @@ def synth_pair_bgr(h: int, w: int, seed: int):
     return out[0], out[1]
 
 
+def pnp_scene(n: int, seed: int, noise: float = 0.5, outlier_frac: float = 0.1, planar: bool = False):
+    """3-D landmarks + their pixel observations under a seeded pose (the Tracker's solvePnPRansac input,
+    /root/reference/src/tracker.cpp:298-309).  Returns obj (n x 3 f32), img (n x 2 f32), K, rvec, tvec."""
+    rng = np.random.default_rng(seed + 15485863)
+    K = np.array([[718.856, 0, 620.5], [0, 718.856, 188.0], [0, 0, 1.0]])
+    X = np.stack([rng.uniform(-10, 10, n), rng.uniform(-3, 3, n), rng.uniform(5, 40, n)], 1)
+    if planar:
+        X[:, 2] = 20.0 + 0.3 * X[:, 0] - 0.2 * X[:, 1]
+    rvec = np.array([0.01, 0.03, -0.005]) * rng.uniform(0.5, 3.0)
+    tvec = np.array([0.1, -0.02, 0.8]) * rng.uniform(0.5, 2.0)
+    th = np.linalg.norm(rvec)
+    k = rvec / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+    Xc = X @ R.T + tvec
+    uv = Xc[:, :2] / Xc[:, 2:3] * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]]
+    uv += rng.normal(0, noise, uv.shape)
+    no = int(outlier_frac * n)
+    oi = rng.choice(n, no, replace=False)
+    uv[oi] = np.stack([rng.uniform(0, 1241, no), rng.uniform(0, 376, no)], 1)
+    return X.astype(np.float32), uv.astype(np.float32), K, rvec, tvec
+
+
 def _smooth_field(h: int, w: int, rng, scales=(16, 64)) -> np.ndarray:
     f = np.zeros((h, w))
     for s in scales:

@@ -65,6 +65,10 @@ SIGNATURES = {
     "mvo_find_essential": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_double, _vp, _vp, _i32p]),
     "mvo_recover_pose": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i32p]),
     "mvo_triangulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mvo_solve_pnp_ransac": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp,
+                                       _vp, _i32p]),
+    "mvo_rodrigues": (C.c_int, [_vp, _vp]),
+    "mvo_pnp_get_hypotheses": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "mvo_score_hypotheses": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int, _vp, _vp, _vp]),
     "mvo_group_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "mvo_group_reset": (C.c_int, [_vp]),

@@ -220,6 +220,41 @@ class Context:
         self._check(self.lib.mvo_triangulate(self.h, _ptr(P0), _ptr(P1), _ptr(p0), _ptr(p1), len(p0), _ptr(X)))
         return X
 
+    def solve_pnp_ransac(self, obj, img, K, dist=None, iterations: int = 100, reproj_err: float = 8.0,
+                         confidence: float = 0.99):
+        """cv::solvePnPRansac(obj, img, K, dist, rvec, tvec, false, iterations, reproj_err, confidence, inliers)
+        -> (ok, rvec, tvec, inliers).  Arguments default to the reference's (src/tracker.cpp:309)."""
+        obj = np.ascontiguousarray(obj, np.float32).reshape(-1, 3)
+        img = self._pts(img)
+        assert len(obj) == len(img)
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        d = None if dist is None else np.ascontiguousarray(dist, np.float64).ravel()
+        rvec, tvec = np.zeros(3), np.zeros(3)
+        inl = np.zeros(max(len(obj), 1), np.int32)
+        n = C.c_int32()
+        rc = self.lib.mvo_solve_pnp_ransac(self.h, _ptr(obj), _ptr(img), len(obj), _ptr(K),
+                                           _ptr(d) if d is not None else None, 0 if d is None else len(d), iterations,
+                                           reproj_err, confidence, _ptr(rvec), _ptr(tvec), _ptr(inl), C.byref(n))
+        if rc == _lib.MVO_ERR_DEGENERATE:
+            return False, rvec, tvec, inl[:0]
+        self._check(rc)
+        return True, rvec, tvec, inl[:n.value].copy()
+
+    def pnp_hypotheses(self, iterations: int = 100):
+        """Parity hook: (subsets, models R|t, counts) of the last solve_pnp_ransac call."""
+        sub = np.zeros((iterations, 5), np.int32)
+        mdl = np.zeros((iterations, 12), np.float64)
+        cnt = np.zeros(iterations, np.int32)
+        self._check(self.lib.mvo_pnp_get_hypotheses(self.h, iterations, _ptr(sub), _ptr(mdl), _ptr(cnt)))
+        return sub, mdl, cnt
+
+    def rodrigues(self, rvec):
+        """cv::Rodrigues(rvec) -> R (3 x 3)."""
+        r = np.ascontiguousarray(rvec, np.float64).reshape(3)
+        R = np.zeros(9)
+        self._check(self.lib.mvo_rodrigues(_ptr(r), _ptr(R)))
+        return R.reshape(3, 3)
+
     def score_hypotheses(self, model: int, p1, p2, m: int, thr: float = 1.0, K=None, want_models: bool = False):
         """C4 sweep: m minimal samples from the OpenCV RNG stream, solved and scored with no early exit."""
         p1, p2 = self._pts(p1), self._pts(p2)

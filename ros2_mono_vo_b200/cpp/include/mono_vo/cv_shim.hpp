@@ -26,6 +26,8 @@ struct Point2f {
 };
 struct Point3f {
   float x = 0, y = 0, z = 0;
+  Point3f() = default;
+  Point3f(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
 };
 
 struct KeyPoint {

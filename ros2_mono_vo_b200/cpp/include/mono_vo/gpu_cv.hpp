@@ -7,6 +7,7 @@
 //   src/initializer.cpp:228     cv::findEssentialMat
 //   src/initializer.cpp:236     cv::recoverPose
 //   src/initializer.cpp:125     cv::triangulatePoints       src/tracker.cpp:149
+//   src/tracker.cpp:309         cv::solvePnPRansac          src/tracker.cpp:315  cv::Rodrigues
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -118,6 +119,40 @@ inline void triangulatePoints(
   mat_to_array(P1, p1, 12);
   points4d.assign(4 * pts0.size(), 0.f);
   check(c, mvo_triangulate(c, p0, p1, &pts0[0].x, &pts1[0].x, static_cast<int>(pts0.size()), points4d.data()), "triangulatePoints");
+}
+
+/// cv::solvePnPRansac(points_3d, points_2d, K, d, rvec, tvec, useExtrinsicGuess = false, iterationsCount, reprojectionError,
+/// confidence, inliers) -- rvec / tvec become 3 x 1 CV_64F, inliers the indices of the winning hypothesis' inliers.
+inline bool solvePnPRansac(
+  mvo_ctx * c, const std::vector<cv::Point3f> & points_3d, const std::vector<cv::Point2f> & points_2d, const cv::Mat & K,
+  const cv::Mat & dist, cv::Mat & rvec, cv::Mat & tvec, bool use_extrinsic_guess, int iterations, float reproj_err,
+  double confidence, std::vector<int> & inliers)
+{
+  if (use_extrinsic_guess) throw std::runtime_error("solvePnPRansac: useExtrinsicGuess is not supported");
+  double k[9], r[3], t[3];
+  mat_to_array(K, k, 9);
+  std::vector<double> d;
+  for (int i = 0; i < dist.rows * dist.cols; ++i) d.push_back(dist.at<double>(i / dist.cols, i % dist.cols));
+  const int n = static_cast<int>(points_3d.size());
+  inliers.assign(n, 0);
+  int n_in = 0;
+  const int rc = mvo_solve_pnp_ransac(c, n ? &points_3d[0].x : nullptr, n ? &points_2d[0].x : nullptr, n, k,
+    d.empty() ? nullptr : d.data(), static_cast<int>(d.size()), iterations, reproj_err, confidence, r, t, inliers.data(), &n_in);
+  if (rc == MVO_ERR_DEGENERATE) { inliers.clear(); return false; }   // OpenCV returns false when no model is found
+  check(c, rc, "solvePnPRansac");
+  inliers.resize(n_in);
+  rvec = cv::Mat(3, 1, CV_64F);
+  tvec = cv::Mat(3, 1, CV_64F);
+  for (int i = 0; i < 3; ++i) { rvec.at<double>(i, 0) = r[i]; tvec.at<double>(i, 0) = t[i]; }
+  return true;
+}
+
+/// cv::Rodrigues(rvec, R)
+inline void Rodrigues(const cv::Mat & rvec, cv::Mat & R)
+{
+  double r[3] = {rvec.at<double>(0, 0), rvec.at<double>(1, 0), rvec.at<double>(2, 0)}, m[9];
+  mvo_rodrigues(r, m);
+  R = mat3x3(m);
 }
 
 /// the cv::Mat form the reference uses (src/initializer.cpp:124-125): points4D becomes 4 x N CV_32F

@@ -105,6 +105,7 @@ void mvo_destroy(mvo_ctx* c) {
   c->lk_pyr[0].release(); c->lk_pyr[1].release(); c->lk_pts_in.release(); c->lk_pts_out.release();
   c->lk_status.release(); c->lk_err.release(); c->lk_npts.release();
   c->rs.release();
+  c->pnp.release();
   for (auto& t : c->timers) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);

@@ -60,6 +60,30 @@ struct RansacBufs {
   }
 };
 
+// solvePnPRansac (pnp.cu)
+struct PnpBufs {
+  int max_pts = 0, cap_iters = 0;
+  mvo::DevBuf<float> obj;             // batch * max_pts * 3 object points
+  mvo::DevBuf<float2> img;            // batch * max_pts image points (pixels)
+  mvo::DevBuf<double2> xn;            // K-normalised image points (rounded to float, as undistortPoints returns them)
+  mvo::DevBuf<uint8_t> mask;          // batch * max_pts
+  mvo::DevBuf<int32_t> inl_idx;       // batch * max_pts : ordered inlier indices of the winner
+  mvo::DevBuf<int32_t> npts;          // batch
+  mvo::DevBuf<double> K;              // batch * 9
+  mvo::DevBuf<int32_t> subsets;       // batch * iters * 5
+  mvo::DevBuf<double> models;         // batch * iters * 12 : R (9) | t (3)
+  mvo::DevBuf<int32_t> ok, counts;    // batch * iters
+  mvo::DevBuf<double> best_model;     // batch * 12
+  mvo::DevBuf<int32_t> result;        // batch * 8 : inliers, iterations run, winning iteration (-1: none)
+  mvo::DevBuf<double> pose_out;       // batch * 8 : rvec, tvec, planar flag
+  void release() {
+    obj.release(); img.release(); xn.release(); mask.release(); inl_idx.release(); npts.release(); K.release();
+    subsets.release(); models.release(); ok.release(); counts.release(); best_model.release(); result.release();
+    pose_out.release();
+    max_pts = cap_iters = 0;
+  }
+};
+
 struct mvo_ctx {
   mvo_config cfg{};
   cudaStream_t stream = nullptr;     // the stream host code currently issues on (main stream, or an aux stream inside a fork)
@@ -120,6 +144,7 @@ struct mvo_ctx {
 
   // ---------------- RANSAC / pose ----------------
   RansacBufs rs;
+  PnpBufs pnp;
   int last_ransac_iters = 0;
 
   // ---------------- stage timing ----------------
@@ -152,6 +177,8 @@ int ransac_find(mvo_ctx* c, int model, double conf);
 int ransac_normalize(mvo_ctx* c);
 int ransac_sweep(mvo_ctx* c, int model, int m);
 int pose_prepare(mvo_ctx* c);
+int pnp_prepare(mvo_ctx* c, int max_pts, int iters);
+int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf);
 int pose_recover(mvo_ctx* c, bool use_mask);      // E in rs.best_model, points in rs.q1/q2, mask in rs.mask
 int pose_triangulate(mvo_ctx* c);                 // P0/P1 in rs.proj, points in rs.p1/p2 -> rs.X4
 

@@ -5,12 +5,16 @@
 #endif
 #include <math.h>
 
+#ifndef MVO_HD
+#define MVO_HD __host__ __device__
+#endif
+
 namespace mvo {
 
 // Null space of an R x C matrix (R < C, full row rank assumed) by Gauss-Jordan elimination with complete
 // pivoting.  A is destroyed.  basis: (C-R) vectors of length C, orthonormalised (modified Gram-Schmidt).
 template <int R, int C>
-__device__ void null_space(double* A /* R*C row-major */, double* basis /* (C-R)*C */) {
+MVO_HD void null_space(double* A /* R*C row-major */, double* basis /* (C-R)*C */) {
   int colperm[C];
 #pragma unroll 1
   for (int j = 0; j < C; ++j) colperm[j] = j;
@@ -95,7 +99,7 @@ __device__ void null_space(double* A /* R*C row-major */, double* basis /* (C-R)
 
 // Solve the N x N system A x = b in place (partial pivoting).  Returns false when singular.
 template <int N>
-__device__ bool lu_solve(double* A /* N*N, destroyed */, double* b /* in: rhs, out: x */) {
+MVO_HD bool lu_solve(double* A /* N*N, destroyed */, double* b /* in: rhs, out: x */) {
 #pragma unroll 1
   for (int k = 0; k < N; ++k) {
     int p = k;
@@ -146,7 +150,7 @@ __device__ bool lu_solve(double* A /* N*N, destroyed */, double* b /* in: rhs, o
 // smallest eigenvalue of the matrices used here (DLT normal matrices) is separated from the next by many
 // orders of magnitude, so three iterations reach machine precision.  A is destroyed.
 template <int N>
-__device__ void smallest_eigvec_spd(double* A, double* x) {
+MVO_HD void smallest_eigvec_spd(double* A, double* x) {
   double tr = 0.0;
 #pragma unroll 1
   for (int i = 0; i < N; ++i) tr += A[i * N + i];
@@ -216,7 +220,7 @@ __device__ void smallest_eigvec_spd(double* A, double* x) {
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix.  A is destroyed (diagonal = eigenvalues),
 // V (row-major, columns = eigenvectors).
 template <int N>
-__device__ void jacobi_eig(double* A, double* V) {
+MVO_HD void jacobi_eig(double* A, double* V) {
 #pragma unroll 1
   for (int i = 0; i < N; ++i)
 #pragma unroll 1
@@ -262,11 +266,11 @@ __device__ void jacobi_eig(double* A, double* V) {
   }
 }
 
-__device__ __forceinline__ double det3(const double* m) {
+MVO_HD __forceinline__ double det3(const double* m) {
   return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[6] * m[5]) + m[2] * (m[3] * m[7] - m[6] * m[4]);
 }
 
-__device__ __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
+MVO_HD __forceinline__ void mat3_mul(const double* a, const double* b, double* c) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -274,7 +278,7 @@ __device__ __forceinline__ void mat3_mul(const double* a, const double* b, doubl
 }
 
 // Real roots of a0 x^3 + a1 x^2 + a2 x + a3, following cv::solveCubic's case analysis.  Returns the count.
-__device__ inline int solve_cubic(double a0, double a1, double a2, double a3, double* x) {
+MVO_HD inline int solve_cubic(double a0, double a1, double a2, double a3, double* x) {
   int n = 0;
   if (a0 == 0) {
     if (a1 == 0) {
@@ -338,7 +342,7 @@ __device__ inline int solve_cubic(double a0, double a1, double a2, double a3, do
 // solved by safeguarded Newton (bisection fallback).  Returns the count (ascending order).  Roots of even
 // multiplicity (tangencies) are not reported.
 template <int DEG>
-__device__ int real_roots(const double* c, double* roots) {
+MVO_HD int real_roots(const double* c, double* roots) {
   int deg = DEG;
   while (deg > 0 && c[deg] == 0.0) --deg;
   if (deg == 0) return 0;

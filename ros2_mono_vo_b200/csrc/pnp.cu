@@ -1,0 +1,565 @@
+// pnp.cu -- cv::solvePnPRansac as the reference's Tracker calls it, for B200.
+//
+// Replaces /root/reference/src/tracker.cpp:309
+//     cv::solvePnPRansac(points_3d, points_2d, K, d, rvec, tvec, false, 100, 8.0, 0.99, inliers)
+// (SURVEY.md 8f "next #1").  Contract: oracle/pnp_oracle.py, pinned to cv2 4.13.0.
+//
+//   pnp_normalize_kernel   image points -> K-normalised coordinates rounded to float (undistortPoints on float input)
+//   pnp_sample_kernel      the registrator's 5-point samples from the OpenCV MWC stream (no subset check)
+//   pnp_epnp_kernel        thread per hypothesis (FP64): EPnP -- PCA control points with cv::SVD's signs (one-sided
+//                          Jacobi, replayed exactly), 12x12 M^T M eigenvectors, three beta approximations + 5
+//                          Gauss-Newton steps, absolute orientation, best reprojection error
+//   pnp_score_kernel       CTA per hypothesis: float squared reprojection error <= thr^2, warp-reduced counts
+//   pnp_select_kernel      replays the sequential adaptive loop (strict '>' update, shrinking niters), writes the
+//                          inlier mask and the ordered inlier list of the winner
+//   pnp_refine_kernel      solvePnP(inliers, ITERATIVE): DLT initialisation + Levenberg-Marquardt as CvLevMarq runs it
+//                          (<= 20 iterations, eps FLT_EPSILON); one CTA per stream, deterministic block reductions
+#include "context.cuh"
+#include "linalg.cuh"
+#include "pnp_math.cuh"
+#include <float.h>
+#include <algorithm>
+
+namespace mvo {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pnp_normalize_kernel(const float2* __restrict__ img, const int32_t* __restrict__ npts, int max_pts,
+                                     const double* __restrict__ K, double2* __restrict__ xn) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts[b]) return;
+  const double* k = K + b * 9;
+  const float2 p = img[(long long)b * max_pts + i];
+  // undistortPoints with zero distortion on float points: (u - cx) * (1 / fx), result stored as float
+  const float x = (float)(((double)p.x - k[2]) * (1.0 / k[0]));
+  const float y = (float)(((double)p.y - k[5]) * (1.0 / k[4]));
+  xn[(long long)b * max_pts + i] = make_double2((double)x, (double)y);
+}
+
+// the registrator's getSubset without a subset check: distinct indices, a repeated draw is redrawn
+__global__ void pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* __restrict__ npts,
+                                  int iters, int32_t* __restrict__ subsets) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const int n = npts[b];
+  int pos = 0;
+  for (int it = 0; it < iters; ++it) {
+    int idx[kPnpK];
+    int i = 0;
+    while (i < kPnpK && pos < rng_len) {
+      const int v = (int)(rng[pos++] % (uint32_t)n);
+      bool dup = false;
+      for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
+      if (dup) continue;
+      idx[i++] = v;
+    }
+    for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = (i == kPnpK) ? idx[j] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, int max_pts,
+                const int32_t* __restrict__ subsets, int iters, double* __restrict__ models, int32_t* __restrict__ ok) {
+  const int b = blockIdx.y, it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= iters) return;
+  double pw[kPnpK][3], us[kPnpK][2];
+  const int32_t* s = subsets + ((long long)b * iters + it) * kPnpK;
+  for (int i = 0; i < kPnpK; ++i) {
+    const long long o = (long long)b * max_pts + s[i];
+    pw[i][0] = (double)obj[o * 3];
+    pw[i][1] = (double)obj[o * 3 + 1];
+    pw[i][2] = (double)obj[o * 3 + 2];
+    const double2 u = xn[o];
+    us[i][0] = u.x;
+    us[i][1] = u.y;
+  }
+  double R[9], t[3];
+  const bool good = epnp_solve<kPnpK>(pw, us, R, t);
+  double* m = models + ((long long)b * iters + it) * 12;
+  for (int q = 0; q < 9; ++q) m[q] = R[q];
+  for (int q = 0; q < 3; ++q) m[9 + q] = t[q];
+  ok[(long long)b * iters + it] = good ? 1 : 0;
+}
+
+// float squared reprojection error of one point (PnPRansacCallback::computeError)
+__device__ __forceinline__ float pnp_err(const double* m, const double* K, float X, float Y, float Z, float2 uv) {
+  const double xc = m[0] * X + m[1] * Y + m[2] * Z + m[9];
+  const double yc = m[3] * X + m[4] * Y + m[5] * Z + m[10];
+  const double zc = m[6] * X + m[7] * Y + m[8] * Z + m[11];
+  const double iz = zc != 0 ? 1.0 / zc : 1.0;
+  const float pu = (float)(xc * iz * K[0] + K[2]), pv = (float)(yc * iz * K[4] + K[5]);
+  const float dx = __fsub_rn(uv.x, pu), dy = __fsub_rn(uv.y, pv);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+__global__ void __launch_bounds__(256)
+pnp_score_kernel(const float* __restrict__ obj, const float2* __restrict__ img, const int32_t* __restrict__ npts,
+                 int max_pts, const double* __restrict__ K, const double* __restrict__ models,
+                 const int32_t* __restrict__ ok, int iters, float thr2, int32_t* __restrict__ counts) {
+  const int b = blockIdx.y, it = blockIdx.x;
+  const long long h = (long long)b * iters + it;
+  if (!ok[h]) {
+    if (threadIdx.x == 0) counts[h] = -1;
+    return;
+  }
+  __shared__ double m[12], k[9];
+  __shared__ int total;
+  if (threadIdx.x < 12) m[threadIdx.x] = models[h * 12 + threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 41) k[threadIdx.x - 32] = K[b * 9 + threadIdx.x - 32];
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  const int n = npts[b];
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const long long o = (long long)b * max_pts + i;
+    c += pnp_err(m, k, obj[o * 3], obj[o * 3 + 1], obj[o * 3 + 2], img[o]) <= thr2 ? 1 : 0;
+  }
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[h] = total;
+}
+
+// RANSACUpdateNumIters
+__device__ int pnp_update_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmax(p, 0.);
+  p = fmin(p, 1.);
+  ep = fmax(ep, 0.);
+  ep = fmin(ep, 1.);
+  double num = fmax(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
+__global__ void __launch_bounds__(1024)
+pnp_select_kernel(const float* __restrict__ obj, const float2* __restrict__ img, const int32_t* __restrict__ npts,
+                  int max_pts, const double* __restrict__ K, const double* __restrict__ models,
+                  const int32_t* __restrict__ counts, int iters, float thr2, double conf, uint8_t* __restrict__ mask,
+                  int32_t* __restrict__ inl_idx, double* __restrict__ best_model, int32_t* __restrict__ result) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = npts[b];
+  __shared__ int s_best, s_run;
+  __shared__ double m[12], k[9];
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (tid == 0) {
+    int niters = iters, best = -1, best_count = 0, it = 0;
+    for (; it < niters; ++it) {
+      const int c = counts[(long long)b * iters + it];
+      if (c > max(best_count, kPnpK - 1)) {
+        best_count = c;
+        best = it;
+        niters = pnp_update_iters(conf, (double)(n - c) / n, kPnpK, niters);
+      }
+    }
+    s_best = best;
+    s_run = it;
+    s_base = 0;
+  }
+  __syncthreads();
+  const int best = s_best;
+  if (best < 0) {
+    for (int i = tid; i < n; i += 1024) mask[(long long)b * max_pts + i] = 0;
+    if (tid == 0) {
+      result[b * 8 + 0] = 0;
+      result[b * 8 + 1] = s_run;
+      result[b * 8 + 2] = -1;
+    }
+    return;
+  }
+  if (tid < 12) m[tid] = models[((long long)b * iters + best) * 12 + tid];
+  if (tid >= 32 && tid < 41) k[tid - 32] = K[b * 9 + tid - 32];
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const long long o = (long long)b * max_pts + i;
+    const int in = (i < n) ? (pnp_err(m, k, obj[o * 3], obj[o * 3 + 1], obj[o * 3 + 2], img[o]) <= thr2 ? 1 : 0) : 0;
+    if (i < n) mask[o] = (uint8_t)in;
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (in) inl_idx[(long long)b * max_pts + off + __popc(bal & ((1u << lane) - 1))] = i;
+    __syncthreads();
+    if (tid == 0)
+      for (int w = 0; w < 32; ++w) s_base += s_warp[w];
+    __syncthreads();
+  }
+  if (tid < 12) best_model[b * 12 + tid] = m[tid];
+  if (tid == 0) {
+    result[b * 8 + 0] = s_base;
+    result[b * 8 + 1] = s_run;
+    result[b * 8 + 2] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide deterministic sum of NV doubles per thread -> out[NV] (valid in every thread after the call)
+constexpr int kPnpRefThreads = 256;
+template <int NV>
+__device__ void block_sum(const double* v, double* s_part /* [8][NV] */, double* out /* smem [NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int q = 0; q < NV; ++q) {
+    const double s = warp_sum_d(v[q]);
+    if (lane == 0) s_part[warp * NV + q] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < kPnpRefThreads / 32; ++w) s += s_part[w * NV + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// projection residual (and Jacobian rows) of one point for parameters (rvec | tvec)
+__device__ __forceinline__ void pnp_point(const double* R, const double* dR /* 27 or null */, const double* t, const double* K,
+                                          double X, double Y, double Z, double mu, double mv, double* e, double* J /* 12 */) {
+  const double xc = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+  const double yc = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+  const double zc = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+  const double z = zc != 0 ? 1.0 / zc : 1.0;
+  const double x = xc * z, y = yc * z;
+  e[0] = x * K[0] + K[2] - mu;
+  e[1] = y * K[4] + K[5] - mv;
+  if (!J) return;
+  const double fx = K[0], fy = K[4];
+  // d(x, y) / d Xc
+  const double dx[3] = {z, 0, -x * z}, dy[3] = {0, z, -y * z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double* d = dR + 9 * i;
+    const double a = d[0] * X + d[1] * Y + d[2] * Z, bq = d[3] * X + d[4] * Y + d[5] * Z, cq = d[6] * X + d[7] * Y + d[8] * Z;
+    J[i] = fx * (dx[0] * a + dx[2] * cq);
+    J[6 + i] = fy * (dy[1] * bq + dy[2] * cq);
+    J[3 + i] = fx * dx[i];
+    J[9 + i] = fy * dy[i];
+  }
+}
+
+__global__ void __launch_bounds__(kPnpRefThreads)
+pnp_refine_kernel(const float* __restrict__ obj, const float2* __restrict__ img, int max_pts,
+                  const double* __restrict__ K, const int32_t* __restrict__ inl_idx, const double* __restrict__ best_model,
+                  const int32_t* __restrict__ result, double* __restrict__ pose_out /* batch * 8: rvec, tvec, flags */) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = result[b * 8 + 0];
+  if (result[b * 8 + 2] < 0 || n <= 0) return;
+  __shared__ double s_part[(kPnpRefThreads / 32) * 43];
+  __shared__ double s_out[43];
+  __shared__ double s_LtL[144];
+  __shared__ double s_param[6], s_prev[6], s_JtJ[36], s_JtErr[6], s_R[9], s_dR[27], s_k[9];
+  __shared__ double s_prev_norm;
+  __shared__ int s_state, s_lambda, s_iters, s_planar;
+  const int32_t* idx = inl_idx + (long long)b * max_pts;
+  const float* O = obj + (long long)b * max_pts * 3;
+  const float2* I = img + (long long)b * max_pts;
+  if (tid < 9) s_k[tid] = K[b * 9 + tid];
+  __syncthreads();
+  const double ifx = 1.0 / s_k[0], ify = 1.0 / s_k[4], cx = s_k[2], cy = s_k[5];
+
+  // ---- planarity of the inlier object points (cvFindExtrinsicCameraParams2: W[2] / W[1] < 1e-3) ----
+  {
+    double v[9 + 3];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) v[q] = 0;
+    for (int i = tid; i < n; i += kPnpRefThreads) {
+      const int p = idx[i];
+      const double X = O[p * 3], Y = O[p * 3 + 1], Z = O[p * 3 + 2];
+      v[0] += X; v[1] += Y; v[2] += Z;
+      v[3] += X * X; v[4] += X * Y; v[5] += X * Z; v[6] += Y * Y; v[7] += Y * Z; v[8] += Z * Z;
+    }
+    block_sum<12>(v, s_part, s_out);
+    if (tid == 0) {
+      const double mx = s_out[0] / n, my = s_out[1] / n, mz = s_out[2] / n;
+      double MM[9] = {s_out[3] - n * mx * mx, s_out[4] - n * mx * my, s_out[5] - n * mx * mz,
+                      0, s_out[6] - n * my * my, s_out[7] - n * my * mz, 0, 0, s_out[8] - n * mz * mz};
+      MM[3] = MM[1]; MM[6] = MM[2]; MM[7] = MM[5];
+      double V[9];
+      jacobi_eig<3>(MM, V);
+      double w0 = MM[0], w1 = MM[4], w2 = MM[8], tq;
+      if (w0 < w1) { tq = w0; w0 = w1; w1 = tq; }
+      if (w1 < w2) { tq = w1; w1 = w2; w2 = tq; }
+      if (w0 < w1) { tq = w0; w0 = w1; w1 = tq; }
+      s_planar = (n < 6 || !(w2 / w1 >= 1e-3)) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- initial pose ----
+  if (!s_planar) {
+    // DLT: L^T L (12 x 12) of rows [X 0 -xX], [0 X -yX] on normalised points; entry (r, c) per thread
+    if (tid < 144) {
+      const int r = tid / 12, c = tid - r * 12;
+      double s = 0;
+      for (int i = 0; i < n; ++i) {
+        const int p = idx[i];
+        const double Xh[4] = {(double)O[p * 3], (double)O[p * 3 + 1], (double)O[p * 3 + 2], 1.0};
+        const float2 uv = I[p];
+        const double x = ((double)uv.x - cx) * ifx, y = ((double)uv.y - cy) * ify;
+        // row 1: [Xh, 0, -x Xh]; row 2: [0, Xh, -y Xh]
+        const double a1 = r < 4 ? Xh[r] : (r < 8 ? 0.0 : -x * Xh[r - 8]);
+        const double b1 = c < 4 ? Xh[c] : (c < 8 ? 0.0 : -x * Xh[c - 8]);
+        const double a2 = r < 4 ? 0.0 : (r < 8 ? Xh[r - 4] : -y * Xh[r - 8]);
+        const double b2 = c < 4 ? 0.0 : (c < 8 ? Xh[c - 4] : -y * Xh[c - 8]);
+        s += a1 * b1 + a2 * b2;
+      }
+      s_LtL[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double A[144], V[144];
+      for (int q = 0; q < 144; ++q) A[q] = s_LtL[q];
+      jacobi_eig<12>(A, V);
+      int best = 0;
+      for (int q = 1; q < 12; ++q)
+        if (A[q * 13] < A[best * 13]) best = q;
+      double RR[12];
+      for (int q = 0; q < 12; ++q) RR[q] = V[q * 12 + best];
+      double M3[9] = {RR[0], RR[1], RR[2], RR[4], RR[5], RR[6], RR[8], RR[9], RR[10]};
+      if (det3(M3) < 0) {
+        for (int q = 0; q < 12; ++q) RR[q] = -RR[q];
+        for (int q = 0; q < 9; ++q) M3[q] = -M3[q];
+      }
+      double sc = 0;
+      for (int q = 0; q < 9; ++q) sc += M3[q] * M3[q];
+      sc = sqrt(sc);
+      double R[9];
+      polar_rotation(M3, R);
+      const double f = sqrt(3.0) / sc;     // norm(R) / norm(RR[:, :3])
+      rotation_to_rvec(R, s_param);
+      s_param[3] = RR[3] * f;
+      s_param[4] = RR[7] * f;
+      s_param[5] = RR[11] * f;
+    }
+  } else if (tid == 0) {
+    // planar / tiny inlier sets: start from the winning hypothesis (OpenCV starts from a homography decomposition;
+    // the Levenberg-Marquardt minimum is the same)
+    const double* m = best_model + b * 12;
+    rotation_to_rvec(m, s_param);
+    s_param[3] = m[9];
+    s_param[4] = m[10];
+    s_param[5] = m[11];
+  }
+  if (tid == 0) {
+    s_lambda = -3;
+    s_iters = 0;
+    s_state = 0;
+  }
+  __syncthreads();
+
+  // ---- CvLevMarq (updateAlt-free variant used by cvFindExtrinsicCameraParams2) ----
+  for (int guard = 0; guard < 600; ++guard) {
+    const int state = s_state;          // 0: need J and err at param; 1: need err at param (check)
+    if (state == 2) break;
+    if (tid == 0) rvec_to_rotation(s_param, s_R, state == 0 ? s_dR : nullptr);
+    __syncthreads();
+    double v[43];
+#pragma unroll 1
+    for (int q = 0; q < 43; ++q) v[q] = 0;
+    for (int i = tid; i < n; i += kPnpRefThreads) {
+      const int p = idx[i];
+      const float2 uv = I[p];
+      double e[2], J[12];
+      pnp_point(s_R, state == 0 ? s_dR : nullptr, s_param + 3, s_k, O[p * 3], O[p * 3 + 1], O[p * 3 + 2], uv.x, uv.y, e,
+                state == 0 ? J : nullptr);
+      v[42] += e[0] * e[0] + e[1] * e[1];
+      if (state == 0) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          v[36 + a] += J[a] * e[0] + J[6 + a] * e[1];
+#pragma unroll
+          for (int c = a; c < 6; ++c) v[a * 6 + c] += J[a] * J[c] + J[6 + a] * J[6 + c];
+        }
+      }
+    }
+    block_sum<43>(v, s_part, s_out);
+    if (tid == 0) {
+      auto step = [&]() {
+        const double lam = exp(s_lambda * log(10.0));
+        double A[36], rhs[6];
+        for (int a = 0; a < 6; ++a) {
+          for (int c = 0; c < 6; ++c) A[a * 6 + c] = s_JtJ[a * 6 + c];
+          A[a * 7] *= 1.0 + lam;
+          rhs[a] = s_JtErr[a];
+        }
+        lu_solve<6>(A, rhs);
+        for (int a = 0; a < 6; ++a) s_param[a] = s_prev[a] - rhs[a];
+      };
+      const double err_norm = sqrt(s_out[42]);
+      if (state == 0) {
+        for (int a = 0; a < 6; ++a) {
+          for (int c = a; c < 6; ++c) s_JtJ[a * 6 + c] = s_JtJ[c * 6 + a] = s_out[a * 6 + c];
+          s_JtErr[a] = s_out[36 + a];
+          s_prev[a] = s_param[a];
+        }
+        s_prev_norm = err_norm;
+        step();
+        s_state = 1;
+      } else {
+        bool accepted = true;
+        if (err_norm > s_prev_norm) {
+          if (++s_lambda <= 16) {
+            step();
+            accepted = false;
+          }
+        }
+        if (accepted) {
+          s_lambda = max(s_lambda - 1, -16);
+          double dn = 0, pn = 0;
+          for (int a = 0; a < 6; ++a) {
+            dn += (s_param[a] - s_prev[a]) * (s_param[a] - s_prev[a]);
+            pn += s_prev[a] * s_prev[a];
+          }
+          if (++s_iters >= 20 || sqrt(dn) / sqrt(pn) < (double)FLT_EPSILON) s_state = 2;
+          else s_state = 0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 6) pose_out[b * 8 + tid] = s_param[tid];
+  if (tid == 0) pose_out[b * 8 + 6] = (double)s_planar;
+}
+
+// ================================================================================================
+int pnp_prepare(mvo_ctx* c, int max_pts, int iters) {
+  PnpBufs& p = c->pnp;
+  const size_t B = (size_t)c->cfg.batch;
+  if (max_pts > p.max_pts) {
+    const size_t n = B * (size_t)max_pts;
+    MVO_CUDA_TRY(c, p.obj.alloc(n * 3));
+    MVO_CUDA_TRY(c, p.img.alloc(n));
+    MVO_CUDA_TRY(c, p.xn.alloc(n));
+    MVO_CUDA_TRY(c, p.mask.alloc(n));
+    MVO_CUDA_TRY(c, p.inl_idx.alloc(n));
+    p.max_pts = max_pts;
+  }
+  if (iters > p.cap_iters) {
+    const size_t n = B * (size_t)iters;
+    MVO_CUDA_TRY(c, p.subsets.alloc(n * kPnpK));
+    MVO_CUDA_TRY(c, p.models.alloc(n * 12));
+    MVO_CUDA_TRY(c, p.ok.alloc(n));
+    MVO_CUDA_TRY(c, p.counts.alloc(n));
+    p.cap_iters = iters;
+  }
+  MVO_CUDA_TRY(c, p.npts.alloc(B));
+  MVO_CUDA_TRY(c, p.K.alloc(B * 9));
+  MVO_CUDA_TRY(c, p.best_model.alloc(B * 12));
+  MVO_CUDA_TRY(c, p.result.alloc(B * 8));
+  MVO_CUDA_TRY(c, p.pose_out.alloc(B * 8));
+  return MVO_OK;
+}
+
+// points in p.obj / p.img, counts in p.npts, K in p.K
+int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
+  PnpBufs& p = c->pnp;
+  RansacBufs& r = c->rs;
+  const int B = c->cfg.batch;
+  const float thr2 = (float)(reproj_err * reproj_err);
+  dim3 gn((p.max_pts + 255) / 256, B);
+  pnp_normalize_kernel<<<gn, 256, 0, c->stream>>>(p.img.p, p.npts.p, p.max_pts, p.K.p, p.xn.p);
+  pnp_sample_kernel<<<B, 32, 0, c->stream>>>(r.rng.p, r.rng_len, p.npts.p, iters, p.subsets.p);
+  dim3 ge((iters + 31) / 32, B);
+  pnp_epnp_kernel<<<ge, 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
+  dim3 gs(iters, B);
+  pnp_score_kernel<<<gs, 256, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.ok.p, iters,
+                                             thr2, p.counts.p);
+  pnp_select_kernel<<<B, 1024, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.counts.p,
+                                              iters, thr2, conf, p.mask.p, p.inl_idx.p, p.best_model.p, p.result.p);
+  pnp_refine_kernel<<<B, kPnpRefThreads, 0, c->stream>>>(p.obj.p, p.img.p, p.max_pts, p.K.p, p.inl_idx.p, p.best_model.p,
+                                                        p.result.p, p.pose_out.p);
+  c->launches += 6;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
+}  // namespace mvo
+
+using namespace mvo;
+
+extern "C" int mvo_solve_pnp_ransac(mvo_ctx* c, const float* obj_xyz, const float* img_xy, int n, const double* K,
+                                    const double* dist, int n_dist, int iterations, double reproj_err, double confidence,
+                                    double* rvec, double* tvec, int32_t* inliers, int* n_inliers) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!obj_xyz || !img_xy || !K || !rvec || !tvec || n < 0 || iterations < 1 || iterations > 4096) {
+    c->set_error("mvo_solve_pnp_ransac: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  for (int i = 0; dist && i < n_dist; ++i)
+    if (dist[i] != 0.0) {
+      c->set_error("mvo_solve_pnp_ransac: non-zero distortion coefficients are not implemented (rectified images only)");
+      return MVO_ERR_UNSUPPORTED;
+    }
+  if (n < 6) {
+    c->set_error("mvo_solve_pnp_ransac: fewer than 6 correspondences (OpenCV switches to P3P / a direct solve)");
+    return n < 4 ? MVO_ERR_DEGENERATE : MVO_ERR_UNSUPPORTED;
+  }
+  if (c->cfg.batch != 1) {
+    c->set_error("the single-call geometry API needs a batch==1 context");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  int rc = ransac_prepare(c, std::max(c->rs.max_pts, 64), std::max(c->rs.cap_iters, 1));   // the RNG table lives there
+  if (rc) return rc;
+  rc = pnp_prepare(c, std::max(n, c->pnp.max_pts), std::max(iterations, c->pnp.cap_iters));
+  if (rc) return rc;
+  PnpBufs& p = c->pnp;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(p.obj.p, obj_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(p.img.p, img_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(p.npts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(p.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+  rc = pnp_run(c, iterations, reproj_err, confidence);
+  if (rc) return rc;
+  int res[8];
+  double pose[8];
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(res, p.result.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(pose, p.pose_out.p, 64, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (n_inliers) *n_inliers = res[0];
+  c->last_ransac_iters = res[1];
+  if (res[2] < 0) {
+    c->set_error("solvePnPRansac found no model");
+    return MVO_ERR_DEGENERATE;
+  }
+  if (inliers && res[0] > 0) {
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(inliers, p.inl_idx.p, (size_t)res[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  for (int i = 0; i < 3; ++i) {
+    rvec[i] = pose[i];
+    tvec[i] = pose[3 + i];
+  }
+  return MVO_OK;
+}
+
+/* parity hook: the hypotheses of the last mvo_solve_pnp_ransac call (stream 0): 5 sample indices, R|t (12 doubles)
+ * and inlier count (-1: solver failed) per iteration */
+extern "C" int mvo_pnp_get_hypotheses(mvo_ctx* c, int iterations, int32_t* subsets, double* models, int32_t* counts) {
+  if (!c || iterations < 1 || iterations > c->pnp.cap_iters) return MVO_ERR_INVALID;
+  PnpBufs& p = c->pnp;
+  if (subsets) MVO_CUDA_TRY(c, cudaMemcpyAsync(subsets, p.subsets.p, (size_t)iterations * kPnpK * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (models) MVO_CUDA_TRY(c, cudaMemcpyAsync(models, p.models.p, (size_t)iterations * 96, cudaMemcpyDeviceToHost, c->stream));
+  if (counts) MVO_CUDA_TRY(c, cudaMemcpyAsync(counts, p.counts.p, (size_t)iterations * 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MVO_OK;
+}
+
+/* cv::Rodrigues(rvec, R): src/tracker.cpp:315 -- host-side 3x3, no device work */
+extern "C" int mvo_rodrigues(const double* rvec, double* R) {
+  if (!rvec || !R) return MVO_ERR_INVALID;
+  const double theta = sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2]);
+  if (theta < DBL_EPSILON) {
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return MVO_OK;
+  }
+  const double c = cos(theta), s = sin(theta), c1 = 1. - c, it = 1. / theta;
+  const double k[3] = {rvec[0] * it, rvec[1] * it, rvec[2] * it};
+  const double rrt[9] = {k[0] * k[0], k[0] * k[1], k[0] * k[2], k[0] * k[1], k[1] * k[1], k[1] * k[2], k[0] * k[2], k[1] * k[2], k[2] * k[2]};
+  const double rx[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+  for (int i = 0; i < 9; ++i) R[i] = c * ((i % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[i] + s * rx[i];
+  return MVO_OK;
+}

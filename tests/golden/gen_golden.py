@@ -123,6 +123,32 @@ def gen_lk_bgr():
     np.savez_compressed(os.path.join(HERE, "lk_bgr.npz"), **out)
 
 
+PNP_CASES = (("easy", 2000, 1, 0.5, 0.05, False), ("outl30", 2000, 2, 1.0, 0.30, False), ("outl50", 500, 3, 0.3, 0.50, False),
+             ("noisy", 100, 4, 2.0, 0.20, False), ("few", 30, 5, 0.5, 0.10, False), ("c3", 5000, 6, 0.7, 0.15, False))
+
+
+def gen_pnp():
+    """cv::solvePnPRansac with the reference's arguments (src/tracker.cpp:309): 100 iterations, 8 px, 0.99."""
+    out = {}
+    for tag, n, seed, noise, outl, planar in PNP_CASES:
+        obj, img, K, _, _ = synth.pnp_scene(n, seed, noise, outl, planar)
+        ok, r, t, inl = cv2.solvePnPRansac(obj, img, K, None, None, None, False, 100, 8.0, 0.99)
+        out.update({f"{tag}_args": np.array([n, seed, noise, outl, int(planar)], np.float64), f"{tag}_sha": sha(np.concatenate([obj.ravel(), img.ravel()])),
+                    f"{tag}_ok": ok, f"{tag}_rvec": r.ravel(), f"{tag}_tvec": t.ravel(), f"{tag}_inliers": inl.ravel().astype(np.int32)})
+        print("pnp", tag, ok, len(inl))
+    # minimal solver + refinement vectors
+    obj, img, K, _, _ = synth.pnp_scene(400, 9, 0.5, 0.0)
+    rng = np.random.default_rng(0)
+    i6 = np.array([rng.choice(400, 6, replace=False) for _ in range(8)])
+    out["hyp_i6"] = i6
+    out["hyp_epnp"] = np.array([np.concatenate([x.ravel() for x in cv2.solvePnP(obj[i], img[i], K, None, flags=cv2.SOLVEPNP_EPNP)[1:]])
+                                for i in i6])
+    ok, r, t = cv2.solvePnP(obj, img, K, None, flags=cv2.SOLVEPNP_ITERATIVE)
+    out["iter_rt"] = np.concatenate([r.ravel(), t.ravel()])
+    out["cv2_version"] = cv2.__version__
+    np.savez_compressed(os.path.join(HERE, "pnp.npz"), **out)
+
+
 def gen_ransac():
     """cv2 outputs at the reference's RANSAC call sites (src/initializer.cpp:82,87,228,236,125)."""
     K = synth.KITTI_K
@@ -168,6 +194,7 @@ if __name__ == "__main__":
     gen_ransac()
     gen_lk()
     gen_lk_bgr()
+    gen_pnp()
     gen_orb("orb_small.npz", 240, 320, 3, 300, True)
     gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
     gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)
