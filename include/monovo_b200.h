@@ -199,6 +199,13 @@ typedef struct mvo_frame_result {
 
 MVO_API int mvo_group_step(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride,
                            int images_on_device, const double K[9], mvo_frame_result* results);
+/* Pipelined form of mvo_group_step: submit enqueues the upload (copy stream, double-buffered staging: pass PINNED host
+ * frames) and the kernels of one step and returns at once; collect waits for the OLDEST submitted step and returns its
+ * results.  Up to two steps may be in flight, so the H2D copy of step t+1 overlaps the kernels of step t.
+ * mvo_stage_ms reports the most recently enqueued step and is only meaningful when nothing else is in flight. */
+MVO_API int mvo_group_submit(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride, int images_on_device,
+                             const double K[9]);
+MVO_API int mvo_group_collect(mvo_ctx* ctx, mvo_frame_result* results);
 /* forget the previous frame of every stream (the next step only extracts features) */
 MVO_API int mvo_group_reset(mvo_ctx* ctx);
 /* per-stage device time (ms) of the last mvo_group_step, measured with CUDA events on the ctx stream.

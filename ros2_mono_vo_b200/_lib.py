@@ -71,6 +71,8 @@ SIGNATURES = {
     "mvo_pnp_get_hypotheses": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "mvo_score_hypotheses": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int, _vp, _vp, _vp]),
     "mvo_group_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "mvo_group_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "mvo_group_collect": (C.c_int, [_vp, _vp]),
     "mvo_group_reset": (C.c_int, [_vp]),
     "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
 }

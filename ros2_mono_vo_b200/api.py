@@ -151,6 +151,24 @@ class Context:
             self._check(self.lib.mvo_group_step(self.h, C.c_void_p(device_ptr), w, h, w, 1, _ptr(Kp), _ptr(res)))
         return res
 
+    def group_submit(self, images: np.ndarray, K, device_ptr: int | None = None, shape=None):
+        """Pipelined group_step: enqueue one step on (pinned) host frames -- or frames resident in HBM (device_ptr +
+        shape=(h, w)) -- and return at once (<= 2 in flight)."""
+        Kp = np.ascontiguousarray(K, np.float64).reshape(9)
+        if device_ptr is not None:
+            h, w = shape
+            self._check(self.lib.mvo_group_submit(self.h, C.c_void_p(device_ptr), w, h, w, 1, _ptr(Kp)))
+            return
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.shape[0] == self.batch and images.strides[2] == 1
+        h, w = images.shape[1:]
+        self._check(self.lib.mvo_group_submit(self.h, _ptr(images), w, h, images.strides[1], 0, _ptr(Kp)))
+
+    def group_collect(self):
+        """Results of the oldest submitted step."""
+        res = np.zeros(self.batch, RESULT_DTYPE)
+        self._check(self.lib.mvo_group_collect(self.h, _ptr(res)))
+        return res
+
     def group_reset(self):
         self._check(self.lib.mvo_group_reset(self.h))
 

@@ -71,6 +71,12 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
   }
   c->main_stream = c->stream;
   for (auto& st : c->aux_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  for (auto& sl : c->slots) {
+    cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.ev_free, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
+  }
   for (auto& ev : c->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto& ev : c->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto& t : c->timers) {
@@ -91,6 +97,18 @@ void mvo_destroy(mvo_ctx* c) {
       cudaStreamSynchronize(st);
       cudaStreamDestroy(st);
     }
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  for (auto& sl : c->slots) {
+    if (sl.ev_up) cudaEventDestroy(sl.ev_up);
+    if (sl.ev_free) cudaEventDestroy(sl.ev_free);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    sl.stage.release();
+    sl.h_res.release();
+    sl.h_flags.release();
+  }
   for (auto& ev : c->ev_fork)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_join)

@@ -84,6 +84,14 @@ struct PnpBufs {
   }
 };
 
+// one in-flight group step (mvo_group_submit / mvo_group_collect keep up to two)
+struct GroupSlot {
+  mvo::DevBuf<uint8_t> stage;                 // batch * h * w staged host frames
+  mvo::PinBuf<mvo_frame_result> h_res;        // pinned result records
+  mvo::PinBuf<int32_t> h_flags;
+  cudaEvent_t ev_up = nullptr, ev_free = nullptr, ev_done = nullptr;
+};
+
 struct mvo_ctx {
   mvo_config cfg{};
   cudaStream_t stream = nullptr;     // the stream host code currently issues on (main stream, or an aux stream inside a fork)
@@ -91,6 +99,10 @@ struct mvo_ctx {
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // group step: F, E(+pose), kNN run beside H
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
   bool own_stream = false;
+  static constexpr int kSlots = 2;
+  cudaStream_t copy_stream = nullptr;  // H2D of staged frames
+  GroupSlot slots[kSlots];
+  int q_head = 0, q_count = 0;         // ring of submitted, not yet collected steps
   std::string err;
   uint64_t launches = 0;
 

@@ -130,6 +130,22 @@ __global__ void gather_results_kernel(const int32_t* kp_count, const int32_t* nm
   out[b] = r;
 }
 
+// staged frames (batch x h rows of `spitch` bytes) -> level 0 of every stream's ORB pyramid, 16 bytes per thread
+__global__ void __launch_bounds__(256)
+unpack_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long src_frame_stride, uint8_t* __restrict__ dst,
+                     int dpitch, long long dst_frame_stride, int w, int h) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (x >= w) return;
+  const uint8_t* s = src + (long long)b * src_frame_stride + (long long)y * spitch + x;
+  uint8_t* d = dst + (long long)b * dst_frame_stride + (long long)y * dpitch + x;   // 16-byte aligned (pitch % 128 == 0)
+  uint8_t v[16];
+  const int nb = min(16, w - x);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = i < nb ? s[i] : 0;
+  *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+}
+
 __global__ void copy_i32_strided_kernel(const int32_t* src, int stride, int32_t* dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i * stride];
@@ -148,10 +164,10 @@ using namespace mvo;
 
 extern "C" {
 
-int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
-                   mvo_frame_result* results) {
+static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
+                         int slot) {
   if (!c) return MVO_ERR_INVALID;
-  if (!images || !K || !results || stride < w) {
+  if (!images || !K || stride < w) {
     c->set_error("mvo_group_step: bad argument");
     return MVO_ERR_INVALID;
   }
@@ -201,8 +217,33 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
   STAGE_BEG(c, ST_TOTAL);
   // ---- ORB ----
   STAGE_BEG(c, ST_ORB);
-  rc = orb_upload(c, images, w, h, stride, 1, images_on_device);
-  if (rc) return rc;
+  {
+    // frames -> level 0 of the ORB pyramids.  Host frames go through a double-buffered staging area on the copy
+    // stream (one DMA for the whole group), so the upload of step t+1 overlaps the kernels of step t.
+    const uint8_t* src = images;
+    int spitch = stride;
+    long long sstride = (long long)h * stride;
+    if (!images_on_device) {
+      GroupSlot& sl = c->slots[slot];
+      MVO_CUDA_TRY(c, sl.stage.alloc((size_t)B * h * w));
+      cudaStreamWaitEvent(c->copy_stream, sl.ev_free, 0);
+      if (stride == w)   // contiguous frames: one flat DMA (a 2-D copy of 1241-byte rows runs far below PCIe speed)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.stage.p, images, (size_t)B * h * w, cudaMemcpyHostToDevice, c->copy_stream));
+      else
+        MVO_CUDA_TRY(c, cudaMemcpy2DAsync(sl.stage.p, w, images, stride, w, (size_t)B * h, cudaMemcpyHostToDevice,
+                                          c->copy_stream));
+      cudaEventRecord(sl.ev_up, c->copy_stream);
+      cudaStreamWaitEvent(c->main_stream, sl.ev_up, 0);
+      src = sl.stage.p;
+      spitch = w;
+      sstride = (long long)h * w;
+    }
+    const LevelGeom& l0 = g.lv[0];
+    dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
+    unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride, w, h);
+    c->launches++;
+    if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
+  }
   rc = orb_run_detect(c, true);
   if (rc) return rc;
   STAGE_END(c, ST_ORB);
@@ -297,23 +338,35 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
                                                                  nullptr, nullptr, nullptr, 0, c->d_results.p, B);
     c->launches++;
   }
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(results, c->d_results.p, (size_t)B * sizeof(mvo_frame_result), cudaMemcpyDeviceToHost,
-                                  c->stream));
-  if (c->h_stage.n < (size_t)B * 4) MVO_CUDA_TRY(c, c->h_stage.alloc((size_t)B * 4 + 4096));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->h_stage.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-  STAGE_END(c, ST_TOTAL);
+  {
+    GroupSlot& sl = c->slots[slot];
+    MVO_CUDA_TRY(c, sl.h_res.alloc(B));
+    MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_res.p, c->d_results.p, (size_t)B * sizeof(mvo_frame_result), cudaMemcpyDeviceToHost,
+                                    c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    STAGE_END(c, ST_TOTAL);
+    cudaEventRecord(sl.ev_done, c->main_stream);
+  }
   MVO_CUDA_TRY(c, cudaGetLastError());
-  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  // new frame becomes the previous one
+  // new frame becomes the previous one (host-side bookkeeping: the enqueued kernels already hold their pointers)
   std::swap(c->kps, c->prev_kps);
   std::swap(c->kp_xy, c->prev_kp_xy);
   std::swap(c->desc, c->prev_desc);
   std::swap(c->kp_count, c->prev_kp_count);
   c->lk_cur ^= 1;
   c->have_prev = true;
-  // capacity / overflow flags
+  return MVO_OK;
+}
+
+// wait for the step enqueued in `slot` and hand its results out
+static int group_finish(mvo_ctx* c, int slot, mvo_frame_result* results) {
+  GroupSlot& sl = c->slots[slot];
+  const int B = c->cfg.batch;
+  MVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_done));
+  memcpy(results, sl.h_res.p, (size_t)B * sizeof(mvo_frame_result));
   int flags0 = 0;
-  for (int b = 0; b < B; ++b) flags0 |= reinterpret_cast<const int*>(c->h_stage.p)[b];
+  for (int b = 0; b < B; ++b) flags0 |= sl.h_flags.p[b];
   if (flags0 & 1) {
     c->set_error("FAST candidate list overflow");
     return MVO_ERR_CAPACITY;
@@ -321,8 +374,53 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
   return MVO_OK;
 }
 
+int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
+                   mvo_frame_result* results) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!results) {
+    c->set_error("mvo_group_step: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  if (c->q_count != 0) {
+    c->set_error("mvo_group_step: submitted steps are still in flight (mvo_group_collect them first)");
+    return MVO_ERR_INVALID;
+  }
+  int rc = group_enqueue(c, images, w, h, stride, images_on_device, K, 0);
+  if (rc) return rc;
+  return group_finish(c, 0, results);
+}
+
+int mvo_group_submit(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K) {
+  if (!c) return MVO_ERR_INVALID;
+  if (c->q_count >= mvo_ctx::kSlots) {
+    c->set_error("mvo_group_submit: two steps are already in flight");
+    return MVO_ERR_CAPACITY;
+  }
+  const int slot = (c->q_head + c->q_count) % mvo_ctx::kSlots;
+  int rc = group_enqueue(c, images, w, h, stride, images_on_device, K, slot);
+  if (rc) return rc;
+  c->q_count++;
+  return MVO_OK;
+}
+
+int mvo_group_collect(mvo_ctx* c, mvo_frame_result* results) {
+  if (!c) return MVO_ERR_INVALID;
+  if (!results || c->q_count == 0) {
+    c->set_error("mvo_group_collect: nothing in flight");
+    return MVO_ERR_INVALID;
+  }
+  const int slot = c->q_head;
+  c->q_head = (c->q_head + 1) % mvo_ctx::kSlots;
+  c->q_count--;
+  return group_finish(c, slot, results);
+}
+
 int mvo_group_reset(mvo_ctx* c) {
   if (!c) return MVO_ERR_INVALID;
+  if (c->q_count != 0) {
+    c->set_error("mvo_group_reset: submitted steps are still in flight");
+    return MVO_ERR_INVALID;
+  }
   c->have_prev = false;
   return MVO_OK;
 }

@@ -85,3 +85,35 @@ def test_group_step_device_resident_input():
         assert np.array_equal(ra, rb)
     a.close()
     b.close()
+
+
+def test_group_submit_collect_equals_step():
+    """The pipelined form (two steps in flight, staged double-buffered uploads) returns the same records."""
+    import torch
+    from ros2_mono_vo_b200 import Context
+    from ros2_mono_vo_b200.api import MvoError
+    h, w, n, batch, nframes = 240, 320, 300, 3, 6
+    seqs = [synth.synth_sequence(h, w, s + 10, nframes) for s in range(batch)]
+    K = seqs[0][1]
+    frames = torch.empty((nframes, batch, h, w), dtype=torch.uint8).pin_memory()
+    for t in range(nframes):
+        for s in range(batch):
+            frames[t, s] = torch.from_numpy(seqs[s][0][t])
+    fn = frames.numpy()
+    a = Context(w, h, nfeatures=n, batch=batch)
+    want = [a.group_step(fn[t], K) for t in range(nframes)]
+    b = Context(w, h, nfeatures=n, batch=batch)
+    got = []
+    b.group_submit(fn[0], K)
+    for t in range(1, nframes):
+        b.group_submit(fn[t], K)
+        got.append(b.group_collect())
+    with pytest.raises(MvoError):
+        b.group_step(fn[0], K)            # a step is still in flight
+    got.append(b.group_collect())
+    with pytest.raises(MvoError):
+        b.group_collect()                 # nothing left
+    for t in range(nframes):
+        assert np.array_equal(got[t], want[t]), t
+    a.close()
+    b.close()
