@@ -70,7 +70,14 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
     c->own_stream = true;
   }
   c->main_stream = c->stream;
-  for (auto& st : c->aux_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  {
+    // the model searches (F, E, H + tail) are chains of small latency-bound kernels: with the highest priority their
+    // CTAs are placed first while the next step's ORB / LK kernels (main stream) fill the rest of the GPU
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int k = 0; k < 4; ++k)
+      cudaStreamCreateWithPriority(&c->aux_stream[k], cudaStreamNonBlocking, k == 2 ? prio_lo : prio_hi);
+  }
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   for (auto& sl : c->slots) {
     cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming);
@@ -79,6 +86,7 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
   }
   for (auto& ev : c->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto& ev : c->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming);
   for (auto& t : c->timers) {
     cudaEventCreate(&t.beg);
     cudaEventCreate(&t.end);
@@ -113,6 +121,7 @@ void mvo_destroy(mvo_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_join)
     if (ev) cudaEventDestroy(ev);
+  if (c->ev_tail) cudaEventDestroy(c->ev_tail);
   c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
   c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();

@@ -96,8 +96,9 @@ struct mvo_ctx {
   mvo_config cfg{};
   cudaStream_t stream = nullptr;     // the stream host code currently issues on (main stream, or an aux stream inside a fork)
   cudaStream_t main_stream = nullptr;
-  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // group step: F, E(+pose), kNN run beside H
+  cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // group step: F, E(+pose), kNN, H + tail
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_tail = nullptr;       // all model searches + the result gather of the latest enqueued step are done
   bool own_stream = false;
   static constexpr int kSlots = 2;
   cudaStream_t copy_stream = nullptr;  // H2D of staged frames

@@ -244,8 +244,16 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     c->launches++;
     if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
   }
+  // the keypoint / descriptor buffers ORB is about to fill were the previous step's "prev" set: its kNN must be done
+  cudaStreamWaitEvent(c->main_stream, c->ev_join[2], 0);
   rc = orb_run_detect(c, true);
   if (rc) return rc;
+  {
+    GroupSlot& sl = c->slots[slot];
+    MVO_CUDA_TRY(c, sl.h_res.alloc(B));
+    MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
   STAGE_END(c, ST_ORB);
   cudaEventRecord(c->ev_fork[0], c->main_stream);
 
@@ -253,6 +261,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   if (c->have_prev) {
     // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
     Fork f(c, c->aux_stream[2], 0, c->ev_fork[0]);
+    cudaStreamWaitEvent(c->stream, c->ev_tail, 0);   // the previous step's gather still reads the match counters
     STAGE_BEG(c, ST_KNN);
     rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
     if (rc) return rc;
@@ -266,6 +275,9 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   if (c->have_prev) {
     rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
     if (rc) return rc;
+    // the correspondence buffers feed the model searches of the previous step until its tail is done; from here on
+    // this step's ORB + LK have overlapped them (software pipelining across the two steps in flight)
+    cudaStreamWaitEvent(c->main_stream, c->ev_tail, 0);
     lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
                                                  c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
     c->launches++;
@@ -322,31 +334,35 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       STAGE_END(c, ST_TRI);
       cudaEventRecord(c->ev_join[1], c->stream);
     }
-    // ---- H RANSAC (thr 1.0), lane 0, main stream ----
-    STAGE_BEG(c, ST_H);
-    rc = ransac_find(c, MVO_MODEL_H, 0.995);
-    if (rc) return rc;
-    copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_h, B);
-    c->launches++;
-    STAGE_END(c, ST_H);
-    for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(c->main_stream, c->ev_join[k], 0);
-    gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f,
-                                                     r.lane[2].result.p, ntri, r.pose.p, 1, c->d_results.p, B);
-    c->launches++;
+    {
+      // ---- H RANSAC (thr 1.0), lane 0, then the join of all searches and the result gather: tail stream ----
+      Fork f(c, c->aux_stream[3], 0, c->ev_fork[1]);
+      STAGE_BEG(c, ST_H);
+      rc = ransac_find(c, MVO_MODEL_H, 0.995);
+      if (rc) return rc;
+      copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_h, B);
+      c->launches++;
+      STAGE_END(c, ST_H);
+      for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(c->stream, c->ev_join[k], 0);
+      gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f,
+                                                       r.lane[2].result.p, ntri, r.pose.p, 1, c->d_results.p, B);
+      c->launches++;
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(c->slots[slot].h_res.p, c->d_results.p, (size_t)B * sizeof(mvo_frame_result),
+                                      cudaMemcpyDeviceToHost, c->stream));
+      STAGE_END(c, ST_TOTAL);
+      cudaEventRecord(c->ev_tail, c->stream);
+      cudaEventRecord(c->slots[slot].ev_done, c->stream);
+    }
   } else {
+    Fork f(c, c->aux_stream[3], 0, c->ev_fork[0]);
     gather_results_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(c->kp_count.p, nullptr, nullptr, nullptr, nullptr,
                                                                  nullptr, nullptr, nullptr, 0, c->d_results.p, B);
     c->launches++;
-  }
-  {
-    GroupSlot& sl = c->slots[slot];
-    MVO_CUDA_TRY(c, sl.h_res.alloc(B));
-    MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_res.p, c->d_results.p, (size_t)B * sizeof(mvo_frame_result), cudaMemcpyDeviceToHost,
-                                    c->stream));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->slots[slot].h_res.p, c->d_results.p, (size_t)B * sizeof(mvo_frame_result),
+                                    cudaMemcpyDeviceToHost, c->stream));
     STAGE_END(c, ST_TOTAL);
-    cudaEventRecord(sl.ev_done, c->main_stream);
+    cudaEventRecord(c->ev_tail, c->stream);
+    cudaEventRecord(c->slots[slot].ev_done, c->stream);
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
   // new frame becomes the previous one (host-side bookkeeping: the enqueued kernels already hold their pointers)

@@ -266,6 +266,56 @@ MVO_HD void jacobi_eig(double* A, double* V) {
   }
 }
 
+// The same cyclic Jacobi, fully unrolled for small N: every index is a compile-time constant after unrolling, so A and
+// V live in registers instead of local memory (the per-point 4 x 4 triangulation problems run this 256 K times a step).
+template <int N>
+MVO_HD __forceinline__ void jacobi_eig_reg(double* A, double* V) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      diag += A[i * N + i] * A[i * N + i];
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+    }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p * N + q];
+        if (apq != 0.0) {
+          const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const double akp = A[k * N + p], akq = A[k * N + q];
+            A[k * N + p] = c * akp - s * akq;
+            A[k * N + q] = s * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const double apk = A[p * N + k], aqk = A[q * N + k];
+            A[p * N + k] = c * apk - s * aqk;
+            A[q * N + k] = s * apk + c * aqk;
+          }
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const double vkp = V[k * N + p], vkq = V[k * N + q];
+            V[k * N + p] = c * vkp - s * vkq;
+            V[k * N + q] = s * vkp + c * vkq;
+          }
+        }
+      }
+  }
+}
+
 MVO_HD __forceinline__ double det3(const double* m) {
   return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[6] * m[5]) + m[2] * (m[3] * m[7] - m[6] * m[4]);
 }

@@ -32,13 +32,18 @@ __device__ __forceinline__ void triangulate_one(const double* P0, const double* 
       S[i * 4 + j] = s;
       S[j * 4 + i] = s;
     }
-  jacobi_eig<4>(S, V);
-  int kmin = 0;
+  jacobi_eig_reg<4>(S, V);
+  // eigenvector of the smallest eigenvalue, selected without dynamic indexing (keeps V in registers)
+  double lmin = S[0];
 #pragma unroll
-  for (int k = 1; k < 4; ++k)
-    if (S[k * 4 + k] < S[kmin * 4 + kmin]) kmin = k;
+  for (int i = 0; i < 4; ++i) X[i] = V[i * 4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) X[i] = V[i * 4 + kmin];
+  for (int k = 1; k < 4; ++k) {
+    const bool less = S[k * 4 + k] < lmin;
+    lmin = less ? S[k * 4 + k] : lmin;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) X[i] = less ? V[i * 4 + k] : X[i];
+  }
 }
 
 __global__ void pose_decompose_kernel(const double* __restrict__ Ein, double* __restrict__ cands) {
