@@ -123,7 +123,7 @@ void mvo_destroy(mvo_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   if (c->ev_tail) cudaEventDestroy(c->ev_tail);
   c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
-  c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->hist.release();
+  c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->cand_sel.release(); c->sel_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();
   c->c2_count.release(); c->kps.release(); c->desc.release(); c->kp_valid.release(); c->kp_count.release();
   c->flags.release(); c->h_stage.release(); c->prev_kps.release(); c->prev_desc.release();

@@ -118,6 +118,8 @@ struct mvo_ctx {
   mvo::DevBuf<uint32_t> cand_xy;      // batch * cand_total : x | y << 16
   mvo::DevBuf<int32_t> cand_score;    // batch * cand_total : FAST score
   mvo::DevBuf<int32_t> cand_count;    // batch * 8
+  mvo::DevBuf<uint32_t> cand_sel;     // batch * cand_total : candidates that survive retainBest(2 n_l)
+  mvo::DevBuf<int32_t> sel_count;     // batch * 8
   mvo::DevBuf<uint32_t> hist;         // batch * 8 * 256 : FAST score histogram
   mvo::DevBuf<unsigned long long> c2_key, c2_key_sorted;  // Harris stage: sort keys
   mvo::DevBuf<float2> c2_ra, c2_ra_sorted;                // (response, angle)

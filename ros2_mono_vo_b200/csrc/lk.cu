@@ -105,27 +105,23 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 }
 __device__ __forceinline__ uint32_t pack_w(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-// Stage the 32x32 J region with top-left (jx0, jy0) as quads: lane = column, 32 independent row loads in flight.
-__device__ __forceinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
-                                           int pitch, int lane) {
+// Stage the 32x32 J region with top-left (jx0, jy0) as quads: lane = column, rows in groups of eight independent
+// loads.  Kept out of line and rolled: the kernel is instruction-cache bound otherwise (ncu: 26 % no-instruction stalls
+// with everything unrolled and inlined at three call sites).
+__device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
+                                        int pitch, int lane) {
+  const bool inside = jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h;
+  const uint8_t* p = J + (inside ? jx0 + lane : safe_reflect(jx0 + lane, w));
   uint32_t pprev = 0;
-  if (jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h) {
-    // region inside the image (the common case): plain strided rows, no border arithmetic
-    const uint8_t* p = J + jy0 * pitch + jx0 + lane;
+#pragma unroll 1
+  for (int r0 = 0; r0 < kJReg; r0 += 8) {
+    uint32_t v[8];
 #pragma unroll
-    for (int r = 0; r < kJReg; ++r) {
-      const uint32_t v = p[r * pitch];
-      const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
-      if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
-      pprev = pr;
-    }
-  } else {
-    const int xj = safe_reflect(jx0 + lane, w);
-#pragma unroll 8
-    for (int r = 0; r < kJReg; ++r) {
-      const uint32_t v = J[safe_reflect(jy0 + r, h) * pitch + xj];
-      const uint32_t pr = v | (__shfl_down_sync(0xffffffffu, v, 1) << 8);
-      if (r > 0) jq[(r - 1) * kJReg + lane] = pprev | (pr << 16);
+    for (int k = 0; k < 8; ++k) v[k] = p[(inside ? jy0 + r0 + k : safe_reflect(jy0 + r0 + k, h)) * pitch];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
+      if (r0 + k > 0) jq[(r0 + k - 1) * kJReg + lane] = pprev | (pr << 16);
       pprev = pr;
     }
   }
@@ -142,54 +138,53 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
   const int xr = safe_reflect(colx, w);
   const bool der_col = lane >= 1 && lane <= kRaw - 2 && colx >= 0 && colx < w;  // derivative column inside the image
   const bool win_col = lane >= 1 && lane <= LKW;                                 // window column c = lane - 1
-  uint32_t v[kRaw];
-  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h) {   // all 32 lanes' columns inside the image
-    const uint8_t* p = I + (iy - 1) * pitch + colx;
-#pragma unroll
-    for (int r = 0; r < kRaw; ++r) v[r] = p[r * pitch];
-  } else {
-#pragma unroll
-    for (int r = 0; r < kRaw; ++r) v[r] = I[safe_reflect(iy - 1 + r, h) * pitch + xr];
-  }
+  const bool inside = ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h;   // all 32 lanes' columns in the image
+  const uint8_t* p = I + (inside ? colx : xr);
   int dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
   uint32_t pair0 = 0, pair1 = 0, pd_prev = 0, pdn_prev = 0;
+  // rows in groups of four independent loads; the walk itself is rolled (code size: see lk_stage_j)
+#pragma unroll 1
+  for (int r0 = 0; r0 < kRaw; r0 += 4) {
+    uint32_t v[4];
 #pragma unroll
-  for (int r = 0; r < kRaw; ++r) {
-    const int c = (int)v[r];
-    const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
-    const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
-    const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
-    if (r >= 2) {
-      const int rr = r - 2;                                  // derivative row, y = iy + rr
+    for (int k = 0; k < 4; ++k) v[k] = p[(inside ? iy - 1 + r0 + k : safe_reflect(iy - 1 + r0 + k, h)) * pitch];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k;
+      const int c = (int)v[k];
+      const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
+      const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
+      const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
+      // derivative row rr = r - 2 (y = iy + rr); meaningful from r = 2 on, harmless before (the results are not stored)
+      const int rr = r - 2;
       const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
       const bool ok = der_col && (iy + rr >= 0) && (iy + rr < h);
       const uint32_t pd = ok ? pack_w(gx, gy) : 0u;
       const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
-      if (rr >= 1) {
-        const int pr = rr - 1;                               // window row
-        const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
-        const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
-        const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
-        const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
-        const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
-        const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
-        if (win_col) {
-          sA11 += vx * vx;
-          sA12 += vx * vy;
-          sA22 += vy * vy;
-          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
-          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
-        }
+      // window row pr = rr - 1
+      const int pr = rr - 1;
+      const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
+      const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
+      const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
+      const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
+      const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
+      const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
+      if (win_col && pr >= 0) {
+        sA11 += vx * vx;
+        sA12 += vx * vy;
+        sA22 += vy * vy;
+        pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
+        pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
       }
       pd_prev = pd;
       pdn_prev = pdn;
+      dx0 = dx1;
+      dx1 = dx2;
+      sm0 = sm1;
+      sm1 = sm2;
+      pair0 = pair1;
+      pair1 = pair2;
     }
-    dx0 = dx1;
-    dx1 = dx2;
-    sm0 = sm1;
-    sm1 = sm2;
-    pair0 = pair1;
-    pair1 = pair2;
   }
 }
 

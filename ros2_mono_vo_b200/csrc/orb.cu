@@ -8,7 +8,9 @@
 //                                  tile (+4 halo) from level l-1 staged in smem with 128-bit loads ->
 //                                  level l store + FAST-9/16 (quick-reject + compacted full score) +
 //                                  3x3 NMS + edge filter + score histogram + 7x7 float blur store.
-//   K2  orb_harris_angle_kernel    warp per surviving candidate (score >= histogram cut): 7x7 Harris
+//   K2a orb_select_kernel          CTA per (level, stream): retainBest(2 n_l) cut from the score histogram (parallel
+//                                  suffix scan) + compaction of the surviving candidates.
+//   K2  orb_harris_angle_kernel    warp per surviving candidate: 7x7 Harris
 //                                  (int32 sums, non-fused FP32) + intensity-centroid angle.
 //   K3  orb_rank_kernel            per level all-pairs rank on a unique 64-bit key -> sorted scatter.
 //   K4  orb_finalize_kernel        retainBest(n_l) cut with ties, cross-level prefix, mvo_keypoint write.
@@ -410,47 +412,72 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
+// K2a: retainBest(2 n_l) by FAST score, one CTA per (level, stream): the cut r = largest score with
+// #(score >= r) >= 2 n_l from the level's score histogram (parallel suffix scan), then the candidates with
+// score >= r (ties kept, as cv::KeyPointsFilter::retainBest) are compacted into a dense list for the Harris kernel.
+constexpr int kSelThreads = 256;
+__global__ void __launch_bounds__(kSelThreads)
+orb_select_kernel(const __grid_constant__ OrbGeom g, const uint32_t* __restrict__ cand_xy,
+                  const int32_t* __restrict__ cand_score, const int32_t* __restrict__ cand_count,
+                  const uint32_t* __restrict__ hist, uint32_t* __restrict__ sel_xy, int32_t* __restrict__ sel_count) {
+  const int level = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cap = g.lv[level].cand_cap, quota = g.lv[level].quota, off = g.lv[level].cand_off;
+  const int count = min(cand_count[b * kLevels + level], cap);
+  __shared__ uint32_t s_warp[kSelThreads / 32];
+  __shared__ int s_thr, s_n;
+  // suffix sums of the histogram: thread t owns score 255 - t, so an inclusive prefix scan over t is the suffix count
+  const uint32_t hv = hist[((long long)b * kLevels + level) * 256 + (255 - tid)];
+  uint32_t incl = hv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) {
+    s_thr = 0;
+    s_n = 0;
+  }
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w2 = 0; w2 < warp; ++w2) base += s_warp[w2];
+  incl += base;
+  const uint32_t k = 2u * (uint32_t)quota;
+  // the first t (largest score) whose suffix count reaches k defines the cut; exactly one thread satisfies this
+  if (count > (int)k && incl >= k && incl - hv < k) s_thr = 255 - tid;
+  __syncthreads();
+  const int thr = s_thr;
+  const long long cbase = (long long)b * g.cand_total + off;
+  for (int i0 = 0; i0 < count; i0 += kSelThreads) {
+    const int i = i0 + tid;
+    const bool keep = i < count && cand_score[cbase + i] >= thr;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_n, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (keep) sel_xy[cbase + wbase + __popc(bal & ((1u << lane) - 1))] = cand_xy[cbase + i];
+  }
+  __syncthreads();
+  if (tid == 0) sel_count[b * kLevels + level] = s_n;
+}
+
 constexpr int kHarrisWarps = 8;
 
 __global__ void __launch_bounds__(kHarrisWarps * 32)
-orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ cand_xy,
-                        const int32_t* __restrict__ cand_score, const int32_t* __restrict__ cand_count,
-                        const uint32_t* __restrict__ hist, unsigned long long* __restrict__ c2_key,
+orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ sel_xy,
+                        const int32_t* __restrict__ sel_count, unsigned long long* __restrict__ c2_key,
                         float2* __restrict__ c2_ra, int32_t* __restrict__ c2_count) {
   const int level = blockIdx.y, b = blockIdx.z;
-  const LevelGeom lv = g.lv[level];
-  __shared__ int s_thr;
-  __shared__ uint32_t s_h[256];
   const int tid = threadIdx.x;
-  const int count = min(cand_count[b * kLevels + level], lv.cand_cap);
+  const int count = sel_count[b * kLevels + level];
   const int warp = tid >> 5, lane = tid & 31;
   if (blockIdx.x * kHarrisWarps >= count) return;
-  // FAST-score cut of retainBest(2 n_l): largest r with #(score >= r) >= 2 n_l; keep score >= r
-  s_h[tid] = hist[((long long)b * kLevels + level) * 256 + tid];
-  __syncthreads();
-  if (tid == 0) {
-    int thr = 0;
-    const int k = 2 * lv.quota;
-    if (count > k) {
-      int acc = 0;
-      for (int r = 255; r >= 0; --r) {
-        acc += s_h[r];
-        if (acc >= k) {
-          thr = r;
-          break;
-        }
-      }
-    }
-    s_thr = thr;
-  }
-  __syncthreads();
-  const uint8_t* img = pyr + (long long)b * g.frame_stride + lv.off;
-  const int pitch = lv.pitch;
-  // grid-stride over this level's candidates: the grid is sized for a typical frame, not for the capacity
+  const int pitch = g.lv[level].pitch, cand_off = g.lv[level].cand_off;
+  const uint8_t* img = pyr + (long long)b * g.frame_stride + g.lv[level].off;
+  // grid-stride over this level's selected candidates: the grid is sized for 2 n_0 plus slack, ties may exceed it
   for (int ci = blockIdx.x * kHarrisWarps + warp; ci < count; ci += gridDim.x * kHarrisWarps) {
-  const long long co = (long long)b * g.cand_total + lv.cand_off + ci;
-  if (cand_score[co] < s_thr) continue;
-  const uint32_t xy = cand_xy[co];
+  const uint32_t xy = sel_xy[(long long)b * g.cand_total + cand_off + ci];
   const int x = xy & 0xffff, y = xy >> 16;
 
   // Harris 7x7 block of Sobel-3 gradients: 49 positions over the 32 lanes (2 rounds)
@@ -507,7 +534,7 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
     const float resp = __fmul_rn(__fsub_rn(t1, t2), s4);
     const float ang = fast_atan2_deg((float)m01, (float)m10);
     const int pos = atomicAdd(c2_count + b * kLevels + level, 1);
-    const long long o = (long long)b * g.cand_total + lv.cand_off + pos;
+    const long long o = (long long)b * g.cand_total + cand_off + pos;
     // ascending key == (response desc, y asc, x asc); -0.f canonicalised so that ties compare equal
     const uint32_t ro = ~float_orderable(__fadd_rn(resp, 0.f));
     c2_key[o] = ((unsigned long long)ro << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
@@ -762,6 +789,8 @@ int orb_prepare(mvo_ctx* c, int w, int h) {
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // xt / yt are stack vectors
   MVO_CUDA_TRY(c, c->cand_xy.alloc(B * g.cand_total));
   MVO_CUDA_TRY(c, c->cand_score.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->cand_sel.alloc(B * g.cand_total));
+  MVO_CUDA_TRY(c, c->sel_count.alloc(B * kLevels));
   MVO_CUDA_TRY(c, c->cand_count.alloc(B * kLevels));
   MVO_CUDA_TRY(c, c->hist.alloc(B * kLevels * 256));
   MVO_CUDA_TRY(c, c->c2_key.alloc(B * g.cand_total));
@@ -876,11 +905,16 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
   int max_cap = 0;
   for (int l = 0; l < kLevels; ++l) max_cap = std::max(max_cap, g.lv[l].cand_cap);
   {
-    // grid-stride kernel: 64 blocks x 8 warps per (level, stream) cover ~512 candidates per pass
-    dim3 grid(std::min(64, (max_cap + kHarrisWarps - 1) / kHarrisWarps), kLevels, g.batch);
-    orb_harris_angle_kernel<<<grid, kHarrisWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->cand_xy.p, c->cand_score.p,
-                                                                      c->cand_count.p, c->hist.p, c->c2_key.p,
-                                                                      c->c2_ra.p, c->c2_count.p);
+    dim3 gsel(kLevels, g.batch);
+    orb_select_kernel<<<gsel, kSelThreads, 0, c->stream>>>(g, c->cand_xy.p, c->cand_score.p, c->cand_count.p, c->hist.p,
+                                                          c->cand_sel.p, c->sel_count.p);
+    c->launches++;
+    // warp per selected candidate; level 0 keeps ~2 n_0 (+ ties): size the grid for that, grid-stride beyond
+    const int want = 2 * g.lv[0].quota + g.lv[0].quota / 4 + 64;
+    dim3 grid(std::min((want + kHarrisWarps - 1) / kHarrisWarps, (max_cap + kHarrisWarps - 1) / kHarrisWarps), kLevels,
+              g.batch);
+    orb_harris_angle_kernel<<<grid, kHarrisWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->cand_sel.p, c->sel_count.p,
+                                                                      c->c2_key.p, c->c2_ra.p, c->c2_count.p);
     c->launches++;
   }
   {
