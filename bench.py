@@ -375,6 +375,22 @@ def main():
         except Exception:
             pass
 
+    # ---- the matching kernel is bound by the integer popc pipe, not by HBM: measured ceiling + live achieved rate ----
+    roofline_knn = None
+    if rank == 0 and stages.get("knn", 0) > 0:
+        try:
+            popc_peak = c1b.measure_popc_peak() if (c1b := Context(64, 64, nfeatures=100, device=local_rank)) else 0.0
+            c1b.close()
+            nq = float(np.mean(res["n_keypoints"]))
+            popc = nq * nq * 8 * S                       # 256-bit descriptors = 8 popc32 per pair
+            ach = popc / (stages["knn"] * 1e-3)
+            roofline_knn = {"kernel": "knn_top2_kernel + knn_finish_kernel", "bound": "integer popc pipe",
+                            "achieved": ach / 1e12, "peak": popc_peak / 1e12, "unit": "Tpopc32/s", "frac": ach / popc_peak,
+                            "peak_source": "measured live (mvo_measure_popc_peak: 8 independent xor+popc chains per thread)",
+                            "algorithmic_popc_per_step": popc, "stage_ms": stages["knn"]}
+        except Exception as e:  # pragma: no cover
+            roofline_knn = {"error": str(e)}
+
     # ---- CPU baseline: the reference's OpenCV path on this box's host cores (rank 0, bounded sample) ----
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -408,6 +424,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_matching": roofline_knn,
             "cpu_baseline": cpu,
             "stages_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
             "orb_match_ms_per_frame": (stages.get("orb", 0) + stages.get("knn", 0)) / S,

@@ -118,6 +118,9 @@ MVO_API int mvo_orb_get_fast(mvo_ctx* ctx, int level, uint32_t* xy, int32_t* sco
  */
 MVO_API int mvo_knn_ratio(mvo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
                           double ratio, mvo_dmatch* out, int* n_out);
+/* measured ceiling of the integer population-count pipe on this GPU (32-bit popc per second): the roofline
+ * denominator of the matching kernel, which is popc-bound, not HBM-bound (bench.py) */
+MVO_API int mvo_measure_popc_peak(mvo_ctx* ctx, double* popc_per_s);
 /* raw top-2 (parity hook): idx/dist are nq x 2, -1 where the train set has fewer than 2 rows */
 MVO_API int mvo_knn2(mvo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt,
                      int32_t* idx, int32_t* dist);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mvo_orb_get_level": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int]),
     "mvo_orb_get_fast": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i32p]),
     "mvo_knn_ratio": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _i32p]),
+    "mvo_measure_popc_peak": (C.c_int, [_vp, _f64p]),
     "mvo_knn2": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "mvo_lk_track": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp]),
     "mvo_find_homography": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, _vp, _vp, _i32p]),

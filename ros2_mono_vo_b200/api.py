@@ -117,6 +117,12 @@ class Context:
         xy, sc = xy[:n.value], sc[:n.value]
         return (xy & 0xffff).astype(np.int32), (xy >> 16).astype(np.int32), sc.copy()
 
+    def measure_popc_peak(self) -> float:
+        """Measured 32-bit popc per second of this GPU (roofline denominator of the matching kernel)."""
+        v = C.c_double()
+        self._check(self.lib.mvo_measure_popc_peak(self.h, C.byref(v)))
+        return float(v.value)
+
     # ---- LK ----------------------------------------------------------------------------------
     def lk_track(self, prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
         prev = np.ascontiguousarray(prev, np.uint8)

@@ -198,3 +198,51 @@ int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_strid
 }
 
 }  // namespace mvo
+
+// ------------------------------------------------------------------------------------------------
+// Measured ceiling of the integer population-count pipe (the bound of knn_top2_kernel): every thread runs eight
+// independent xor + popc chains, grid = 148 SMs x 8 CTAs.  Returns 32-bit popc per second.
+namespace mvo {
+__global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t seed, int iters, uint32_t* out) {
+  uint32_t x = seed ^ (blockIdx.x * 256u + threadIdx.x);
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 += __popc(x ^ a7);
+    a1 += __popc(x ^ a0);
+    a2 += __popc(x ^ a1);
+    a3 += __popc(x ^ a2);
+    a4 += __popc(x ^ a3);
+    a5 += __popc(x ^ a4);
+    a6 += __popc(x ^ a5);
+    a7 += __popc(x ^ a6);
+    x += 0x9e3779b9u;
+  }
+  if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0xdeadbeefu) out[0] = x;   // keep the chains alive
+}
+}  // namespace mvo
+
+extern "C" int mvo_measure_popc_peak(mvo_ctx* c, double* popc_per_s) {
+  if (!c || !popc_per_s) return MVO_ERR_INVALID;
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  MVO_CUDA_TRY(c, c->knn_counts.alloc(4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = 148 * 8, iters = 1 << 14;
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    mvo::popc_peak_kernel<<<blocks, 256, 0, c->stream>>>(0x1234567u + rep, iters, reinterpret_cast<uint32_t*>(c->knn_counts.p));
+    cudaEventRecord(e1, c->stream);
+    MVO_CUDA_TRY(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms > 0) best = std::max(best, (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  c->launches += 4;
+  *popc_per_s = best;
+  return MVO_OK;
+}

@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t bytes_gt_thr(uint32_t d) {
 }
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(kLevelThreads, 4) orb_level_kernel(const LevelArgs a) {
+__global__ void __launch_bounds__(kLevelThreads, 5) orb_level_kernel(const LevelArgs a) {
   __shared__ __align__(16) uint8_t tile[SROWS * TS];
   // scratch: resize staging (source rows + vertical pass, 8.8 fixed point) is dead before the blur row buffer is live
   __shared__ __align__(16) uint8_t scratch[SRC_ROWS_MAX * SRC_COLS_MAX + SROWS * SRC_COLS_MAX * 2];
@@ -229,11 +229,21 @@ __global__ void __launch_bounds__(kLevelThreads, 4) orb_level_kernel(const Level
     __syncthreads();
   }
 
-  // ---- FAST-9/16 ---------------------------------------------------------------------------
+  // ---- FAST-9/16 and the ORB-internal blur, interleaved -------------------------------------------------------
+  // Both only read the finished tile, so their phases share barriers (three instead of seven) and threads that run
+  // out of FAST work pick up blur work:
+  //   A  FAST quick reject (packed, 4 px per thread)        +  blur row pass      -> barrier
+  //   B  full FAST score of the survivor list               +  blur column pass   -> barrier
+  //   C  3x3 NMS + edge filter over the survivor list -> barrier -> D  append to the level's candidate list
+  float* rowbuf = reinterpret_cast<float*>(scratch);  // (TH + 6) x TW floats = 9728 B; the resize staging is dead
+  const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3];
   if (a.do_fast) {
     // phase 1, four pixels per thread: an arc of 9 contains one pixel of every antipodal pair, so a corner needs
-    // |centre - ring| > thr on one of (0, 8) and on one of (4, 12); packed bytes, VABSDIFF4
-    if (tid < kFastCols * kFastLanes) {
+    // |centre - ring| > thr on one of (0, 8) and on one of (4, 12); packed bytes, VABSDIFF4.  A thread keeps the
+    // survivors of its three rows as a 12-bit mask; one warp scan + one shared atomic per warp places them in the
+    // survivor list (per-pixel atomics cost more than the test itself).
+    {
+      const bool active = tid < kFastCols * kFastLanes;
       const int rl = tid / kFastCols, wi = tid - rl * kFastCols;
       const int xl0 = 4 * wi - 4, gx0 = tx0 + xl0;
       const int jlo = max(max(-1 - xl0, kEdge - 1 - gx0), 0), jhi = min(min(TW - xl0, w - kEdge - gx0), 3);
@@ -241,84 +251,55 @@ __global__ void __launch_bounds__(kLevelThreads, 4) orb_level_kernel(const Level
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j >= jlo && j <= jhi) xmask |= 0x80u << (8 * j);
+      if (!active) xmask = 0;
       const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+      uint32_t found = 0;
       if (xmask) {
-        for (int yl = rl - 1; yl <= TH; yl += kFastLanes) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int yl = rl - 1 + k * kFastLanes;
           const int gy = ty0 + yl;
-          if (gy < kEdge - 1 || gy >= h - (kEdge - 1)) continue;
-          const int wq = ((yl + HALO) * TS + TX0 + xl0) >> 2;
-          const uint32_t c = t32[wq];
-          uint32_t m = bytes_gt_thr(__vabsdiffu4(c, t32[wq + 3 * (TS / 4)])) |
-                       bytes_gt_thr(__vabsdiffu4(c, t32[wq - 3 * (TS / 4)]));
-          m &= xmask;
-          if (!m) continue;
-          const uint32_t l = t32[wq - 1], r = t32[wq + 1];
-          const uint32_t p12 = __byte_perm(l, c, 0x4321);   // pixels x-3 .. x
-          const uint32_t p4 = __byte_perm(c, r, 0x6543);    // pixels x+3 .. x+6
-          m &= bytes_gt_thr(__vabsdiffu4(c, p4)) | bytes_gt_thr(__vabsdiffu4(c, p12));
-          while (m) {
-            const int j = (__ffs(m) - 1) >> 3;
-            m &= m - 1;
-            work[atomicAdd(&n_work, 1)] = (uint16_t)((yl + 1) * FW + xl0 + j + 1);
+          if (yl <= TH && gy >= kEdge - 1 && gy < h - (kEdge - 1)) {
+            const int wq = ((yl + HALO) * TS + TX0 + xl0) >> 2;
+            const uint32_t c = t32[wq];
+            uint32_t m = bytes_gt_thr(__vabsdiffu4(c, t32[wq + 3 * (TS / 4)])) |
+                         bytes_gt_thr(__vabsdiffu4(c, t32[wq - 3 * (TS / 4)]));
+            m &= xmask;
+            if (m) {
+              const uint32_t l = t32[wq - 1], r = t32[wq + 1];
+              const uint32_t p12 = __byte_perm(l, c, 0x4321);   // pixels x-3 .. x
+              const uint32_t p4 = __byte_perm(c, r, 0x6543);    // pixels x+3 .. x+6
+              m &= bytes_gt_thr(__vabsdiffu4(c, p4)) | bytes_gt_thr(__vabsdiffu4(c, p12));
+              // bit 7 of byte j -> bit j
+              const uint32_t nib = ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+              found |= nib << (4 * k);
+            }
           }
         }
       }
-    }
-    __syncthreads();
-    // phase 2: full score of the compacted survivors
-    const int nw = n_work;
-    for (int i = tid; i < nw; i += kLevelThreads) {
-      const int p = work[i];
-      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
-      const int best = fast_full_score(tile, (yl + HALO) * TS + TX0 + xl);
-      if (best > kFastThr) score[(yl + 1) * FS + xl + 1] = (uint8_t)(best - 1);
-    }
-    __syncthreads();
-    // phase 3: 3x3 non-max suppression + 31 px edge filter, again over the survivor list only
-    for (int i = tid; i < nw; i += kLevelThreads) {
-      const int p = work[i];
-      const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
-      if (xl < 0 || xl >= TW || yl < 0 || yl >= TH) continue;
-      const int gx = tx0 + xl, gy = ty0 + yl;
-      const uint8_t* s = score + (yl + 1) * FS + xl + 1;
-      const int v = s[0];
-      if (v > 0 && gx >= kEdge && gx < w - kEdge && gy >= kEdge && gy < h - kEdge) {
-        if (v > s[-1] && v > s[1] && v > s[-FS - 1] && v > s[-FS] && v > s[-FS + 1] && v > s[FS - 1] &&
-            v > s[FS] && v > s[FS + 1]) {
-          const int e = atomicAdd(&n_emit, 1);
-          emit_xy[e] = (uint32_t)gx | ((uint32_t)gy << 16);
-          emit_sc[e] = (uint8_t)v;
-          atomicAdd(&hist_s[v], 1u);
-        }
+      const int cnt = __popc(found);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += t;
       }
-    }
-    __syncthreads();
-    const int ne = n_emit;
-    if (ne > 0) {
-      if (tid == 0) emit_base = atomicAdd(a.cand_count + b * kLevels + a.level, ne);
-      __syncthreads();
-      const int base = emit_base;
-      for (int i = tid; i < ne; i += kLevelThreads) {
-        const int pos = base + i;
-        if (pos < a.cand_cap) {
-          const long long o = (long long)b * a.cand_total + a.cand_off + pos;
-          a.cand_xy[o] = emit_xy[i];
-          a.cand_score[o] = emit_sc[i];
-        } else {
-          atomicOr(a.flags + b, 1);
-        }
+      int base = 0;
+      if ((tid & 31) == 31 && incl) base = atomicAdd(&n_work, incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + incl - cnt;
+      while (found) {
+        const int bit = __ffs(found) - 1;
+        found &= found - 1;
+        const int yl = rl - 1 + (bit >> 2) * kFastLanes;
+        work[pos++] = (uint16_t)((yl + 1) * FW + xl0 + (bit & 3) + 1);
       }
-      if (hist_s[tid]) atomicAdd(a.hist + ((long long)b * kLevels + a.level) * 256 + tid, hist_s[tid]);
     }
   }
-
-  // ---- ORB-internal 7x7 sigma-2 blur: float sepFilter, FMA order of OpenCV's AVX2 path -------
   {
-    float* rowbuf = reinterpret_cast<float*>(scratch);  // (TH + 6) x TW floats = 9728 B
-    __syncthreads();                                     // scratch (resize staging) is dead
-    const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3];
+    // blur row pass: float sepFilter, FMA order of OpenCV's AVX2 path; 4 pixels per thread from three aligned words
+    // (the halo already holds REFLECT_101 pixels)
     const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
-    // row pass: 4 pixels per thread from three aligned words (the halo already holds REFLECT_101 pixels)
     for (int i = tid; i < (TH + 6) * (TW / 4); i += kLevelThreads) {
       const int yr = i / (TW / 4), xg = i - yr * (TW / 4);
       const int wq = ((yr + 1) * TS + TX0 + 4 * xg) >> 2;
@@ -337,45 +318,94 @@ __global__ void __launch_bounds__(kLevelThreads, 4) orb_level_kernel(const Level
       float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float s = __fmul_rn(g0, f[j]);
-        s = __fmaf_rn(g1, f[j + 1], s);
-        s = __fmaf_rn(g2, f[j + 2], s);
-        s = __fmaf_rn(g3, f[j + 3], s);
-        s = __fmaf_rn(g2, f[j + 4], s);
-        s = __fmaf_rn(g1, f[j + 5], s);
-        s = __fmaf_rn(g0, f[j + 6], s);
-        o[j] = s;
+        float sacc = __fmul_rn(g0, f[j]);
+        sacc = __fmaf_rn(g1, f[j + 1], sacc);
+        sacc = __fmaf_rn(g2, f[j + 2], sacc);
+        sacc = __fmaf_rn(g3, f[j + 3], sacc);
+        sacc = __fmaf_rn(g2, f[j + 4], sacc);
+        sacc = __fmaf_rn(g1, f[j + 5], sacc);
+        sacc = __fmaf_rn(g0, f[j + 6], sacc);
+        o[j] = sacc;
       }
       reinterpret_cast<float4*>(rowbuf)[i] = make_float4(o[0], o[1], o[2], o[3]);
     }
-    __syncthreads();
-    // column pass: 4 pixels x 4 rows per thread, symmetric taps added first (OpenCV's symmetric column filter)
-    if (tid < (TW / 4) * (TH / 4)) {
-      const int xg = tid & (TW / 4 - 1), yl0 = (tid / (TW / 4)) * 4;
-      const float4* rb = reinterpret_cast<const float4*>(rowbuf) + yl0 * (TW / 4) + xg;
-      float4 r[10];
+  }
+  __syncthreads();   // ---- barrier 1: survivor list and row buffer complete
+
+  const int nw = a.do_fast ? n_work : 0;
+  // phase B: full score of the compacted survivors
+  for (int i = tid; i < nw; i += kLevelThreads) {
+    const int p = work[i];
+    const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
+    const int best = fast_full_score(tile, (yl + HALO) * TS + TX0 + xl);
+    if (best > kFastThr) score[(yl + 1) * FS + xl + 1] = (uint8_t)(best - 1);
+  }
+  {
+    // blur column pass: 4 pixels x 2 rows per thread, symmetric taps added first (OpenCV's symmetric column filter)
+    const int xg = tid & (TW / 4 - 1), yl0 = (tid / (TW / 4)) * 2;
+    const float4* rb = reinterpret_cast<const float4*>(rowbuf) + yl0 * (TW / 4) + xg;
+    float4 r[8];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) r[k] = rb[k * (TW / 4)];
+    for (int k = 0; k < 8; ++k) r[k] = rb[k * (TW / 4)];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gy = ty0 + yl0 + j;
-        uint32_t packed = 0;
+    for (int j = 0; j < 2; ++j) {
+      const int gy = ty0 + yl0 + j;
+      uint32_t packed = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float m3 = reinterpret_cast<const float*>(&r[j + 3])[q];
-          const float m2 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 2])[q], reinterpret_cast<const float*>(&r[j + 4])[q]);
-          const float m1 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 1])[q], reinterpret_cast<const float*>(&r[j + 5])[q]);
-          const float m0 = __fadd_rn(reinterpret_cast<const float*>(&r[j])[q], reinterpret_cast<const float*>(&r[j + 6])[q]);
-          float s = __fmul_rn(g3, m3);
-          s = __fmaf_rn(g2, m2, s);
-          s = __fmaf_rn(g1, m1, s);
-          s = __fmaf_rn(g0, m0, s);
-          const int v = min(max(__float2int_rn(s), 0), 255);
-          packed |= (uint32_t)v << (8 * q);
-        }
-        if (gy < h) *reinterpret_cast<uint32_t*>(blur + (long long)gy * a.pitch + tx0 + 4 * xg) = packed;
+      for (int q = 0; q < 4; ++q) {
+        const float m3 = reinterpret_cast<const float*>(&r[j + 3])[q];
+        const float m2 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 2])[q], reinterpret_cast<const float*>(&r[j + 4])[q]);
+        const float m1 = __fadd_rn(reinterpret_cast<const float*>(&r[j + 1])[q], reinterpret_cast<const float*>(&r[j + 5])[q]);
+        const float m0 = __fadd_rn(reinterpret_cast<const float*>(&r[j])[q], reinterpret_cast<const float*>(&r[j + 6])[q]);
+        float sacc = __fmul_rn(g3, m3);
+        sacc = __fmaf_rn(g2, m2, sacc);
+        sacc = __fmaf_rn(g1, m1, sacc);
+        sacc = __fmaf_rn(g0, m0, sacc);
+        uint32_t v;
+        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(v) : "f"(sacc));   // saturate_cast<uchar>(cvRound(s))
+        packed |= v << (8 * q);
+      }
+      if (gy < h) *reinterpret_cast<uint32_t*>(blur + (long long)gy * a.pitch + tx0 + 4 * xg) = packed;
+    }
+  }
+  if (!a.do_fast) return;
+  __syncthreads();   // ---- barrier 2: scores complete
+
+  // phase C: 3x3 non-max suppression + 31 px edge filter, again over the survivor list only
+  for (int i = tid; i < nw; i += kLevelThreads) {
+    const int p = work[i];
+    const int yl = p / FW - 1, xl = p - (yl + 1) * FW - 1;
+    if (xl < 0 || xl >= TW || yl < 0 || yl >= TH) continue;
+    const int gx = tx0 + xl, gy = ty0 + yl;
+    const uint8_t* sc = score + (yl + 1) * FS + xl + 1;
+    const int v = sc[0];
+    if (v > 0 && gx >= kEdge && gx < w - kEdge && gy >= kEdge && gy < h - kEdge) {
+      if (v > sc[-1] && v > sc[1] && v > sc[-FS - 1] && v > sc[-FS] && v > sc[-FS + 1] && v > sc[FS - 1] &&
+          v > sc[FS] && v > sc[FS + 1]) {
+        const int e = atomicAdd(&n_emit, 1);
+        emit_xy[e] = (uint32_t)gx | ((uint32_t)gy << 16);
+        emit_sc[e] = (uint8_t)v;
+        atomicAdd(&hist_s[v], 1u);
       }
     }
+  }
+  __syncthreads();   // ---- barrier 3
+  const int ne = n_emit;
+  if (ne > 0) {
+    if (tid == 0) emit_base = atomicAdd(a.cand_count + b * kLevels + a.level, ne);
+    __syncthreads();
+    const int base = emit_base;
+    for (int i = tid; i < ne; i += kLevelThreads) {
+      const int pos = base + i;
+      if (pos < a.cand_cap) {
+        const long long o = (long long)b * a.cand_total + a.cand_off + pos;
+        a.cand_xy[o] = emit_xy[i];
+        a.cand_score[o] = emit_sc[i];
+      } else {
+        atomicOr(a.flags + b, 1);
+      }
+    }
+    if (hist_s[tid]) atomicAdd(a.hist + ((long long)b * kLevels + a.level) * 256 + tid, hist_s[tid]);
   }
 }
 
