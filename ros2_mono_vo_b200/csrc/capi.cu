@@ -151,6 +151,7 @@ int mvo_orb_num_levels(void) { return kLevels; }
 int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels,
                                mvo_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   MVO_CHECK_ARG(c, img && kps && n_out && cap >= 0, "mvo_orb_detect_and_compute: null argument");
   MVO_CHECK_ARG(c, channels == 1 || channels == 3, "channels must be 1 or 3");
   MVO_CHECK_ARG(c, stride >= w * channels, "stride smaller than a row");
@@ -196,6 +197,7 @@ int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int
 int mvo_orb_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels,
                     const mvo_keypoint* kps_in, int n, uint8_t* desc, uint8_t* valid) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   MVO_CHECK_ARG(c, img && kps_in && desc && n >= 0, "mvo_orb_compute: null argument");
   MVO_CHECK_ARG(c, channels == 1 || channels == 3, "channels must be 1 or 3");
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
@@ -278,6 +280,7 @@ static int knn_host(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int 
 int mvo_knn_ratio(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, double ratio, mvo_dmatch* out,
                   int* n_out) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   MVO_CHECK_ARG(c, n_out && nq >= 0 && nt >= 0 && (nq == 0 || (q && out)) && (nt == 0 || t),
                 "mvo_knn_ratio: bad argument");
   *n_out = 0;
@@ -299,6 +302,7 @@ int mvo_knn_ratio(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt
 
 int mvo_knn2(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   MVO_CHECK_ARG(c, nq >= 0 && nt >= 0 && (nq == 0 || (q && idx && dist)) && (nt == 0 || t), "mvo_knn2: bad argument");
   if (nq == 0) return MVO_OK;
   int rc = knn_host(c, q, nq, t, nt, 0.7);

@@ -167,6 +167,16 @@ struct mvo_ctx {
   StageTimer timers[kNumStages];
 };
 
+// single-call entry points share streams and scratch with the group pipeline: refuse to run while submitted steps are
+// still in flight
+#define MVO_REQUIRE_IDLE(c)                                                                          \
+  do {                                                                                               \
+    if ((c)->q_count != 0) {                                                                         \
+      (c)->set_error("submitted group steps are still in flight (mvo_group_collect them first)");   \
+      return MVO_ERR_INVALID;                                                                        \
+    }                                                                                                \
+  } while (0)
+
 namespace mvo {
 
 // host-side module entry points (defined in the respective .cu files)

@@ -661,6 +661,7 @@ using namespace mvo;
 extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next, int w, int h, int stride,
                             int channels, const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   if (!prev || !next || n < 0 || (n > 0 && (!prev_xy || !next_xy || !status || !err))) {
     c->set_error("mvo_lk_track: null argument");
     return MVO_ERR_INVALID;

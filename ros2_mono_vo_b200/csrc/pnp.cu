@@ -485,6 +485,7 @@ extern "C" int mvo_solve_pnp_ransac(mvo_ctx* c, const float* obj_xyz, const floa
                                     const double* dist, int n_dist, int iterations, double reproj_err, double confidence,
                                     double* rvec, double* tvec, int32_t* inliers, int* n_inliers) {
   if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
   if (!obj_xyz || !img_xy || !K || !rvec || !tvec || n < 0 || iterations < 1 || iterations > 4096) {
     c->set_error("mvo_solve_pnp_ransac: bad argument");
     return MVO_ERR_INVALID;

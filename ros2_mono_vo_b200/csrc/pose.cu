@@ -230,6 +230,7 @@ int pose_triangulate(mvo_ctx* c) {
 using namespace mvo;
 
 static int pose_upload(mvo_ctx* c, const float* p1, const float* p2, int n, const double* K) {
+  MVO_REQUIRE_IDLE(c);
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if (c->cfg.batch != 1) {
     c->set_error("the single-call geometry API needs a batch==1 context");

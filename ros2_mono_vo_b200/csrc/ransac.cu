@@ -1158,6 +1158,7 @@ int ransac_sweep(mvo_ctx* c, int model, int m) {
 using namespace mvo;
 
 static int upload_points(mvo_ctx* c, const float* p1, const float* p2, int n, double thr2, const double* K, int cap_iters) {
+  MVO_REQUIRE_IDLE(c);
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if (c->cfg.batch != 1) {
     c->set_error("the single-call geometry API needs a batch==1 context");

@@ -44,6 +44,29 @@ int main(int argc, char** argv) {
   int sh = 0, sf = 0;
   for (auto v : mh) sh += v != 0;
   for (auto v : mf) sf += v != 0;
+  // Tracker::update, src/tracker.cpp:298-316: landmarks + their observations -> pose
+  int pnp_inl = -1;
+  double rt[6] = {0, 0, 0, 0, 0, 0};
+  if (argc >= 9) {
+    const int np = atoi(argv[8]);
+    std::vector<cv::Point3f> obj(np);
+    std::vector<cv::Point2f> img(np);
+    FILE* fo = fopen(argv[6], "rb");
+    FILE* fi = fopen(argv[7], "rb");
+    if (!fo || !fi || fread(obj.data(), 12, np, fo) != (size_t)np || fread(img.data(), 8, np, fi) != (size_t)np) return 2;
+    fclose(fo);
+    fclose(fi);
+    cv::Mat rvec, tvec, Rm, dist(1, 5, CV_64F);
+    std::vector<int> inl;
+    cv::Mat Kp(3, 3, CV_64F);
+    Kp.at<double>(0, 0) = Kp.at<double>(1, 1) = 718.856; Kp.at<double>(0, 2) = 620.5; Kp.at<double>(1, 2) = 188.0; Kp.at<double>(2, 2) = 1;
+    if (mono_vo::gpu::solvePnPRansac(c, obj, img, Kp, dist, rvec, tvec, false, 100, 8.0, 0.99, inl)) {
+      pnp_inl = (int)inl.size();
+      mono_vo::gpu::Rodrigues(rvec, Rm);
+      for (int i = 0; i < 3; ++i) { rt[i] = rvec.at<double>(i, 0); rt[3 + i] = tvec.at<double>(i, 0); }
+    }
+  }
+  printf("pnp %d %.12g %.12g %.12g %.12g %.12g %.12g ", pnp_inl, rt[0], rt[1], rt[2], rt[3], rt[4], rt[5]);
   printf("kps %zu %zu detect %zu matches %zu tracked %zu score_h %d score_f %d good %d desc %dx%d first %.3f %.3f %d\n",
          k0.size(), k1.size(), kd.size(), m.size(), a.size(), sh, sf, good, d0.rows, d0.cols, k0[0].pt.x, k0[0].pt.y,
          (int)d0.at<unsigned char>(0, 0));

@@ -45,9 +45,17 @@ def test_adapter_matches_python_mirror(tmp_path):
     p0, p1 = tmp_path / "f0.raw", tmp_path / "f1.raw"
     f0.tofile(p0)
     f1.tofile(p1)
-    r = subprocess.run([exe, str(p0), str(p1), str(w), str(h), str(n)], capture_output=True, text=True, timeout=300)
+    obj, img, Kp, _, _ = synth.pnp_scene(500, 8, 0.5, 0.2)
+    po_, pi_ = tmp_path / "obj.raw", tmp_path / "img.raw"
+    obj.tofile(po_)
+    img.tofile(pi_)
+    r = subprocess.run([exe, str(p0), str(p1), str(w), str(h), str(n), str(po_), str(pi_), str(len(obj))],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     tok = r.stdout.split()
+    assert tok[0] == "pnp"
+    pnp_inl, pnp_rt = int(tok[1]), np.array(tok[2:8], np.float64)
+    tok = tok[8:]
     got = {tok[i]: tok[i + 1] for i in range(0, len(tok) - 1) if tok[i] in ("detect", "matches", "tracked", "score_h",
                                                                              "score_f", "good")}
     from ros2_mono_vo_b200 import Context
@@ -65,4 +73,6 @@ def test_adapter_matches_python_mirror(tmp_path):
     assert int(tok[1]) == len(k0) and int(tok[2]) == len(k1)
     assert int(got["detect"]) == len(k0) and int(got["matches"]) == len(m) and int(got["tracked"]) == int(ok.sum())
     assert int(got["score_h"]) == nh and int(got["score_f"]) == nf and int(got["good"]) == good
+    okp, rv, tv, inl = ctx.solve_pnp_ransac(obj, img, Kp)
+    assert okp and pnp_inl == len(inl) and np.abs(pnp_rt - np.concatenate([rv, tv])).max() < 1e-9
     ctx.close()

@@ -149,3 +149,21 @@ def test_degenerate_inputs(ctx):
     same = np.tile(np.array([[10.0, 20.0]], np.float32), (50, 1))
     with pytest.raises(MvoError):
         ctx.find_homography(same, same, 1.0)
+
+
+def test_hypothesis_sweep_full_size_properties(ctx):
+    """BASELINE configs[3] at full size: 16384 H / F / E hypotheses over 5000 correspondences.  Size-independent
+    properties: the sweep is deterministic, its first 512 hypotheses are exactly the 512-hypothesis sweep (same RNG
+    stream, same models, same counts), every count is within [0, N], and the best count explains the inlier share."""
+    K = synth.KITTI_K
+    p1, p2, *_ = synth.scene_correspondences(5000, 52, outlier_frac=0.3)
+    for model, name, k in ((0, "H", 4), (1, "F", 7), (2, "E", 5)):
+        idx_s, cnt_s, _ = ctx.score_hypotheses(model, p1, p2, 512, thr=1.0, K=K)
+        idx, cnt, _ = ctx.score_hypotheses(model, p1, p2, 16384, thr=1.0, K=K)
+        idx2, cnt2, _ = ctx.score_hypotheses(model, p1, p2, 16384, thr=1.0, K=K)
+        assert idx.shape == (16384, k) and np.array_equal(idx, idx2) and np.array_equal(cnt, cnt2), name
+        assert np.array_equal(idx[:512], idx_s) and np.array_equal(cnt[:512], cnt_s), name
+        assert all(len(set(r)) == k for r in idx[::257].tolist())
+        assert cnt.max() <= 5000 and cnt.min() >= -1
+        if name != "H":                      # a general 3-D scene: the epipolar models explain ~70 % of the points
+            assert cnt.max() > 0.6 * 5000, (name, int(cnt.max()))
