@@ -18,6 +18,9 @@ namespace mvo {
 
 constexpr int LKW = 21;
 constexpr int kLkWarps = 4;
+#ifndef MVO_LK_MINB
+#define MVO_LK_MINB 5
+#endif
 constexpr int kRaw = 24;      // raw patch side: 22 interp rows + 1 Scharr ring
 constexpr int kJReg = 32;     // staged J region side
 constexpr int kJMargin = 5;
@@ -110,21 +113,27 @@ __device__ __forceinline__ uint32_t pack_w(int lo, int hi) { return ((uint32_t)l
 // with everything unrolled and inlined at three call sites).
 __device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
                                         int pitch, int lane) {
-  const bool inside = jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h;
-  const uint8_t* p = J + (inside ? jx0 + lane : safe_reflect(jx0 + lane, w));
+  // lane = column of the region.  The border arithmetic is warp-uniform: one branch picks the plain strided walk
+  // (region inside the image, the common case) or the reflecting one.
   uint32_t pprev = 0;
+  auto walk = [&](const uint8_t* p, auto row_off) {
 #pragma unroll 1
-  for (int r0 = 0; r0 < kJReg; r0 += 8) {
-    uint32_t v[8];
+    for (int r0 = 0; r0 < kJReg; r0 += 8) {
+      uint32_t v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = p[(inside ? jy0 + r0 + k : safe_reflect(jy0 + r0 + k, h)) * pitch];
+      for (int k = 0; k < 8; ++k) v[k] = p[row_off(r0 + k)];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
-      if (r0 + k > 0) jq[(r0 + k - 1) * kJReg + lane] = pprev | (pr << 16);
-      pprev = pr;
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
+        if (r0 + k > 0) jq[(r0 + k - 1) * kJReg + lane] = pprev | (pr << 16);
+        pprev = pr;
+      }
     }
-  }
+  };
+  if (jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h)
+    walk(J + jy0 * pitch + jx0 + lane, [&](int r) { return r * pitch; });
+  else
+    walk(J + safe_reflect(jx0 + lane, w), [&](int r) { return safe_reflect(jy0 + r, h) * pitch; });
 }
 
 // Fused template setup of one window on one image plane: lane = raw column (x = ix - 1 + lane, 24 columns), the 24
@@ -138,57 +147,62 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
   const int xr = safe_reflect(colx, w);
   const bool der_col = lane >= 1 && lane <= kRaw - 2 && colx >= 0 && colx < w;  // derivative column inside the image
   const bool win_col = lane >= 1 && lane <= LKW;                                 // window column c = lane - 1
-  const bool inside = ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h;   // all 32 lanes' columns in the image
-  const uint8_t* p = I + (inside ? colx : xr);
   int dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
   uint32_t pair0 = 0, pair1 = 0, pd_prev = 0, pdn_prev = 0;
-  // rows in groups of four independent loads; the walk itself is rolled (code size: see lk_stage_j)
+  // rows in groups of four independent loads; the walk itself is rolled (code size: see lk_stage_j).  row_off / row_ok
+  // carry the (warp-uniform) border handling: plain strides when the 32 x 24 footprint lies inside the image.
+  auto walk = [&](const uint8_t* p, auto row_off, auto row_ok) {
 #pragma unroll 1
-  for (int r0 = 0; r0 < kRaw; r0 += 4) {
-    uint32_t v[4];
+    for (int r0 = 0; r0 < kRaw; r0 += 4) {
+      uint32_t v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = p[(inside ? iy - 1 + r0 + k : safe_reflect(iy - 1 + r0 + k, h)) * pitch];
+      for (int k = 0; k < 4; ++k) v[k] = p[row_off(r0 + k)];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r0 + k;
-      const int c = (int)v[k];
-      const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
-      const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
-      const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
-      // derivative row rr = r - 2 (y = iy + rr); meaningful from r = 2 on, harmless before (the results are not stored)
-      const int rr = r - 2;
-      const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
-      const bool ok = der_col && (iy + rr >= 0) && (iy + rr < h);
-      const uint32_t pd = ok ? pack_w(gx, gy) : 0u;
-      const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
-      // window row pr = rr - 1
-      const int pr = rr - 1;
-      const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
-      const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
-      const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
-      const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
-      const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
-      const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
-      if (win_col && pr >= 0) {
-        sA11 += vx * vx;
-        sA12 += vx * vy;
-        sA22 += vy * vy;
-        pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
-        pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + k;
+        const int c = (int)v[k];
+        const int lv_ = __shfl_up_sync(0xffffffffu, c, 1), rv = __shfl_down_sync(0xffffffffu, c, 1);
+        const int dx2 = rv - lv_, sm2 = 3 * (lv_ + rv) + 10 * c;
+        const uint32_t pair2 = (uint32_t)c | ((uint32_t)rv << 8);
+        // derivative row rr = r - 2 (y = iy + rr); meaningful from r = 2 on, harmless before (the results are not stored)
+        const int rr = r - 2;
+        const int gx = 3 * (dx0 + dx2) + 10 * dx1, gy = sm2 - sm0;
+        const uint32_t pd = (der_col && row_ok(rr)) ? pack_w(gx, gy) : 0u;
+        const uint32_t pdn = __shfl_down_sync(0xffffffffu, pd, 1);
+        // window row pr = rr - 1
+        const int pr = rr - 1;
+        const int iv = dp2a_lo_su(Wb, pair1, dp2a_lo_su(Wt, pair0, 1 << 8)) >> 9;
+        const int x00 = (int)(short)(pd_prev & 0xffffu), x01 = (int)(short)(pdn_prev & 0xffffu);
+        const int x10 = (int)(short)(pd & 0xffffu), x11 = (int)(short)(pdn & 0xffffu);
+        const int y00 = (int)pd_prev >> 16, y01 = (int)pdn_prev >> 16, y10 = (int)pd >> 16, y11 = (int)pdn >> 16;
+        const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
+        const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
+        if (win_col && pr >= 0) {
+          sA11 += vx * vx;
+          sA12 += vx * vy;
+          sA22 += vy * vy;
+          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
+          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+        }
+        pd_prev = pd;
+        pdn_prev = pdn;
+        dx0 = dx1;
+        dx1 = dx2;
+        sm0 = sm1;
+        sm1 = sm2;
+        pair0 = pair1;
+        pair1 = pair2;
       }
-      pd_prev = pd;
-      pdn_prev = pdn;
-      dx0 = dx1;
-      dx1 = dx2;
-      sm0 = sm1;
-      sm1 = sm2;
-      pair0 = pair1;
-      pair1 = pair2;
     }
-  }
+  };
+  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h)
+    walk(I + (iy - 1) * pitch + colx, [&](int r) { return r * pitch; }, [&](int) { return true; });
+  else
+    walk(I + xr, [&](int r) { return safe_reflect(iy - 1 + r, h) * pitch; },
+         [&](int rr) { return iy + rr >= 0 && iy + rr < h; });
 }
 
-__global__ void __launch_bounds__(kLkWarps * 32, 5)
+__global__ void __launch_bounds__(kLkWarps * 32, MVO_LK_MINB)
 lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
                 const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
                 float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
