@@ -195,11 +195,50 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
       }
     }
   };
-  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h)
-    walk(I + (iy - 1) * pitch + colx, [&](int r) { return r * pitch; }, [&](int) { return true; });
-  else
+  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h) {
+    // Footprint inside the image (the common case): no derivative is masked, so interpolation and Scharr commute --
+    // everything is exact integer arithmetic up to the final shifts.  Interpolate the raw patch first
+    // (T = sum w * raw, two IDP.2A per value), then take the Scharr of T: sum w * der == Scharr(T).  One shuffled
+    // value per row instead of packed derivative pairs, no 8-multiply interpolation of Ix / Iy.
+    const uint8_t* p = I + (iy - 1) * pitch + colx;
+    int t1 = 0;   // T of the previous row
+#pragma unroll 1
+    for (int r0 = 0; r0 < kRaw; r0 += 4) {
+      uint32_t v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = p[(r0 + k) * pitch];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + k;                                   // raw row; T row r - 2; window row pr = r - 3
+        const uint32_t c = v[k];
+        const uint32_t rv = __shfl_down_sync(0xffffffffu, c, 1);
+        const uint32_t pair2 = c | (rv << 8);
+        const int tn = dp2a_lo_su(Wb, pair2, dp2a_lo_su(Wt, pair1, 0));
+        const int tl = __shfl_up_sync(0xffffffffu, tn, 1), tr = __shfl_down_sync(0xffffffffu, tn, 1);
+        const int dx2 = tr - tl, sm2 = 3 * (tl + tr) + 10 * tn;
+        const int pr = r - 3;
+        const int vx = (3 * (dx0 + dx2) + 10 * dx1 + (1 << 13)) >> 14;
+        const int vy = (sm2 - sm0 + (1 << 13)) >> 14;
+        const int iv = (t1 + (1 << 8)) >> 9;
+        if (win_col && pr >= 0) {
+          sA11 += vx * vx;
+          sA12 += vx * vy;
+          sA22 += vy * vy;
+          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
+          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+        }
+        dx0 = dx1;
+        dx1 = dx2;
+        sm0 = sm1;
+        sm1 = sm2;
+        t1 = tn;
+        pair1 = pair2;
+      }
+    }
+  } else {
     walk(I + xr, [&](int r) { return safe_reflect(iy - 1 + r, h) * pitch; },
          [&](int rr) { return iy + rr >= 0 && iy + rr < h; });
+  }
 }
 
 __global__ void __launch_bounds__(kLkWarps * 32, MVO_LK_MINB)
