@@ -107,6 +107,13 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Exact warp sum of 32-bit addends whose total needs more than 32 bits: the low and the high 16 bits are reduced
+// separately by the warp-reduction unit (REDUX.SUM, one instruction each instead of ten shuffles + ten adds).
+__device__ __forceinline__ long long warp_sum_wide(int v) {
+  const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+  const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+  return ((long long)hi << 16) + lo;
+}
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -309,9 +309,9 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
         Iyv[j] = (int)d >> 16;
       }
     }
-    const float A11 = __fmul_rn((float)warp_sum_ll(sA11), flt_scale);
-    const float A12 = __fmul_rn((float)warp_sum_ll(sA12), flt_scale);
-    const float A22 = __fmul_rn((float)warp_sum_ll(sA22), flt_scale);
+    const float A11 = __fmul_rn((float)warp_sum_wide(sA11), flt_scale);
+    const float A12 = __fmul_rn((float)warp_sum_wide(sA12), flt_scale);
+    const float A22 = __fmul_rn((float)warp_sum_wide(sA22), flt_scale);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dA = __fsub_rn(A11, A22);
     const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -351,8 +351,8 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
           sb2 += diff * Iyv[j];
         }
       }
-      const float b1 = __fmul_rn((float)warp_sum_ll(sb1), flt_scale);
-      const float b2 = __fmul_rn((float)warp_sum_ll(sb2), flt_scale);
+      const float b1 = __fmul_rn((float)warp_sum_wide(sb1), flt_scale);
+      const float b2 = __fmul_rn((float)warp_sum_wide(sb2), flt_scale);
       const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       cx = __fadd_rn(cx, dx);
@@ -393,7 +393,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
             se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j]);
           }
         }
-        se = warp_sum(se);
+        se = __reduce_add_sync(0xffffffffu, se);
         e = __fdiv_rn((float)se, (float)(32 * LKW * LKW));
       }
     }
@@ -578,7 +578,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
             }
           }
         }
-        se = warp_sum(se);
+        se = __reduce_add_sync(0xffffffffu, se);
         e = __fdiv_rn((float)se, (float)(32 * LKW * CN * LKW));
       }
     }
