@@ -108,32 +108,53 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 }
 __device__ __forceinline__ uint32_t pack_w(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
 
-// Stage the 32x32 J region with top-left (jx0, jy0) as quads: lane = column, rows in groups of eight independent
-// loads.  Kept out of line and rolled: the kernel is instruction-cache bound otherwise (ncu: 26 % no-instruction stalls
-// with everything unrolled and inlined at three call sites).
+// Stage the 32x32 J region with top-left (jx0, jy0) as quads.  Kept out of line: the kernel is instruction-cache bound
+// otherwise (ncu: 26 % no-instruction stalls with everything unrolled and inlined at three call sites).
+// Region inside the image (the common case, warp-uniform branch): lane = (row group of eight quad rows, aligned
+// 4-pixel word column).  A lane walks its nine pixel rows with two aligned 32-bit loads per row, cuts the five
+// pixels it needs out of the eight loaded bytes with two PRMT whose selectors carry the misalignment of jx0, and
+// stores four quads per row with one 128-bit STS: ~11 instructions per 4 quads instead of ~12 per quad for the
+// byte-per-lane walk (which remains for regions that touch the border and reflect).
 __device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
                                         int pitch, int lane) {
-  // lane = column of the region.  The border arithmetic is warp-uniform: one branch picks the plain strided walk
-  // (region inside the image, the common case) or the reflecting one.
-  uint32_t pprev = 0;
-  auto walk = [&](const uint8_t* p, auto row_off) {
-#pragma unroll 1
-    for (int r0 = 0; r0 < kJReg; r0 += 8) {
-      uint32_t v[8];
+  if (jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h) {
+    const int g = lane >> 3, wi = lane & 7;
+    const uint32_t sh = (uint32_t)(jx0 & 3);
+    const uint32_t sel01 = 0x2110u + 0x1111u * sh, sel23 = 0x4332u + 0x1111u * sh;
+    const uint8_t* p = J + (jy0 + 8 * g) * pitch + (jx0 & ~3) + 4 * wi;
+    // pixel row jy0 + 32 feeds only quad row 31, which no window reads; it may lie below the image: clamp it
+    const int rmax = h - 1 - (jy0 + 8 * g);
+    uint4* out = reinterpret_cast<uint4*>(jq + 8 * g * kJReg + 4 * wi);
+    uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(p)), w1 = __ldg(reinterpret_cast<const uint32_t*>(p + 4));
+    uint32_t t01 = __byte_perm(w0, w1, sel01), t23 = __byte_perm(w0, w1, sel23);   // pixel pairs (0,1)(1,2) / (2,3)(3,4)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = p[row_off(r0 + k)];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
-        if (r0 + k > 0) jq[(r0 + k - 1) * kJReg + lane] = pprev | (pr << 16);
-        pprev = pr;
-      }
+    for (int k = 0; k < 8; ++k) {
+      const uint8_t* pr = p + min(k + 1, rmax) * pitch;
+      w0 = __ldg(reinterpret_cast<const uint32_t*>(pr));
+      w1 = __ldg(reinterpret_cast<const uint32_t*>(pr + 4));
+      const uint32_t b01 = __byte_perm(w0, w1, sel01), b23 = __byte_perm(w0, w1, sel23);
+      out[k * (kJReg / 4)] = make_uint4(__byte_perm(t01, b01, 0x5410), __byte_perm(t01, b01, 0x7632),
+                                        __byte_perm(t23, b23, 0x5410), __byte_perm(t23, b23, 0x7632));
+      t01 = b01;
+      t23 = b23;
     }
-  };
-  if (jx0 >= 0 && jx0 + kJReg <= w && jy0 >= 0 && jy0 + kJReg <= h)
-    walk(J + jy0 * pitch + jx0 + lane, [&](int r) { return r * pitch; });
-  else
-    walk(J + safe_reflect(jx0 + lane, w), [&](int r) { return safe_reflect(jy0 + r, h) * pitch; });
+    return;
+  }
+  // lane = column of the region, reflecting row / column walk
+  const uint8_t* p = J + safe_reflect(jx0 + lane, w);
+  uint32_t pprev = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < kJReg; r0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[safe_reflect(jy0 + r0 + k, h) * pitch];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
+      if (r0 + k > 0) jq[(r0 + k - 1) * kJReg + lane] = pprev | (pr << 16);
+      pprev = pr;
+    }
+  }
 }
 
 // Fused template setup of one window on one image plane: lane = raw column (x = ix - 1 + lane, 24 columns), the 24
