@@ -173,11 +173,12 @@ def sequence_camera(h: int, w: int) -> np.ndarray:
     return np.array([[f, 0.0, (w - 1) / 2.0], [0.0, f, (h - 1) / 2.0], [0.0, 0.0, 1.0]])
 
 
-def synth_sequence(h: int, w: int, stream: int, nframes: int):
+def synth_sequence(h: int, w: int, stream: int, nframes: int, return_poses: bool = False):
     """A seeded camera translating through a rigid non-planar scene (C2/C5 sequences): every frame is one
     resampling of the base frame with a smooth inverse-depth map (depths 6..50, ~0.5 units of forward motion
     per frame, i.e. KITTI-like depth/baseline ratios of 12..100).
-    Returns (frames, K)."""
+    Returns (frames, K), or (frames, K, T) with return_poses: T[k] is the position of camera k in the coordinates
+    of camera 0 (no rotation)."""
     rng = np.random.default_rng(1000 * stream + 17)
     base = synth_frame(h, w, 1000 * stream)
     K = sequence_camera(h, w)
@@ -185,9 +186,13 @@ def synth_sequence(h: int, w: int, stream: int, nframes: int):
     inv_depth = 1.0 / depth
     frames = [base]
     T = np.zeros(3)
+    poses = [T.copy()]
     for _ in range(1, nframes):
         T = T + np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02), rng.uniform(0.4, 0.6)])
         frames.append(warp_parallax(base, T, inv_depth, K))
+        poses.append(T.copy())
+    if return_poses:
+        return frames, K, np.stack(poses)
     return frames, K
 
 

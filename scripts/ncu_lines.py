@@ -1,0 +1,19 @@
+"""Per-source-line instruction shares of one kernel from an ncu report:
+   ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > f.csv ; python scripts/ncu_lines.py f.csv [min_pct]"""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
+cur = None; agg = {}; tot = 0; stot = 0
+for row in rows:
+    if not row: continue
+    if row[0] == 'File Path': cur = row[1].split('/')[-1]; continue
+    if row[0] == 'Function Name': continue
+    if row[0] == 'Line No':
+        ii = row.index('Instructions Executed'); si = row.index('# Samples'); continue
+    if row[0] != '':
+        try: n = int(row[ii]); s = int(row[si])
+        except ValueError: continue
+        ln = int(row[0]); a = agg.get((cur, ln), (0, 0, row[1])); agg[(cur, ln)] = (a[0] + n, a[1] + s, row[1]); tot += n; stot += s
+print('total warp instructions', tot, 'samples', stot)
+for (f, ln), (n, s, src) in sorted(agg.items()):
+    if n > tot * thr / 100: print(f"{f}:{ln:4d} inst {n/tot*100:5.2f}% smp {s/stot*100:5.2f}%  {src.strip()[:100]}")
