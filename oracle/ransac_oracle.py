@@ -461,11 +461,51 @@ def find_homography(p1, p2, thr: float, seed: int = 0xFFFFFFFFFFFFFFFF):
     return H, mask, iters
 
 
+def lmeds(model: str, p1, p2, conf: float, seed: int = 0xFFFFFFFFFFFFFFFF):
+    """LMeDSPointSetRegistrator::run (OpenCV modules/calib3d/src/ptsetreg.cpp): the same subsets as RANSAC, the model
+    with the least median error wins (strict '<', models of one sample in solver order), then
+    sigma = 2.5 * 1.4826 * (1 + 5 / (N - k)) * sqrt(median), at least 0.001; inliers = err <= sigma^2.
+    Returns (model or None, mask u8, iterations run, success)."""
+    k = MODEL_POINTS[model]
+    n = len(p1)
+    kernel = {"F": f7_kernel}[model]
+    errfn = {"F": f_errors}[model]
+    niters = max(update_iters(conf, 0.45, k, MAX_ITERS[model]), 3)
+    rng = CvRNG(seed)
+    best, min_median = None, np.inf
+    it = 0
+    while it < niters:
+        idx = get_subset(model, p1, p2, rng)
+        if idx is None:
+            break
+        for mdl in kernel(p1[idx], p2[idx]):
+            err = np.sort(errfn(mdl, p1, p2))
+            median = float(err[n // 2])
+            if median < min_median:
+                min_median, best = median, mdl
+        it += 1
+    if best is None:
+        return None, np.zeros(n, np.uint8), it, False
+    sigma = max(2.5 * 1.4826 * (1 + 5.0 / (n - k)) * np.sqrt(min_median), 0.001)
+    mask = (errfn(best, p1, p2) <= f32(sigma * sigma)).astype(np.uint8)
+    return best, mask, it, int(mask.sum()) >= k
+
+
 def find_fundamental(p1, p2, thr: float, conf: float = 0.99, seed: int = 0xFFFFFFFFFFFFFFFF):
+    """cv::findFundamentalMat(p1, p2, FM_RANSAC, thr, conf, mask): N >= 15 RANSAC; 8 <= N < 15 silently LMedS
+    (the Tracker can get there: /root/reference/src/tracker.cpp:239-248 with min_tracked_points = 10); N == 7 the
+    7-point solution itself with an all-ones mask; N < 7 nothing.  Returns (F or None, mask, iterations)."""
     p1 = np.asarray(p1, f32)
     p2 = np.asarray(p2, f32)
-    if len(p1) < 15:
-        raise NotImplementedError("N < 15 switches OpenCV to LMedS (not restated)")
+    n = len(p1)
+    if n < 7:
+        return None, np.zeros(n, np.uint8), 0
+    if n == 7:
+        models = f7_kernel(p1, p2)
+        return (models[0] if models else None), np.ones(n, np.uint8), 1
+    if n < 15:
+        F, mask, iters, ok = lmeds("F", p1, p2, conf, seed)
+        return (F if ok else None), mask, iters
     F, mask, iters, _ = ransac("F", p1, p2, thr, conf, seed)
     return F, mask, iters
 

@@ -505,7 +505,7 @@ ransac_score_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2
 }
 
 // ---- select: replay of the sequential adaptive loop ---------------------------------------------
-__device__ __forceinline__ int update_iters(double p, double ep, int model_points, int max_iters) {
+__host__ __device__ __forceinline__ int update_iters(double p, double ep, int model_points, int max_iters) {
   p = fmax(p, 0.);
   p = fmin(p, 1.);
   ep = fmax(ep, 0.);
@@ -515,7 +515,7 @@ __device__ __forceinline__ int update_iters(double p, double ep, int model_point
   if (denom < DBL_MIN) return 0;
   num = log(num);
   denom = log(denom);
-  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
 }
 
 // result per stream: [0] inlier count, [1] iterations run, [2] winning iteration, [3] winning model slot
@@ -654,6 +654,103 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
   if (tid == 0) {
     res[0] = s_cnt;
     res[1] = T;
+    res[2] = wit;
+    res[3] = wm;
+  }
+}
+
+// ---- LMedS: what cv::findFundamentalMat(FM_RANSAC) silently runs for 8 <= N < 15 -------------------------
+// (LMeDSPointSetRegistrator::run; the Tracker gets there with min_tracked_points = 10: /root/reference/src/tracker.cpp:
+// 239-248.)  Same subsets as RANSAC; thread = iteration: median (element N/2 of the sorted errors) of each of its
+// models, block-wide minimum with the sequential loop's tie rule (strict '<': first iteration, first model), then
+// sigma = 2.5 * 1.4826 * (1 + 5 / (N - 7)) * sqrt(median) >= 0.001 and mask = err <= sigma^2.
+__global__ void __launch_bounds__(1024)
+f_lmeds_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const int32_t* __restrict__ npts, int max_pts,
+               const int32_t* __restrict__ state, int cap_iters, int niters, const double* __restrict__ models,
+               const int32_t* __restrict__ nmodels, double* __restrict__ best_model, uint8_t* __restrict__ mask,
+               int32_t* __restrict__ result) {
+  constexpr int MAXM = MT<MVO_MODEL_F>::MAXM, NMAX = 16;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(npts[b], NMAX);
+  const int nsub = min(min(state[b * 8 + 1], cap_iters), niters);
+  const float2* a = p1 + (long long)b * max_pts;
+  const float2* c = p2 + (long long)b * max_pts;
+  __shared__ unsigned long long s_warp[32];
+  __shared__ double s_m[9];
+  __shared__ int s_cnt;
+  unsigned long long key = ~0ull;
+  if (tid < nsub) {
+    const int nm = nmodels[(long long)b * cap_iters + tid];
+    for (int m = 0; m < nm; ++m) {
+      const double* M = models + (((long long)b * cap_iters + tid) * MAXM + m) * 9;
+      float e[NMAX];
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) e[i] = i < n ? f_error(M, a[i], c[i]) : __int_as_float(0x7f800000);
+      // N/2-th smallest: count-based selection keeps e[] in registers (no data-dependent indexing)
+      float med = __int_as_float(0x7f800000);
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        int less = 0, leq = 0;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+          less += e[j] < e[i] ? 1 : 0;
+          leq += e[j] <= e[i] ? 1 : 0;
+        }
+        if (i < n && less <= n / 2 && n / 2 < leq) med = e[i];
+      }
+      const unsigned bits = __float_as_uint(med);
+      if (med >= 0.f && bits < 0x7f800000u) {   // finite (a NaN / inf median never beats DBL_MAX in OpenCV either)
+        const unsigned long long k2 = ((unsigned long long)bits << 32) | ((unsigned long long)tid << 8) | (unsigned)m;
+        key = min(key, k2);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+  if (lane == 0) s_warp[warp] = key;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (warp == 0) {
+    key = s_warp[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (lane == 0) s_warp[0] = key;
+  }
+  __syncthreads();
+  key = s_warp[0];
+  int32_t* res = result + b * 8;
+  uint8_t* mk = mask + (long long)b * max_pts;
+  if (key == ~0ull) {
+    if (tid < n) mk[tid] = 0;
+    if (tid < 9) best_model[b * 9 + tid] = 0.0;
+    if (tid == 0) {
+      res[0] = 0;
+      res[1] = nsub;
+      res[2] = -1;
+      res[3] = -1;
+    }
+    return;
+  }
+  const int wit = (int)((key >> 8) & 0xFFFFFF), wm = (int)(key & 0xFF);
+  if (tid < 9) {
+    const double v = models[(((long long)b * cap_iters + wit) * MAXM + wm) * 9 + tid];
+    s_m[tid] = v;
+    best_model[b * 9 + tid] = v;
+  }
+  __syncthreads();
+  const double median = (double)__uint_as_float((unsigned)(key >> 32));
+  double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(median);
+  sigma = fmax(sigma, 0.001);
+  const float t = (float)(sigma * sigma);
+  if (tid < n) {
+    const int in = f_error(s_m, a[tid], c[tid]) <= t ? 1 : 0;
+    mk[tid] = (uint8_t)in;
+    if (in) atomicAdd(&s_cnt, 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    res[0] = s_cnt;
+    res[1] = nsub;
     res[2] = wit;
     res[3] = wm;
   }
@@ -1193,6 +1290,58 @@ static int download_result(mvo_ctx* c, int n, double* model, uint8_t* mask, int*
   return MVO_OK;
 }
 
+// cv::findFundamentalMat below 15 correspondences: N == 7 returns the 7-point solution of the points themselves with an
+// all-ones mask; 8 <= N < 15 runs LMedS (niters from confidence and a fixed 45 % outlier ratio, at least 3).
+static int ransac_f_small(mvo_ctx* c, const float* p1, const float* p2, int n, double conf, double* F, uint8_t* mask,
+                          int* n_inliers) {
+  constexpr int MAXIT = MT<MVO_MODEL_F>::MAXIT;
+  int rc = upload_points(c, p1, p2, n, 1.0, nullptr, MAXIT);
+  if (rc) return rc;
+  RansacBufs& r = c->rs;
+  MVO_CUDA_TRY(c, cudaMemsetAsync(r.ln().state.p, 0, 32, c->stream));
+  int niters = 1;
+  if (n == 7) {
+    const int32_t st[8] = {0, 1, 0, 0, 0, 0, 0, 0}, idx[7] = {0, 1, 2, 3, 4, 5, 6};
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.ln().state.p, st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.ln().subsets.p, idx, sizeof(idx), cudaMemcpyHostToDevice, c->stream));
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // st / idx live on this stack frame
+  } else {
+    niters = std::max(update_iters(conf, 0.45, 7, MAXIT), 3);
+    sample_pass<MVO_MODEL_F>(c, niters, kDraws, kMaxAttempts);
+  }
+  ransac_solve_kernel<MVO_MODEL_F><<<dim3((niters + 63) / 64, 1), 64, 0, c->stream>>>(
+      r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p, r.ln().state.p, r.cap_iters, 0, niters, r.ln().models.p,
+      r.ln().nmodels.p);
+  c->launches++;
+  if (n == 7) {
+    int nm = 0;
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(&nm, r.ln().nmodels.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (F) MVO_CUDA_TRY(c, cudaMemcpyAsync(F, r.ln().models.p, 72, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->last_ransac_iters = 1;
+    if (nm <= 0) {
+      c->set_error("mvo_find_fundamental: the 7-point solver found no model");
+      return MVO_ERR_DEGENERATE;
+    }
+    if (mask) std::fill(mask, mask + n, (uint8_t)1);
+    if (n_inliers) *n_inliers = n;
+    return MVO_OK;
+  }
+  f_lmeds_kernel<<<1, 1024, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.ln().state.p, r.cap_iters, niters,
+                                            r.ln().models.p, r.ln().nmodels.p, r.ln().best_model.p, r.ln().mask.p, r.ln().result.p);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  int n_in = 0;
+  rc = download_result(c, n, F, mask, &n_in);
+  if (n_inliers) *n_inliers = n_in;
+  if (rc) return rc;
+  if (n_in < 7) {   // OpenCV: run() fails (empty matrix) although the mask has been written
+    c->set_error("mvo_find_fundamental: LMedS kept fewer than 7 inliers");
+    return MVO_ERR_DEGENERATE;
+  }
+  return MVO_OK;
+}
+
 extern "C" {
 
 int mvo_find_homography(mvo_ctx* c, const float* p1, const float* p2, int n, double thr, double* H, uint8_t* mask,
@@ -1220,12 +1369,13 @@ int mvo_find_fundamental(mvo_ctx* c, const float* p1, const float* p2, int n, do
     c->set_error("mvo_find_fundamental: null argument");
     return MVO_ERR_INVALID;
   }
-  if (n < 15) {
-    c->set_error("mvo_find_fundamental: N < 15 switches OpenCV to LMedS, which is not implemented");
-    return n < 7 ? MVO_ERR_DEGENERATE : MVO_ERR_UNSUPPORTED;
+  if (n < 7) {
+    c->set_error("mvo_find_fundamental: fewer than 7 correspondences");
+    return MVO_ERR_DEGENERATE;
   }
   if (thr <= 0) thr = 3;
   if (conf < DBL_EPSILON || conf > 1 - DBL_EPSILON) conf = 0.99;
+  if (n < 15) return ransac_f_small(c, p1, p2, n, conf, F, mask, n_inliers);   // OpenCV: direct (N == 7) or LMedS
   int rc = upload_points(c, p1, p2, n, thr * thr, nullptr, 1000);
   if (rc) return rc;
   rc = ransac_find(c, MVO_MODEL_F, conf);

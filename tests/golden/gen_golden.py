@@ -185,6 +185,22 @@ def gen_ransac():
     np.savez_compressed(os.path.join(HERE, "ransac.npz"), **out)
 
 
+def gen_f_small():
+    """cv::findFundamentalMat(FM_RANSAC) below 15 correspondences (the Tracker's has_parallax can get there with
+    min_tracked_points = 10, src/tracker.cpp:239-248): N == 7 direct, 8 <= N < 15 LMedS."""
+    out = {"cv2_version": cv2.__version__}
+    cases = [(n, 100 + s) for s in range(6) for n in (7, 8, 10, 13, 14)]
+    out["cases"] = np.array(cases, np.int32)
+    for n, seed in cases:
+        p1, p2, R, t, inl = synth.scene_correspondences(n, seed, outlier_frac=0.2, noise_px=0.3)
+        F, mask = cv2.findFundamentalMat(p1, p2, cv2.FM_RANSAC, 1.0, 0.99)
+        out[f"n{n}_s{seed}_sha"] = sha(np.concatenate([p1, p2]))
+        out[f"n{n}_s{seed}_F"] = np.zeros((0, 3)) if F is None else F
+        out[f"n{n}_s{seed}_mask"] = mask.ravel()
+        print("f_small", n, seed, None if F is None else F.shape, int(mask.sum()))
+    np.savez_compressed(os.path.join(HERE, "f_small.npz"), **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:            # e.g. `python gen_golden.py gen_lk_bgr`: regenerate single fixtures
@@ -192,6 +208,7 @@ if __name__ == "__main__":
             globals()[name]()
         sys.exit(0)
     gen_ransac()
+    gen_f_small()
     gen_lk()
     gen_lk_bgr()
     gen_pnp()

@@ -167,3 +167,35 @@ def test_hypothesis_sweep_full_size_properties(ctx):
         assert cnt.max() <= 5000 and cnt.min() >= -1
         if name != "H":                      # a general 3-D scene: the epipolar models explain ~70 % of the points
             assert cnt.max() > 0.6 * 5000, (name, int(cnt.max()))
+
+
+def test_find_fundamental_below_15_points(ctx):
+    """findFundamentalMat(FM_RANSAC) with N < 15 (Tracker::has_parallax with min_tracked_points = 10,
+    /root/reference/src/tracker.cpp:239-248): N == 14 LMedS mask identical to cv2; 8 <= N <= 13 the count OpenCV returns
+    (one minimal sample, see tests/test_oracle_ransac.py); N == 7 the 7-point solution with an all-ones mask; N < 7 nothing."""
+    from ros2_mono_vo_b200.api import MvoError
+    g = load_golden("f_small.npz")
+    for n, seed in g["cases"].tolist():
+        p1, p2, *_ = synth.scene_correspondences(n, seed, outlier_frac=0.2, noise_px=0.3)
+        assert sha(np.concatenate([p1, p2])) == str(g[f"n{n}_s{seed}_sha"])
+        F, mask, cnt = ctx.find_fundamental(p1, p2, 1.0, 0.99)
+        ref_mask, ref_F = g[f"n{n}_s{seed}_mask"], g[f"n{n}_s{seed}_F"]
+        assert cnt == int(mask.sum()) == int(ref_mask.sum())
+        if n == 7:
+            assert mask.all()
+            assert min(np.abs(F - f).max() for f in ref_F.reshape(-1, 3, 3)) < 1e-6
+        elif n == 14:
+            assert np.array_equal(mask, ref_mask)
+            assert np.abs(F - ref_F).max() < 1e-6
+    # against the oracle on other seeds (N == 14: the only size where the LMedS median is not degenerate)
+    for seed in range(200, 210):
+        p1, p2, *_ = synth.scene_correspondences(14, seed, outlier_frac=0.3, noise_px=0.5)
+        F, mask, cnt = ctx.find_fundamental(p1, p2, 1.0, 0.99)
+        Fo, mo, _ = ro.find_fundamental(p1, p2, 1.0, 0.99)
+        assert np.array_equal(mask, mo)
+    with pytest.raises(MvoError):
+        ctx.find_fundamental(p1[:6], p2[:6], 1.0, 0.99)
+    # the regular path is untouched right after a small call
+    p1, p2, *_ = synth.scene_correspondences(500, 7, outlier_frac=0.25)
+    _, mf, _ = ctx.find_fundamental(p1, p2, 1.0, 0.99)
+    assert np.array_equal(mf, ro.find_fundamental(p1, p2, 1.0, 0.99)[1])

@@ -99,3 +99,27 @@ def test_update_iters():
     assert ro.update_iters(0.99, 1.0, 7, 1000) == 1000
     assert ro.update_iters(0.995, 0.3, 4, 2000) == int(np.rint(np.log(0.005) / np.log(1 - 0.7 ** 4)))
     assert ro.update_iters(0.99, 0.9, 5, 17) == 17            # never grows past the current cap
+
+
+def test_find_fundamental_below_15_points_vs_cv2():
+    """cv::findFundamentalMat(FM_RANSAC) silently changes algorithm below 15 correspondences (LMedS; the 7-point solution
+    itself at N == 7).  N == 14: mask and F identical to cv2.  8 <= N <= 13: the median of a model that fits its 7
+    sample points exactly is numerically zero for EVERY sample, so which sample wins is rounding noise inside OpenCV
+    too -- but the result is always "exactly one minimal sample": 7 inliers, which is all the reference consumes
+    (countNonZero, src/tracker.cpp:249)."""
+    g = load_golden("f_small.npz")
+    for n, seed in g["cases"].tolist():
+        p1, p2, *_ = synth.scene_correspondences(n, seed, outlier_frac=0.2, noise_px=0.3)
+        assert sha(np.concatenate([p1, p2])) == str(g[f"n{n}_s{seed}_sha"])
+        F, mask, iters = ro.find_fundamental(p1, p2, 1.0, 0.99)
+        ref_mask, ref_F = g[f"n{n}_s{seed}_mask"], g[f"n{n}_s{seed}_F"]
+        assert int(mask.sum()) == int(ref_mask.sum())
+        if n == 7:
+            assert mask.all() and iters == 1
+            assert min(np.abs(F - f).max() for f in ref_F.reshape(-1, 3, 3)) < 1e-8
+        elif n == 14:
+            assert iters == 300 and np.array_equal(mask, ref_mask)
+            assert np.abs(F - ref_F).max() < 1e-8
+        else:
+            assert int(mask.sum()) == 7
+    assert ro.find_fundamental(p1[:6], p2[:6], 1.0)[0] is None
