@@ -215,6 +215,9 @@ MVO_API int mvo_group_reset(mvo_ctx* ctx);
  * names: "orb", "orb_dense" (the fused per-level kernels inside "orb"), "knn", "lk", "ransac_h", "ransac_f",
  * "ransac_e", "pose", "triangulate", "total" */
 MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);
+/* start / end of a stage of the last enqueued step relative to the start of that step (ms): the schedule of the step's
+ * dependency graph over the context's CUDA streams (profiling aid; same validity rule as mvo_stage_ms) */
+MVO_API int mvo_stage_span_ms(mvo_ctx* ctx, const char* stage, float* beg_ms, float* end_ms);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mvo_group_collect": (C.c_int, [_vp, _vp]),
     "mvo_group_reset": (C.c_int, [_vp]),
     "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
+    "mvo_stage_span_ms": (C.c_int, [_vp, C.c_char_p, _f32p, _f32p]),
 }
 
 _lib = None

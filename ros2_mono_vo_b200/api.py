@@ -186,6 +186,15 @@ class Context:
             out[s] = float(v.value)
         return out
 
+    def stage_spans_ms(self) -> dict:
+        """(start, end) of every stage of the last enqueued step, relative to the start of that step."""
+        out = {}
+        a, b = C.c_float(), C.c_float()
+        for s in self.STAGES:
+            self._check(self.lib.mvo_stage_span_ms(self.h, s.encode(), C.byref(a), C.byref(b)))
+            out[s] = (float(a.value), float(b.value))
+        return out
+
     # ---- two-view geometry -------------------------------------------------------------------
     @staticmethod
     def _pts(p):

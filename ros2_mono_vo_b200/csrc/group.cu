@@ -457,4 +457,19 @@ int mvo_stage_ms(mvo_ctx* c, const char* stage, float* ms) {
   return MVO_ERR_INVALID;
 }
 
+int mvo_stage_span_ms(mvo_ctx* c, const char* stage, float* beg_ms, float* end_ms) {
+  if (!c || !stage || !beg_ms || !end_ms) return MVO_ERR_INVALID;
+  for (int s = 0; s < mvo_ctx::kNumStages; ++s) {
+    if (strcmp(stage, kStageNames[s]) == 0) {
+      *beg_ms = *end_ms = 0.f;
+      if (!c->timers[s].used || !c->timers[ST_TOTAL].used) return MVO_OK;
+      MVO_CUDA_TRY(c, cudaEventElapsedTime(beg_ms, c->timers[ST_TOTAL].beg, c->timers[s].beg));
+      MVO_CUDA_TRY(c, cudaEventElapsedTime(end_ms, c->timers[ST_TOTAL].beg, c->timers[s].end));
+      return MVO_OK;
+    }
+  }
+  c->set_error("mvo_stage_span_ms: unknown stage");
+  return MVO_ERR_INVALID;
+}
+
 }  // extern "C"

@@ -267,6 +267,15 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
                 const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
                 float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
   __shared__ LkWarpSmem sm_all[kLkWarps];
+  // window pixel k = lane + 32 j  ->  byte offset of its quad inside the staged J region.  A shared table read with one
+  // LDS per sample: fourteen offsets per lane do not fit beside the template in 96 registers, and rebuilding them
+  // (k / 21, k % 21) costs five integer instructions per sample in the iteration loop.
+  __shared__ uint16_t qtab[kSlots * 32];
+  for (int k = threadIdx.x; k < kSlots * 32; k += kLkWarps * 32) {
+    const int r = k / LKW, c = k - r * LKW;
+    qtab[k] = (uint16_t)((r * kJReg + c) * 4);
+  }
+  __syncthreads();
   const int b = blockIdx.y;
   const int n = min(npts_dev[b], max_pts);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,14 +286,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
   float nx = 0.f, ny = 0.f, e = 0.f;
   int st = 1;
   const float flt_scale = 1.f / (1 << 20);
-  // window pixel k = lane + 32 j  ->  offset of its quad inside the staged J region
-  int qoff[kSlots];
-#pragma unroll
-  for (int j = 0; j < kSlots; ++j) {
-    const int k = lane + 32 * j;
-    const int r = k / LKW, c = k - r * LKW;
-    qoff[j] = r * kJReg + c;
-  }
+  const uint16_t* qt = qtab + lane;
 
   for (int L = g.nlevels - 1; L >= 0; --L) {
     const LkLevel lv = g.lv[L];
@@ -366,7 +368,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
 #pragma unroll
       for (int j = 0; j < kSlots; ++j) {
         if (lane + 32 * j < kWin) {
-          const uint32_t q = jb[qoff[j]];
+          const uint32_t q = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(jb) + qt[32 * j]);
           const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j];
           sb1 += diff * Ixv[j];
           sb2 += diff * Iyv[j];
@@ -410,7 +412,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
 #pragma unroll
         for (int j = 0; j < kSlots; ++j) {
           if (lane + 32 * j < kWin) {
-            const uint32_t q = jb[qoff[j]];
+            const uint32_t q = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(jb) + qt[32 * j]);
             se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j]);
           }
         }

@@ -1,19 +1,25 @@
-"""Per-source-line instruction shares of one kernel from an ncu report:
-   ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > f.csv ; python scripts/ncu_lines.py f.csv [min_pct]"""
+"""Per-source-line instruction shares of the kernels in an ncu report:
+   ncu -i X.ncu-rep --page source --print-source cuda,sass --csv > f.csv ; python scripts/ncu_lines.py f.csv [min_pct] [function substring]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.4
-cur = None; agg = {}; tot = 0; stot = 0
+want = sys.argv[3] if len(sys.argv) > 3 else None
+cur = None; fn = None; per = {}
 for row in rows:
     if not row: continue
     if row[0] == 'File Path': cur = row[1].split('/')[-1]; continue
-    if row[0] == 'Function Name': continue
+    if row[0] == 'Function Name': fn = row[1]; continue
+    if row[0] == 'Kernel Name': fn = row[1]; continue
     if row[0] == 'Line No':
         ii = row.index('Instructions Executed'); si = row.index('# Samples'); continue
     if row[0] != '':
-        try: n = int(row[ii]); s = int(row[si])
+        try: n = int(row[ii]); s = int(row[si]); ln = int(row[0])
         except ValueError: continue
-        ln = int(row[0]); a = agg.get((cur, ln), (0, 0, row[1])); agg[(cur, ln)] = (a[0] + n, a[1] + s, row[1]); tot += n; stot += s
-print('total warp instructions', tot, 'samples', stot)
-for (f, ln), (n, s, src) in sorted(agg.items()):
-    if n > tot * thr / 100: print(f"{f}:{ln:4d} inst {n/tot*100:5.2f}% smp {s/stot*100:5.2f}%  {src.strip()[:100]}")
+        agg = per.setdefault(fn, {})
+        a = agg.get((cur, ln), (0, 0, row[1])); agg[(cur, ln)] = (a[0] + n, a[1] + s, row[1])
+for fn, agg in per.items():
+    if want and want not in fn: continue
+    tot = sum(v[0] for v in agg.values()); stot = max(sum(v[1] for v in agg.values()), 1)
+    print('==', fn, 'warp instructions', tot, 'samples', stot)
+    for (f, ln), (n, s, src) in sorted(agg.items()):
+        if n > tot * thr / 100: print(f"{f}:{ln:4d} inst {n/tot*100:5.2f}% smp {s/stot*100:5.2f}%  {src.strip()[:100]}")
