@@ -194,6 +194,8 @@ int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_strid
 
 int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn = 1);
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device);
+// level 0 of LK pyramid buffer `which` (gray): base pointer of stream 0, row pitch, distance between streams
+uint8_t* lk_level0(mvo_ctx* c, int which, int* pitch, long long* frame_stride);
 int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, const int32_t* npts_dev, int max_pts,
            float2* out_dev, uint8_t* status_dev, float* err_dev);
 

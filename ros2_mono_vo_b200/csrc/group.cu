@@ -130,10 +130,12 @@ __global__ void gather_results_kernel(const int32_t* kp_count, const int32_t* nm
   out[b] = r;
 }
 
-// staged frames (batch x h rows of `spitch` bytes) -> level 0 of every stream's ORB pyramid, 16 bytes per thread
+// staged frames (batch x h rows of `spitch` bytes) -> level 0 of every stream's ORB pyramid and of its LK pyramid, 16 bytes
+// per thread (one launch instead of a 2-D device copy per stream)
 __global__ void __launch_bounds__(256)
 unpack_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long src_frame_stride, uint8_t* __restrict__ dst,
-                     int dpitch, long long dst_frame_stride, int w, int h) {
+                     int dpitch, long long dst_frame_stride, uint8_t* __restrict__ dst2, int dpitch2,
+                     long long dst2_frame_stride, int w, int h) {
   const int y = blockIdx.y, b = blockIdx.z;
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
   if (x >= w) return;
@@ -144,6 +146,8 @@ unpack_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long src_
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = i < nb ? s[i] : 0;
   *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+  // second copy: level 0 of the LK pyramid (it outlives the ORB pyramid by one step)
+  if (dst2) *reinterpret_cast<uint4*>(dst2 + (long long)b * dst2_frame_stride + (long long)y * dpitch2 + x) = *reinterpret_cast<const uint4*>(v);
 }
 
 __global__ void copy_i32_strided_kernel(const int32_t* src, int stride, int32_t* dst, int n) {
@@ -240,7 +244,11 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     }
     const LevelGeom& l0 = g.lv[0];
     dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
-    unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride, w, h);
+    int lk_pitch = 0;
+    long long lk_fs = 0;
+    uint8_t* lk0 = lk_level0(c, c->lk_cur, &lk_pitch, &lk_fs);
+    unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride, lk0,
+                                                      lk_pitch, lk_fs, w, h);
     c->launches++;
     if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
   }
@@ -270,7 +278,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   }
   // ---- LK pyramid of the new frame (level 0 = ORB level 0, device to device) ----
   STAGE_BEG(c, ST_LK);
-  rc = lk_build_pyramid(c, cur, c->pyr.p + g.lv[0].off, g.lv[0].pitch, 2);
+  rc = lk_build_pyramid(c, cur, nullptr, 0, 3);   // level 0 was written by the unpack kernel
   if (rc) return rc;
   if (c->have_prev) {
     rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);

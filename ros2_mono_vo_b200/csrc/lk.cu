@@ -663,8 +663,17 @@ int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn) {
   return MVO_OK;
 }
 
+uint8_t* lk_level0(mvo_ctx* c, int which, int* pitch, long long* frame_stride) {
+  LkGeom g;
+  lk_geometry(c->lk_w, c->lk_h, g);
+  *pitch = g.lv[0].pitch;
+  *frame_stride = g.frame_stride;
+  return c->lk_pyr[which].p + g.lv[0].off;
+}
+
 // copy level 0 (batch frames, h x stride each) into LK pyramid buffer `which`, then build levels 1..
-// on_device: 0 host images, 1 device images, 2 the ORB pyramid's level 0 (gray only)
+// on_device: 0 host images, 1 device images, 2 the ORB pyramid's level 0 (gray only), 3 level 0 is already in place
+// (the group step's unpack kernel writes it together with the ORB level 0)
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device) {
   LkGeom g;
   lk_geometry(c->lk_w, c->lk_h, g);
@@ -684,6 +693,8 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
     lk_split3_kernel<<<grid, 256, 0, c->stream>>>(src, stride, (long long)fbytes, base, g.lv[0].pitch, g.frame_stride,
                                                   c->lk_w, c->lk_h);
     c->launches++;
+  } else if (on_device == 3) {
+    // nothing to copy
   } else if (on_device == 2) {
     // source is a batch of pitched device images with frame stride given by `stride` == pitch and
     // frame distance c->geom.frame_stride (ORB pyramid level 0)
