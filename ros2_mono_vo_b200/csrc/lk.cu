@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(kLkWarpsCn * 32)
 lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ pyrI, const uint8_t* __restrict__ pyrJ,
                    const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev, int max_pts,
                    float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+  static_assert(CN <= 3, "the 32-bit per-lane accumulators below are sized for at most three channels");
   __shared__ LkWarpSmemCn<CN> sm_all[kLkWarpsCn];
   const int b = blockIdx.y;
   const int n = min(npts_dev[b], max_pts);
@@ -489,7 +490,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
     }
     int w00, w01, w10, w11;
     lk_weights(__fsub_rn(qx, (float)ix), __fsub_rn(qy, (float)iy), w00, w01, w10, w11);
-    long long tA11 = 0, tA12 = 0, tA22 = 0;
+    int tA11 = 0, tA12 = 0, tA22 = 0;   // per-lane sums over CN <= 3 channels stay below 2^31 (<= 21 * 4080^2 per channel)
     __syncwarp();
 #pragma unroll 1
     for (int ch = 0; ch < CN; ++ch) {
@@ -501,9 +502,9 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
       tA22 += sA22;
     }
     __syncwarp();
-    const float A11 = __fmul_rn((float)warp_sum_ll(tA11), flt_scale);
-    const float A12 = __fmul_rn((float)warp_sum_ll(tA12), flt_scale);
-    const float A22 = __fmul_rn((float)warp_sum_ll(tA22), flt_scale);
+    const float A11 = __fmul_rn((float)warp_sum_wide(tA11), flt_scale);
+    const float A12 = __fmul_rn((float)warp_sum_wide(tA12), flt_scale);
+    const float A22 = __fmul_rn((float)warp_sum_wide(tA22), flt_scale);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dA = __fsub_rn(A11, A22);
     const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -534,7 +535,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
       lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), v00, v01, v10, v11);
       const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
       const int joff = (iny - jy0) * kJReg + (inx - jx0);
-      long long tb1 = 0, tb2 = 0;
+      int tb1 = 0, tb2 = 0;   // <= CN * 14 * 8160 * 4080 < 2^31
 #pragma unroll 1
       for (int ch = 0; ch < CN; ++ch) {
         const uint32_t* jb = sm.jq[ch] + joff;
@@ -553,8 +554,8 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
         tb1 += sb1;
         tb2 += sb2;
       }
-      const float b1 = __fmul_rn((float)warp_sum_ll(tb1), flt_scale);
-      const float b2 = __fmul_rn((float)warp_sum_ll(tb2), flt_scale);
+      const float b1 = __fmul_rn((float)warp_sum_wide(tb1), flt_scale);
+      const float b2 = __fmul_rn((float)warp_sum_wide(tb2), flt_scale);
       const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       cx = __fadd_rn(cx, dx);

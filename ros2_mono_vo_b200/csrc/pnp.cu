@@ -6,9 +6,10 @@
 //
 //   pnp_normalize_kernel   image points -> K-normalised coordinates rounded to float (undistortPoints on float input)
 //   pnp_sample_kernel      the registrator's 5-point samples from the OpenCV MWC stream (no subset check)
-//   pnp_epnp_kernel        thread per hypothesis (FP64): EPnP -- PCA control points with cv::SVD's signs (one-sided
-//                          Jacobi, replayed exactly), 12x12 M^T M eigenvectors, three beta approximations + 5
-//                          Gauss-Newton steps, absolute orientation, best reprojection error
+//   pnp_epnp_kernel        warp per hypothesis (FP64): EPnP -- PCA control points with cv::SVD's signs (one-sided
+//                          Jacobi, replayed exactly), 12x12 M^T M eigenvectors by a warp-cooperative cyclic Jacobi, the
+//                          three beta approximations + 5 Gauss-Newton steps + absolute orientation on three lanes,
+//                          best reprojection error
 //   pnp_score_kernel       CTA per hypothesis: float squared reprojection error <= thr^2, warp-reduced counts
 //   pnp_select_kernel      replays the sequential adaptive loop (strict '>' update, shrinking niters), writes the
 //                          inlier mask and the ordered inlier list of the winner
@@ -35,31 +36,67 @@ __global__ void pnp_normalize_kernel(const float2* __restrict__ img, const int32
   xn[(long long)b * max_pts + i] = make_double2((double)x, (double)y);
 }
 
-// the registrator's getSubset without a subset check: distinct indices, a repeated draw is redrawn
-__global__ void pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* __restrict__ npts,
-                                  int iters, int32_t* __restrict__ subsets) {
-  const int b = blockIdx.x;
-  if (threadIdx.x != 0) return;
+// the registrator's getSubset without a subset check: distinct indices, a repeated draw is redrawn.  The walk over
+// the RNG stream is sequential by nature (one thread); the stream itself is staged through shared memory in chunks by
+// the whole warp, so the walker pays shared-memory instead of global-memory latency per draw.
+constexpr int kPnpRngChunk = 1024;
+__global__ void __launch_bounds__(32)
+pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* __restrict__ npts, int iters,
+                  int32_t* __restrict__ subsets) {
+  __shared__ uint32_t s_rng[kPnpRngChunk];
+  __shared__ int s_pos, s_it, s_i, s_idx[kPnpK];
+  const int b = blockIdx.x, lane = threadIdx.x;
   const int n = npts[b];
-  int pos = 0;
-  for (int it = 0; it < iters; ++it) {
-    int idx[kPnpK];
-    int i = 0;
-    while (i < kPnpK && pos < rng_len) {
-      const int v = (int)(rng[pos++] % (uint32_t)n);
-      bool dup = false;
-      for (int j = 0; j < i; ++j) dup = dup || (idx[j] == v);
-      if (dup) continue;
-      idx[i++] = v;
-    }
-    for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = (i == kPnpK) ? idx[j] : 0;
+  if (lane == 0) {
+    s_pos = 0;
+    s_it = 0;
+    s_i = 0;
   }
+  __syncwarp();
+  for (int base = 0; base < rng_len; base += kPnpRngChunk) {
+    if (s_it >= iters) break;
+    const int len = min(kPnpRngChunk, rng_len - base);
+    for (int k = lane; k < len; k += 32) s_rng[k] = rng[base + k];
+    __syncwarp();
+    if (lane == 0) {
+      int pos = s_pos, it = s_it, i = s_i;
+      int idx[kPnpK];
+      for (int j = 0; j < kPnpK; ++j) idx[j] = s_idx[j];
+      while (it < iters && pos < base + len) {
+        const int v = (int)(s_rng[pos++ - base] % (uint32_t)n);
+        bool dup = false;
+        for (int j = 0; j < kPnpK; ++j) dup = dup || (j < i && idx[j] == v);
+        if (dup) continue;
+#pragma unroll
+        for (int j = 0; j < kPnpK; ++j)
+          if (j == i) idx[j] = v;
+        if (++i == kPnpK) {
+          for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = idx[j];
+          ++it;
+          i = 0;
+        }
+      }
+      s_pos = pos;
+      s_it = it;
+      s_i = i;
+      for (int j = 0; j < kPnpK; ++j) s_idx[j] = idx[j];
+    }
+    __syncwarp();
+  }
+  // the stream ran out (cannot happen with the table sizes in use): the remaining subsets are marked unusable
+  if (lane == 0)
+    for (int it = s_it; it < iters; ++it)
+      for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = 0;
 }
 
-__global__ void __launch_bounds__(32)
+// One warp per hypothesis (epnp_solve_warp, pnp_math.cuh).
+constexpr int kEpnpWarps = 2;
+__global__ void __launch_bounds__(kEpnpWarps * 32)
 pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, int max_pts,
                 const int32_t* __restrict__ subsets, int iters, double* __restrict__ models, int32_t* __restrict__ ok) {
-  const int b = blockIdx.y, it = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_A[kEpnpWarps][144], s_V[kEpnpWarps][144];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it = blockIdx.x * kEpnpWarps + warp;
   if (it >= iters) return;
   double pw[kPnpK][3], us[kPnpK][2];
   const int32_t* s = subsets + ((long long)b * iters + it) * kPnpK;
@@ -73,11 +110,13 @@ pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, i
     us[i][1] = u.y;
   }
   double R[9], t[3];
-  const bool good = epnp_solve<kPnpK>(pw, us, R, t);
-  double* m = models + ((long long)b * iters + it) * 12;
-  for (int q = 0; q < 9; ++q) m[q] = R[q];
-  for (int q = 0; q < 3; ++q) m[9 + q] = t[q];
-  ok[(long long)b * iters + it] = good ? 1 : 0;
+  const bool good = epnp_solve_warp<kPnpK>(pw, us, s_A[warp], s_V[warp], lane, R, t);
+  if (lane == 0) {
+    double* m = models + ((long long)b * iters + it) * 12;
+    for (int q = 0; q < 9; ++q) m[q] = R[q];
+    for (int q = 0; q < 3; ++q) m[9 + q] = t[q];
+    ok[(long long)b * iters + it] = good ? 1 : 0;
+  }
 }
 
 // float squared reprojection error of one point (PnPRansacCallback::computeError)
@@ -250,7 +289,7 @@ pnp_refine_kernel(const float* __restrict__ obj, const float2* __restrict__ img,
   if (result[b * 8 + 2] < 0 || n <= 0) return;
   __shared__ double s_part[(kPnpRefThreads / 32) * 43];
   __shared__ double s_out[43];
-  __shared__ double s_LtL[144];
+  __shared__ double s_LtL[144], s_V12[144];
   __shared__ double s_param[6], s_prev[6], s_JtJ[36], s_JtErr[6], s_R[9], s_dR[27], s_k[9];
   __shared__ double s_prev_norm;
   __shared__ int s_state, s_lambda, s_iters, s_planar;
@@ -310,10 +349,11 @@ pnp_refine_kernel(const float* __restrict__ obj, const float2* __restrict__ img,
       s_LtL[tid] = s;
     }
     __syncthreads();
+    if (tid < 32) jacobi_eig_warp<12>(s_LtL, s_V12, tid);
+    __syncthreads();
     if (tid == 0) {
-      double A[144], V[144];
-      for (int q = 0; q < 144; ++q) A[q] = s_LtL[q];
-      jacobi_eig<12>(A, V);
+      const double* A = s_LtL;
+      const double* V = s_V12;
       int best = 0;
       for (int q = 1; q < 12; ++q)
         if (A[q * 13] < A[best * 13]) best = q;
@@ -463,8 +503,8 @@ int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
   dim3 gn((p.max_pts + 255) / 256, B);
   pnp_normalize_kernel<<<gn, 256, 0, c->stream>>>(p.img.p, p.npts.p, p.max_pts, p.K.p, p.xn.p);
   pnp_sample_kernel<<<B, 32, 0, c->stream>>>(r.rng.p, r.rng_len, p.npts.p, iters, p.subsets.p);
-  dim3 ge((iters + 31) / 32, B);
-  pnp_epnp_kernel<<<ge, 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
+  dim3 ge((iters + kEpnpWarps - 1) / kEpnpWarps, B);
+  pnp_epnp_kernel<<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
   dim3 gs(iters, B);
   pnp_score_kernel<<<gs, 256, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.ok.p, iters,
                                              thr2, p.counts.p);

@@ -241,10 +241,13 @@ MVO_HD void rvec_to_rotation(const double* r, double* R, double* J) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// EPnP on N points with normalised image coordinates.  Returns false when the solution is not finite.
+// EPnP on N points with normalised image coordinates, in three pieces so that the kernel can run the 12 x 12
+// eigen-decomposition between the first two warp-cooperatively and the three beta approximations of the third on
+// different lanes (pnp.cu); epnp_solve below chains them on one thread (host harness, oracle checks).
+
+// piece 1: control points (PCA with cv::SVD's signs), barycentric coordinates, M^T M (12 x 12)
 template <int N>
-MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rout, double* tout) {
-  double cws[4][3];
+MVO_HD void epnp_build(const double (*pw)[3], const double (*us)[2], double (*cws)[3], double (*alphas)[4], double* MtM) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     double s = 0;
@@ -272,7 +275,6 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
   }
   PNP_DBG("cws %.10g %.10g %.10g | %.10g %.10g %.10g | %.10g %.10g %.10g | %.10g %.10g %.10g\n", cws[0][0], cws[0][1], cws[0][2], cws[1][0], cws[1][1], cws[1][2], cws[2][0], cws[2][1], cws[2][2], cws[3][0], cws[3][1], cws[3][2]);
   // barycentric coordinates
-  double alphas[N][4];
   {
     double CC[9], ci[9];
 #pragma unroll
@@ -299,7 +301,6 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
   }
   PNP_DBG("alphas0 %.10g %.10g %.10g %.10g alphas4 %.10g %.10g %.10g %.10g\n", alphas[0][0], alphas[0][1], alphas[0][2], alphas[0][3], alphas[N-1][0], alphas[N-1][1], alphas[N-1][2], alphas[N-1][3]);
   // M^T M (12 x 12) from the 2N rows [a_j, 0, -a_j u] and [0, a_j, -a_j v]
-  double MtM[144], V[144];
   for (int i = 0; i < 144; ++i) MtM[i] = 0;
   for (int i = 0; i < N; ++i) {
     double r1[12], r2[12];
@@ -318,8 +319,11 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
   for (int a = 0; a < 12; ++a)
     for (int b = 0; b < a; ++b) MtM[a * 12 + b] = MtM[b * 12 + a];
   PNP_DBG("MtM00 %.10g MtM[5][7] %.10g trace-ish %.10g\n", MtM[0], MtM[5*12+7], MtM[0]+MtM[13]+MtM[26]+MtM[143]);
-  jacobi_eig<12>(MtM, V);
-  PNP_DBG("eig %.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g\n", MtM[0], MtM[13], MtM[26], MtM[39], MtM[52], MtM[65], MtM[78], MtM[91], MtM[104], MtM[117], MtM[130], MtM[143]);
+}
+
+// piece 2: after the eigen-decomposition (MtM diagonal = eigenvalues, V columns = eigenvectors): the four eigenvectors of
+// the smallest eigenvalues, the 6 x 10 distance-constraint matrix L and rho
+MVO_HD void epnp_basis(const double* MtM, const double* V, const double (*cws)[3], double (*v)[12], double* L, double* rho) {
   // the four eigenvectors of the smallest eigenvalues, smallest first
   int sel[4];
   {
@@ -333,7 +337,6 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
       sel[q] = best;
     }
   }
-  double v[4][12];
   for (int q = 0; q < 4; ++q)
     for (int k = 0; k < 12; ++k) v[q][k] = V[k * 12 + sel[q]];
 #ifdef MVO_PNP_ROT
@@ -341,7 +344,6 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
     for (int k = 0; k < 12; ++k) { const double a = v[0][k], b = v[1][k]; v[0][k] = cr * a + sr * b; v[1][k] = -sr * a + cr * b; } }
 #endif
   // L (6 x 10) and rho
-  double L[60], rho[6];
   {
     int a = 0, b = 1;
     for (int j = 0; j < 6; ++j) {
@@ -373,141 +375,137 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
     }
   }
   PNP_DBG("sel %d %d %d %d L0 %.10g %.10g %.10g rho %.10g %.10g %.10g %.10g %.10g %.10g\n", sel[0], sel[1], sel[2], sel[3], L[0], L[1], L[2], rho[0], rho[1], rho[2], rho[3], rho[4], rho[5]);
-  double best_err = 0;
-  bool have = false;
-  for (int mode = 0; mode < 3; ++mode) {
-    double betas[4] = {0, 0, 0, 0};
-    if (mode == 0) {
-      double A[24], x[4];
-      const int cols[4] = {0, 1, 3, 6};
-      for (int i = 0; i < 6; ++i)
+}
+
+// piece 3: one of the three beta approximations (mode 0: N = 4 betas, 1: N = 2, 2: N = 3) + five Gauss-Newton steps +
+// absolute orientation; returns the mean reprojection error of the candidate (R, t)
+template <int N>
+MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const double (*v)[12], const double (*alphas)[4],
+                        const double (*pw)[3], const double (*us)[2], double* R, double* t) {
+  double betas[4] = {0, 0, 0, 0};
+  if (mode == 0) {
+    double A[24], x[4];
+    const int cols[4] = {0, 1, 3, 6};
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) A[i * 4 + j] = L[i * 10 + cols[j]];
-      ls_solve<6, 4>(A, rho, x);
-      if (x[0] < 0) {
-        betas[0] = sqrt(-x[0]);
-        betas[1] = -x[1] / betas[0];
-        betas[2] = -x[2] / betas[0];
-        betas[3] = -x[3] / betas[0];
-      } else {
-        betas[0] = sqrt(x[0]);
-        betas[1] = x[1] / betas[0];
-        betas[2] = x[2] / betas[0];
-        betas[3] = x[3] / betas[0];
-      }
-    } else if (mode == 1) {
-      double A[18], x[3];
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) A[i * 3 + j] = L[i * 10 + j];
-      ls_solve<6, 3>(A, rho, x);
-      if (x[0] < 0) {
-        betas[0] = sqrt(-x[0]);
-        betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
-      } else {
-        betas[0] = sqrt(x[0]);
-        betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
-      }
-      if (x[1] < 0) betas[0] = -betas[0];
+      for (int j = 0; j < 4; ++j) A[i * 4 + j] = L[i * 10 + cols[j]];
+    ls_solve<6, 4>(A, rho, x);
+    if (x[0] < 0) {
+      betas[0] = sqrt(-x[0]);
+      betas[1] = -x[1] / betas[0];
+      betas[2] = -x[2] / betas[0];
+      betas[3] = -x[3] / betas[0];
     } else {
-      double A[30], x[5];
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 5; ++j) A[i * 5 + j] = L[i * 10 + j];
-      ls_solve<6, 5>(A, rho, x);
-      if (x[0] < 0) {
-        betas[0] = sqrt(-x[0]);
-        betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
-      } else {
-        betas[0] = sqrt(x[0]);
-        betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
-      }
-      if (x[1] < 0) betas[0] = -betas[0];
-      betas[2] = x[3] / betas[0];
+      betas[0] = sqrt(x[0]);
+      betas[1] = x[1] / betas[0];
+      betas[2] = x[2] / betas[0];
+      betas[3] = x[3] / betas[0];
     }
-    PNP_DBG("mode %d betas0 %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
-    // five Gauss-Newton steps on the six distance constraints
-    for (int it = 0; it < 5; ++it) {
-      double A[24], bb[6], x[4];
-      for (int i = 0; i < 6; ++i) {
-        const double* l = L + 10 * i;
-        const double b0 = betas[0], b1 = betas[1], b2 = betas[2], b3 = betas[3];
-        A[i * 4 + 0] = 2 * l[0] * b0 + l[1] * b1 + l[3] * b2 + l[6] * b3;
-        A[i * 4 + 1] = l[1] * b0 + 2 * l[2] * b1 + l[4] * b2 + l[7] * b3;
-        A[i * 4 + 2] = l[3] * b0 + l[4] * b1 + 2 * l[5] * b2 + l[8] * b3;
-        A[i * 4 + 3] = l[6] * b0 + l[7] * b1 + l[8] * b2 + 2 * l[9] * b3;
-        bb[i] = rho[i] - (l[0] * b0 * b0 + l[1] * b0 * b1 + l[2] * b1 * b1 + l[3] * b0 * b2 + l[4] * b1 * b2 +
-                          l[5] * b2 * b2 + l[6] * b0 * b3 + l[7] * b1 * b3 + l[8] * b2 * b3 + l[9] * b3 * b3);
-      }
-      ls_solve<6, 4>(A, bb, x);
-      PNP_DBG("  gn %d betas %.6g %.6g %.6g %.6g x %.6g %.6g %.6g %.6g bb %.6g %.6g A0 %.6g %.6g %.6g %.6g Lsum %.10g\n", it, betas[0], betas[1], betas[2], betas[3], x[0], x[1], x[2], x[3], bb[0], bb[5], A[0], A[1], A[2], A[3], L[0]+L[11]+L[22]+L[33]+L[44]+L[55]+L[59]);
+  } else if (mode == 1) {
+    double A[18], x[3];
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) betas[q] += x[q];
+      for (int j = 0; j < 3; ++j) A[i * 3 + j] = L[i * 10 + j];
+    ls_solve<6, 3>(A, rho, x);
+    if (x[0] < 0) {
+      betas[0] = sqrt(-x[0]);
+      betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+    } else {
+      betas[0] = sqrt(x[0]);
+      betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
     }
-    PNP_DBG("mode %d betas %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
-    // control points in the camera frame, sign, absolute orientation
-    double ccs[4][3];
+    if (x[1] < 0) betas[0] = -betas[0];
+  } else {
+    double A[30], x[5];
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) ccs[j][k] = betas[0] * v[0][3 * j + k] + betas[1] * v[1][3 * j + k] + betas[2] * v[2][3 * j + k] + betas[3] * v[3][3 * j + k];
-    double sign = 1.0;
-    {
-      const double z0 = alphas[0][0] * ccs[0][2] + alphas[0][1] * ccs[1][2] + alphas[0][2] * ccs[2][2] + alphas[0][3] * ccs[3][2];
-      if (z0 < 0) sign = -1.0;
+      for (int j = 0; j < 5; ++j) A[i * 5 + j] = L[i * 10 + j];
+    ls_solve<6, 5>(A, rho, x);
+    if (x[0] < 0) {
+      betas[0] = sqrt(-x[0]);
+      betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+    } else {
+      betas[0] = sqrt(x[0]);
+      betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
     }
-    double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
-    double pcs[N][3];
-    for (int i = 0; i < N; ++i)
+    if (x[1] < 0) betas[0] = -betas[0];
+    betas[2] = x[3] / betas[0];
+  }
+  PNP_DBG("mode %d betas0 %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
+  // five Gauss-Newton steps on the six distance constraints
+  for (int it = 0; it < 5; ++it) {
+    double A[24], bb[6], x[4];
+    for (int i = 0; i < 6; ++i) {
+      const double* l = L + 10 * i;
+      const double b0 = betas[0], b1 = betas[1], b2 = betas[2], b3 = betas[3];
+      A[i * 4 + 0] = 2 * l[0] * b0 + l[1] * b1 + l[3] * b2 + l[6] * b3;
+      A[i * 4 + 1] = l[1] * b0 + 2 * l[2] * b1 + l[4] * b2 + l[7] * b3;
+      A[i * 4 + 2] = l[3] * b0 + l[4] * b1 + 2 * l[5] * b2 + l[8] * b3;
+      A[i * 4 + 3] = l[6] * b0 + l[7] * b1 + l[8] * b2 + 2 * l[9] * b3;
+      bb[i] = rho[i] - (l[0] * b0 * b0 + l[1] * b0 * b1 + l[2] * b1 * b1 + l[3] * b0 * b2 + l[4] * b1 * b2 +
+                        l[5] * b2 * b2 + l[6] * b0 * b3 + l[7] * b1 * b3 + l[8] * b2 * b3 + l[9] * b3 * b3);
+    }
+    ls_solve<6, 4>(A, bb, x);
+    PNP_DBG("  gn %d betas %.6g %.6g %.6g %.6g x %.6g %.6g %.6g %.6g bb %.6g %.6g A0 %.6g %.6g %.6g %.6g Lsum %.10g\n", it, betas[0], betas[1], betas[2], betas[3], x[0], x[1], x[2], x[3], bb[0], bb[5], A[0], A[1], A[2], A[3], L[0]+L[11]+L[22]+L[33]+L[44]+L[55]+L[59]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        pcs[i][k] = sign * (alphas[i][0] * ccs[0][k] + alphas[i][1] * ccs[1][k] + alphas[i][2] * ccs[2][k] + alphas[i][3] * ccs[3][k]);
-        pc0[k] += pcs[i][k];
-        pw0[k] += pw[i][k];
-      }
+    for (int q = 0; q < 4; ++q) betas[q] += x[q];
+  }
+  PNP_DBG("mode %d betas %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
+  // control points in the camera frame, sign, absolute orientation
+  double ccs[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ccs[j][k] = betas[0] * v[0][3 * j + k] + betas[1] * v[1][3 * j + k] + betas[2] * v[2][3 * j + k] + betas[3] * v[3][3 * j + k];
+  double sign = 1.0;
+  {
+    const double z0 = alphas[0][0] * ccs[0][2] + alphas[0][1] * ccs[1][2] + alphas[0][2] * ccs[2][2] + alphas[0][3] * ccs[3][2];
+    if (z0 < 0) sign = -1.0;
+  }
+  double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
+  double pcs[N][3];
+  for (int i = 0; i < N; ++i)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      pc0[k] /= N;
-      pw0[k] /= N;
-    }
-    double ABt[9];
-    for (int q = 0; q < 9; ++q) ABt[q] = 0;
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ABt[3 * j + k] += (pcs[i][j] - pc0[j]) * (pw[i][k] - pw0[k]);
-    double R[9], t[3];
-    polar_rotation(ABt, R);
-    if (det3(R) < 0) {
-      R[6] = -R[6];
-      R[7] = -R[7];
-      R[8] = -R[8];
+      pcs[i][k] = sign * (alphas[i][0] * ccs[0][k] + alphas[i][1] * ccs[1][k] + alphas[i][2] * ccs[2][k] + alphas[i][3] * ccs[3][k]);
+      pc0[k] += pcs[i][k];
+      pw0[k] += pw[i][k];
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) t[k] = pc0[k] - (R[3 * k] * pw0[0] + R[3 * k + 1] * pw0[1] + R[3 * k + 2] * pw0[2]);
-    double err = 0;
-    for (int i = 0; i < N; ++i) {
-      const double X = R[0] * pw[i][0] + R[1] * pw[i][1] + R[2] * pw[i][2] + t[0];
-      const double Y = R[3] * pw[i][0] + R[4] * pw[i][1] + R[5] * pw[i][2] + t[1];
-      const double iz = 1.0 / (R[6] * pw[i][0] + R[7] * pw[i][1] + R[8] * pw[i][2] + t[2]);
-      const double du = us[i][0] - X * iz, dv = us[i][1] - Y * iz;
-      err += sqrt(du * du + dv * dv);
-    }
-    err /= N;
-    PNP_DBG("mode %d err %.10g t %.10g %.10g %.10g R0 %.10g %.10g %.10g\n", mode, err, t[0], t[1], t[2], R[0], R[1], R[2]);
-    // OpenCV keeps candidate 1 unless a later one is strictly better (NaN errors never win)
-    if (!have || err < best_err) {
-      if (!have || mode > 0) {
-        best_err = err;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) Rout[q] = R[q];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) tout[q] = t[q];
-      }
-      have = true;
-    }
+  for (int k = 0; k < 3; ++k) {
+    pc0[k] /= N;
+    pw0[k] /= N;
   }
+  double ABt[9];
+  for (int q = 0; q < 9; ++q) ABt[q] = 0;
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ABt[3 * j + k] += (pcs[i][j] - pc0[j]) * (pw[i][k] - pw0[k]);
+  polar_rotation(ABt, R);
+  if (det3(R) < 0) {
+    R[6] = -R[6];
+    R[7] = -R[7];
+    R[8] = -R[8];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = pc0[k] - (R[3 * k] * pw0[0] + R[3 * k + 1] * pw0[1] + R[3 * k + 2] * pw0[2]);
+  double err = 0;
+  for (int i = 0; i < N; ++i) {
+    const double X = R[0] * pw[i][0] + R[1] * pw[i][1] + R[2] * pw[i][2] + t[0];
+    const double Y = R[3] * pw[i][0] + R[4] * pw[i][1] + R[5] * pw[i][2] + t[1];
+    const double iz = 1.0 / (R[6] * pw[i][0] + R[7] * pw[i][1] + R[8] * pw[i][2] + t[2]);
+    const double du = us[i][0] - X * iz, dv = us[i][1] - Y * iz;
+    err += sqrt(du * du + dv * dv);
+  }
+  err /= N;
+  PNP_DBG("mode %d err %.10g t %.10g %.10g %.10g R0 %.10g %.10g %.10g\n", mode, err, t[0], t[1], t[2], R[0], R[1], R[2]);
+  return err;
+}
+
+template <int N>
+MVO_HD bool epnp_finite(const double* Rout, const double* tout) {
   bool fin = true;
 #pragma unroll
   for (int q = 0; q < 9; ++q) fin = fin && isfinite(Rout[q]);
@@ -515,5 +513,69 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
   for (int q = 0; q < 3; ++q) fin = fin && isfinite(tout[q]);
   return fin;
 }
+
+// Returns false when the solution is not finite.
+template <int N>
+MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rout, double* tout) {
+  double cws[4][3], alphas[N][4], MtM[144], V[144];
+  epnp_build<N>(pw, us, cws, alphas, MtM);
+  jacobi_eig<12>(MtM, V);
+  double v[4][12], L[60], rho[6];
+  epnp_basis(MtM, V, cws, v, L, rho);
+  double best_err = 0;
+  for (int mode = 0; mode < 3; ++mode) {
+    double R[9], t[3];
+    const double err = epnp_mode<N>(mode, L, rho, v, alphas, pw, us, R, t);
+    // OpenCV keeps candidate 1 unless a later one is strictly better (NaN errors never win)
+    if (mode == 0 || err < best_err) {
+      best_err = err;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Rout[q] = R[q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tout[q] = t[q];
+    }
+  }
+  return epnp_finite<N>(Rout, tout);
+}
+
+#ifdef __CUDACC__
+// The form the kernel runs: one warp per problem.  Every lane builds the (tiny) problem redundantly; the 12 x 12
+// eigen-decomposition -- nine tenths of a single thread's time -- runs warp-cooperatively on shared memory
+// (jacobi_eig_warp: same rotation order and expressions as jacobi_eig); the three beta approximations run on lanes
+// 0, 1, 2 side by side and the winner is picked with OpenCV's rule.  sA / sV: 144 doubles of shared memory each.
+// The result is returned in every lane.
+template <int N>
+__device__ bool epnp_solve_warp(const double (*pw)[3], const double (*us)[2], double* sA, double* sV, int lane, double* Rout,
+                                double* tout) {
+  double cws[4][3], alphas[N][4];
+  {
+    double MtM[144];
+    epnp_build<N>(pw, us, cws, alphas, MtM);
+    for (int q = lane; q < 144; q += 32) sA[q] = MtM[q];   // identical in every lane
+  }
+  __syncwarp();
+  jacobi_eig_warp<12>(sA, sV, lane);
+  __syncwarp();
+  double v[4][12], L[60], rho[6];
+  epnp_basis(sA, sV, cws, v, L, rho);
+  const int mode = lane < 3 ? lane : 0;
+  const double err = epnp_mode<N>(mode, L, rho, v, alphas, pw, us, Rout, tout);
+  // OpenCV keeps candidate 0 unless a later one is strictly better (NaN errors never win)
+  const double e0 = __shfl_sync(0xffffffffu, err, 0), e1 = __shfl_sync(0xffffffffu, err, 1), e2 = __shfl_sync(0xffffffffu, err, 2);
+  int win = 0;
+  double best = e0;
+  if (e1 < best) {
+    best = e1;
+    win = 1;
+  }
+  if (e2 < best) win = 2;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) Rout[q] = __shfl_sync(0xffffffffu, Rout[q], win);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) tout[q] = __shfl_sync(0xffffffffu, tout[q], win);
+  __syncwarp();   // sA / sV may be reused by the caller
+  return epnp_finite<N>(Rout, tout);
+}
+#endif
 
 }  // namespace mvo

@@ -6,14 +6,23 @@
 #include <cuda_runtime.h>
 #include "../../ros2_mono_vo_b200/csrc/pnp_math.cuh"
 
+// one warp: the form pnp_epnp_kernel runs (epnp_solve_warp: warp-cooperative 12 x 12 Jacobi, the three beta
+// approximations on three lanes)
 __global__ void epnp_device(const double* in, double* out) {
+  __shared__ double sA[144], sV[144];
   double pw[mvo::kPnpK][3], us[mvo::kPnpK][2];
   for (int i = 0; i < mvo::kPnpK; ++i) {
     for (int k = 0; k < 3; ++k) pw[i][k] = in[i * 5 + k];
     us[i][0] = in[i * 5 + 3];
     us[i][1] = in[i * 5 + 4];
   }
-  out[12] = mvo::epnp_solve<mvo::kPnpK>(pw, us, out, out + 9) ? 1.0 : 0.0;
+  double R[9], t[3];
+  const bool ok = mvo::epnp_solve_warp<mvo::kPnpK>(pw, us, sA, sV, threadIdx.x, R, t);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 9; ++i) out[i] = R[i];
+    for (int i = 0; i < 3; ++i) out[9 + i] = t[i];
+    out[12] = ok ? 1.0 : 0.0;
+  }
 }
 
 int main(int argc, char** argv) {
@@ -24,12 +33,12 @@ int main(int argc, char** argv) {
     if (scanf("%lf %lf %lf %lf %lf", &pw[i][0], &pw[i][1], &pw[i][2], &us[i][0], &us[i][1]) != 5) return 2;
   double R[9], t[3], r[3], R2[9], J[27];
   bool ok;
-  if (argc > 1) {   // --device: the same function in a one-thread kernel
+  if (argc > 1) {   // --device: the warp form the kernels run
     double hin[25], hout[13], *din, *dout;
     for (int i = 0; i < 5; ++i) { hin[i * 5] = pw[i][0]; hin[i * 5 + 1] = pw[i][1]; hin[i * 5 + 2] = pw[i][2]; hin[i * 5 + 3] = us[i][0]; hin[i * 5 + 4] = us[i][1]; }
     cudaMalloc(&din, sizeof(hin)); cudaMalloc(&dout, sizeof(hout));
     cudaMemcpy(din, hin, sizeof(hin), cudaMemcpyHostToDevice);
-    epnp_device<<<1, 1>>>(din, dout);
+    epnp_device<<<1, 32>>>(din, dout);
     if (cudaMemcpy(hout, dout, sizeof(hout), cudaMemcpyDeviceToHost) != cudaSuccess) return 3;
     for (int i = 0; i < 9; ++i) R[i] = hout[i];
     for (int i = 0; i < 3; ++i) t[i] = hout[9 + i];

@@ -1,6 +1,6 @@
 """csrc/pnp_math.cuh (the per-hypothesis arithmetic of pnp.cu) compiled for the HOST by nvcc and checked against
 oracle/pnp_oracle.py -- the same source the kernels run, testable without a GPU.  On a GPU box the same binary also
-runs the function inside a one-thread kernel (`--device`): that is how an nvcc -O3 miscompile of this code was found."""
+runs the warp-cooperative form the kernels use (`--device`, one warp): that is how an nvcc -O3 miscompile of this code was found."""
 import os
 import subprocess
 
