@@ -239,15 +239,15 @@ pnp_select_kernel(const float* __restrict__ obj, const float2* __restrict__ img,
 // block-wide deterministic sum of NV doubles per thread -> out[NV] (valid in every thread after the call)
 constexpr int kPnpRefThreads = 256;
 template <int NV>
-__device__ void block_sum(const double* v, double* s_part /* [8][NV] */, double* out /* smem [NV] */) {
+__device__ void block_sum(const double* v, double* s_part /* [8][NV] */, double* out /* smem [NV] */, int first = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
-  for (int q = 0; q < NV; ++q) {
+  for (int q = first; q < NV; ++q) {   // entries below `first` are known to be zero (not accumulated by the caller)
     const double s = warp_sum_d(v[q]);
     if (lane == 0) s_part[warp * NV + q] = s;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
+  if (threadIdx.x >= first && threadIdx.x < NV) {
     double s = 0;
     for (int w = 0; w < kPnpRefThreads / 32; ++w) s += s_part[w * NV + threadIdx.x];
     out[threadIdx.x] = s;
@@ -416,7 +416,7 @@ pnp_refine_kernel(const float* __restrict__ obj, const float2* __restrict__ img,
         }
       }
     }
-    block_sum<43>(v, s_part, s_out);
+    block_sum<43>(v, s_part, s_out, state == 0 ? 0 : 42);   // the check evaluation only needs the error norm
     if (tid == 0) {
       auto step = [&]() {
         const double lam = exp(s_lambda * log(10.0));

@@ -109,7 +109,7 @@ MVO_HD void ls_solve(const double* A, const double* b, double* x) {
     Atb[i] = s;
   }
   PNP_DBG("ls%d AtA %.6g %.6g %.6g %.6g Atb %.6g %.6g %.6g\n", N, AtA[0], AtA[1], AtA[N+1], AtA[N*N-1], Atb[0], Atb[1], Atb[N-1]);
-  jacobi_eig<N>(AtA, V);
+  jacobi_eig_reg<N>(AtA, V);   // N <= 5: fully unrolled, AtA and V stay in registers
   PNP_DBG("ls%d eig %.6g %.6g %.6g V0 %.6g %.6g %.6g\n", N, AtA[0], AtA[N+1], AtA[N*N-1], V[0], V[1], V[2]);
   double lmax = 0;
   for (int i = 0; i < N; ++i) lmax = fmax(lmax, AtA[i * N + i]);
