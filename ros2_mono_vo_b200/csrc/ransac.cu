@@ -27,9 +27,15 @@ namespace mvo {
 constexpr int kDraws = 32768;         // largest RNG window of one sampler pass (uint16 offsets)
 constexpr int kMaxAttempts = 16384;   // getSubset attempts followed per pass (large window)
 constexpr int kSegIters = 2048;       // subsets produced per sampler pass
-constexpr int kRound0 = 128;          // iterations evaluated before the first early-exit check
-constexpr int kDraws0 = 4096;         // window / attempts of the round-0 sampler pass
+constexpr int kRound0 = 128;          // iterations evaluated before the second early-exit check
+constexpr int kDraws0 = 4096;         // window / attempts of that sampler pass
 constexpr int kAttempts0 = 1024;
+#ifndef MVO_RANSAC_ROUND_A
+#define MVO_RANSAC_ROUND_A 32
+#endif
+constexpr int kRoundA = MVO_RANSAC_ROUND_A;   // iterations evaluated before the first early-exit check (0: no such round)
+constexpr int kDrawsA = 1024;
+constexpr int kAttemptsA = 256;
 
 template <int MODEL> struct MT;
 template <> struct MT<MVO_MODEL_H> { static constexpr int K = 4, MAXIT = 2000, MAXM = 1; };
@@ -1194,7 +1200,14 @@ static int find_model(mvo_ctx* c, double conf) {
   RansacBufs& r = c->rs;
   constexpr int MAXIT = MT<MODEL>::MAXIT;
   MVO_CUDA_TRY(c, cudaMemsetAsync(r.ln().state.p, 0, (size_t)c->cfg.batch * 32, c->stream));
-  // round 0: the first kRound0 iterations; usually the adaptive loop has already stopped inside them
+  // OpenCV's loop stops after a handful of iterations when most correspondences are inliers (1 - conf is reached
+  // quickly): the first round is small so that easy frames do not pay for 128 solved and scored hypotheses
+  if (kRoundA > 0) {
+    sample_pass<MODEL>(c, kRoundA, kDrawsA, kAttemptsA);
+    solve_score<MODEL>(c, 0, kRoundA);
+    select_pass<MODEL>(c, kRoundA, conf);
+  }
+  // the first kRound0 iterations; usually the adaptive loop has stopped inside them
   sample_pass<MODEL>(c, kRound0, kDraws0, kAttempts0);
   solve_score<MODEL>(c, 0, kRound0);
   select_pass<MODEL>(c, kRound0, conf);
