@@ -33,6 +33,7 @@ constexpr int kAttempts0 = 1024;
 #ifndef MVO_RANSAC_ROUND_A
 #define MVO_RANSAC_ROUND_A 32
 #endif
+constexpr int kScoreGrid = 128;       // CTAs per stream of the scoring kernel (it strides over the hypotheses)
 constexpr int kRoundA = MVO_RANSAC_ROUND_A;   // iterations evaluated before the first early-exit check (0: no such round)
 constexpr int kDrawsA = 1024;
 constexpr int kAttemptsA = 256;
@@ -480,34 +481,37 @@ ransac_score_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2
                     const double* __restrict__ models, const int32_t* __restrict__ nmodels,
                     const float* __restrict__ thr2, int32_t* __restrict__ counts) {
   constexpr int MAXM = MT<MODEL>::MAXM;
-  const int b = blockIdx.y, h = h0 + blockIdx.x;
+  const int b = blockIdx.y;
   if (state[b * 8 + 3]) return;
   const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
-  if (h >= nsub || h < state[b * 8 + 4]) return;
-  const int nm = nmodels[(long long)b * cap_iters + h];
+  const int hbeg = max(h0, state[b * 8 + 4]);
   __shared__ double s_m[MAXM * 9];
   __shared__ float s_mf[MAXM * 9];
   __shared__ int s_cnt[MAXM];
   const int tid = threadIdx.x;
-  if (tid < nm * 9) {
-    const double v = models[((long long)b * cap_iters + h) * MAXM * 9 + tid];
-    s_m[tid] = v;
-    s_mf[tid] = (float)v;
-  }
-  if (tid < MAXM) s_cnt[tid] = 0;
-  __syncthreads();
   const int n = npts[b];
   const float t = thr2[b];
   const long long base = (long long)b * max_pts;
-  for (int m = 0; m < nm; ++m) {
-    int c = 0;
-    for (int i = tid; i < n; i += kScoreThreads)
-      c += (model_error<MODEL>(s_m + m * 9, s_mf + m * 9, p1, p2, q1, q2, base + i) <= t) ? 1 : 0;
-    c = warp_sum(c);
-    if ((tid & 31) == 0) atomicAdd(&s_cnt[m], c);
+  for (int h = hbeg + blockIdx.x; h < nsub; h += gridDim.x) {   // CTA per hypothesis, strided when the grid is capped
+    const int nm = nmodels[(long long)b * cap_iters + h];
+    if (tid < nm * 9) {
+      const double v = models[((long long)b * cap_iters + h) * MAXM * 9 + tid];
+      s_m[tid] = v;
+      s_mf[tid] = (float)v;
+    }
+    if (tid < MAXM) s_cnt[tid] = 0;
+    __syncthreads();
+    for (int m = 0; m < nm; ++m) {
+      int c = 0;
+      for (int i = tid; i < n; i += kScoreThreads)
+        c += (model_error<MODEL>(s_m + m * 9, s_mf + m * 9, p1, p2, q1, q2, base + i) <= t) ? 1 : 0;
+      c = warp_sum(c);
+      if ((tid & 31) == 0) atomicAdd(&s_cnt[m], c);
+    }
+    __syncthreads();
+    if (tid < MAXM) counts[((long long)b * cap_iters + h) * MAXM + tid] = (tid < nm) ? s_cnt[tid] : -1;
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid < MAXM) counts[((long long)b * cap_iters + h) * MAXM + tid] = (tid < nm) ? s_cnt[tid] : -1;
 }
 
 // ---- select: replay of the sequential adaptive loop ---------------------------------------------
@@ -1178,7 +1182,7 @@ static void solve_score(mvo_ctx* c, int h0, int h1) {
     ransac_solve_kernel<MODEL><<<gs, tpb, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p,
                                                           r.ln().state.p, r.cap_iters, h0, h1, r.ln().models.p, r.ln().nmodels.p);
   }
-  dim3 gc(count, B);
+  dim3 gc(std::min(count, kScoreGrid), B);
   ransac_score_kernel<MODEL><<<gc, kScoreThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.npts.p, r.max_pts,
                                                                  r.ln().state.p, r.cap_iters, h0, h1, r.ln().models.p,
                                                                  r.ln().nmodels.p, r.ln().thr2.p, r.ln().counts.p);
@@ -1211,7 +1215,8 @@ static int find_model(mvo_ctx* c, double conf) {
   sample_pass<MODEL>(c, kRound0, kDraws0, kAttempts0);
   solve_score<MODEL>(c, 0, kRound0);
   select_pass<MODEL>(c, kRound0, conf);
-  // round 1: everything up to maxIters (empty launches for streams that are done)
+  // last round: everything up to maxIters (empty launches for streams that are done; the scoring grid is capped so that
+  // those empty launches do not flood the CTA dispatcher while the next step's kernels run beside them)
   sample_pass<MODEL>(c, MAXIT, kDraws, kMaxAttempts);
   solve_score<MODEL>(c, 0, MAXIT);
   select_pass<MODEL>(c, MAXIT, conf);
