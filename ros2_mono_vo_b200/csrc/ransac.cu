@@ -344,11 +344,17 @@ __device__ __forceinline__ double mid_key(double a, double b) {
   return __longlong_as_double(km);
 }
 
-__device__ __forceinline__ double poly_eval(const double* q, int qd, double x, double& dv) {
-  double v = q[qd];
+// value and derivative of q (degree qd, ascending coefficients) by Horner:  v = q[qd]; for i = qd-1 .. 0: dv = dv x + v,
+// v = v x + q[i].
+// Run on a register-resident copy of the coefficients, zero-padded to degree 10 and fully unrolled: the leading zero
+// terms leave v = dv = 0 until the true leading coefficient is reached, so value and derivative are bit-identical to the
+// variable-degree loop -- without a local-memory load in every step of the dependent chain (the 5-point root finder
+// spends its time here: ~25 evaluations per root and derivative level).
+__device__ __forceinline__ double poly_eval10(const double (&q)[11], double x, double& dv) {
+  double v = q[10];
   dv = 0.0;
-#pragma unroll 1
-  for (int i = qd - 1; i >= 0; --i) {
+#pragma unroll
+  for (int i = 9; i >= 0; --i) {
     dv = dv * x + v;
     v = v * x + q[i];
   }
@@ -356,10 +362,10 @@ __device__ __forceinline__ double poly_eval(const double* q, int qd, double x, d
 }
 
 // root of q inside (lo, hi) given a sign change: Newton safeguarded by bisection in key space
-__device__ inline double bracket_root(const double* q, int qd, double lo, double hi, double flo) {
+__device__ inline double bracket_root(const double (&q)[11], double lo, double hi, double flo) {
   double xl = (flo < 0.0) ? lo : hi, xh = (flo < 0.0) ? hi : lo;   // f(xl) < 0 < f(xh)
   double x = mid_key(lo, hi), dfx;
-  double fx = poly_eval(q, qd, x, dfx);
+  double fx = poly_eval10(q, x, dfx);
   double dxold = fabs(hi - lo);
 #pragma unroll 1
   for (int it = 0; it < 100; ++it) {
@@ -374,7 +380,7 @@ __device__ inline double bracket_root(const double* q, int qd, double lo, double
     const bool conv = dxold <= 4e-16 * fabs(xn);
     x = xn;
     if (conv) break;
-    fx = poly_eval(q, qd, x, dfx);
+    fx = poly_eval10(q, x, dfx);
   }
   return x;
 }
@@ -425,16 +431,19 @@ e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1
     bool found = false;
     double root = 0.0;
     if (lvl_on && l16 <= ncrit) {
+      double qr[11];   // register copy, zero above the degree
+#pragma unroll
+      for (int i = 0; i <= 10; ++i) qr[i] = (i <= qd) ? q[i] : 0.0;
       const double lo = (l16 == 0) ? -bound : lo_s;
       const double hi = (l16 < ncrit) ? hi_s : bound;
       double d0;
-      const double flo = poly_eval(q, qd, lo, d0), fhi = poly_eval(q, qd, hi, d0);
+      const double flo = poly_eval10(qr, lo, d0), fhi = poly_eval10(qr, hi, d0);
       if (fhi == 0.0) {
         found = true;
         root = hi;
       } else if (flo != 0.0 && ((flo < 0.0) != (fhi < 0.0))) {
         found = true;
-        root = bracket_root(q, qd, lo, hi, flo);
+        root = bracket_root(qr, lo, hi, flo);
       }
     }
     const unsigned bal = (__ballot_sync(full, found) >> (16 * half)) & 0xffffu;
