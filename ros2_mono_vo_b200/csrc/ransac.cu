@@ -310,15 +310,18 @@ ransac_solve_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2
 // ---- 5-point solver, split for latency: per-thread algebra, then 16 lanes per hypothesis for the roots ----
 constexpr int kE5Scratch = 36 + 39 + 11;   // EE basis, Bm, det polynomial
 
-__global__ void __launch_bounds__(64)
+constexpr int kE5SetupWarps = 4;   // one warp per hypothesis (e5_setup_warp)
+__global__ void __launch_bounds__(kE5SetupWarps * 32)
 e5_setup_kernel(const double2* __restrict__ q1, const double2* __restrict__ q2, int max_pts,
                 const int32_t* __restrict__ subsets, const int32_t* __restrict__ state, int cap_iters, int h0, int h1,
                 double* __restrict__ scratch) {
+  __shared__ double s_M[kE5SetupWarps][200];
   const int b = blockIdx.y;
   if (state[b * 8 + 3]) return;
-  const int h = h0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = h0 + blockIdx.x * kE5SetupWarps + warp;
   const int nsub = min(min(state[b * 8 + 1], cap_iters), h1);
-  if (h >= nsub || h < state[b * 8 + 4]) return;
+  if (h >= nsub || h < state[b * 8 + 4]) return;   // warp-uniform
   const int32_t* idx = subsets + ((long long)b * cap_iters + h) * 5;
   double2 a[5], c[5];
   for (int i = 0; i < 5; ++i) {
@@ -326,11 +329,13 @@ e5_setup_kernel(const double2* __restrict__ q1, const double2* __restrict__ q2, 
     c[i] = q2[(long long)b * max_pts + idx[i]];
   }
   double EE[36], Bm[39], detp[11];
-  const bool ok = e5_setup(a, c, EE, Bm, detp);
+  const bool ok = e5_setup_warp(a, c, s_M[warp], lane, EE, Bm, detp);
   double* out = scratch + ((long long)b * cap_iters + h) * kE5Scratch;
-  for (int i = 0; i < 36; ++i) out[i] = EE[i];
-  for (int i = 0; i < 39; ++i) out[36 + i] = Bm[i];
-  for (int i = 0; i < 11; ++i) out[75 + i] = ok ? detp[i] : 0.0;
+  if (lane == 0) {
+    for (int i = 0; i < 36; ++i) out[i] = EE[i];
+    for (int i = 0; i < 39; ++i) out[36 + i] = ok ? Bm[i] : 0.0;
+    for (int i = 0; i < 11; ++i) out[75 + i] = ok ? detp[i] : 0.0;
+  }
 }
 
 // midpoint of [a, b] in the ordered-integer representation of IEEE doubles: at most ~11 steps to pin the
@@ -1181,7 +1186,8 @@ static void solve_score(mvo_ctx* c, int h0, int h1) {
   while (tpb < 64 && (long long)B * count > 148LL * 4 * tpb) tpb <<= 1;
   dim3 gs((count + tpb - 1) / tpb, B);
   if (MODEL == MVO_MODEL_E) {
-    e5_setup_kernel<<<gs, tpb, 0, c->stream>>>(r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p, r.ln().state.p, r.cap_iters, h0, h1,
+    dim3 gw((count + kE5SetupWarps - 1) / kE5SetupWarps, B);
+    e5_setup_kernel<<<gw, kE5SetupWarps * 32, 0, c->stream>>>(r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p, r.ln().state.p, r.cap_iters, h0, h1,
                                                r.ln().e5_scratch.p);
     dim3 gr((count + kRootsThreads / 16 - 1) / (kRootsThreads / 16), B);
     e5_roots_kernel<<<gr, kRootsThreads, 0, c->stream>>>(r.ln().state.p, r.cap_iters, h0, h1, r.ln().e5_scratch.p, r.ln().models.p,

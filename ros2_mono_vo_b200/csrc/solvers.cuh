@@ -254,6 +254,132 @@ __device__ inline bool e5_setup(const double2* q1, const double2* q2, double* EE
   return true;
 }
 
+// Part 1 as one warp runs it (e5_setup_kernel): the same arithmetic in the same order, with the two expensive pieces
+// spread over the lanes -- lane r builds row r of the 10 x 20 constraint matrix, and the Gauss-Jordan elimination works
+// on the matrix in shared memory with lane = column.  The small serial pieces (null space, E E^T, B(z), det B) are
+// computed redundantly by every lane.  Msh: 200 doubles of shared memory.  The outputs are identical in every lane.
+__device__ inline bool e5_setup_warp(const double2* q1, const double2* q2, double* Msh, int lane, double* EE, double* Bm /* 39 */,
+                                     double* detp /* 11 */) {
+  double A[5 * 9];
+  for (int i = 0; i < 5; ++i) {
+    const double x1 = q1[i].x, y1 = q1[i].y, x2 = q2[i].x, y2 = q2[i].y;
+    double* a = A + i * 9;
+    a[0] = x2 * x1; a[1] = x2 * y1; a[2] = x2; a[3] = y2 * x1; a[4] = y2 * y1; a[5] = y2; a[6] = x1; a[7] = y1; a[8] = 1;
+  }
+  null_space<5, 9>(A, EE);
+  double e[9][4];
+  for (int k = 0; k < 9; ++k)
+    for (int j = 0; j < 4; ++j) e[k][j] = EE[j * 9 + k];
+  double eet[6][10];
+  const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  for (int r = 0; r < 3; ++r)
+    for (int c = r; c < 3; ++c) {
+      double* q = eet[sym[r][c]];
+      for (int i = 0; i < 10; ++i) q[i] = 0;
+      for (int k = 0; k < 3; ++k) pmul_ll(e[r * 3 + k], e[c * 3 + k], q, 1.0);
+    }
+  double tr[10];
+  for (int i = 0; i < 10; ++i) tr[i] = eet[0][i] + eet[3][i] + eet[5][i];
+  // lane r builds row r
+  if (lane < 10) {
+    double row[20];
+    for (int i = 0; i < 20; ++i) row[i] = 0;
+    if (lane == 0) {
+      double q[10];
+      for (int i = 0; i < 10; ++i) q[i] = 0;
+      pmul_ll(e[4], e[8], q, 1.0);
+      pmul_ll(e[5], e[7], q, -1.0);
+      pmul_ql(q, e[0], row, 1.0);
+      for (int i = 0; i < 10; ++i) q[i] = 0;
+      pmul_ll(e[3], e[8], q, 1.0);
+      pmul_ll(e[5], e[6], q, -1.0);
+      pmul_ql(q, e[1], row, -1.0);
+      for (int i = 0; i < 10; ++i) q[i] = 0;
+      pmul_ll(e[3], e[7], q, 1.0);
+      pmul_ll(e[4], e[6], q, -1.0);
+      pmul_ql(q, e[2], row, 1.0);
+    } else {
+      const int r = (lane - 1) / 3, c = (lane - 1) - r * 3;
+      for (int k = 0; k < 3; ++k) pmul_ql(eet[sym[r][k]], e[k * 3 + c], row, 2.0);
+      pmul_ql(tr, e[r * 3 + c], row, -1.0);
+    }
+    for (int j = 0; j < 20; ++j) Msh[lane * 20 + j] = row[j];
+  }
+  __syncwarp();
+  // Gauss-Jordan on the first 10 columns (partial pivoting), lane = column: M -> [I | G]
+  bool singular = false;
+#pragma unroll 1
+  for (int k = 0; k < 10; ++k) {
+    int p = k;
+    double best = fabs(Msh[k * 20 + k]);
+    for (int i = k + 1; i < 10; ++i) {
+      const double v = fabs(Msh[i * 20 + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (best == 0.0) {   // warp-uniform
+      singular = true;
+      break;
+    }
+    __syncwarp();
+    if (p != k && lane >= k && lane < 20) {
+      const double t = Msh[k * 20 + lane];
+      Msh[k * 20 + lane] = Msh[p * 20 + lane];
+      Msh[p * 20 + lane] = t;
+    }
+    __syncwarp();
+    const double inv = 1.0 / Msh[k * 20 + k];
+    __syncwarp();
+    if (lane >= k && lane < 20) Msh[k * 20 + lane] *= inv;
+    __syncwarp();
+    double f[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) f[i] = Msh[i * 20 + k];
+    __syncwarp();
+    if (lane >= k && lane < 20) {
+      const double mk = Msh[k * 20 + lane];
+#pragma unroll
+      for (int i = 0; i < 10; ++i)
+        if (i != k && f[i] != 0.0) Msh[i * 20 + lane] -= f[i] * mk;
+    }
+    __syncwarp();
+  }
+  if (singular) return false;
+  // B(z): rows <x2z> - z<x2>, <y2z> - z<y2>, <xyz> - z<xy>; tail = [xz2, xz, x, yz2, yz, y, z3, z2, z, 1]
+  for (int i = 0; i < 3; ++i) {
+    const double* ga = Msh + (4 + 2 * i) * 20 + 10;
+    const double* gb = Msh + (5 + 2 * i) * 20 + 10;
+    double* bx = Bm + i * 13;
+    double* by = bx + 4;
+    double* b1 = bx + 8;
+    bx[0] = ga[2];           bx[1] = ga[1] - gb[2]; bx[2] = ga[0] - gb[1]; bx[3] = -gb[0];
+    by[0] = ga[5];           by[1] = ga[4] - gb[5]; by[2] = ga[3] - gb[4]; by[3] = -gb[3];
+    b1[0] = ga[9];           b1[1] = ga[8] - gb[9]; b1[2] = ga[7] - gb[8]; b1[3] = ga[6] - gb[7]; b1[4] = -gb[6];
+  }
+  // det B(z): degree 10
+  for (int i = 0; i < 11; ++i) detp[i] = 0;
+  auto accum = [&](const double* p0, int d0, const double* p1, int d1, const double* p2, int d2, double s) {
+    for (int i = 0; i <= d0; ++i)
+      for (int j = 0; j <= d1; ++j) {
+        const double v = s * p0[i] * p1[j];
+        for (int k = 0; k <= d2; ++k) detp[i + j + k] += v * p2[k];
+      }
+  };
+  const double* B0 = Bm;
+  const double* B1 = Bm + 13;
+  const double* B2 = Bm + 26;
+  accum(B0, 3, B1 + 4, 3, B2 + 8, 4, 1.0);
+  accum(B0, 3, B1 + 8, 4, B2 + 4, 3, -1.0);
+  accum(B0 + 4, 3, B1, 3, B2 + 8, 4, -1.0);
+  accum(B0 + 4, 3, B1 + 8, 4, B2, 3, 1.0);
+  accum(B0 + 8, 4, B1, 3, B2 + 4, 3, 1.0);
+  accum(B0 + 8, 4, B1 + 4, 3, B2, 3, -1.0);
+  __syncwarp();   // Msh may be reused by the caller
+  return true;
+}
+
 // Part 2: the essential matrix of one real root z of det B(z).  Returns false for degenerate roots.
 __device__ inline bool e5_model_from_root(double z, const double* EE, const double* Bm, double* E /* 9 */) {
   double bz[9];
