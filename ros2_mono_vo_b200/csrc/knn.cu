@@ -6,7 +6,7 @@
 //
 // knn_top2_kernel: a warp owns Q=4 query descriptors in registers; the train set streams through a
 // swizzled shared-memory tile (conflict-free 128-bit reads, one train row per lane); distances are
-// xor + __popc over the two uint4 halves, with three carry-save adders in front of the population counts (five
+// xor + __popc over the two uint4 halves, with two carry-save adders in front of the population counts (six
 // POPC per pair instead of eight: POPC issues at a quarter of the ALU rate); every lane keeps a private top-2 of packed keys
 // (dist << 22 | trainIdx), merged at the end by a warp-shuffle top-2 reduction.  The train range
 // can be split over blockIdx.y to fill the 148 SMs for a single stream.
@@ -16,6 +16,9 @@
 
 namespace mvo {
 
+#ifndef MVO_KNN_CSA
+#define MVO_KNN_CSA 2   // carry-save adders per pair: 2 -> six POPC (217 us per 32 x 2000^2 pairs), 3 -> five POPC (229 us, ALU-bound), 0 -> eight (253 us)
+#endif
 constexpr int kKnnQ = 4;             // queries per warp
 constexpr int kKnnWarps = 8;
 constexpr int kKnnThreads = kKnnWarps * 32;
@@ -83,15 +86,20 @@ knn_top2_kernel(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_de
       const uint32_t idx = (uint32_t)(base + r);
 #pragma unroll
       for (int i = 0; i < kKnnQ; ++i) {
-        // Hamming distance of 256 bits with five population counts instead of eight: three carry-save adders (two
-        // LOP3 each, on the ALU pipe) compress seven of the eight xor words into two "ones" words and three "twos"
-        // words.  POPC issues at a quarter of the ALU rate, so this moves work from the saturated pipe to an idle one.
+        // Hamming distance of 256 bits with six population counts instead of eight: two carry-save adders (two LOP3
+        // each, on the ALU pipe) compress six of the eight xor words into two "ones" words and two "twos" words.
+        // POPC issues at a quarter of the ALU rate, so this moves work from the saturated pipe to a less busy one; a
+        // third adder (five POPC) makes the ALU pipe the bottleneck.
         const uint32_t x0 = qr[i][0] ^ a.x, x1 = qr[i][1] ^ a.y, x2 = qr[i][2] ^ a.z, x3 = qr[i][3] ^ a.w;
         const uint32_t x4 = qr[i][4] ^ c.x, x5 = qr[i][5] ^ c.y, x6 = qr[i][6] ^ c.z, x7 = qr[i][7] ^ c.w;
         const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
         const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
+#if MVO_KNN_CSA == 2
+        const int d = __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2 * (__popc(c0) + __popc(c1));
+#else
         const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
         const int d = __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+#endif
         top2_insert(k0[i], k1[i], ((uint32_t)d << 22) | idx);
       }
     }
