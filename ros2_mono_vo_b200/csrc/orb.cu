@@ -528,9 +528,10 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
       sc += ix * iy;
     }
   }
-  sa = warp_sum(sa);
-  sb = warp_sum(sb);
-  sc = warp_sum(sc);
+  // |sums| < 2^31 (49 x 1020^2; 31 x 15 x 31 x 255): one REDUX.SUM each instead of a five-step shuffle tree
+  sa = __reduce_add_sync(0xffffffffu, sa);
+  sb = __reduce_add_sync(0xffffffffu, sb);
+  sc = __reduce_add_sync(0xffffffffu, sc);
 
   // intensity centroid over the radius-15 disc: lane = column u + 15; fully unrolled so that the 31 row loads
   // of a lane are independent and in flight together (disc half-widths fold to constants)
@@ -551,8 +552,8 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
     }
     m10 = u * colsum;
   }
-  m10 = warp_sum(m10);
-  m01 = warp_sum(m01);
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
 
   if (lane == 0) {
     const float s4 = __uint_as_float(0x25ddced1u);  // ((1/(4*7*255))^4 accumulated in float
