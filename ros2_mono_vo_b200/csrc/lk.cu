@@ -159,10 +159,11 @@ __device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict_
 
 // Fused template setup of one window on one image plane: lane = raw column (x = ix - 1 + lane, 24 columns), the 24
 // raw rows are walked in registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation
-// of I / Ix / Iy, normal-matrix sums.  Results go to pd (Ix | Iy << 16) and pi (I) in pixel order k = r * 21 + c.
+// of I / Ix / Iy.  Results go to pd (Ix | Iy << 16) and pi (I) in pixel order k = r * 21 + c; the normal-matrix sums are
+// taken by the caller when it reads the window back (14 samples per lane instead of 24 rows per lane).
 __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch,
                                                int lane, int w00, int w01, int w10, int w11, uint32_t* pd_out,
-                                               uint16_t* pi_out, int& sA11, int& sA12, int& sA22) {
+                                               uint16_t* pi_out) {
   const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
   const int colx = ix - 1 + lane;
   const int xr = safe_reflect(colx, w);
@@ -199,9 +200,6 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
         const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
         const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
         if (win_col && pr >= 0) {
-          sA11 += vx * vx;
-          sA12 += vx * vy;
-          sA22 += vy * vy;
           pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
           pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
         }
@@ -242,9 +240,6 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
         const int vy = (sm2 - sm0 + (1 << 13)) >> 14;
         const int iv = (t1 + (1 << 8)) >> 9;
         if (win_col && pr >= 0) {
-          sA11 += vx * vx;
-          sA12 += vx * vy;
-          sA22 += vy * vy;
           pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
           pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
         }
@@ -317,9 +312,9 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
     // ---- fused template setup (lk_setup_patch): the window lands in smem in pixel order k = r * 21 + c
     int sA11 = 0, sA12 = 0, sA22 = 0;
     __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
-    lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch.d, sm.patch.i, sA11, sA12, sA22);
+    lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch.d, sm.patch.i);
     __syncwarp();
-    // window values owned by this lane (pixel k = lane + 32 j)
+    // window values owned by this lane (pixel k = lane + 32 j) and the normal-matrix sums (exact integers)
     int Iv[kSlots], Ixv[kSlots], Iyv[kSlots];
 #pragma unroll
     for (int j = 0; j < kSlots; ++j) {
@@ -330,6 +325,9 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
         Iv[j] = sm.patch.i[k];
         Ixv[j] = (int)(short)(d & 0xffffu);
         Iyv[j] = (int)d >> 16;
+        sA11 += Ixv[j] * Ixv[j];
+        sA12 += Ixv[j] * Iyv[j];
+        sA22 += Iyv[j] * Iyv[j];
       }
     }
     const float A11 = __fmul_rn((float)warp_sum_wide(sA11), flt_scale);
@@ -493,15 +491,22 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
     int tA11 = 0, tA12 = 0, tA22 = 0;   // per-lane sums over CN <= 3 channels stay below 2^31 (<= 21 * 4080^2 per channel)
     __syncwarp();
 #pragma unroll 1
-    for (int ch = 0; ch < CN; ++ch) {
-      int sA11 = 0, sA12 = 0, sA22 = 0;
-      lk_setup_patch(I + (long long)ch * g.frame_stride, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.d[ch],
-                     sm.i[ch], sA11, sA12, sA22);
-      tA11 += sA11;
-      tA12 += sA12;
-      tA22 += sA22;
-    }
+    for (int ch = 0; ch < CN; ++ch)
+      lk_setup_patch(I + (long long)ch * g.frame_stride, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.d[ch], sm.i[ch]);
     __syncwarp();
+#pragma unroll 1
+    for (int ch = 0; ch < CN; ++ch)
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) {
+        const int k = lane + 32 * j;
+        if (k < kWin) {
+          const uint32_t d = sm.d[ch][k];
+          const int gx = (int)(short)(d & 0xffffu), gy = (int)d >> 16;
+          tA11 += gx * gx;
+          tA12 += gx * gy;
+          tA22 += gy * gy;
+        }
+      }
     const float A11 = __fmul_rn((float)warp_sum_wide(tA11), flt_scale);
     const float A12 = __fmul_rn((float)warp_sum_wide(tA12), flt_scale);
     const float A22 = __fmul_rn((float)warp_sum_wide(tA22), flt_scale);
