@@ -192,6 +192,8 @@ int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_strid
             const uint8_t* t_dev, const int32_t* nt_dev, int t_stride_rows, int max_nt, double ratio,
             int batch);
 
+int upload_gray_rows(mvo_ctx* c, const uint8_t* host, int w, int h, int stride, int batch, uint8_t* dst, int dpitch,
+                     long long dst_frame_stride);
 int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn = 1);
 int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int on_device);
 // level 0 of LK pyramid buffer `which` (gray): base pointer of stream 0, row pitch, distance between streams

@@ -708,6 +708,9 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
       MVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)b * g.frame_stride, g.lv[0].pitch,
                                         img + (size_t)b * c->geom.frame_stride, stride, c->lk_w, c->lk_h,
                                         cudaMemcpyDeviceToDevice, c->stream));
+  } else if (!on_device) {
+    const int rc = upload_gray_rows(c, img, c->lk_w, c->lk_h, stride, B, base, g.lv[0].pitch, g.frame_stride);
+    if (rc) return rc;
   } else {
     for (int b = 0; b < B; ++b)
       MVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)b * g.frame_stride, g.lv[0].pitch,

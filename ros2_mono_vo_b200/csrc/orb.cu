@@ -842,15 +842,45 @@ int orb_prepare(mvo_ctx* c, int w, int h) {
   return MVO_OK;
 }
 
+// rows of `w` gray bytes: (src, spitch, frame distance) -> (dst, dpitch, frame distance); 16 bytes per thread
+__global__ void __launch_bounds__(256)
+gray_rows_kernel(const uint8_t* __restrict__ src, int spitch, long long src_frame_stride, uint8_t* __restrict__ dst,
+                 int dpitch, long long dst_frame_stride, int w, int h) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (x >= w) return;
+  const uint8_t* s = src + (long long)b * src_frame_stride + (long long)y * spitch + x;
+  uint8_t v[16];
+  const int nb = min(16, w - x);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = i < nb ? s[i] : 0;
+  *reinterpret_cast<uint4*>(dst + (long long)b * dst_frame_stride + (long long)y * dpitch + x) = *reinterpret_cast<const uint4*>(v);
+}
+
+// Host gray frames (batch x h rows of `stride` bytes) -> pitched device rows.  One flat DMA into a staging buffer plus
+// an unpack kernel: a 2-D copy of 1241-byte rows from pageable memory runs far below PCIe speed (the synchronous ORB /
+// LK calls spent a quarter of their time in it).
+int upload_gray_rows(mvo_ctx* c, const uint8_t* host, int w, int h, int stride, int batch, uint8_t* dst, int dpitch,
+                     long long dst_frame_stride) {
+  const size_t fbytes = (size_t)h * stride;
+  MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * batch));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, host, fbytes * batch, cudaMemcpyHostToDevice, c->stream));
+  dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, batch);
+  gray_rows_kernel<<<grid, 256, 0, c->stream>>>(c->img_in.p, stride, (long long)fbytes, dst, dpitch, dst_frame_stride, w, h);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  return MVO_OK;
+}
+
 // images: batch frames, each h x stride bytes (host or device)
 int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels, int on_device) {
   const OrbGeom& g = c->geom;
   const LevelGeom& l0 = g.lv[0];
-  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (channels == 1) {
+    if (!on_device) return upload_gray_rows(c, img, w, h, stride, g.batch, c->pyr.p + l0.off, l0.pitch, g.frame_stride);
     for (int b = 0; b < g.batch; ++b)
       MVO_CUDA_TRY(c, cudaMemcpy2DAsync(c->pyr.p + (size_t)b * g.frame_stride + l0.off, l0.pitch,
-                                        img + (size_t)b * h * stride, stride, w, h, kind, c->stream));
+                                        img + (size_t)b * h * stride, stride, w, h, cudaMemcpyDeviceToDevice, c->stream));
     return MVO_OK;
   }
   if (channels != 3) return MVO_ERR_INVALID;
