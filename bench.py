@@ -347,7 +347,8 @@ def main():
                 st1[k] = st1.get(k, 0.0) + v / n1
         dt = (time.perf_counter() - t0) / n1
         single = {"ms_per_frame_e2e": 1e3 * dt, "fps": 1.0 / dt, "launches_per_frame": None,
-                  "stages_ms": {k: round(v, 4) for k, v in st1.items()}}
+                  "stages_ms": {k: round(v, 4) for k, v in st1.items()},
+                  "tracking_only_ms": round(st1.get("lk", 0) + st1.get("ransac_e", 0) + st1.get("pose", 0), 4)}
         l0 = c1.launch_count
         c1.group_step(host_np[0, :1], K)
         single["launches_per_frame"] = c1.launch_count - l0
@@ -432,6 +433,8 @@ def main():
             "cpu_baseline": cpu,
             "stages_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
             "orb_match_ms_per_frame": (stages.get("orb", 0) + stages.get("knn", 0)) / S,
+            # configs[1] as worded (LK tracking + essential matrix + recoverPose only): sum of those stage times
+            "tracking_only_ms_per_frame": (stages.get("lk", 0) + stages.get("ransac_e", 0) + stages.get("pose", 0)) / S,
             "single_stream": single,
             "last_result_stream0": {k: int(res[0][k]) for k in ("n_keypoints", "n_matches", "n_tracked", "score_h",
                                                                  "score_f", "n_inliers_e", "n_pose_good",
