@@ -116,7 +116,8 @@ def lk_track(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray):
             next_pt = (next_pts * f32(2.0)).astype(f32)
         next_pts = next_pt.copy()
         pp = (prev_pt - half).astype(f32)
-        ip = np.floor(pp).astype(np.int64)
+        # cvFloor of a NaN is INT_MIN (cvtss2si): such a point is out of range on every level
+        ip = np.where(np.isnan(pp), -2 ** 31, np.floor(np.nan_to_num(pp))).astype(np.int64)
         oob = (ip[:, 0] < -WIN) | (ip[:, 0] >= w) | (ip[:, 1] < -WIN) | (ip[:, 1] >= h)
         if level == 0:
             status[oob] = 0

@@ -299,7 +299,8 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
     }
     const float qx = __fsub_rn(ppx, 10.f), qy = __fsub_rn(ppy, 10.f);
     const int ix = (int)floorf(qx), iy = (int)floorf(qy);
-    if (ix < -LKW || ix >= w || iy < -LKW || iy >= h) {
+    // (a NaN coordinate floors to INT_MIN in OpenCV: out of range on every level)
+    if (ix < -LKW || ix >= w || iy < -LKW || iy >= h || qx != qx || qy != qy) {
       if (L == 0) {
         st = 0;
         e = 0.f;
@@ -479,7 +480,8 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
     }
     const float qx = __fsub_rn(ppx, 10.f), qy = __fsub_rn(ppy, 10.f);
     const int ix = (int)floorf(qx), iy = (int)floorf(qy);
-    if (ix < -LKW || ix >= w || iy < -LKW || iy >= h) {
+    // (a NaN coordinate floors to INT_MIN in OpenCV: out of range on every level)
+    if (ix < -LKW || ix >= w || iy < -LKW || iy >= h || qx != qx || qy != qy) {
       if (L == 0) {
         st = 0;
         e = 0.f;

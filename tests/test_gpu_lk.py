@@ -93,3 +93,17 @@ def test_lk_bgr_vs_cv2_golden(ctx, tag):
     assert (s3 != os3).mean() < 0.002
     mm = (s3 == 1) & (os3 == 1)
     assert np.abs(n3[mm] - o3[mm]).max() < POS_TOL
+
+
+def test_lk_outside_and_nan_points(ctx):
+    """Points outside the image and a NaN coordinate (values from cv2 4.13.0 on the same pair: status 0 1 0 0 1 1; OpenCV
+    floors a NaN to INT_MIN, i.e. out of range on every level, and still returns the propagated coordinates)."""
+    f0, f1 = synth.synth_pair(480, 640, 2)
+    pts = np.array([[np.nan, 5], [100, 100], [-50, -50], [700, 500], [639.9, 479.9], [0, 0]], np.float32)
+    nxt, st, err = ctx.lk_track(f0, f1, pts)
+    onxt, ost, oerr = lo.lk_track(f0, f1, pts)
+    assert st.tolist() == [0, 1, 0, 0, 1, 1] and np.array_equal(st, ost)
+    assert np.isnan(nxt[0, 0]) and nxt[0, 1] == 5.0 and err[0] == 0.0
+    assert np.abs(nxt[1:] - onxt[1:]).max() < POS_TOL
+    assert np.abs(nxt[1:] - np.array([[101.367386, 99.107544], [-48.246277, -51.015106], [700.7065, 500.23755],
+                                      [640.7122, 480.0799], [1.4291534, -1.006732]])).max() < POS_TOL
