@@ -72,14 +72,11 @@ lk_pyrdown_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, u
 
 // ---- tracking -------------------------------------------------------------------------------
 // Per-warp scratch.  The two uses never overlap in time: the template patch (I, Ix|Iy) is written by the fused
-// setup and read back into registers before the first J region of the level is staged.
+// setup (one 64-bit store per pixel) and read back into registers before the first J region of the level is staged.
 struct LkWarpSmem {
   union {
     uint32_t jq[kJReg * kJReg];        // J "quads": (J[y][x], J[y][x+1], J[y+1][x], J[y+1][x+1]) per position
-    struct {
-      uint32_t d[kSlots * 32];         // Ix (low 16, signed) | Iy (high 16, signed)
-      uint16_t i[kSlots * 32];         // I (Q5)
-    } patch;
+    uint2 patch[kSlots * 32];          // template window: x = Ix (low 16, signed) | Iy (high 16, signed), y = I (Q5)
   };
 };
 
@@ -159,11 +156,10 @@ __device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict_
 
 // Fused template setup of one window on one image plane: lane = raw column (x = ix - 1 + lane, 24 columns), the 24
 // raw rows are walked in registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation
-// of I / Ix / Iy.  Results go to pd (Ix | Iy << 16) and pi (I) in pixel order k = r * 21 + c; the normal-matrix sums are
+// of I / Ix / Iy.  Results go to pt (x = Ix | Iy << 16, y = I) in pixel order k = r * 21 + c; the normal-matrix sums are
 // taken by the caller when it reads the window back (14 samples per lane instead of 24 rows per lane).
 __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch,
-                                               int lane, int w00, int w01, int w10, int w11, uint32_t* pd_out,
-                                               uint16_t* pi_out) {
+                                               int lane, int w00, int w01, int w10, int w11, uint2* pt_out) {
   const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
   const int colx = ix - 1 + lane;
   const int xr = safe_reflect(colx, w);
@@ -200,8 +196,7 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
         const int vx = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
         const int vy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
         if (win_col && pr >= 0) {
-          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
-          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+          pt_out[pr * LKW + lane - 1] = make_uint2(pack_w(vx, vy), (uint32_t)iv);
         }
         pd_prev = pd;
         pdn_prev = pdn;
@@ -240,8 +235,7 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
         const int vy = (sm2 - sm0 + (1 << 13)) >> 14;
         const int iv = (t1 + (1 << 8)) >> 9;
         if (win_col && pr >= 0) {
-          pd_out[pr * LKW + lane - 1] = pack_w(vx, vy);
-          pi_out[pr * LKW + lane - 1] = (uint16_t)iv;
+          pt_out[pr * LKW + lane - 1] = make_uint2(pack_w(vx, vy), (uint32_t)iv);
         }
         dx0 = dx1;
         dx1 = dx2;
@@ -313,7 +307,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
     // ---- fused template setup (lk_setup_patch): the window lands in smem in pixel order k = r * 21 + c
     int sA11 = 0, sA12 = 0, sA22 = 0;
     __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
-    lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch.d, sm.patch.i);
+    lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch);
     __syncwarp();
     // window values owned by this lane (pixel k = lane + 32 j) and the normal-matrix sums (exact integers)
     int Iv[kSlots], Ixv[kSlots], Iyv[kSlots];
@@ -322,8 +316,9 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
       const int k = lane + 32 * j;
       Iv[j] = Ixv[j] = Iyv[j] = 0;
       if (k < kWin) {
-        const uint32_t d = sm.patch.d[k];
-        Iv[j] = sm.patch.i[k];
+        const uint2 tv = sm.patch[k];
+        const uint32_t d = tv.x;
+        Iv[j] = (int)tv.y;
         Ixv[j] = (int)(short)(d & 0xffffu);
         Iyv[j] = (int)d >> 16;
         sA11 += Ixv[j] * Ixv[j];
@@ -436,8 +431,7 @@ constexpr int kLkWarpsCn = 2;
 template <int CN>
 struct LkWarpSmemCn {
   uint32_t jq[CN][kJReg * kJReg];
-  uint32_t d[CN][kSlots * 32];
-  uint16_t i[CN][kSlots * 32];
+  uint2 t[CN][kSlots * 32];            // x = Ix | Iy << 16, y = I
 };
 
 template <int CN>
@@ -494,7 +488,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
     __syncwarp();
 #pragma unroll 1
     for (int ch = 0; ch < CN; ++ch)
-      lk_setup_patch(I + (long long)ch * g.frame_stride, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.d[ch], sm.i[ch]);
+      lk_setup_patch(I + (long long)ch * g.frame_stride, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.t[ch]);
     __syncwarp();
 #pragma unroll 1
     for (int ch = 0; ch < CN; ++ch)
@@ -502,7 +496,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
       for (int j = 0; j < kSlots; ++j) {
         const int k = lane + 32 * j;
         if (k < kWin) {
-          const uint32_t d = sm.d[ch][k];
+          const uint32_t d = sm.t[ch][k].x;
           const int gx = (int)(short)(d & 0xffffu), gy = (int)d >> 16;
           tA11 += gx * gx;
           tA12 += gx * gy;
@@ -552,8 +546,9 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
           const int k = lane + 32 * j;
           if (k < kWin) {
             const uint32_t q = jb[qoff[j]];
-            const uint32_t d = sm.d[ch][k];
-            const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)sm.i[ch][k];
+            const uint2 tv = sm.t[ch][k];
+            const uint32_t d = tv.x;
+            const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)tv.y;
             sb1 += diff * (int)(short)(d & 0xffffu);
             sb2 += diff * ((int)d >> 16);
           }
@@ -605,7 +600,7 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
             const int k = lane + 32 * j;
             if (k < kWin) {
               const uint32_t q = jb[qoff[j]];
-              se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)sm.i[ch][k]);
+              se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)sm.t[ch][k].y);
             }
           }
         }
