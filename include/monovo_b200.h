@@ -135,6 +135,10 @@ MVO_API int mvo_lk_track(mvo_ctx* ctx, const uint8_t* prev, const uint8_t* next,
                          int stride, int channels, const float* prev_xy, int n, float* next_xy,
                          uint8_t* status, float* err);
 
+/* Parity tap of the last mvo_lk_track call: pyramid level `level` (0 = the image) of the previous (which = 0) or next
+ * (which = 1) image, channel plane `plane` (0 for gray; 0..2 = B, G, R for BGR input).  out may be NULL (size query). */
+MVO_API int mvo_lk_get_level(mvo_ctx* ctx, int which, int level, int plane, uint8_t* out, int out_stride, int* w, int* h);
+
 /* ------------------------------------------------------------------------------------------------
  * two-view geometry (deterministic parallel RANSAC; OpenCV's RNG stream and adaptive stop replayed)
  * p1/p2: n x 2 f32 interleaved (std::vector<cv::Point2f>).  mask: n bytes (0/1), may be NULL.

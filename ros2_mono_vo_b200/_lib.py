@@ -56,6 +56,7 @@ SIGNATURES = {
     "mvo_orb_num_levels": (C.c_int, []),
     "mvo_orb_level_size": (C.c_int, [_vp, C.c_int, _i32p, _i32p]),
     "mvo_orb_get_level": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int]),
+    "mvo_lk_get_level": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mvo_orb_get_fast": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i32p]),
     "mvo_knn_ratio": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_double, _vp, _i32p]),
     "mvo_measure_popc_peak": (C.c_int, [_vp, _f64p]),

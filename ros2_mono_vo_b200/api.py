@@ -186,6 +186,15 @@ class Context:
             out[s] = float(v.value)
         return out
 
+    def lk_level(self, which: int, level: int, plane: int = 0):
+        """Parity tap: pyramid level of the previous (0) / next (1) image of the last lk_track call; None past the top."""
+        w, h = C.c_int(), C.c_int()
+        if self.lib.mvo_lk_get_level(self.h, which, level, plane, None, 0, C.byref(w), C.byref(h)) != _lib.MVO_OK:
+            return None
+        out = np.zeros((h.value, w.value), np.uint8)
+        self._check(self.lib.mvo_lk_get_level(self.h, which, level, plane, _ptr(out), out.strides[0], C.byref(w), C.byref(h)))
+        return out
+
     def stage_spans_ms(self) -> dict:
         """(start, end) of every stage of the last enqueued step, relative to the start of that step."""
         out = {}

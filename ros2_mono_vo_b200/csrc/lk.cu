@@ -4,7 +4,8 @@
 // (status identical, positions within 0.01 px of OpenCV; here the integer sums are exact, which is tighter
 // than OpenCV's own float accumulation).
 //
-//   lk_pyrdown_kernel  integer 5x5 [1 4 6 4 1]^2 pyrDown, smem tile with REFLECT_101 halo.
+//   lk_pyrdown_tile_kernel  integer 5x5 [1 4 6 4 1]^2 pyrDown: word loads, packed 16-bit vertical pass (lk_pyrdown_kernel:
+//                      the byte-per-thread version, for images narrower than a tile).
 //   lk_track_kernel    one warp per point, all pyramid levels inside the kernel (no inter-point dependency):
 //                      24x24 raw patch in smem -> Scharr derivatives computed on the fly (no derivative
 //                      image is ever written: saves 5.3 P0 bytes of dense traffic per frame) -> Q14 bilinear
@@ -67,6 +68,77 @@ lk_pyrdown_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, u
     const int r = 2 * threadIdx.y, c = threadIdx.x;
     const int v = hsum[r][c] + 4 * hsum[r + 1][c] + 6 * hsum[r + 2][c] + 4 * hsum[r + 3][c] + hsum[r + 4][c];
     dst[(long long)oy * dpitch + ox] = (uint8_t)((v + 128) >> 8);
+  }
+}
+
+// The same filter with word-sized traffic (the byte-per-thread kernel above spends ~150 instructions per output pixel and
+// is kept for images narrower than one tile): 64 x 16 output tile, source rows staged with aligned 32-bit loads (row
+// indices reflected at load time, the at most two reflected columns on either image edge patched in shared memory),
+// horizontal pass two outputs per item from three words, vertical pass on packed 16-bit pairs (5-tap sums of 5-tap sums
+// stay below 2^16), four outputs per 32-bit store.
+constexpr int PD2W = 64, PD2H = 16;
+constexpr int PD2_ROWS = 2 * PD2H + 3;            // 35 source rows
+constexpr int PD2_WORDS = (2 * PD2W + 8) / 4;     // 34 words: source columns 2 ox0 - 4 .. 2 ox0 + 131
+constexpr int PD2_STRIDE = PD2_WORDS + 1;         // smem row stride in words
+__global__ void __launch_bounds__(256)
+lk_pyrdown_tile_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw,
+                       int dh, int dpitch, long long frame_stride_src, long long frame_stride_dst) {
+  __shared__ uint32_t tile[PD2_ROWS * PD2_STRIDE];
+  __shared__ __align__(8) uint16_t hs[PD2_ROWS * PD2W];
+  const int b = blockIdx.z, tid = threadIdx.x;
+  src += (long long)b * frame_stride_src;
+  dst += (long long)b * frame_stride_dst;
+  const int ox0 = blockIdx.x * PD2W, oy0 = blockIdx.y * PD2H;
+  const int sx0 = 2 * ox0 - 4, sy0 = 2 * oy0 - 2;   // sx0 is a multiple of 4
+  for (int i = tid; i < PD2_ROWS * PD2_WORDS; i += 256) {
+    const int r = i / PD2_WORDS, wq = i - r * PD2_WORDS;
+    const int y = min(max(reflect101(sy0 + r, sh), 0), sh - 1);
+    const int x = sx0 + 4 * wq;
+    uint32_t v = 0;
+    if (x >= 0 && x < spitch) v = __ldg(reinterpret_cast<const uint32_t*>(src + (long long)y * spitch + x));
+    tile[r * PD2_STRIDE + wq] = v;
+  }
+  __syncthreads();
+  // REFLECT_101 columns: -2, -1 on the left edge, sw, sw + 1 on the right edge (nothing further out feeds a stored output)
+  uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+  if (sx0 < 0 || sx0 + 4 * PD2_WORDS > sw) {
+    for (int i = tid; i < PD2_ROWS * 4; i += 256) {
+      const int r = i >> 2, k = i & 3;
+      const int col = (k < 2) ? (k - 2) : (sw + k - 2);          // -2, -1, sw, sw + 1
+      const int from = min(max(reflect101(col, sw), 0), sw - 1);
+      if (col >= sx0 && col < sx0 + 4 * PD2_WORDS && from >= sx0 && from < sx0 + 4 * PD2_WORDS)
+        tb[r * PD2_STRIDE * 4 + col - sx0] = tb[r * PD2_STRIDE * 4 + from - sx0];
+    }
+    __syncthreads();
+  }
+  // horizontal [1 4 6 4 1]: outputs 2 cp and 2 cp + 1 of row r from the words cp, cp + 1, cp + 2
+  for (int i = tid; i < PD2_ROWS * (PD2W / 2); i += 256) {
+    const int r = i / (PD2W / 2), cp = i - r * (PD2W / 2);
+    const uint32_t* t = tile + r * PD2_STRIDE + cp;
+    const uint32_t w0 = t[0], w1 = t[1], w2 = t[2];
+    const uint32_t b2 = (w0 >> 16) & 0xff, b3 = w0 >> 24, b4 = w1 & 0xff, b5 = (w1 >> 8) & 0xff, b6 = (w1 >> 16) & 0xff,
+                   b7 = w1 >> 24, b8 = w2 & 0xff;
+    const uint32_t h0 = b2 + b6 + 4 * (b3 + b5) + 6 * b4, h1 = b4 + b8 + 4 * (b5 + b7) + 6 * b6;
+    *reinterpret_cast<uint32_t*>(hs + r * PD2W + 2 * cp) = h0 | (h1 << 16);
+  }
+  __syncthreads();
+  // vertical [1 4 6 4 1] on packed pairs, + 128 >> 8: four outputs per thread
+  {
+    const int oyl = tid >> 4, g = tid & 15;
+    const int oy = oy0 + oyl, ox = ox0 + 4 * g;
+    if (oy < dh && ox < dw) {
+      const uint2* hp = reinterpret_cast<const uint2*>(hs + (2 * oyl) * PD2W + 4 * g);
+      const uint2 a = hp[0], bq = hp[PD2W / 4], c = hp[2 * (PD2W / 4)], d = hp[3 * (PD2W / 4)], e = hp[4 * (PD2W / 4)];
+      const uint32_t lo = a.x + e.x + 4 * (bq.x + d.x) + 6 * c.x + 0x00800080u;   // per 16-bit lane <= 65280 + 128
+      const uint32_t hi = a.y + e.y + 4 * (bq.y + d.y) + 6 * c.y + 0x00800080u;
+      const uint32_t px = __byte_perm(lo, hi, 0x7531);                             // the high byte of every lane == >> 8
+      uint8_t* o = dst + (long long)oy * dpitch + ox;
+      if (ox + 3 < dw) {
+        *reinterpret_cast<uint32_t*>(o) = px;
+      } else {
+        for (int k = 0; k < dw - ox; ++k) o[k] = (uint8_t)(px >> (8 * k));
+      }
+    }
   }
 }
 
@@ -717,9 +789,15 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
   for (int l = 1; l < g.nlevels; ++l) {
     const LkLevel& s = g.lv[l - 1];
     const LkLevel& d = g.lv[l];
-    dim3 grid((d.w + PDW - 1) / PDW, (d.h + PDH - 1) / PDH, B * cn), block(PDW, PDH);
-    lk_pyrdown_kernel<<<grid, block, 0, c->stream>>>(base + s.off, s.w, s.h, s.pitch, base + d.off, d.w, d.h, d.pitch,
-                                                     g.frame_stride, g.frame_stride);
+    if (s.w >= 8 && s.h >= 4) {
+      dim3 grid((d.w + PD2W - 1) / PD2W, (d.h + PD2H - 1) / PD2H, B * cn);
+      lk_pyrdown_tile_kernel<<<grid, 256, 0, c->stream>>>(base + s.off, s.w, s.h, s.pitch, base + d.off, d.w, d.h, d.pitch,
+                                                          g.frame_stride, g.frame_stride);
+    } else {
+      dim3 grid((d.w + PDW - 1) / PDW, (d.h + PDH - 1) / PDH, B * cn), block(PDW, PDH);
+      lk_pyrdown_kernel<<<grid, block, 0, c->stream>>>(base + s.off, s.w, s.h, s.pitch, base + d.off, d.w, d.h, d.pitch,
+                                                       g.frame_stride, g.frame_stride);
+    }
     c->launches++;
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
@@ -750,6 +828,24 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
 }  // namespace mvo
 
 using namespace mvo;
+
+// parity tap: pyramid level `level` of the previous (which = 0) / next (which = 1) image of the last mvo_lk_track call
+// (channel plane `plane` for BGR input)
+extern "C" int mvo_lk_get_level(mvo_ctx* c, int which, int level, int plane, uint8_t* out, int out_stride, int* w, int* h) {
+  if (!c || which < 0 || which > 1 || level < 0 || plane < 0 || c->lk_w <= 0 || plane >= c->lk_cn) return MVO_ERR_INVALID;
+  LkGeom g;
+  lk_geometry(c->lk_w, c->lk_h, g);
+  if (level >= g.nlevels) return MVO_ERR_INVALID;
+  const LkLevel& lv = g.lv[level];
+  if (w) *w = lv.w;
+  if (h) *h = lv.h;
+  if (!out) return MVO_OK;
+  if (out_stride < lv.w) return MVO_ERR_INVALID;
+  MVO_CUDA_TRY(c, cudaMemcpy2DAsync(out, out_stride, c->lk_pyr[which].p + (size_t)plane * g.frame_stride + lv.off, lv.pitch, lv.w,
+                                    lv.h, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return MVO_OK;
+}
 
 extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next, int w, int h, int stride,
                             int channels, const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err) {

@@ -107,3 +107,28 @@ def test_lk_outside_and_nan_points(ctx):
     assert np.abs(nxt[1:] - onxt[1:]).max() < POS_TOL
     assert np.abs(nxt[1:] - np.array([[101.367386, 99.107544], [-48.246277, -51.015106], [700.7065, 500.23755],
                                       [640.7122, 480.0799], [1.4291534, -1.006732]])).max() < POS_TOL
+
+
+@pytest.mark.parametrize("h,w,bgr", [(376, 1241, False), (480, 640, False), (1080, 1920, False), (97, 131, False), (200, 333, True)])
+def test_lk_pyramid_levels_bit_exact(h, w, bgr):
+    """Every pyramid level equals cv::pyrDown's chain (oracle lo.pyr_down, pinned to cv2.pyrDown in tests/test_oracle_lk.py):
+    image sizes that end inside a tile, widths that are / are not multiples of the tile, odd sizes, BGR planes."""
+    from ros2_mono_vo_b200 import Context
+    f0, f1 = (synth.synth_pair_bgr if bgr else synth.synth_pair)(h, w, 7)
+    c = Context(w, h, nfeatures=100)
+    try:
+        c.lk_track(f0, f1, np.array([[w / 2, h / 2]], np.float32))
+        for which, img in ((0, f0), (1, f1)):
+            for plane in range(3 if bgr else 1):
+                ref = np.ascontiguousarray(img[:, :, plane]) if bgr else img
+                level = 0
+                while True:
+                    got = c.lk_level(which, level, plane)
+                    if got is None:
+                        break
+                    assert got.shape == ref.shape and np.array_equal(got, ref), (which, plane, level)
+                    ref = lo.pyr_down(ref)
+                    level += 1
+                assert level >= 3
+    finally:
+        c.close()
