@@ -20,7 +20,7 @@ namespace mvo {
 constexpr int LKW = 21;
 constexpr int kLkWarps = 4;
 #ifndef MVO_LK_MINB
-#define MVO_LK_MINB 5
+#define MVO_LK_MINB 7
 #endif
 constexpr int kRaw = 24;      // raw patch side: 22 interp rows + 1 Scharr ring
 constexpr int kJReg = 32;     // staged J region side
@@ -146,10 +146,8 @@ lk_pyrdown_tile_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spit
 // Per-warp scratch.  The two uses never overlap in time: the template patch (I, Ix|Iy) is written by the fused
 // setup (one 64-bit store per pixel) and read back into registers before the first J region of the level is staged.
 struct LkWarpSmem {
-  union {
-    uint32_t jq[kJReg * kJReg];        // J "quads": (J[y][x], J[y][x+1], J[y+1][x], J[y+1][x+1]) per position
-    uint2 patch[kSlots * 32];          // template window: x = Ix (low 16, signed) | Iy (high 16, signed), y = I (Q5)
-  };
+  uint32_t jq[kJReg * kJReg];        // J "quads": (J[y][x], J[y][x+1], J[y+1][x], J[y+1][x+1]) per position
+  uint2 patch[kSlots * 32];          // template window: x = Ix (low 16, signed) | Iy (high 16, signed), y = I (Q5)
 };
 
 __device__ __forceinline__ int safe_reflect(int i, int n) { return min(max(reflect101(i, n), 0), n - 1); }
@@ -378,24 +376,20 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
 
     // ---- fused template setup (lk_setup_patch): the window lands in smem in pixel order k = r * 21 + c
     int sA11 = 0, sA12 = 0, sA22 = 0;
-    __syncwarp();   // previous level's J quads are dead: the patch arrays alias them
+    __syncwarp();   // every lane is done with the previous level's template
     lk_setup_patch(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch);
     __syncwarp();
-    // window values owned by this lane (pixel k = lane + 32 j) and the normal-matrix sums (exact integers)
-    int Iv[kSlots], Ixv[kSlots], Iyv[kSlots];
+    // normal-matrix sums (exact integers) over the window pixels owned by this lane (pixel k = lane + 32 j).  The
+    // template itself stays in shared memory: 42 registers less per thread buy two more CTAs per SM.
+    const uint2* tp = sm.patch + lane;
 #pragma unroll
     for (int j = 0; j < kSlots; ++j) {
-      const int k = lane + 32 * j;
-      Iv[j] = Ixv[j] = Iyv[j] = 0;
-      if (k < kWin) {
-        const uint2 tv = sm.patch[k];
-        const uint32_t d = tv.x;
-        Iv[j] = (int)tv.y;
-        Ixv[j] = (int)(short)(d & 0xffffu);
-        Iyv[j] = (int)d >> 16;
-        sA11 += Ixv[j] * Ixv[j];
-        sA12 += Ixv[j] * Iyv[j];
-        sA22 += Iyv[j] * Iyv[j];
+      if (lane + 32 * j < kWin) {
+        const uint32_t d = tp[32 * j].x;
+        const int gx = (int)(short)(d & 0xffffu), gy = (int)d >> 16;
+        sA11 += gx * gx;
+        sA12 += gx * gy;
+        sA22 += gy * gy;
       }
     }
     const float A11 = __fmul_rn((float)warp_sum_wide(sA11), flt_scale);
@@ -435,9 +429,10 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
       for (int j = 0; j < kSlots; ++j) {
         if (lane + 32 * j < kWin) {
           const uint32_t q = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(jb) + qt[32 * j]);
-          const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j];
-          sb1 += diff * Ixv[j];
-          sb2 += diff * Iyv[j];
+          const uint2 tv = tp[32 * j];
+          const int diff = (dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)tv.y;
+          sb1 += diff * (int)(short)(tv.x & 0xffffu);
+          sb2 += diff * ((int)tv.x >> 16);
         }
       }
       const float b1 = __fmul_rn((float)warp_sum_wide(sb1), flt_scale);
@@ -479,7 +474,7 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
         for (int j = 0; j < kSlots; ++j) {
           if (lane + 32 * j < kWin) {
             const uint32_t q = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(jb) + qt[32 * j]);
-            se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - Iv[j]);
+            se += abs((dp2a_hi_su(Vb, q, dp2a_lo_su(Vt, q, 1 << 8)) >> 9) - (int)tp[32 * j].y);
           }
         }
         se = __reduce_add_sync(0xffffffffu, se);
