@@ -9,7 +9,7 @@
 //   lk_track_kernel    one warp per point, all pyramid levels inside the kernel (no inter-point dependency):
 //                      24x24 raw patch in smem -> Scharr derivatives computed on the fly (no derivative
 //                      image is ever written: saves 5.3 P0 bytes of dense traffic per frame) -> Q14 bilinear
-//                      patch / gradient values in registers -> 2x2 normal matrix by warp reduction ->
+//                      patch / gradient values in shared memory -> 2x2 normal matrix by warp reduction ->
 //                      <= 30 Gauss-Newton iterations sampling J from a 32x32 smem region (texture-free
 //                      bilinear), re-staged only when the window leaves it.
 #include "context.cuh"
