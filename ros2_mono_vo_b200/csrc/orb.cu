@@ -41,6 +41,9 @@ constexpr int SRC_ROWS_MAX = 56;
 constexpr int SRC_COLS_MAX = 128;
 constexpr int FW = TW + 2, FH = TH + 2;  // FAST score region (1 halo for NMS)
 constexpr int FS = 68;                   // score row stride
+#ifndef MVO_ORB_MINB
+#define MVO_ORB_MINB 6   // 40 registers, no spills, 6 CTAs / SM (5: 48 registers, 3 % slower; 7: spills)
+#endif
 constexpr int kLevelThreads = 256;
 constexpr int kFastCols = (TW + 8) / 4;  // 18 aligned 4-pixel groups cover x = -4 .. TW+3
 constexpr int kFastLanes = kLevelThreads / kFastCols;  // 14 row lanes
@@ -98,7 +101,7 @@ __device__ __forceinline__ uint32_t bytes_gt_thr(uint32_t d) {
 }
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(kLevelThreads, 5) orb_level_kernel(const LevelArgs a) {
+__global__ void __launch_bounds__(kLevelThreads, MVO_ORB_MINB) orb_level_kernel(const LevelArgs a) {
   __shared__ __align__(16) uint8_t tile[SROWS * TS];
   // scratch: resize staging (source rows + vertical pass, 8.8 fixed point) is dead before the blur row buffer is live
   __shared__ __align__(16) uint8_t scratch[SRC_ROWS_MAX * SRC_COLS_MAX + SROWS * SRC_COLS_MAX * 2];
