@@ -144,10 +144,16 @@ __global__ void __launch_bounds__(kLevelThreads, MVO_ORB_MINB) orb_level_kernel(
     const int c1e = min((int)(tab_x[SCOLS - 1] & 0xffff) + 1, a.sw - 1);
     const int nch = min((c1e - c0a) / 16 + 1, SRC_COLS_MAX / 16);
     // stage A: source rows, 128-bit loads
-    for (int i = tid; i < nrows * nch; i += kLevelThreads) {
-      const int r = i / nch, k = i - r * nch;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * a.spitch + c0a + k * 16));
-      *reinterpret_cast<uint4*>(src_s + r * (SRC_COLS_MAX / 4) + k * 4) = v;
+    {
+      // thread = (row within a pass of 32 rows, 16-byte chunk): no division by the run-time chunk count
+      static_assert(SRC_COLS_MAX / 16 == 8 && kLevelThreads == 256, "stage A maps 8 chunks x 32 rows per pass");
+      const int k = tid & 7;
+      if (k < nch) {
+        for (int r = tid >> 3; r < nrows; r += kLevelThreads / 8) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r0 + r) * a.spitch + c0a + k * 16));
+          *reinterpret_cast<uint4*>(src_s + r * (SRC_COLS_MAX / 4) + k * 4) = v;
+        }
+      }
     }
     __syncthreads();
     // stage V: vertical pass, one staged word (4 source pixels) per lane, one output row per warp and round
