@@ -432,7 +432,8 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, int stride, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: Harris response + IC angle, one warp per candidate that survives retainBest(2 n_l) by FAST score
+// K2: Harris response, one warp per candidate that survives retainBest(2 n_l) by FAST score (the IC angle is computed
+// later, for the n_l candidates that survive the Harris ranking: orb_brief_kernel)
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   const float p1 = __uint_as_float(0x4265226fu), p3 = __uint_as_float(0xc19556eeu);
   const float p5 = __uint_as_float(0x410e9fbfu), p7 = __uint_as_float(0xc0228ad9u);
@@ -542,28 +543,6 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
   sb = __reduce_add_sync(0xffffffffu, sb);
   sc = __reduce_add_sync(0xffffffffu, sc);
 
-  // intensity centroid over the radius-15 disc: lane = column u + 15; fully unrolled so that the 31 row loads
-  // of a lane are independent and in flight together (disc half-widths fold to constants)
-  int m10 = 0, m01 = 0;
-  if (lane < 31) {
-    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    const int u = lane - 15;
-    const int au = abs(u);
-    const uint8_t* q = img + (long long)y * pitch + x + u;
-    int colsum = 0;
-#pragma unroll
-    for (int v = -15; v <= 15; ++v) {
-      if (au <= kUmax[v < 0 ? -v : v]) {
-        const int p = q[v * pitch];
-        colsum += p;
-        m01 += v * p;
-      }
-    }
-    m10 = u * colsum;
-  }
-  m10 = __reduce_add_sync(0xffffffffu, m10);
-  m01 = __reduce_add_sync(0xffffffffu, m01);
-
   if (lane == 0) {
     const float s4 = __uint_as_float(0x25ddced1u);  // ((1/(4*7*255))^4 accumulated in float
     const float k = __uint_as_float(0x3d23d70au);   // 0.04f
@@ -572,13 +551,12 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
     const float apb = __fadd_rn(fa, fb);
     const float t2 = __fmul_rn(__fmul_rn(k, apb), apb);
     const float resp = __fmul_rn(__fsub_rn(t1, t2), s4);
-    const float ang = fast_atan2_deg((float)m01, (float)m10);
     const int pos = atomicAdd(c2_count + b * kLevels + level, 1);
     const long long o = (long long)b * g.cand_total + cand_off + pos;
     // ascending key == (response desc, y asc, x asc); -0.f canonicalised so that ties compare equal
     const uint32_t ro = ~float_orderable(__fadd_rn(resp, 0.f));
     c2_key[o] = ((unsigned long long)ro << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
-    c2_ra[o] = make_float2(resp, ang);
+    c2_ra[o] = make_float2(resp, 0.f);   // the angle is computed for the survivors only (orb_brief_kernel)
   }
   }  // candidate loop
 }
@@ -677,18 +655,49 @@ orb_finalize_kernel(const __grid_constant__ OrbGeom g, const unsigned long long*
 // K5: rotated BRIEF, warp per keypoint, lane = descriptor byte (16 samples)
 constexpr int kBriefWarps = 8;
 __global__ void __launch_bounds__(kBriefWarps * 32)
-orb_brief_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ blur, const mvo_keypoint* __restrict__ kps,
-                 const int32_t* __restrict__ kp_count, uint8_t* __restrict__ desc, uint8_t* __restrict__ valid) {
+orb_brief_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                 mvo_keypoint* __restrict__ kps, const int32_t* __restrict__ kp_count, uint8_t* __restrict__ desc,
+                 uint8_t* __restrict__ valid, int compute_angle) {
   const int b = blockIdx.y;
   const int n = kp_count[b];
   const int i = blockIdx.x * kBriefWarps + (threadIdx.x >> 5);
   if (i >= n) return;
   const int lane = threadIdx.x & 31;
-  const mvo_keypoint kp = kps[(long long)b * g.kp_cap + i];
+  mvo_keypoint kp = kps[(long long)b * g.kp_cap + i];
   const int l = min(max(kp.octave, 0), kLevels - 1);
   const LevelGeom lv = g.lv[l];
   const int cx = __float2int_rn(__fmul_rn(kp.x, lv.inv_scale));
   const int cy = __float2int_rn(__fmul_rn(kp.y, lv.inv_scale));
+  if (compute_angle) {
+    // IC angle of a detected keypoint (it lies >= 31 px inside its level) on the UNBLURRED level
+    const uint8_t* img = pyr + (long long)b * g.frame_stride + lv.off;
+    const int pitch = lv.pitch, x = cx, y = cy;
+    // intensity centroid over the radius-15 disc: lane = column u + 15; fully unrolled so that the 31 row loads
+    // of a lane are independent and in flight together (disc half-widths fold to constants)
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+      constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+      const int u = lane - 15;
+      const int au = abs(u);
+      const uint8_t* q = img + (long long)y * pitch + x + u;
+      int colsum = 0;
+#pragma unroll
+      for (int v = -15; v <= 15; ++v) {
+        if (au <= kUmax[v < 0 ? -v : v]) {
+          const int p = q[v * pitch];
+          colsum += p;
+          m01 += v * p;
+        }
+      }
+      m10 = u * colsum;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+
+    kp.angle = fast_atan2_deg((float)m01, (float)m10);
+    if (lane == 0) kps[(long long)b * g.kp_cap + i].angle = kp.angle;
+  }
+  if (!desc) return;
   uint8_t* out = desc + ((long long)b * g.kp_cap + i) * 32;
   const bool ok = (kp.octave >= 0 && kp.octave < kLevels && cx >= kEdge && cx < lv.w - kEdge && cy >= kEdge &&
                    cy < lv.h - kEdge);
@@ -996,10 +1005,11 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
   orb_finalize_kernel<<<g.batch, 1024, 0, c->stream>>>(g, c->c2_key_sorted.p, c->c2_ra_sorted.p, c->c2_count.p,
                                                       c->kps.p, c->kp_xy.p, c->kp_count.p, c->flags.p);
   c->launches++;
-  if (want_desc) {
+  {
+    // IC angle of the surviving keypoints, then (want_desc) their rBRIEF descriptors
     dim3 grid((g.kp_cap + kBriefWarps - 1) / kBriefWarps, g.batch);
-    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->blur.p, c->kps.p, c->kp_count.p, c->desc.p,
-                                                              nullptr);
+    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->blur.p, c->kps.p, c->kp_count.p,
+                                                              want_desc ? c->desc.p : nullptr, nullptr, 1);
     c->launches++;
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
@@ -1011,8 +1021,8 @@ int orb_run_brief_given(mvo_ctx* c, int n) {
   const OrbGeom& g = c->geom;
   dim3 grid((n + kBriefWarps - 1) / kBriefWarps, 1);
   if (n > 0) {
-    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->blur.p, c->kps.p, c->kp_count.p, c->desc.p,
-                                                              c->kp_valid.p);
+    orb_brief_kernel<<<grid, kBriefWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->blur.p, c->kps.p, c->kp_count.p, c->desc.p,
+                                                              c->kp_valid.p, 0);
     c->launches++;
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
