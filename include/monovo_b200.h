@@ -223,6 +223,17 @@ MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);
  * dependency graph over the context's CUDA streams (profiling aid; same validity rule as mvo_stage_ms) */
 MVO_API int mvo_stage_span_ms(mvo_ctx* ctx, const char* stage, float* beg_ms, float* end_ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * profiling / parity aids (not part of the reference-facing surface)
+ * mvo_debug_set: "lk_impl" = 1 | 2 selects the first- / second-generation gray LK kernel (identical results; the old
+ *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels.
+ * mvo_debug_time: re-runs one stage of the group pipeline `reps` times on the state left by the last mvo_group_step
+ *                (at least two steps must have run) and returns the average device time per run in ms, measured with
+ *                CUDA events on the context stream.  what = "lk_track" | "knn" | "orb" | "orb_dense" | "lk_pyramid".
+ */
+MVO_API int mvo_debug_set(mvo_ctx* ctx, const char* key, int value);
+MVO_API int mvo_debug_time(mvo_ctx* ctx, const char* what, int reps, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

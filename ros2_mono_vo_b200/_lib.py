@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmonovo_b200.so")
+# MVO_B200_LIB: an alternative build of the same library (kernel variants for A/B timing, scripts/lk_variants.py)
+LIB_PATH = os.environ.get("MVO_B200_LIB") or os.path.join(HERE, "libmonovo_b200.so")
 
 MVO_OK, MVO_ERR_INVALID, MVO_ERR_CUDA, MVO_ERR_CAPACITY, MVO_ERR_UNSUPPORTED, MVO_ERR_DEGENERATE = 0, -1, -2, -3, -4, -5
 
@@ -78,6 +79,8 @@ SIGNATURES = {
     "mvo_group_reset": (C.c_int, [_vp]),
     "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
     "mvo_stage_span_ms": (C.c_int, [_vp, C.c_char_p, _f32p, _f32p]),
+    "mvo_debug_set": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "mvo_debug_time": (C.c_int, [_vp, C.c_char_p, C.c_int, _f32p]),
 }
 
 _lib = None

@@ -178,6 +178,16 @@ class Context:
     def group_reset(self):
         self._check(self.lib.mvo_group_reset(self.h))
 
+    def debug_set(self, key: str, value: int):
+        """Profiling / parity knob (mvo_debug_set): e.g. ("lk_impl", 1) selects the first-generation LK kernel."""
+        self._check(self.lib.mvo_debug_set(self.h, key.encode(), int(value)))
+
+    def debug_time(self, what: str, reps: int = 10) -> float:
+        """Average device ms of one stage re-run on the state of the last group step (mvo_debug_time)."""
+        v = C.c_float()
+        self._check(self.lib.mvo_debug_time(self.h, what.encode(), int(reps), C.byref(v)))
+        return float(v.value)
+
     def stage_ms(self) -> dict:
         out = {}
         v = C.c_float()

@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" entry points of libmonovo_b200.so (context, ORB, kNN).  See include/monovo_b200.h.
 #include "context.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <mutex>
@@ -58,6 +59,7 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
   c->cfg = *cfg;
   if (c->cfg.max_points <= 0) c->cfg.max_points = 2 * c->cfg.nfeatures;
   if (c->cfg.ransac_seed == 0) c->cfg.ransac_seed = 0xFFFFFFFFFFFFFFFFull;
+  if (const char* e = getenv("MVO_LK_IMPL")) c->dbg_lk_impl = atoi(e);      // A/B aid: see mvo_debug_set
   if (cfg->cuda_stream) {
     c->stream = (cudaStream_t)cfg->cuda_stream;
   } else {

@@ -156,11 +156,19 @@ struct mvo_ctx {
   mvo::DevBuf<float> lk_err;
   mvo::DevBuf<int32_t> lk_npts;               // batch
   int lk_w = 0, lk_h = 0, lk_max_pts = 0, lk_cn = 1;   // lk_cn: image planes per stream (1 gray, 3 BGR)
+  // TMA descriptors (CUtensorMap, 128 bytes each) of every level of the two LK pyramid buffers: {x, y, stream} byte
+  // tensors with 48 x 24 / 48 x 29 boxes (lk.cu: lk_track2_kernel stages its tiles with cp.async.bulk.tensor)
+  alignas(64) unsigned char lk_tmaps[2][2][mvo::kLkLevels][128];   // [buffer][template | next-image box][level]
+  bool lk_tmaps_ok = false;
 
   // ---------------- RANSAC / pose ----------------
   RansacBufs rs;
   PnpBufs pnp;
   int last_ransac_iters = 0;
+
+  // ---------------- profiling / parity knobs (mvo_debug_set) ----------------
+  int dbg_lk_impl = 2;     // 1: first-generation lk_track_kernel (in-tree cross-check), 2: lk_track2_kernel
+  int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
 
   // ---------------- stage timing ----------------
   static constexpr int kNumStages = 10;

@@ -480,4 +480,57 @@ int mvo_stage_span_ms(mvo_ctx* c, const char* stage, float* beg_ms, float* end_m
   return MVO_ERR_INVALID;
 }
 
+int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
+  if (!c || !key) return MVO_ERR_INVALID;
+  if (strcmp(key, "lk_impl") == 0) c->dbg_lk_impl = value;
+  else if (strcmp(key, "knn_impl") == 0) c->dbg_knn_impl = value;
+  else {
+    c->set_error("mvo_debug_set: unknown key");
+    return MVO_ERR_INVALID;
+  }
+  return MVO_OK;
+}
+
+// Re-run one stage on the state the last group step left behind: the latest frame's pyramid is lk_pyr[lk_cur ^ 1] and its
+// keypoints / descriptors are the prev_* buffers (the step swapped them); the frame before is lk_pyr[lk_cur] / kps / desc.
+int mvo_debug_time(mvo_ctx* c, const char* what, int reps, float* ms) {
+  if (!c || !what || !ms || reps < 1) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  if (!c->have_prev || c->geom_w < 0) {
+    c->set_error("mvo_debug_time: run at least two group steps first");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const int B = c->cfg.batch, cap = c->geom.kp_cap;
+  c->stream = c->main_stream;
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  StageTimer& t = c->timers[ST_TOTAL];
+  int rc = MVO_OK;
+  for (int r = -1; r < reps && rc == MVO_OK; ++r) {   // r == -1: warm-up
+    if (r == 0) cudaEventRecord(t.beg, c->stream);
+    if (strcmp(what, "lk_track") == 0)
+      rc = lk_run(c, c->lk_cur ^ 1, c->lk_cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p,
+                  c->lk_err.p);
+    else if (strcmp(what, "lk_pyramid") == 0)
+      rc = lk_build_pyramid(c, c->lk_cur, nullptr, 0, 3);
+    else if (strcmp(what, "knn") == 0)
+      rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
+    else if (strcmp(what, "orb") == 0)
+      rc = orb_run_detect(c, true);
+    else if (strcmp(what, "orb_dense") == 0)
+      rc = orb_run_levels_only(c);
+    else {
+      c->set_error("mvo_debug_time: unknown stage");
+      return MVO_ERR_INVALID;
+    }
+  }
+  if (rc) return rc;
+  cudaEventRecord(t.end, c->stream);
+  MVO_CUDA_TRY(c, cudaEventSynchronize(t.end));
+  MVO_CUDA_TRY(c, cudaEventElapsedTime(ms, t.beg, t.end));
+  *ms /= (float)reps;
+  if (strncmp(what, "orb", 3) == 0) c->have_prev = false;   // the older frame's keypoint buffers were overwritten
+  return MVO_OK;
+}
+
 }  // extern "C"

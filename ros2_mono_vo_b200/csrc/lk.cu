@@ -13,7 +13,10 @@
 //                      <= 30 Gauss-Newton iterations sampling J from a 32x32 smem region (texture-free
 //                      bilinear), re-staged only when the window leaves it.
 #include "context.cuh"
+#include <cuda.h>
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
 namespace mvo {
 
@@ -228,6 +231,7 @@ __device__ __noinline__ void lk_stage_j(uint32_t* jq, const uint8_t* __restrict_
 // raw rows are walked in registers: Scharr (3,10,3) derivatives from shuffled neighbours, Q14 bilinear interpolation
 // of I / Ix / Iy.  Results go to pt (x = Ix | Iy << 16, y = I) in pixel order k = r * 21 + c; the normal-matrix sums are
 // taken by the caller when it reads the window back (14 samples per lane instead of 24 rows per lane).
+template <bool kFastPath = true>
 __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch,
                                                int lane, int w00, int w01, int w10, int w11, uint2* pt_out) {
   const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
@@ -279,7 +283,7 @@ __device__ __forceinline__ void lk_setup_patch(const uint8_t* __restrict__ I, in
       }
     }
   };
-  if (ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h) {
+  if (kFastPath && ix >= 1 && ix - 1 + 32 <= w && iy >= 1 && iy - 1 + kRaw <= h) {
     // Footprint inside the image (the common case): no derivative is masked, so interpolation and Scharr commute --
     // everything is exact integer arithmetic up to the final shifts.  Interpolate the raw patch first
     // (T = sum w * raw, two IDP.2A per value), then take the Scharr of T: sum w * der == Scharr(T).  One shuffled
@@ -481,6 +485,474 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
         e = __fdiv_rn((float)se, (float)(32 * LKW * LKW));
       }
     }
+  }
+  if (lane == 0) {
+    const long long o = (long long)b * max_pts + i;
+    out_pts[o] = make_float2(nx, ny);
+    status[o] = (uint8_t)st;
+    err[o] = e;
+  }
+}
+
+
+// ---- lk_track2_kernel: TMA-staged tiles, vertical sample runs, shuffle-free setup --------------------------------
+// Second generation of the gray tracker (the first one, lk_track_kernel above, stays in the library as the cross-check:
+// mvo_debug_set(ctx, "lk_impl", 1) selects it at run time; both produce bit-identical results).
+//
+//   * Tiles by TMA.  The two tiles a level needs -- the raw 24 x 24 template patch around the point in the previous image
+//     and the 30 x 29 pixel region of the next image the window samples -- are 2-D byte windows at arbitrary alignment:
+//     one cp.async.bulk.tensor (a 32 x 29 box of a per-level 3-D tensor map {x, y, stream}) per tile, issued by one lane,
+//     completion on a per-warp mbarrier.  The tile lands with its top-left pixel at byte 0, so no alignment arithmetic is
+//     left in the kernel, no registers are held by loads in flight, and both loads are issued ahead of use: the template
+//     positions depend only on the input point, so the patch of level L - 1 is prefetched while level L iterates; the J
+//     region of a level is requested before its template is computed (ncu r02b: a third of the first version's stall
+//     samples were the staging loads).
+//   * The 441 window samples are owned as 63 vertical RUNS of seven pixels (run = 3 * column + row third); lane L owns
+//     runs L and L + 32.  Template setup needs no shuffle: every lane walks its own 10 raw rows x 4 raw columns per run,
+//     interpolates the 3 x 9 T values it needs itself (6 IDP.2A per row) and takes the Scharr of T in registers.
+//   * The J quads of a run sit at base + i * pitch: immediate offsets, no offset table, and with a quad pitch of 29 words
+//     (bank = x - 3 y mod 32) the 32 lanes of a sample slot hit 32 different banks (the 32-word pitch of the first kernel
+//     is 1.7-way conflicted: ncu r01t, 40 % of its shared wavefronts).
+//   * Code size is part of the design: the first unrolled version of this kernel (47 KB) thrashed the 32 KB instruction
+//     cache (ncu r02b: 95.7 % hit rate, GPC instruction fetch at 72 % of peak); the two runs of the setup share one body.
+constexpr int kJW = 29;                 // quad columns == pitch in words
+constexpr int kJH = 28;                 // quad rows
+constexpr int kJSlackX = kJW - LKW;     // 8: inx - jx0 in [0, 8]
+constexpr int kJSlackY = kJH - LKW;     // 7
+constexpr int kJMarginX = 4, kJMarginY = 3;
+constexpr int kRuns = 63, kRunLen = 7;
+// TMA boxes: the innermost coordinate of a tiled copy must be 16-byte aligned (anything else faults with "illegal
+// instruction" on sm_100a: scratch/tma_probe.cu), so a tile starts at x & ~15 and is 48 bytes wide: 15 + 30 columns.
+constexpr int kTileW = 48, kTileWords = kTileW / 4;
+constexpr int kTileHJ = kJH + 1;        // next-image tile: 29 rows
+constexpr int kTileHI = kRaw;           // template tile: 24 rows
+
+#ifndef MVO_LK2_TI_SMEM
+#define MVO_LK2_TI_SMEM 1               // 1: template intensities stay in shared memory (14 registers less), 0: registers
+#endif
+
+struct __align__(128) LkWarpSmem2 {
+  // TMA destinations are 128-byte aligned.  The quad builder reads one word past the end of its tile (into jq: harmless).
+  uint32_t rawI[kTileHI * kTileWords];       // template tile: 1152 B
+  union {
+    struct {
+      uint32_t rawJ[352];                    // next-image tile: 29 rows x 48 bytes = 1392 B, padded to 1408
+      uint32_t jq[kJH * kJW];                // quads of the staged J region: 3248 B
+    };
+    uint2 patch[kWin];                       // border setup: template in pixel order (3528 B), gathered into tx / ti; no J
+  };                                         // tile is in flight then
+  uint32_t tx[2 * kRunLen * 32];             // template Ix | Iy << 16, slot-major: [k][lane], k = 7 * run_of_lane + i
+  int32_t ti[2 * kRunLen * 32];              // template I (Q5)
+  unsigned long long bar[2];                 // mbarriers: [0] template tile, [1] J tile
+};
+static_assert(sizeof(LkWarpSmem2) == 9472, "six 4-warp CTAs per SM");
+static_assert(kTileHJ * kTileWords <= 352 && kTileHI * kTileWords * 4 % 128 == 0, "tile buffers");
+struct LkTmaps {
+  CUtensorMap m[2][kLkLevels];               // [0]: previous image (template), [1]: next image; one map per level
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// (bounded: a tile that never arrives -- a broken tensor map -- traps instead of hanging the GPU)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  for (int spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1 << 24)) __trap();
+}
+// one box (48 bytes x `rows`) of stream b at (x, y), x a multiple of 16: global -> shared, completion (box bytes) on
+// `bar`.  Issued by one lane.
+__device__ __forceinline__ void tma_tile(void* dst, const CUtensorMap* map, int x, int y, int b, unsigned long long* bar,
+                                         int rows) {
+  // generic-proxy accesses to the destination (this warp's earlier reads) are ordered before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, kTileW * rows);
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(b), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// quads of the staged tile: lane = (row phase g = lane >> 3, word column wi = lane & 7), quad rows g, g + 4, ...: with the
+// 29-word pitch the 32 stores of a step go to 32 different banks, and the four word loads are conflict-free too.
+__device__ __forceinline__ void lk_build_quads(uint32_t* jq, const uint32_t* rawJ, int lane, int sub) {
+  const int g = lane >> 3, wi = lane & 7;
+  const uint32_t* p = rawJ + g * kTileWords + (sub >> 2) + wi;   // sub = jx0 & 15: column of the region inside the tile
+  const uint32_t sh = (uint32_t)(sub & 3);
+  const uint32_t sel01 = 0x2110u + 0x1111u * sh, sel23 = 0x4332u + 0x1111u * sh;
+  uint32_t* out = jq + g * kJW + 4 * wi;
+#pragma unroll
+  for (int k = 0; k < kJH / 4; ++k) {
+    const uint32_t w0 = p[4 * k * kTileWords], w1 = p[4 * k * kTileWords + 1];
+    const uint32_t w2 = p[(4 * k + 1) * kTileWords], w3 = p[(4 * k + 1) * kTileWords + 1];
+    const uint32_t t01 = __byte_perm(w0, w1, sel01), t23 = __byte_perm(w0, w1, sel23);
+    const uint32_t b01 = __byte_perm(w2, w3, sel01), b23 = __byte_perm(w2, w3, sel23);
+    uint32_t* o = out + 4 * k * kJW;
+    o[0] = __byte_perm(t01, b01, 0x5410);
+    if (wi < 7) {   // quads 29 .. 31 do not exist
+      o[1] = __byte_perm(t01, b01, 0x7632);
+      o[2] = __byte_perm(t23, b23, 0x5410);
+      o[3] = __byte_perm(t23, b23, 0x7632);
+    }
+  }
+}
+
+// J region that touches the image border: lane = pixel column, reflecting row / column walk straight from global memory
+__device__ __noinline__ void lk_stage_j2_border(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
+                                                int pitch, int lane) {
+  const uint8_t* p = J + safe_reflect(jx0 + lane, w);
+  uint32_t pprev = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[safe_reflect(jy0 + r0 + k, h) * pitch];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t pr = v[k] | (__shfl_down_sync(0xffffffffu, v[k], 1) << 8);
+      const int qr = r0 + k - 1;
+      if (qr >= 0 && qr < kJH && lane < kJW) jq[qr * kJW + lane] = pprev | (pr << 16);
+      pprev = pr;
+    }
+  }
+}
+
+// Border windows: the first kernel's row walk writes the template in pixel order (it handles reflected image rows /
+// columns and zeroed derivatives outside the image); out of line, rare.
+__device__ __noinline__ void lk_setup_border(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch, int lane,
+                                             int w00, int w01, int w10, int w11, uint2* pt_out) {
+  lk_setup_patch<false>(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, pt_out);
+}
+
+// One run of the interior setup: raw rows 7 rseg .. 7 rseg + 9, raw columns c .. c + 3 of the staged tile (its top-left
+// pixel is (ix - 1, iy - 1)) -> seven template samples (window rows 7 rseg + i, column c) into this lane's slots.
+__device__ __forceinline__ void lk_setup_run(const uint32_t* __restrict__ raw, int c, int rseg, uint32_t Wt, uint32_t Wb,
+                                             uint32_t* __restrict__ tx, int32_t* __restrict__ ti) {
+  // c: byte column inside the tile (window column + (ix - 1) & 15)
+  const uint32_t* rp = raw + (kRunLen * rseg) * kTileWords + (c >> 2);
+  const uint32_t fs = (uint32_t)(c & 3) * 8u;
+  uint32_t Wp = 0, Mp = 0;
+  int tcp = 0, dx0 = 0, dx1 = 0, sm0 = 0, sm1 = 0;
+#pragma unroll
+  for (int j = 0; j < kRunLen + 3; ++j) {
+    const uint32_t W = __funnelshift_r(rp[j * kTileWords], rp[j * kTileWords + 1], fs);   // raw bytes c .. c + 3 of row j
+    const uint32_t M = __byte_perm(W, 0u, 0x4421);                                          // (b1, b2) in the low half
+    if (j >= 1) {
+      const int tl = dp2a_lo_su(Wb, W, dp2a_lo_su(Wt, Wp, 0));
+      const int tc = dp2a_lo_su(Wb, M, dp2a_lo_su(Wt, Mp, 0));
+      const int tr = dp2a_hi_su(Wb, W, dp2a_hi_su(Wt, Wp, 0));
+      const int dx2 = tr - tl, sm2 = 3 * (tl + tr) + 10 * tc;
+      if (j >= 3) {
+        const int vx = (3 * (dx0 + dx2) + 10 * dx1 + (1 << 13)) >> 14;
+        const int vy = (sm2 - sm0 + (1 << 13)) >> 14;
+        tx[(j - 3) * 32] = __byte_perm((uint32_t)vx, (uint32_t)vy, 0x5410);
+        ti[(j - 3) * 32] = (tcp + (1 << 8)) >> 9;
+      }
+      dx0 = dx1;
+      dx1 = dx2;
+      sm0 = sm1;
+      sm1 = sm2;
+      tcp = tc;
+    }
+    Wp = W;
+    Mp = M;
+  }
+}
+
+// Out of line (code size): wait for the requested tile and / or fetch a new one so that the quads cover the window at
+// (inx, iny).  Returns the region origin and the parity of the J barrier.
+__device__ __noinline__ int3 lk_restage(LkWarpSmem2& sm, const CUtensorMap* map, const uint8_t* __restrict__ J, int inx,
+                                        int iny, int w, int h, int pitch, int lane, int b, bool jpend, int jx0, int jy0,
+                                        uint32_t parJ) {
+  bool have_tile = jpend;   // a tile is in flight (it covers the start position of the level by construction)
+  if (!(jpend) || inx < jx0 || inx - jx0 > kJSlackX || iny < jy0 || iny - jy0 > kJSlackY) {
+    if (jpend) {            // in flight but useless: drain it before the buffer is reused
+      mbar_wait(&sm.bar[1], parJ);
+      parJ ^= 1;
+    }
+    jx0 = inx - kJMarginX;
+    jy0 = iny - kJMarginY;
+    __syncwarp();           // every lane is done with the quads / the tile
+    have_tile = jx0 >= 0 && jx0 + kJW + 1 <= w && jy0 >= 0 && jy0 + kTileHJ <= h;
+    if (have_tile && lane == 0) tma_tile(sm.rawJ, map, jx0 & ~15, jy0, b, &sm.bar[1], kTileHJ);
+  }
+  if (have_tile) {
+    mbar_wait(&sm.bar[1], parJ);
+    parJ ^= 1;
+    lk_build_quads(sm.jq, sm.rawJ, lane, jx0 & 15);
+  } else {
+    lk_stage_j2_border(sm.jq, J, jx0, jy0, w, h, pitch, lane);
+  }
+  __syncwarp();
+  return make_int3(jx0, jy0, (int)parJ);
+}
+
+#ifndef MVO_LK2_MINB
+#define MVO_LK2_MINB 5
+#endif
+#ifndef MVO_LK2_WARPS
+#define MVO_LK2_WARPS 4
+#endif
+constexpr int kLk2Warps = MVO_LK2_WARPS;
+
+__global__ void __launch_bounds__(kLk2Warps * 32, MVO_LK2_MINB)
+lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTmaps tm, const uint8_t* __restrict__ pyrI,
+                 const uint8_t* __restrict__ pyrJ, const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev,
+                 int max_pts, float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+  __shared__ LkWarpSmem2 sm_all[kLk2Warps];
+  const int b = blockIdx.y;
+  const int n = min(npts_dev[b], max_pts);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kLk2Warps + warp;
+  if (i >= n) return;
+  LkWarpSmem2& sm = sm_all[warp];
+  if (lane == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parI = 0, parJ = 0;
+  const float2 p0 = pts[(long long)b * max_pts + i];
+  float nx = 0.f, ny = 0.f, e = 0.f;
+  int st = 1;
+  const float flt_scale = 1.f / (1 << 20);
+  // the two runs of this lane: run -> (column c, row third rseg); lane 31 has no second run
+  const int c0 = lane / 3, r0s = lane - 3 * c0;
+  const bool has1 = lane + 32 < kRuns;
+  const int run1 = has1 ? lane + 32 : kRuns - 1;
+  const int c1 = run1 / 3, r1s = run1 - 3 * c1;
+  const int qoff0 = (kRunLen * r0s) * kJW + c0, qoff1 = (kRunLen * r1s) * kJW + c1;
+  uint32_t* const txl = sm.tx + lane;
+  int32_t* const til = sm.ti + lane;
+
+  // template tile of a level: position and fast-path test depend on the input point only
+  auto tmpl_pos = [&](int L, int& ix, int& iy, float& qx, float& qy) {
+    const float s = 1.f / (float)(1 << L);
+    qx = __fsub_rn(__fmul_rn(p0.x, s), 10.f);
+    qy = __fsub_rn(__fmul_rn(p0.y, s), 10.f);
+    ix = (int)floorf(qx);
+    iy = (int)floorf(qy);
+    const int w = g.lv[L].w, h = g.lv[L].h;
+    // (a NaN coordinate floors to INT_MIN in OpenCV: out of range on every level)
+    const bool in_range = !(ix < -LKW || ix >= w || iy < -LKW || iy >= h || qx != qx || qy != qy);
+    const bool interior = in_range && ix >= 1 && ix + 23 <= w && iy >= 1 && iy + 23 <= h;
+    return in_range ? (interior ? 2 : 1) : 0;
+  };
+  bool ireq = false;   // the template tile of the coming level has been requested
+  {
+    int ix, iy;
+    float qx, qy;
+    ireq = tmpl_pos(g.nlevels - 1, ix, iy, qx, qy) == 2;
+    if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][g.nlevels - 1], (ix - 1) & ~15, iy - 1, b, &sm.bar[0], kTileHI);
+  }
+
+  for (int L = g.nlevels - 1; L >= 0; --L) {
+    const LkLevel lv = g.lv[L];
+    const uint8_t* I = pyrI + (long long)b * g.frame_stride + lv.off;
+    const uint8_t* J = pyrJ + (long long)b * g.frame_stride + lv.off;
+    const int w = lv.w, h = lv.h, pitch = lv.pitch;
+    if (L == g.nlevels - 1) {
+      const float s = 1.f / (float)(1 << L);
+      nx = __fmul_rn(p0.x, s);
+      ny = __fmul_rn(p0.y, s);
+    } else {
+      nx = __fmul_rn(nx, 2.f);
+      ny = __fmul_rn(ny, 2.f);
+    }
+    int ix, iy;
+    float qx, qy;
+    const int kind = tmpl_pos(L, ix, iy, qx, qy);
+    if (kind == 0) {
+      if (L == 0) {
+        st = 0;
+        e = 0.f;
+      }
+      ireq = false;
+      continue;    // (tmpl_pos is monotone over the levels: no tile was requested for this one)
+    }
+    // ---- request the J region around the start position of this level (it is needed after the template setup) ----
+    float cx = __fsub_rn(nx, 10.f), cy = __fsub_rn(ny, 10.f);
+    int jx0 = -100000, jy0 = -100000;
+    bool jpend = false;
+    {
+      const int inx = (int)floorf(cx), iny = (int)floorf(cy);
+      const int tx0 = inx - kJMarginX, ty0 = iny - kJMarginY;
+      // (a border template builds its window in scratch that aliases the J tile: no request ahead of it then)
+      if (kind == 2 && tx0 >= 0 && tx0 + kJW + 1 <= w && ty0 >= 0 && ty0 + kTileHJ <= h) {
+        jx0 = tx0;
+        jy0 = ty0;
+        jpend = true;
+        __syncwarp();   // every lane is done with the previous level's J tile and quads
+        if (lane == 0) tma_tile(sm.rawJ, &tm.m[1][L], jx0 & ~15, jy0, b, &sm.bar[1], kTileHJ);
+      }
+    }
+    int w00, w01, w10, w11;
+    lk_weights(__fsub_rn(qx, (float)ix), __fsub_rn(qy, (float)iy), w00, w01, w10, w11);
+
+    // ---- template of this level: tx / ti slots of this lane ----
+    if (kind == 2) {
+      if (!ireq) {   // (a level above was out of range: nothing was prefetched)
+        __syncwarp();
+        if (lane == 0) tma_tile(sm.rawI, &tm.m[0][L], (ix - 1) & ~15, iy - 1, b, &sm.bar[0], kTileHI);
+      }
+      mbar_wait(&sm.bar[0], parI);
+      parI ^= 1;
+      const uint32_t Wt = pack_w(w00, w01), Wb = pack_w(w10, w11);
+      const int sub = (ix - 1) & 15;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t)
+        lk_setup_run(sm.rawI, sub + (t ? c1 : c0), t ? r1s : r0s, Wt, Wb, txl + t * kRunLen * 32, til + t * kRunLen * 32);
+    } else {
+      __syncwarp();   // patch aliases the quads of the previous level
+      lk_setup_border(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, sm.patch);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < kRunLen; ++k) {
+        const uint2 a = sm.patch[(kRunLen * r0s + k) * LKW + c0], bq = sm.patch[(kRunLen * r1s + k) * LKW + c1];
+        txl[k * 32] = a.x;
+        til[k * 32] = (int)a.y;
+        txl[(kRunLen + k) * 32] = bq.x;
+        til[(kRunLen + k) * 32] = (int)bq.y;
+      }
+    }
+    // prefetch the template tile of the next level (the tile buffer has been consumed)
+    ireq = false;
+    if (L > 0) {
+      int nix, niy;
+      float nqx, nqy;
+      ireq = tmpl_pos(L - 1, nix, niy, nqx, nqy) == 2;
+      __syncwarp();
+      if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][L - 1], (nix - 1) & ~15, niy - 1, b, &sm.bar[0], kTileHI);
+    }
+    uint32_t txy[2 * kRunLen];
+#pragma unroll
+    for (int k = 0; k < 2 * kRunLen; ++k) txy[k] = (k >= kRunLen && !has1) ? 0u : txl[k * 32];   // lane 31: no 2nd run
+#if !MVO_LK2_TI_SMEM
+    int tir[2 * kRunLen];
+#pragma unroll
+    for (int k = 0; k < 2 * kRunLen; ++k) tir[k] = til[k * 32];
+#define LK2_TI(k) tir[k]
+#else
+#define LK2_TI(k) til[(k) * 32]
+#endif
+    int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * kRunLen; ++k) {
+      const int gx = (int)(short)(txy[k] & 0xffffu), gy = (int)txy[k] >> 16;
+      sA11 += gx * gx;
+      sA12 += gx * gy;
+      sA22 += gy * gy;
+    }
+    const float A11 = __fmul_rn((float)warp_sum_wide(sA11), flt_scale);
+    const float A12 = __fmul_rn((float)warp_sum_wide(sA12), flt_scale);
+    const float A22 = __fmul_rn((float)warp_sum_wide(sA22), flt_scale);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dA = __fsub_rn(A11, A22);
+    const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * LKW * LKW));
+    const bool degenerate = (double)min_eig < 1e-4 || D < 1.1920929e-07f;
+    if (degenerate && L == 0) st = 0;
+    D = __fdiv_rn(1.f, D);
+    float pdx = 0.f, pdy = 0.f;
+
+    // (re)stage the J region so that it covers the window at integer position (inx, iny)
+    auto cover = [&](int inx, int iny) {
+      if (jpend || inx < jx0 || inx - jx0 > kJSlackX || iny < jy0 || iny - jy0 > kJSlackY) {
+        const int3 r = lk_restage(sm, &tm.m[1][L], J, inx, iny, w, h, pitch, lane, b, jpend, jx0, jy0, parJ);
+        jx0 = r.x;
+        jy0 = r.y;
+        parJ = (uint32_t)r.z;
+        jpend = false;
+      }
+    };
+
+    for (int it = 0; it < 30 && !degenerate; ++it) {
+      const int inx = (int)floorf(cx), iny = (int)floorf(cy);
+      if (inx < -LKW || inx >= w || iny < -LKW || iny >= h) {
+        if (L == 0) st = 0;
+        break;
+      }
+      cover(inx, iny);
+      int v00, v01, v10, v11;
+      lk_weights(__fsub_rn(cx, (float)inx), __fsub_rn(cy, (float)iny), v00, v01, v10, v11);
+      const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+      const uint32_t* jb = sm.jq + (iny - jy0) * kJW + (inx - jx0);
+      const uint32_t* q0 = jb + qoff0;
+      const uint32_t* q1 = jb + qoff1;
+      int sb1 = 0, sb2 = 0;
+#pragma unroll
+      for (int k = 0; k < kRunLen; ++k) {
+        const uint32_t qa = q0[k * kJW], qb = q1[k * kJW];
+        const int da = (dp2a_hi_su(Vb, qa, dp2a_lo_su(Vt, qa, 1 << 8)) >> 9) - LK2_TI(k);
+        const int db = (dp2a_hi_su(Vb, qb, dp2a_lo_su(Vt, qb, 1 << 8)) >> 9) - LK2_TI(kRunLen + k);
+        sb1 += da * (int)(short)(txy[k] & 0xffffu) + db * (int)(short)(txy[kRunLen + k] & 0xffffu);
+        sb2 += da * ((int)txy[k] >> 16) + db * ((int)txy[kRunLen + k] >> 16);
+      }
+      const float b1 = __fmul_rn((float)warp_sum_wide(sb1), flt_scale);
+      const float b2 = __fmul_rn((float)warp_sum_wide(sb2), flt_scale);
+      const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      cx = __fadd_rn(cx, dx);
+      cy = __fadd_rn(cy, dy);
+      nx = __fadd_rn(cx, 10.f);
+      ny = __fadd_rn(cy, 10.f);
+      if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+      if (it > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+        nx = __fsub_rn(nx, __fmul_rn(dx, 0.5f));
+        ny = __fsub_rn(ny, __fmul_rn(dy, 0.5f));
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+    if (L == 0 && st) {
+      const float fx = __fsub_rn(nx, 10.f), fy = __fsub_rn(ny, 10.f);
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -LKW || inx >= w || iny < -LKW || iny >= h) {
+        st = 0;
+      } else {
+        cover(inx, iny);
+        int v00, v01, v10, v11;
+        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), v00, v01, v10, v11);
+        const uint32_t Vt = pack_w(v00, v01), Vb = pack_w(v10, v11);
+        const uint32_t* jb = sm.jq + (iny - jy0) * kJW + (inx - jx0);
+        const uint32_t* q0 = jb + qoff0;
+        const uint32_t* q1 = jb + qoff1;
+        int se = 0;
+#pragma unroll
+        for (int k = 0; k < kRunLen; ++k) {
+          const uint32_t qa = q0[k * kJW], qb = q1[k * kJW];
+          se += abs((dp2a_hi_su(Vb, qa, dp2a_lo_su(Vt, qa, 1 << 8)) >> 9) - LK2_TI(k));
+          const int eb = abs((dp2a_hi_su(Vb, qb, dp2a_lo_su(Vt, qb, 1 << 8)) >> 9) - LK2_TI(kRunLen + k));
+          se += has1 ? eb : 0;
+        }
+        se = __reduce_add_sync(0xffffffffu, se);
+        e = __fdiv_rn((float)se, (float)(32 * LKW * LKW));
+      }
+    }
+    if (jpend) {   // a requested tile nobody consumed (degenerate level, window left the image): drain it
+      mbar_wait(&sm.bar[1], parJ);
+      parJ ^= 1;
+    }
+#undef LK2_TI
   }
   if (lane == 0) {
     const long long o = (long long)b * max_pts + i;
@@ -716,11 +1188,56 @@ static void lk_geometry(int w, int h, LkGeom& g) {
   g.frame_stride = (long long)align_up((size_t)off + 256, 256);
 }
 
+// tensor maps of the pyramid levels (driver entry point through the runtime: the library does not link libcuda)
+static int lk_make_tmaps(mvo_ctx* c, const LkGeom& g, int planes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVO_CUDA_TRY(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      c->set_error("cuTensorMapEncodeTiled is not available in this driver");
+      return MVO_ERR_CUDA;
+    }
+    encode = (EncodeFn)fn;
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  for (int k = 0; k < 2; ++k)
+    for (int kind = 0; kind < 2; ++kind)     // 0: template tiles (24 rows), 1: next-image tiles (29 rows)
+      for (int l = 0; l < g.nlevels; ++l) {
+        const LkLevel& lv = g.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)lv.pitch, (cuuint64_t)align_up((size_t)lv.h, 8), (cuuint64_t)planes};
+        const cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)g.frame_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileW, (cuuint32_t)(kind ? kTileHJ : kTileHI), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = encode(reinterpret_cast<CUtensorMap*>(c->lk_tmaps[k][kind][l]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                  c->lk_pyr[k].p + lv.off, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          c->set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+          return MVO_ERR_CUDA;
+        }
+      }
+  c->lk_tmaps_ok = true;
+  return MVO_OK;
+}
+
 int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn) {
   LkGeom g;
   lk_geometry(w, h, g);
   const size_t B = (size_t)c->cfg.batch;
+  const uint8_t* old_base[2] = {c->lk_pyr[0].p, c->lk_pyr[1].p};
   for (int k = 0; k < 2; ++k) MVO_CUDA_TRY(c, c->lk_pyr[k].alloc(B * cn * g.frame_stride));
+  if (!c->lk_tmaps_ok || c->lk_w != w || c->lk_h != h || c->lk_cn != cn || old_base[0] != c->lk_pyr[0].p ||
+      old_base[1] != c->lk_pyr[1].p) {
+    c->lk_tmaps_ok = false;
+    const int rc = lk_make_tmaps(c, g, (int)(B * cn));
+    if (rc) return rc;
+  }
   MVO_CUDA_TRY(c, c->lk_pts_in.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_pts_out.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_status.alloc(B * (size_t)max_pts));
@@ -811,8 +1328,17 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
                                                                     pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
     } else {
       dim3 grid((max_pts + kLkWarps - 1) / kLkWarps, c->cfg.batch);
-      lk_track_kernel<<<grid, kLkWarps * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev,
-                                                            npts_dev, max_pts, out_dev, status_dev, err_dev);
+      // mvo_debug_set("lk_impl", 1): the first-generation kernel (kept as the in-tree cross-check; identical results)
+      if (c->dbg_lk_impl == 1)
+        lk_track_kernel<<<grid, kLkWarps * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev,
+                                                              npts_dev, max_pts, out_dev, status_dev, err_dev);
+      else {
+        LkTmaps tm;
+        memcpy(tm.m[0], c->lk_tmaps[prev_which][0], sizeof(tm.m[0]));
+        memcpy(tm.m[1], c->lk_tmaps[next_which][1], sizeof(tm.m[1]));
+        lk_track2_kernel<<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
+            g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
+      }
     }
     c->launches++;
   }
