@@ -120,6 +120,248 @@ knn_top2_kernel(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_de
   }
 }
 
+// ================================================================================================
+// knn_mma_kernel: the same top-2 on the 5th-generation tensor cores.
+//
+// With descriptor bits mapped to +-1, q . t = 256 - 2 * Hamming(q, t): the all-pairs distance matrix is a dense
+// {+-8}-valued int8 GEMM (tcgen05.mma kind::i8, accumulators in TMEM, exact: |64 s| <= 2^14).  A CTA owns 128 queries
+// and streams its slice of the train set through 128-row tiles:
+//   * the packed descriptors (32 B per row) are expanded to the canonical K-major no-swizzle core-matrix layout
+//     (8 rows x 16 B atoms, LBO = 128 B between K-adjacent atoms, SBO = 2 KB between 8-row groups) straight into shared
+//     memory by the CTA's threads (PRMT sign replication, no table): the expanded operands never exist in global memory
+//     (8 x the traffic of the packed form);
+//   * one elected thread issues the eight K = 32 MMAs of a tile into one of two 128-column TMEM accumulators and
+//     commits to an mbarrier; the expansion of tile j + 1 and the selection epilogue of tile j overlap MMA j + 1;
+//   * epilogue: eight warps (TMEM lane quarter x column half) read the 128 x 128 int32 block with tcgen05.ld and keep a
+//     per-row top-2 on PACKED 16-bit keys, two columns per instruction: the accumulator 64 s is a multiple of 128, so
+//     (64 s) ^ 0x8000 | (127 - column) is an order-preserving 16-bit key (larger = nearer, ties -> lower column).
+//     PRMT + LOP + three VIMNMX.U16x2 per column pair.  A tile's winners are decoded into the usual 32-bit key
+//     (dist << 22 | trainIdx) only when they beat the row's current second best.
+// Results are bit-identical to knn_top2_kernel (tests/test_gpu_knn.py runs both).
+constexpr int kMmaM = 128, kMmaN = 128, kMmaK = 256;          // CTA tile: queries x train rows x descriptor bits
+constexpr int kMmaThreads = 256;
+constexpr int kOperandBytes = kMmaM * kMmaK;                  // 32 KB per expanded tile
+constexpr int kKnnMmaSmem = 3 * kOperandBytes + 2 * kMmaM * 8 + 64;
+
+__device__ __forceinline__ uint32_t knn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// canonical K-major, no swizzle: element (row r, byte k) at (r / 8) * 2048 + (k / 16) * 128 + (r % 8) * 16 + k % 16
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(2048u >> 4) << 32) | (1ull << 46);
+}
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
+constexpr uint32_t kUmmaIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kMmaN >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);
+
+// One packed descriptor half-row (16 bytes = 128 bits) of row r -> 128 operand bytes (+8 for a set bit, -8 for a clear
+// one) in eight 16-byte atoms.  No table: a byte whose selector nibble has bit 3 set makes PRMT replicate the sign bit of
+// the selected source byte, so PRMT(word << (7 - i), 0xBA98) turns bit i of the four bytes of a word into four 0x00 / 0xFF
+// mask bytes; one LOP3 maps them to 0xF8 / 0x08.  Element order inside a row: (word, bit, byte) -- any fixed order works
+// as long as queries and train rows share it.
+// the sign bit of each byte replicated over the byte (generic PRMT: selector nibbles 8..B; __byte_perm masks that bit off)
+__device__ __forceinline__ uint32_t prmt_sign4(uint32_t x) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(d) : "r"(x));
+  return d;
+}
+__device__ __forceinline__ void knn_expand_row(uint8_t* __restrict__ dst, const uint4 v, int r, int h) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint8_t* o = dst + (r >> 3) * 2048 + (8 * h) * 128 + (r & 7) * 16;
+#pragma unroll
+  for (int wi = 0; wi < 4; ++wi) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = (prmt_sign4(w[wi] << (7 - i)) & 0xF0F0F0F0u) ^ 0xF8F8F8F8u;
+    *reinterpret_cast<uint4*>(o + (2 * wi) * 128) = make_uint4(e[0], e[1], e[2], e[3]);
+    *reinterpret_cast<uint4*>(o + (2 * wi + 1) * 128) = make_uint4(e[4], e[5], e[6], e[7]);
+  }
+}
+// the 16 bytes thread `tid` expands of tile rows [row0, row0 + 128): row tid / 2, half tid % 2 (zero bits past nrows)
+__device__ __forceinline__ uint4 knn_load_row(const uint4* __restrict__ src, int row0, int nrows, int tid) {
+  const int r = tid >> 1, h = tid & 1;
+  return (row0 + r < nrows) ? __ldg(src + (long long)(row0 + r) * 2 + h) : make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 2)
+knn_mma_kernel(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq_dev, int q_stride_rows,
+               const uint8_t* __restrict__ t, const int32_t* __restrict__ nt_dev, int t_stride_rows,
+               uint2* __restrict__ partial, int max_nq, int nsplit) {
+  extern __shared__ __align__(128) uint8_t knn_smem[];
+  uint8_t* sA = knn_smem;
+  uint8_t* sB = knn_smem + kOperandBytes;                              // two stages
+  uint2* merge = reinterpret_cast<uint2*>(knn_smem + 3 * kOperandBytes);   // [2][128] (k0, k1) of the two column halves
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(merge + 2 * kMmaM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int b = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nq = min(nq_dev[b], max_nq), nt = nt_dev[b];
+  const int q0 = blockIdx.x * kMmaM;
+  if (q0 >= nq) return;                                                // (uniform: before any barrier / allocation)
+  const int tiles_total = (nt + kMmaN - 1) / kMmaN;
+  const int tiles_per = (tiles_total + nsplit - 1) / nsplit;
+  const int t_begin = blockIdx.y * tiles_per * kMmaN;
+  const int t_end = min(nt, t_begin + tiles_per * kMmaN);
+  const int ntiles = t_end > t_begin ? (t_end - t_begin + kMmaN - 1) / kMmaN : 0;
+
+  // ---- setup: barriers, TMEM, the query operand ----
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(knn_smem_u32(&bars[s])), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(knn_smem_u32(tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  const uint4* qv = reinterpret_cast<const uint4*>(q + (long long)b * q_stride_rows * 32);
+  const uint4* tv = reinterpret_cast<const uint4*>(t + (long long)b * t_stride_rows * 32);
+  knn_expand_row(sA, knn_load_row(qv, q0, nq, tid), tid >> 1, tid & 1);
+  if (ntiles > 0) knn_expand_row(sB, knn_load_row(tv, t_begin, t_end, tid), tid >> 1, tid & 1);
+  // the packed rows of the next tile are fetched one iteration ahead of their expansion
+  uint4 vnext = ntiles > 1 ? knn_load_row(tv, t_begin + kMmaN, t_end, tid) : make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto issue_tile = [&](int stage) {                                   // one thread: eight K = 32 steps, then commit
+    const uint32_t a0 = knn_smem_u32(sA), b0 = knn_smem_u32(sB + stage * kOperandBytes);
+    const uint32_t d = tmem_base + (uint32_t)(stage * kMmaN);
+#pragma unroll
+    for (int k = 0; k < kMmaK / 32; ++k) {
+      const uint64_t da = umma_desc(a0 + k * 256), db = umma_desc(b0 + k * 256);
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+          "}" ::"r"(d),
+          "l"(da), "l"(db), "r"(kUmmaIdesc), "r"(k > 0 ? 1 : 0)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     knn_smem_u32(&bars[stage]))
+                 : "memory");
+  };
+  if (ntiles > 0 && tid == 0) issue_tile(0);
+
+  const int lq = warp & 3, ch = warp >> 2;                             // TMEM lane quarter, column half
+  uint32_t k0 = kInvalidKey, k1 = kInvalidKey;                         // this row's top-2 over this warp's columns
+  for (int j = 0; j < ntiles; ++j) {
+    const int stage = j & 1;
+    if (j + 1 < ntiles) {
+      knn_expand_row(sB + (stage ^ 1) * kOperandBytes, vnext, tid >> 1, tid & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (j + 2 < ntiles) vnext = knn_load_row(tv, t_begin + (j + 2) * kMmaN, t_end, tid);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                                   // next operand complete, other accumulator drained
+    if (j + 1 < ntiles && tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_tile(stage ^ 1);
+    }
+    // ---- wait for MMA j ----
+    {
+      const uint32_t parity = (uint32_t)((j >> 1) & 1), bar = knn_smem_u32(&bars[stage]);
+      uint32_t ok = 0;
+      for (int spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1 << 24)) __trap();                                // (a broken descriptor must not hang the GPU)
+      }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- selection epilogue: 64 columns of this thread's row ----
+    const int col0 = ch * 64;                                          // first column (inside the tile) of this warp
+    const int valid = min(kMmaN, t_end - (t_begin + j * kMmaN)) - col0; // columns of this warp that are train rows
+    uint32_t m1 = 0, m2 = 0;                                           // packed (even column | odd column << 16), 0 = none
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(32 * lq) << 16) + (uint32_t)(stage * kMmaN + col0 + 32 * half), acc);
+      if (valid >= 64) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const int cc = 32 * half + c;                                // column inside this warp's 64
+          // low halves of two accumulators, sign bit flipped, column tags in the seven zero bits
+          const uint32_t key = __byte_perm(acc[c], acc[c + 1], 0x5410) ^
+                               (0x80008000u | (uint32_t)(127 - cc) | ((uint32_t)(126 - cc) << 16));
+          const uint32_t lo = __vminu2(m1, key);
+          m1 = __vmaxu2(m1, key);
+          m2 = __vmaxu2(m2, lo);
+        }
+      } else {                                                         // the last tile of the train range: mask the tail
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const int cc = 32 * half + c;
+          uint32_t key = __byte_perm(acc[c], acc[c + 1], 0x5410) ^
+                         (0x80008000u | (uint32_t)(127 - cc) | ((uint32_t)(126 - cc) << 16));
+          key &= (cc < valid ? 0xFFFFu : 0u) | (cc + 1 < valid ? 0xFFFF0000u : 0u);
+          const uint32_t lo = __vminu2(m1, key);
+          m1 = __vmaxu2(m1, key);
+          m2 = __vmaxu2(m2, lo);
+        }
+      }
+    }
+    // the tile's two best of this row; decoded only if they can change the row's top-2 (later tiles have larger
+    // indices: an equal distance never displaces an earlier entry)
+    {
+      const uint32_t a_lo = m1 & 0xFFFFu, a_hi = m1 >> 16;
+      const uint32_t best = max(a_lo, a_hi);
+      const uint32_t second = max(min(a_lo, a_hi), a_lo >= a_hi ? (m2 & 0xFFFFu) : (m2 >> 16));
+      const int base_idx = t_begin + j * kMmaN + col0;
+      auto decode = [&](uint32_t k16) {
+        const int s64 = (int)(short)((k16 & 0xFF80u) ^ 0x8000u);       // 64 * (256 - 2 dist)
+        const uint32_t dist = (uint32_t)(128 - (s64 >> 7));
+        return (dist << 22) | (uint32_t)(base_idx + 127 - (int)(k16 & 0x7Fu));
+      };
+      if (best != 0) {
+        const uint32_t kb = decode(best);
+        if (kb < k1) {
+          top2_insert(k0, k1, kb);
+          if (second != 0) top2_insert(k0, k1, decode(second));
+        }
+      }
+    }
+  }
+  // ---- merge the two column halves of a row, write this split's (k0, k1) ----
+  merge[ch * kMmaM + 32 * lq + lane] = make_uint2(k0, k1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < kMmaM && q0 + tid < nq) {
+    const uint2 a = merge[tid], c = merge[kMmaM + tid];
+    uint32_t r0 = a.x, r1 = a.y;
+    top2_insert(r0, r1, c.x);
+    top2_insert(r0, r1, c.y);
+    partial[((long long)b * nsplit + blockIdx.y) * max_nq + q0 + tid] = make_uint2(r0, r1);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 knn_finish_kernel(const uint2* __restrict__ partial, const int32_t* __restrict__ nq_dev, int max_nq, int nsplit,
                   double ratio, uint2* __restrict__ best, mvo_dmatch* __restrict__ matches,
@@ -201,9 +443,24 @@ int knn_run(mvo_ctx* c, const uint8_t* q_dev, const int32_t* nq_dev, int q_strid
   const int tiles = std::max(1, (max_nt + kKnnTile - 1) / kKnnTile);
   int nsplit = (2 * 148 + qblocks * batch - 1) / (qblocks * batch);
   nsplit = std::max(1, std::min(std::min(nsplit, kKnnMaxSplit), tiles));
-  dim3 grid(qblocks, nsplit, batch);
-  knn_top2_kernel<<<grid, kKnnThreads, 0, c->stream>>>(q_dev, nq_dev, q_stride_rows, t_dev, nt_dev, t_stride_rows,
-                                                      partial, max_nq, nsplit);
+  if (c->dbg_knn_impl != 1) {
+    // tensor-core path: 128-query CTAs, the train range split so that the grid covers the SMs several times
+    static bool attr_set = false;
+    if (!attr_set) {
+      MVO_CUDA_TRY(c, cudaFuncSetAttribute(knn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnMmaSmem));
+      attr_set = true;
+    }
+    const int qtiles = std::max(1, (max_nq + kMmaM - 1) / kMmaM);
+    const int ttiles = std::max(1, (max_nt + kMmaN - 1) / kMmaN);
+    nsplit = (6 * 148 + qtiles * batch - 1) / (qtiles * batch);
+    nsplit = std::max(1, std::min(std::min(nsplit, kKnnMaxSplit), ttiles));
+    knn_mma_kernel<<<dim3(qtiles, nsplit, batch), kMmaThreads, kKnnMmaSmem, c->stream>>>(
+        q_dev, nq_dev, q_stride_rows, t_dev, nt_dev, t_stride_rows, partial, max_nq, nsplit);
+  } else {
+    dim3 grid(qblocks, nsplit, batch);
+    knn_top2_kernel<<<grid, kKnnThreads, 0, c->stream>>>(q_dev, nq_dev, q_stride_rows, t_dev, nt_dev, t_stride_rows,
+                                                        partial, max_nq, nsplit);
+  }
   c->launches++;
   knn_finish_kernel<<<batch, 1024, 0, c->stream>>>(partial, nq_dev, max_nq, nsplit, ratio, best, c->knn_matches.p,
                                                   c->knn_nmatch.p);

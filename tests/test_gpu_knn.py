@@ -8,10 +8,13 @@ from oracle import knn_oracle as ko
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["tcgen05", "popc"])
+def ctx(request):
+    """Every test runs on both matching kernels: the tensor-core one (knn_mma_kernel, the default) and the xor + popc
+    one (knn_top2_kernel, the in-tree cross-check)."""
     from ros2_mono_vo_b200 import Context
     c = Context(640, 480, nfeatures=1000)
+    c.debug_set("knn_impl", 1 if request.param == "popc" else 0)
     yield c
     c.close()
 
@@ -79,3 +82,30 @@ def test_knn_linearity_property(ctx):
     assert np.array_equal(d0, d2)
     untied = d0[:, 0] != d0[:, 1]
     assert np.array_equal(perm[i2[untied, 0]], i0[untied, 0])
+
+
+def test_knn_extreme_distances_and_cross_tile_ties(ctx):
+    """Distances 0 and 256 (the ends of the tensor kernel's 16-bit key range), and exact ties between train rows that
+    sit in different 128-row tiles and in both halves of a split train range: lowest index wins."""
+    rng = np.random.default_rng(21)
+    q = rng.integers(0, 256, (300, 32)).astype(np.uint8)
+    t = rng.integers(0, 256, (1500, 32)).astype(np.uint8)
+    t[5] = q[0]; t[700] = q[0]; t[1400] = q[0]              # three exact copies of query 0 in three tiles
+    t[130] = ~q[1]                                          # distance 256 from query 1
+    t[900] = q[2]; t[901] = q[2]                            # adjacent columns (the two packed 16-bit lanes)
+    idx, dist = ctx.knn2(q, t)
+    oidx, odist = ko.knn2(q, t)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
+    assert idx[0].tolist() == [5, 700] and dist[0].tolist() == [0, 0]
+    assert idx[2].tolist() == [900, 901]
+    # a train set of complements only: every distance is large, one is exactly 256
+    tc = ~q[:200]
+    idx, dist = ctx.knn2(q[:200], tc)
+    oidx, odist = ko.knn2(q[:200], tc)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
+    # all-identical train rows across many tiles
+    tt = np.repeat(q[:1], 1000, axis=0)
+    idx, dist = ctx.knn2(q[:3], tt)
+    assert idx[0].tolist() == [0, 1] and dist[0].tolist() == [0, 0]
+    oidx, odist = ko.knn2(q[:3], tt)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist, odist)
