@@ -224,6 +224,87 @@ MVO_API int mvo_stage_ms(mvo_ctx* ctx, const char* stage, float* ms);
 MVO_API int mvo_stage_span_ms(mvo_ctx* ctx, const char* stage, float* beg_ms, float* end_ms);
 
 /* ------------------------------------------------------------------------------------------------
+ * stream-group product surface: BGR8 input and the full per-stream outputs of a group step -- everything the
+ * reference's data flow consumes (Frame::extract_observations needs keypoints + descriptors, src/frame.cpp:8-17; the
+ * tracker needs the tracked points, src/tracker.cpp:70-77; landmark creation needs the masks and the 3-D points,
+ * src/initializer.cpp:283-298).
+ */
+enum {
+  MVO_OUT_KEYPOINTS = 1,  /* keypoints + descriptors of frame t                                   */
+  MVO_OUT_MATCHES = 2,    /* ratio-test matches (t-1 -> t)                                        */
+  MVO_OUT_TRACKS = 4,     /* LK next position / status / err of every keypoint of frame t-1       */
+  MVO_OUT_MODELS = 8,     /* H, F, E and their inlier masks, the recoverPose mask                 */
+  MVO_OUT_POINTS3D = 16,  /* triangulated homogeneous points                                      */
+  MVO_OUT_ALL = 31
+};
+typedef struct mvo_group_config {
+  int32_t channels;   /* frames given to mvo_group_step / submit / track: 1 = gray8, 3 = BGR8 (the node feeds BGR8,
+                         src/mono_vo.cpp:94: ORB runs on the fused BGR->gray conversion, LK on the three colour planes
+                         exactly as cv::calcOpticalFlowPyrLK does on 3-channel Mats) */
+  uint32_t outputs;   /* MVO_OUT_* mask: these outputs are copied to pinned host memory inside every step */
+} mvo_group_config;
+/* valid while no step is in flight; forgets the previous frame of every stream */
+MVO_API int mvo_group_configure(mvo_ctx* ctx, const mvo_group_config* cfg);
+/* bytes copied device -> host per step with the configured outputs (result records included) */
+MVO_API int mvo_group_output_bytes(mvo_ctx* ctx, size_t* bytes);
+
+/* Outputs of one stream for the step most recently returned by mvo_group_step / mvo_group_collect.  The pointers are
+ * views into pinned host memory owned by the context (no copy); they stay valid until the next mvo_group_submit /
+ * mvo_group_step / mvo_group_configure call.  Sections that were not requested (or have no previous frame) are NULL / 0.
+ *   keypoints / descriptors : n_keypoints entries, canonical order (as mvo_orb_detect_and_compute)
+ *   matches                 : n_matches entries, query = keypoints of frame t-1, train = keypoints of frame t
+ *   track_*                 : n_prev entries, one per keypoint of frame t-1 (as mvo_lk_track returns them)
+ *   mask_*                  : n_tracked entries over the ordered list of tracks with status && err < 30, i.e. the
+ *                             p1 / p2 vectors of src/tracker.cpp:70-77; mask_pose is recoverPose's in/out mask (0 / 255)
+ *   X4                      : 4 rows of n_tracked floats, row r at X4 + r * x4_stride (cv::triangulatePoints' 4 x N Mat)
+ */
+typedef struct mvo_stream_outputs {
+  int32_t n_keypoints, n_matches, n_prev, n_tracked;
+  const mvo_keypoint* keypoints;
+  const uint8_t* descriptors;
+  const mvo_dmatch* matches;
+  const float* track_xy;
+  const uint8_t* track_status;
+  const float* track_err;
+  const uint8_t* mask_h;
+  const uint8_t* mask_f;
+  const uint8_t* mask_e;
+  const uint8_t* mask_pose;
+  const float* X4;
+  int64_t x4_stride;
+  double H[9], F[9], E[9];
+  int32_t flags;        /* bit0: FAST candidate list overflowed, bit1: keypoints truncated to the capacity */
+  int32_t reserved;
+} mvo_stream_outputs;
+MVO_API int mvo_group_outputs(mvo_ctx* ctx, int stream, mvo_stream_outputs* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * stream-group tracking frame == Tracker::update's per-frame path (src/tracker.cpp:274-316) for every stream:
+ *   LK(previous frame -> new frame) on the stream's tracked observations (track_frame_with_optical_flow, :57-92),
+ *   keep status && err < 30 in order, solvePnPRansac(landmarks, tracked points, K, 100, 8.0, 0.99) (:309).
+ * The tracked set (image positions + landmark coordinates) stays on the device and is the next frame's input;
+ * mvo_group_set_tracks replaces it for one stream (after initialisation / a new keyframe, src/tracker.cpp:176-235).
+ * The first call after create / configure / set of a new size only stores the frame (Tracker::update :285-289).
+ */
+typedef struct mvo_track_result {
+  int32_t n_prev;         /* observations tracked from                                    */
+  int32_t n_tracked;      /* kept (status && err < 30): the new frame's observations      */
+  int32_t n_pnp_inliers;  /* inliers of the winning solvePnPRansac hypothesis             */
+  int32_t pnp_ok;         /* 1: rvec / tvec valid (solvePnPRansac returned true)          */
+  double rvec[3];
+  double tvec[3];
+} mvo_track_result;
+/* xy: n x 2 f32 pixel positions in the stream's latest frame, xyz: n x 3 f32 landmark coordinates */
+MVO_API int mvo_group_set_tracks(mvo_ctx* ctx, int stream, const float* xy, const float* xyz, int n);
+MVO_API int mvo_group_track(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride, int images_on_device,
+                            const double K[9], mvo_track_result* results);
+/* the stream's observations after the last mvo_group_track: position, index into the previous frame's observation
+ * list (so the host can carry descriptor / landmark ids along, src/tracker.cpp:73-76), and the PnP inlier indices
+ * (into the new list).  Any pointer may be NULL; cap = capacity of each array. */
+MVO_API int mvo_group_get_tracks(mvo_ctx* ctx, int stream, float* xy, int32_t* src_idx, int32_t* pnp_inliers, int cap,
+                                 int* n_tracked, int* n_inliers);
+
+/* ------------------------------------------------------------------------------------------------
  * profiling / parity aids (not part of the reference-facing surface)
  * mvo_debug_set: "lk_impl" = 1 | 2 selects the first- / second-generation gray LK kernel (identical results; the old
  *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels.

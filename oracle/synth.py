@@ -196,6 +196,12 @@ def synth_sequence(h: int, w: int, stream: int, nframes: int, return_poses: bool
     return frames, K
 
 
+def sequence_depth(h: int, w: int, stream: int) -> np.ndarray:
+    """The depth map synth_sequence(h, w, stream, ...) renders with (same generator state)."""
+    rng = np.random.default_rng(1000 * stream + 17)
+    return 6.0 + 44.0 * _smooth_field(h, w, rng)
+
+
 def rodrigues(rvec) -> np.ndarray:
     rvec = np.asarray(rvec, dtype=np.float64)
     th = np.linalg.norm(rvec)

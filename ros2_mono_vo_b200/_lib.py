@@ -36,6 +36,27 @@ class MvoFrameResult(C.Structure):
                 ("R", C.c_double * 9), ("t", C.c_double * 3)]
 
 
+class MvoGroupConfig(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("outputs", C.c_uint32)]
+
+
+class MvoStreamOutputs(C.Structure):
+    _fields_ = [("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_prev", C.c_int32), ("n_tracked", C.c_int32),
+                ("keypoints", C.c_void_p), ("descriptors", C.c_void_p), ("matches", C.c_void_p),
+                ("track_xy", C.c_void_p), ("track_status", C.c_void_p), ("track_err", C.c_void_p),
+                ("mask_h", C.c_void_p), ("mask_f", C.c_void_p), ("mask_e", C.c_void_p), ("mask_pose", C.c_void_p),
+                ("X4", C.c_void_p), ("x4_stride", C.c_int64),
+                ("H", C.c_double * 9), ("F", C.c_double * 9), ("E", C.c_double * 9),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MvoTrackResult(C.Structure):
+    _fields_ = [("n_prev", C.c_int32), ("n_tracked", C.c_int32), ("n_pnp_inliers", C.c_int32), ("pnp_ok", C.c_int32),
+                ("rvec", C.c_double * 3), ("tvec", C.c_double * 3)]
+
+
+MVO_OUT_KEYPOINTS, MVO_OUT_MATCHES, MVO_OUT_TRACKS, MVO_OUT_MODELS, MVO_OUT_POINTS3D, MVO_OUT_ALL = 1, 2, 4, 8, 16, 31
+
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -77,6 +98,12 @@ SIGNATURES = {
     "mvo_group_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "mvo_group_collect": (C.c_int, [_vp, _vp]),
     "mvo_group_reset": (C.c_int, [_vp]),
+    "mvo_group_configure": (C.c_int, [_vp, C.POINTER(MvoGroupConfig)]),
+    "mvo_group_output_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "mvo_group_outputs": (C.c_int, [_vp, C.c_int, C.POINTER(MvoStreamOutputs)]),
+    "mvo_group_set_tracks": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
+    "mvo_group_track": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "mvo_group_get_tracks": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _i32p, _i32p]),
     "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
     "mvo_stage_span_ms": (C.c_int, [_vp, C.c_char_p, _f32p, _f32p]),
     "mvo_debug_set": (C.c_int, [_vp, C.c_char_p, C.c_int]),

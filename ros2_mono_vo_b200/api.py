@@ -23,6 +23,9 @@ RESULT_DTYPE = np.dtype([("n_keypoints", np.int32), ("n_matches", np.int32), ("n
                          ("score_h", np.int32), ("score_f", np.int32), ("n_inliers_e", np.int32),
                          ("n_pose_good", np.int32), ("n_triangulated", np.int32),
                          ("R", np.float64, (9,)), ("t", np.float64, (3,))])
+TRACK_RESULT_DTYPE = np.dtype([("n_prev", np.int32), ("n_tracked", np.int32), ("n_pnp_inliers", np.int32),
+                               ("pnp_ok", np.int32), ("rvec", np.float64, (3,)), ("tvec", np.float64, (3,))])
+assert TRACK_RESULT_DTYPE.itemsize == C.sizeof(_lib.MvoTrackResult)
 assert RESULT_DTYPE.itemsize == C.sizeof(_lib.MvoFrameResult)
 assert KP_DTYPE.itemsize == C.sizeof(_lib.MvoKeypoint) == 28
 assert DMATCH_DTYPE.itemsize == C.sizeof(_lib.MvoDMatch) == 16
@@ -142,32 +145,115 @@ class Context:
     # ---- stream-group front-end step ---------------------------------------------------------
     STAGES = ("orb", "knn", "lk", "ransac_h", "ransac_f", "ransac_e", "pose", "triangulate", "total", "orb_dense")
 
+    channels = 1
+
+    def group_configure(self, channels: int = 1, outputs: int = 0):
+        """Frame format of the group entry points (1 = gray8, 3 = BGR8) and the MVO_OUT_* outputs copied to pinned host
+        memory inside every step (mvo_group_configure)."""
+        cfg = _lib.MvoGroupConfig(channels, outputs)
+        self._check(self.lib.mvo_group_configure(self.h, C.byref(cfg)))
+        self.channels = channels
+
+    def group_output_bytes(self) -> int:
+        v = C.c_size_t()
+        self._check(self.lib.mvo_group_output_bytes(self.h, C.byref(v)))
+        return int(v.value)
+
+    def _frames_arg(self, images: np.ndarray):
+        """(pointer, w, h, row stride in bytes) of a batch x h x w [x 3] u8 host array"""
+        assert images.dtype == np.uint8 and images.shape[0] == self.batch and images.strides[-1] == 1
+        assert images.ndim == (3 if self.channels == 1 else 4)
+        if self.channels == 3:
+            assert images.shape[3] == 3 and images.strides[2] == 3
+        h, w = images.shape[1:3]
+        assert self.batch == 1 or images.strides[0] == h * images.strides[1]   # numpy leaves the stride of a length-1 axis arbitrary
+        return _ptr(images), w, h, images.strides[1]
+
     def group_step(self, images: np.ndarray, K, device_ptr: int | None = None, shape=None):
-        """One front-end frame for every stream of the group.  images: batch x h x w u8 (host), or pass
-        device_ptr (+ shape=(h, w)) for frames already resident in HBM.  Returns a structured array."""
+        """One front-end frame for every stream of the group.  images: batch x h x w u8 (host; batch x h x w x 3 after
+        group_configure(channels=3)), or pass device_ptr (+ shape=(h, w)) for frames already resident in HBM.  Returns a
+        structured array."""
         Kp = np.ascontiguousarray(K, np.float64).reshape(9)
         res = np.zeros(self.batch, RESULT_DTYPE)
         if device_ptr is None:
             images = np.ascontiguousarray(images, np.uint8)
-            assert images.ndim == 3 and images.shape[0] == self.batch
-            h, w = images.shape[1:]
-            self._check(self.lib.mvo_group_step(self.h, _ptr(images), w, h, images.strides[1], 0, _ptr(Kp), _ptr(res)))
+            p, w, h, stride = self._frames_arg(images)
+            self._check(self.lib.mvo_group_step(self.h, p, w, h, stride, 0, _ptr(Kp), _ptr(res)))
         else:
             h, w = shape
-            self._check(self.lib.mvo_group_step(self.h, C.c_void_p(device_ptr), w, h, w, 1, _ptr(Kp), _ptr(res)))
+            self._check(self.lib.mvo_group_step(self.h, C.c_void_p(device_ptr), w, h, w * self.channels, 1, _ptr(Kp), _ptr(res)))
         return res
 
     def group_submit(self, images: np.ndarray, K, device_ptr: int | None = None, shape=None):
         """Pipelined group_step: enqueue one step on (pinned) host frames -- or frames resident in HBM (device_ptr +
-        shape=(h, w)) -- and return at once (<= 2 in flight)."""
+        shape=(h, w)) -- and return at once (<= 2 in flight).  Host frames must stay valid and unchanged until the step
+        has been collected."""
         Kp = np.ascontiguousarray(K, np.float64).reshape(9)
         if device_ptr is not None:
             h, w = shape
-            self._check(self.lib.mvo_group_submit(self.h, C.c_void_p(device_ptr), w, h, w, 1, _ptr(Kp)))
+            self._check(self.lib.mvo_group_submit(self.h, C.c_void_p(device_ptr), w, h, w * self.channels, 1, _ptr(Kp)))
             return
-        assert images.dtype == np.uint8 and images.ndim == 3 and images.shape[0] == self.batch and images.strides[2] == 1
-        h, w = images.shape[1:]
-        self._check(self.lib.mvo_group_submit(self.h, _ptr(images), w, h, images.strides[1], 0, _ptr(Kp)))
+        p, w, h, stride = self._frames_arg(images)
+        self._check(self.lib.mvo_group_submit(self.h, p, w, h, stride, 0, _ptr(Kp)))
+
+    def group_outputs(self, stream: int, copy: bool = True) -> dict:
+        """Full outputs of one stream for the step most recently returned by group_step / group_collect (the sections
+        chosen with group_configure).  copy=False returns views into the context's pinned memory (valid until the next
+        submit / step)."""
+        o = _lib.MvoStreamOutputs()
+        self._check(self.lib.mvo_group_outputs(self.h, int(stream), C.byref(o)))
+
+        def view(ptr, dtype, shape):
+            if not ptr:
+                return None
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            a = np.frombuffer((C.c_uint8 * n).from_address(ptr), dtype=dtype).reshape(shape)
+            return a.copy() if copy else a
+
+        nk, nm, npv, nt = o.n_keypoints, o.n_matches, o.n_prev, o.n_tracked
+        out = {"n_keypoints": nk, "n_matches": nm, "n_prev": npv, "n_tracked": nt, "flags": o.flags,
+               "keypoints": view(o.keypoints, KP_DTYPE, (nk,)), "descriptors": view(o.descriptors, np.uint8, (nk, 32)),
+               "matches": view(o.matches, DMATCH_DTYPE, (nm,)),
+               "track_xy": view(o.track_xy, np.float32, (npv, 2)), "track_status": view(o.track_status, np.uint8, (npv,)),
+               "track_err": view(o.track_err, np.float32, (npv,)),
+               "mask_h": view(o.mask_h, np.uint8, (nt,)), "mask_f": view(o.mask_f, np.uint8, (nt,)),
+               "mask_e": view(o.mask_e, np.uint8, (nt,)), "mask_pose": view(o.mask_pose, np.uint8, (nt,)),
+               "H": np.array(o.H).reshape(3, 3), "F": np.array(o.F).reshape(3, 3), "E": np.array(o.E).reshape(3, 3)}
+        if o.X4:
+            full = view(o.X4, np.float32, (4, int(o.x4_stride)))
+            out["X4"] = full[:, :nt].copy() if copy else full[:, :nt]
+        else:
+            out["X4"] = None
+        return out
+
+    # ---- stream-group tracking frame (Tracker::update) ------------------------------------------
+    def group_set_tracks(self, stream: int, xy, xyz):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        assert len(xy) == len(xyz)
+        self._check(self.lib.mvo_group_set_tracks(self.h, int(stream), _ptr(xy), _ptr(xyz), len(xy)))
+
+    def group_track(self, images: np.ndarray, K):
+        """LK from every stream's latest frame to the new one on its tracked observations + solvePnPRansac against
+        their landmarks (mvo_group_track).  Returns a structured array of mvo_track_result."""
+        Kp = np.ascontiguousarray(K, np.float64).reshape(9)
+        res = np.zeros(self.batch, TRACK_RESULT_DTYPE)
+        images = np.ascontiguousarray(images, np.uint8)
+        p, w, h, stride = self._frames_arg(images)
+        self._check(self.lib.mvo_group_track(self.h, p, w, h, stride, 0, _ptr(Kp), _ptr(res)))
+        return res
+
+    def group_get_tracks(self, stream: int):
+        """(xy, index into the previous observation list, PnP inlier indices) of one stream after group_track."""
+        nt, ni = C.c_int32(), C.c_int32()
+        self._check(self.lib.mvo_group_get_tracks(self.h, int(stream), None, None, None, 0, C.byref(nt), C.byref(ni)))
+        cap = max(nt.value, ni.value, 1)
+        xy = np.zeros((cap, 2), np.float32)
+        src = np.zeros(cap, np.int32)
+        inl = np.zeros(cap, np.int32)
+        self._check(self.lib.mvo_group_get_tracks(self.h, int(stream), _ptr(xy), _ptr(src), _ptr(inl), cap, C.byref(nt),
+                                                  C.byref(ni)))
+        return xy[:nt.value], src[:nt.value], inl[:ni.value]
 
     def group_collect(self):
         """Results of the oldest submitted step."""

@@ -77,21 +77,33 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
     // CTAs are placed first while the next step's ORB / LK kernels (main stream) fill the rest of the GPU
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t first = cudaSuccess;
+    auto keep = [&first](cudaError_t r) {
+      if (first == cudaSuccess && r != cudaSuccess) first = r;
+    };
     for (int k = 0; k < 4; ++k)
-      cudaStreamCreateWithPriority(&c->aux_stream[k], cudaStreamNonBlocking, k == 2 ? prio_lo : prio_hi);
-  }
-  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-  for (auto& sl : c->slots) {
-    cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&sl.ev_free, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
-  }
-  for (auto& ev : c->ev_fork) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  for (auto& ev : c->ev_join) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming);
-  for (auto& t : c->timers) {
-    cudaEventCreate(&t.beg);
-    cudaEventCreate(&t.end);
+      keep(cudaStreamCreateWithPriority(&c->aux_stream[k], cudaStreamNonBlocking, k == 2 ? prio_lo : prio_hi));
+    keep(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    keep(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+    for (auto& sl : c->slots) {
+      keep(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
+      keep(cudaEventCreateWithFlags(&sl.ev_free, cudaEventDisableTiming));
+      keep(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
+    for (auto& ev : c->ev_fork) keep(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c->ev_join) keep(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    keep(cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+    for (cudaEvent_t* ev : {&c->ev_o_orb, &c->ev_o_lk, &c->ev_out_orb, &c->ev_out_lk})
+      keep(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    for (auto& t : c->timers) {
+      keep(cudaEventCreate(&t.beg));
+      keep(cudaEventCreate(&t.end));
+    }
+    if (first != cudaSuccess) {   // a NULL aux stream would silently be the legacy default stream
+      g_create_error = std::string("mvo_create: stream / event creation failed: ") + cudaGetErrorString(first);
+      mvo_destroy(c);
+      return MVO_ERR_CUDA;
+    }
   }
   *out = c;
   return MVO_OK;
@@ -111,6 +123,12 @@ void mvo_destroy(mvo_ctx* c) {
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamDestroy(c->copy_stream);
   }
+  if (c->out_stream) {
+    cudaStreamSynchronize(c->out_stream);
+    cudaStreamDestroy(c->out_stream);
+  }
+  for (cudaEvent_t ev : {c->ev_o_orb, c->ev_o_lk, c->ev_out_orb, c->ev_out_lk})
+    if (ev) cudaEventDestroy(ev);
   for (auto& sl : c->slots) {
     if (sl.ev_up) cudaEventDestroy(sl.ev_up);
     if (sl.ev_free) cudaEventDestroy(sl.ev_free);

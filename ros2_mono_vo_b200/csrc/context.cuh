@@ -90,6 +90,16 @@ struct GroupSlot {
   mvo::PinBuf<mvo_frame_result> h_res;        // pinned result records
   mvo::PinBuf<int32_t> h_flags;
   cudaEvent_t ev_up = nullptr, ev_free = nullptr, ev_done = nullptr;
+  mvo::PinBuf<uint8_t> h_out;                 // full per-stream outputs (mvo_group_configure), sections of OutLayout
+  int had_prev = 0;                           // the step enqueued in this slot had a previous frame
+};
+
+// sections of a slot's pinned output block (byte offsets; every section holds batch * cap entries)
+struct OutLayout {
+  size_t kps = 0, desc = 0, matches = 0, lk_xy = 0, lk_status = 0, lk_err = 0, mask[4] = {0, 0, 0, 0}, models = 0, x4 = 0,
+         prev_count = 0, total = 0;
+  int cap = 0, batch = 0;
+  uint32_t mask_bits = 0;
 };
 
 struct mvo_ctx {
@@ -102,6 +112,24 @@ struct mvo_ctx {
   bool own_stream = false;
   static constexpr int kSlots = 2;
   cudaStream_t copy_stream = nullptr;  // H2D of staged frames
+  cudaStream_t out_stream = nullptr;   // D2H of the full per-stream outputs
+  cudaEvent_t ev_o_orb = nullptr, ev_o_lk = nullptr;   // main stream: ORB outputs / LK outputs of the step are final
+  cudaEvent_t ev_out_orb = nullptr, ev_out_lk = nullptr;   // out stream: their D2H copies are done
+  // ---------------- group product surface (mvo_group_configure) ----------------
+  int grp_cn = 1;                      // channels of the frames given to the group entry points
+  uint32_t out_mask = 0;               // MVO_OUT_*
+  OutLayout out_layout;
+  int out_slot = -1;                   // slot whose outputs mvo_group_outputs hands out (last finished step)
+  mvo::DevBuf<uint8_t> e_mask_keep;    // findEssentialMat's mask (recoverPose overwrites it in place)
+  // ---------------- group tracking frame (mvo_group_track) ----------------
+  mvo::DevBuf<float2> trk_xy[2];       // batch * trk_cap : observations of the latest / the new frame
+  mvo::DevBuf<float> trk_obj[2];       // batch * trk_cap * 3 : their landmark coordinates
+  mvo::DevBuf<int32_t> trk_n[2];       // batch
+  mvo::DevBuf<int32_t> trk_src;        // batch * trk_cap : index of each new observation in the previous list
+  mvo::DevBuf<mvo_track_result> d_trk_res;
+  mvo::PinBuf<mvo_track_result> h_trk_res;
+  int trk_cur = 0, trk_cap = 0;
+  bool trk_have_frame = false;         // lk_pyr[lk_cur ^ 1] holds the latest frame of every stream
   GroupSlot slots[kSlots];
   int q_head = 0, q_count = 0;         // ring of submitted, not yet collected steps
   std::string err;

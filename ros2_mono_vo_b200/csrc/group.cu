@@ -155,6 +155,110 @@ __global__ void copy_i32_strided_kernel(const int32_t* src, int stride, int32_t*
   if (i < n) dst[i] = src[i * stride];
 }
 
+// staged BGR8 frames (batch x h rows of `spitch` bytes, 3 bytes per pixel) -> gray level 0 of every stream's ORB pyramid
+// ((B*3735 + G*19235 + R*9798 + 16384) >> 15 == cvtColor BGR2GRAY) and the three colour planes of level 0 of
+// its LK pyramid (cv::calcOpticalFlowPyrLK tracks on all channels of a 3-channel Mat); 4 pixels per thread, one aligned
+// 32-bit store per destination.  gray may be NULL (tracking frame: LK only).
+__global__ void __launch_bounds__(256)
+unpack_bgr_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long src_frame_stride, uint8_t* __restrict__ gray,
+                         int gpitch, long long gray_frame_stride, uint8_t* __restrict__ planes, int ppitch,
+                         long long plane_stride, int w, int h) {
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x >= w) return;
+  const uint8_t* s = src + (long long)b * src_frame_stride + (long long)y * spitch + 3 * x;
+  const int nb = min(4, w - x);
+  uint32_t g = 0, p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < nb) {
+      const uint32_t cb = s[3 * i], cg = s[3 * i + 1], cr = s[3 * i + 2];
+      g |= ((cb * 3735u + cg * 19235u + cr * 9798u + 16384u) >> 15) << (8 * i);
+      p0 |= cb << (8 * i);
+      p1 |= cg << (8 * i);
+      p2 |= cr << (8 * i);
+    }
+  }
+  if (gray) *reinterpret_cast<uint32_t*>(gray + (long long)b * gray_frame_stride + (long long)y * gpitch + x) = g;
+  uint8_t* d = planes + (long long)b * 3 * plane_stride + (long long)y * ppitch + x;
+  *reinterpret_cast<uint32_t*>(d) = p0;
+  *reinterpret_cast<uint32_t*>(d + plane_stride) = p1;
+  *reinterpret_cast<uint32_t*>(d + 2 * plane_stride) = p2;
+}
+
+__global__ void replicate_k_kernel(double* K, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > 0 && b < batch)
+    for (int i = 0; i < 9; ++i) K[b * 9 + i] = K[i];
+}
+
+// Tracker::track_frame_with_optical_flow's filter (src/tracker.cpp:70-77) for the tracking frame: observations with
+// status && err < err_thr are kept in order; their new positions and landmark coordinates become the stream's next
+// observation list and the input of solvePnPRansac.  Fewer than 6 kept points: PnP is skipped (npts 0).
+__global__ void __launch_bounds__(1024)
+track_collect_kernel(const float2* __restrict__ next_xy, const uint8_t* __restrict__ status, const float* __restrict__ err,
+                     const float* __restrict__ obj, const int32_t* __restrict__ nprev, int cap, float err_thr,
+                     float2* __restrict__ out_xy, float* __restrict__ out_obj, int32_t* __restrict__ out_n,
+                     int32_t* __restrict__ src_idx, float2* __restrict__ pnp_img, float* __restrict__ pnp_obj,
+                     int32_t* __restrict__ pnp_n, int pnp_cap) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(nprev[b], cap);
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 1024) {
+    const int i = i0 + tid;
+    const long long o = (long long)b * cap + i;
+    const int ok = (i < n) ? (status[o] != 0 && err[o] < err_thr) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (ok) {
+      const int k = off + __popc(bal & ((1u << lane) - 1));
+      const long long d = (long long)b * cap + k, dp = (long long)b * pnp_cap + k;
+      const float2 p = next_xy[o];
+      const float X = obj[o * 3], Y = obj[o * 3 + 1], Z = obj[o * 3 + 2];
+      out_xy[d] = p;
+      out_obj[d * 3] = X; out_obj[d * 3 + 1] = Y; out_obj[d * 3 + 2] = Z;
+      src_idx[d] = i;
+      pnp_img[dp] = p;
+      pnp_obj[dp * 3] = X; pnp_obj[dp * 3 + 1] = Y; pnp_obj[dp * 3 + 2] = Z;
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int w = 0; w < 32; ++w) s_base += s_warp[w];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out_n[b] = s_base;
+    pnp_n[b] = s_base >= 6 ? s_base : 0;
+  }
+}
+
+__global__ void gather_track_results_kernel(const int32_t* nprev, const int32_t* ntracked, const int32_t* pnp_result,
+                                            const double* pose_out, int have_prev, mvo_track_result* out, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  mvo_track_result r;
+  memset(&r, 0, sizeof(r));
+  if (have_prev) {
+    r.n_prev = nprev[b];
+    r.n_tracked = ntracked[b];
+    const bool ok = r.n_tracked >= 6 && pnp_result[b * 8 + 2] >= 0;
+    r.n_pnp_inliers = ok ? pnp_result[b * 8 + 0] : 0;
+    r.pnp_ok = ok ? 1 : 0;
+    if (ok)
+      for (int i = 0; i < 3; ++i) {
+        r.rvec[i] = pose_out[b * 8 + i];
+        r.tvec[i] = pose_out[b * 8 + 3 + i];
+      }
+  }
+  out[b] = r;
+}
+
 }  // namespace mvo
 
 using namespace mvo;
@@ -166,17 +270,62 @@ using namespace mvo;
     (c)->timers[s].used = true;                       \
   } while (0)
 
+// layout of a slot's pinned output block for the configured outputs
+static int out_prepare(mvo_ctx* c, int cap) {
+  OutLayout& L = c->out_layout;
+  const size_t B = (size_t)c->cfg.batch;
+  if (L.cap != cap || L.batch != (int)B || L.mask_bits != c->out_mask) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      const size_t o = off;
+      off += align_up(bytes, 256);
+      return o;
+    };
+    L = OutLayout();
+    L.cap = cap;
+    L.batch = (int)B;
+    L.mask_bits = c->out_mask;
+    L.prev_count = take(B * 4);
+    if (c->out_mask & MVO_OUT_KEYPOINTS) {
+      L.kps = take(B * cap * sizeof(mvo_keypoint));
+      L.desc = take(B * cap * 32);
+    }
+    if (c->out_mask & MVO_OUT_MATCHES) L.matches = take(B * cap * sizeof(mvo_dmatch));
+    if (c->out_mask & MVO_OUT_TRACKS) {
+      L.lk_xy = take(B * cap * 8);
+      L.lk_status = take(B * cap);
+      L.lk_err = take(B * cap * 4);
+    }
+    if (c->out_mask & MVO_OUT_MODELS) {
+      for (int k = 0; k < 4; ++k) L.mask[k] = take(B * cap);
+      L.models = take(B * 27 * 8);
+    }
+    if (c->out_mask & MVO_OUT_POINTS3D) L.x4 = take(B * 4 * cap * 4);
+    L.total = off;
+  }
+  for (auto& sl : c->slots) MVO_CUDA_TRY(c, sl.h_out.alloc(L.total));
+  return MVO_OK;
+}
+
+// device -> pinned host copy of `rows` rows of `width` bytes whose source rows are `spitch` bytes apart
+static cudaError_t copy_rows_d2h(void* dst, const void* src, size_t width, size_t spitch, size_t rows, cudaStream_t st) {
+  if (spitch == width) return cudaMemcpyAsync(dst, src, width * rows, cudaMemcpyDeviceToHost, st);
+  return cudaMemcpy2DAsync(dst, width, src, spitch, width, rows, cudaMemcpyDeviceToHost, st);
+}
+
 extern "C" {
 
 static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
                          int slot) {
   if (!c) return MVO_ERR_INVALID;
-  if (!images || !K || stride < w) {
+  const int cn = c->grp_cn;
+  if (!images || !K || stride < w * cn) {
     c->set_error("mvo_group_step: bad argument");
     return MVO_ERR_INVALID;
   }
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   const int B = c->cfg.batch;
+  c->trk_have_frame = false;   // the tracking-frame chain (mvo_group_track) does not survive a front-end step
   int rc = orb_prepare(c, w, h);
   if (rc) return rc;
   const OrbGeom& g = c->geom;
@@ -189,8 +338,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     MVO_CUDA_TRY(c, c->d_results.alloc(B));
     c->have_prev = false;
   }
-  if (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap || c->lk_cn != 1) {
-    rc = lk_prepare(c, w, h, cap);
+  if (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap || c->lk_cn != cn) {
+    rc = lk_prepare(c, w, h, std::max(cap, c->lk_max_pts), cn);
     if (rc) return rc;
     c->have_prev = false;
   }
@@ -202,6 +351,15 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   if (rc) return rc;
   RansacBufs& r = c->rs;
   for (auto& t : c->timers) t.used = false;
+  const uint32_t om = c->out_mask;
+  const OutLayout& L = c->out_layout;
+  if (om) {
+    rc = out_prepare(c, cap);
+    if (rc) return rc;
+    if (om & MVO_OUT_MODELS) MVO_CUDA_TRY(c, c->e_mask_keep.alloc((size_t)B * r.max_pts));
+  }
+  uint8_t* const hout = c->slots[slot].h_out.p;
+  c->slots[slot].had_prev = c->have_prev ? 1 : 0;
 
   // Fork / join: kNN only needs the descriptors, the three model searches only need the LK correspondences, so
   // they run beside each other on auxiliary CUDA streams (each search in its own RansacLane).
@@ -227,28 +385,36 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     const uint8_t* src = images;
     int spitch = stride;
     long long sstride = (long long)h * stride;
+    const int rowb = w * cn;     // bytes of one frame row
     if (!images_on_device) {
       GroupSlot& sl = c->slots[slot];
-      MVO_CUDA_TRY(c, sl.stage.alloc((size_t)B * h * w));
+      MVO_CUDA_TRY(c, sl.stage.alloc((size_t)B * h * rowb));
       cudaStreamWaitEvent(c->copy_stream, sl.ev_free, 0);
-      if (stride == w)   // contiguous frames: one flat DMA (a 2-D copy of 1241-byte rows runs far below PCIe speed)
-        MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.stage.p, images, (size_t)B * h * w, cudaMemcpyHostToDevice, c->copy_stream));
+      if (stride == rowb)   // contiguous frames: one flat DMA (a 2-D copy of 1241-byte rows runs far below PCIe speed)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.stage.p, images, (size_t)B * h * rowb, cudaMemcpyHostToDevice, c->copy_stream));
       else
-        MVO_CUDA_TRY(c, cudaMemcpy2DAsync(sl.stage.p, w, images, stride, w, (size_t)B * h, cudaMemcpyHostToDevice,
+        MVO_CUDA_TRY(c, cudaMemcpy2DAsync(sl.stage.p, rowb, images, stride, rowb, (size_t)B * h, cudaMemcpyHostToDevice,
                                           c->copy_stream));
       cudaEventRecord(sl.ev_up, c->copy_stream);
       cudaStreamWaitEvent(c->main_stream, sl.ev_up, 0);
       src = sl.stage.p;
-      spitch = w;
-      sstride = (long long)h * w;
+      spitch = rowb;
+      sstride = (long long)h * rowb;
     }
     const LevelGeom& l0 = g.lv[0];
-    dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
     int lk_pitch = 0;
     long long lk_fs = 0;
     uint8_t* lk0 = lk_level0(c, c->lk_cur, &lk_pitch, &lk_fs);
-    unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride, lk0,
-                                                      lk_pitch, lk_fs, w, h);
+    // the LK pyramid about to be overwritten was read by the LK track of two steps ago and by nothing since
+    if (cn == 1) {
+      dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
+      unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride,
+                                                        lk0, lk_pitch, lk_fs, w, h);
+    } else {
+      dim3 grid((w + 4 * 256 - 1) / (4 * 256), h, B);
+      unpack_bgr_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch,
+                                                            g.frame_stride, lk0, lk_pitch, lk_fs, w, h);
+    }
     c->launches++;
     if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
   }
@@ -261,9 +427,20 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     MVO_CUDA_TRY(c, sl.h_res.alloc(B));
     MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
     MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (om && c->have_prev)
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.prev_count, c->prev_kp_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
   }
   STAGE_END(c, ST_ORB);
   cudaEventRecord(c->ev_fork[0], c->main_stream);
+  if (om & MVO_OUT_KEYPOINTS) {
+    // keypoints + descriptors of the new frame leave on the output stream while the step goes on
+    cudaEventRecord(c->ev_o_orb, c->main_stream);
+    cudaStreamWaitEvent(c->out_stream, c->ev_o_orb, 0);
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.kps, c->kps.p, (size_t)B * cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost,
+                                    c->out_stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.desc, c->desc.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, c->out_stream));
+    cudaEventRecord(c->ev_out_orb, c->out_stream);
+  }
 
   const int cur = c->lk_cur, prev = cur ^ 1;
   if (c->have_prev) {
@@ -281,6 +458,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   rc = lk_build_pyramid(c, cur, nullptr, 0, 3);   // level 0 was written by the unpack kernel
   if (rc) return rc;
   if (c->have_prev) {
+    cudaStreamWaitEvent(c->main_stream, c->ev_out_lk, 0);   // the previous step's track outputs have left the LK buffers
     rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
     if (rc) return rc;
     // the correspondence buffers feed the model searches of the previous step until its tail is done; from here on
@@ -289,6 +467,14 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
                                                  c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
     c->launches++;
+    if (om & MVO_OUT_TRACKS) {
+      cudaEventRecord(c->ev_o_lk, c->main_stream);
+      cudaStreamWaitEvent(c->out_stream, c->ev_o_lk, 0);
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_xy, c->lk_pts_out.p, (size_t)B * cap * 8, cudaMemcpyDeviceToHost, c->out_stream));
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_status, c->lk_status.p, (size_t)B * cap, cudaMemcpyDeviceToHost, c->out_stream));
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_err, c->lk_err.p, (size_t)B * cap * 4, cudaMemcpyDeviceToHost, c->out_stream));
+      cudaEventRecord(c->ev_out_lk, c->out_stream);
+    }
   }
   STAGE_END(c, ST_LK);
 
@@ -328,6 +514,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       rc = ransac_find(c, MVO_MODEL_E, 0.99);
       if (rc) return rc;
       STAGE_END(c, ST_E);
+      if (om & MVO_OUT_MODELS)   // recoverPose rewrites the mask in place (mask_io): keep findEssentialMat's own
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(c->e_mask_keep.p, r.ln().mask.p, (size_t)B * r.max_pts, cudaMemcpyDeviceToDevice, c->stream));
       STAGE_BEG(c, ST_POSE);
       rc = pose_recover(c, true);
       if (rc) return rc;
@@ -357,8 +545,24 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       c->launches++;
       MVO_CUDA_TRY(c, cudaMemcpyAsync(c->slots[slot].h_res.p, c->d_results.p, (size_t)B * sizeof(mvo_frame_result),
                                       cudaMemcpyDeviceToHost, c->stream));
+      // full outputs that the next step's kNN / searches overwrite: they leave before ev_tail releases those buffers
+      if (om & MVO_OUT_MATCHES)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.matches, c->knn_matches.p, (size_t)B * cap * sizeof(mvo_dmatch),
+                                        cudaMemcpyDeviceToHost, c->stream));
+      if (om & MVO_OUT_MODELS) {
+        const uint8_t* msrc[4] = {r.lane[0].mask.p, r.lane[1].mask.p, c->e_mask_keep.p, r.lane[2].mask.p};
+        for (int k = 0; k < 4; ++k)
+          MVO_CUDA_TRY(c, copy_rows_d2h(hout + L.mask[k], msrc[k], (size_t)cap, (size_t)r.max_pts, (size_t)B, c->stream));
+        for (int k = 0; k < 3; ++k)
+          MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.models + (size_t)k * B * 72, r.lane[k].best_model.p, (size_t)B * 72,
+                                          cudaMemcpyDeviceToHost, c->stream));
+      }
+      if (om & MVO_OUT_POINTS3D)
+        MVO_CUDA_TRY(c, copy_rows_d2h(hout + L.x4, r.X4.p, (size_t)cap * 4, (size_t)r.max_pts * 4, (size_t)B * 4, c->stream));
       STAGE_END(c, ST_TOTAL);
       cudaEventRecord(c->ev_tail, c->stream);
+      if (om & MVO_OUT_KEYPOINTS) cudaStreamWaitEvent(c->stream, c->ev_out_orb, 0);
+      if (om & MVO_OUT_TRACKS) cudaStreamWaitEvent(c->stream, c->ev_out_lk, 0);
       cudaEventRecord(c->slots[slot].ev_done, c->stream);
     }
   } else {
@@ -370,6 +574,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
                                     cudaMemcpyDeviceToHost, c->stream));
     STAGE_END(c, ST_TOTAL);
     cudaEventRecord(c->ev_tail, c->stream);
+    if (om & MVO_OUT_KEYPOINTS) cudaStreamWaitEvent(c->stream, c->ev_out_orb, 0);
     cudaEventRecord(c->slots[slot].ev_done, c->stream);
   }
   MVO_CUDA_TRY(c, cudaGetLastError());
@@ -389,10 +594,17 @@ static int group_finish(mvo_ctx* c, int slot, mvo_frame_result* results) {
   const int B = c->cfg.batch;
   MVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_done));
   memcpy(results, sl.h_res.p, (size_t)B * sizeof(mvo_frame_result));
-  int flags0 = 0;
-  for (int b = 0; b < B; ++b) flags0 |= sl.h_flags.p[b];
-  if (flags0 & 1) {
-    c->set_error("FAST candidate list overflow");
+  c->out_slot = slot;
+  int flags0 = 0, first = -1;
+  for (int b = 0; b < B; ++b) {
+    if (sl.h_flags.p[b] && first < 0) first = b;
+    flags0 |= sl.h_flags.p[b];
+  }
+  // same rule as the single-call path: an overflow of either list is an error for the step; the records of the other
+  // streams are valid and mvo_group_outputs(...).flags says which streams were hit
+  if (flags0 & 3) {
+    c->set_error(std::string(flags0 & 1 ? "FAST candidate list overflow" : "keypoint capacity exceeded") + " (first on stream " +
+                 std::to_string(first) + ")");
     return MVO_ERR_CAPACITY;
   }
   return MVO_OK;
@@ -446,6 +658,251 @@ int mvo_group_reset(mvo_ctx* c) {
     return MVO_ERR_INVALID;
   }
   c->have_prev = false;
+  return MVO_OK;
+}
+
+int mvo_group_configure(mvo_ctx* c, const mvo_group_config* cfg) {
+  if (!c || !cfg) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  if ((cfg->channels != 1 && cfg->channels != 3) || (cfg->outputs & ~(uint32_t)MVO_OUT_ALL)) {
+    c->set_error("mvo_group_configure: channels must be 1 or 3, outputs a mask of MVO_OUT_*");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->main_stream));
+  if (cfg->channels != c->grp_cn) {
+    c->have_prev = false;
+    c->trk_have_frame = false;
+  }
+  c->grp_cn = cfg->channels;
+  c->out_mask = cfg->outputs;
+  c->out_slot = -1;
+  return MVO_OK;
+}
+
+int mvo_group_output_bytes(mvo_ctx* c, size_t* bytes) {
+  if (!c || !bytes) return MVO_ERR_INVALID;
+  const size_t B = (size_t)c->cfg.batch;
+  const size_t cap = (size_t)(c->cfg.nfeatures + c->cfg.nfeatures / 4 + 64);
+  size_t n = B * sizeof(mvo_frame_result) + B * 4;   // result records + overflow flags
+  const uint32_t om = c->out_mask;
+  if (om) n += B * 4;
+  if (om & MVO_OUT_KEYPOINTS) n += B * cap * (sizeof(mvo_keypoint) + 32);
+  if (om & MVO_OUT_MATCHES) n += B * cap * sizeof(mvo_dmatch);
+  if (om & MVO_OUT_TRACKS) n += B * cap * 13;
+  if (om & MVO_OUT_MODELS) n += B * cap * 4 + B * 27 * 8;
+  if (om & MVO_OUT_POINTS3D) n += B * cap * 16;
+  *bytes = n;
+  return MVO_OK;
+}
+
+int mvo_group_outputs(mvo_ctx* c, int stream, mvo_stream_outputs* out) {
+  if (!c || !out) return MVO_ERR_INVALID;
+  if (stream < 0 || stream >= c->cfg.batch || c->out_slot < 0) {
+    c->set_error("mvo_group_outputs: no finished step, or stream out of range");
+    return MVO_ERR_INVALID;
+  }
+  const GroupSlot& sl = c->slots[c->out_slot];
+  const OutLayout& L = c->out_layout;
+  const uint32_t om = L.mask_bits;
+  const mvo_frame_result& r = sl.h_res.p[stream];
+  const size_t B = (size_t)c->cfg.batch, cap = (size_t)L.cap, b = (size_t)stream;
+  const uint8_t* h = sl.h_out.p;
+  memset(out, 0, sizeof(*out));
+  out->n_keypoints = r.n_keypoints;
+  out->flags = sl.h_flags.p[stream];
+  if (!om || !h) return MVO_OK;
+  if (om & MVO_OUT_KEYPOINTS) {
+    out->keypoints = reinterpret_cast<const mvo_keypoint*>(h + L.kps) + b * cap;
+    out->descriptors = h + L.desc + b * cap * 32;
+  }
+  if (!sl.had_prev) return MVO_OK;
+  out->n_matches = r.n_matches;
+  out->n_tracked = r.n_tracked;
+  out->n_prev = reinterpret_cast<const int32_t*>(h + L.prev_count)[stream];
+  if (om & MVO_OUT_MATCHES) out->matches = reinterpret_cast<const mvo_dmatch*>(h + L.matches) + b * cap;
+  if (om & MVO_OUT_TRACKS) {
+    out->track_xy = reinterpret_cast<const float*>(h + L.lk_xy) + b * cap * 2;
+    out->track_status = h + L.lk_status + b * cap;
+    out->track_err = reinterpret_cast<const float*>(h + L.lk_err) + b * cap;
+  }
+  if (om & MVO_OUT_MODELS) {
+    out->mask_h = h + L.mask[0] + b * cap;
+    out->mask_f = h + L.mask[1] + b * cap;
+    out->mask_e = h + L.mask[2] + b * cap;
+    out->mask_pose = h + L.mask[3] + b * cap;
+    const double* m = reinterpret_cast<const double*>(h + L.models);
+    memcpy(out->H, m + (0 * B + b) * 9, 72);
+    memcpy(out->F, m + (1 * B + b) * 9, 72);
+    memcpy(out->E, m + (2 * B + b) * 9, 72);
+  }
+  if (om & MVO_OUT_POINTS3D) {
+    out->X4 = reinterpret_cast<const float*>(h + L.x4) + b * 4 * cap;
+    out->x4_stride = (int64_t)cap;
+  }
+  return MVO_OK;
+}
+
+// ---- tracking frame (Tracker::update's per-frame path) ---------------------------------------------------------------
+static int track_prepare(mvo_ctx* c, int w, int h) {
+  const size_t B = (size_t)c->cfg.batch;
+  const int cap = std::max(c->cfg.max_points, c->cfg.nfeatures + c->cfg.nfeatures / 4 + 64);
+  if (c->trk_cap != cap) {
+    for (int k = 0; k < 2; ++k) {
+      MVO_CUDA_TRY(c, c->trk_xy[k].alloc(B * cap));
+      MVO_CUDA_TRY(c, c->trk_obj[k].alloc(B * cap * 3));
+      MVO_CUDA_TRY(c, c->trk_n[k].alloc(B));
+      MVO_CUDA_TRY(c, cudaMemsetAsync(c->trk_n[k].p, 0, B * 4, c->main_stream));
+    }
+    MVO_CUDA_TRY(c, c->trk_src.alloc(B * cap));
+    MVO_CUDA_TRY(c, c->d_trk_res.alloc(B));
+    MVO_CUDA_TRY(c, c->h_trk_res.alloc(B));
+    c->trk_cap = cap;
+    c->trk_cur = 0;
+  }
+  if (w > 0 && (c->lk_w != w || c->lk_h != h || c->lk_max_pts < cap || c->lk_cn != c->grp_cn)) {
+    const int rc = lk_prepare(c, w, h, std::max(cap, c->lk_max_pts), c->grp_cn);
+    if (rc) return rc;
+    c->have_prev = false;
+    c->trk_have_frame = false;
+  }
+  return MVO_OK;
+}
+
+int mvo_group_set_tracks(mvo_ctx* c, int stream, const float* xy, const float* xyz, int n) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  if (stream < 0 || stream >= c->cfg.batch || n < 0 || (n > 0 && (!xy || !xyz))) {
+    c->set_error("mvo_group_set_tracks: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  int rc = track_prepare(c, 0, 0);
+  if (rc) return rc;
+  if (n > c->trk_cap) {
+    c->set_error("mvo_group_set_tracks: more observations than mvo_config.max_points");
+    return MVO_ERR_CAPACITY;
+  }
+  const size_t o = (size_t)stream * c->trk_cap;
+  const int k = c->trk_cur;
+  if (n > 0) {
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->trk_xy[k].p + o, xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->main_stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->trk_obj[k].p + o * 3, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, c->main_stream));
+  }
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->trk_n[k].p + stream, &n, 4, cudaMemcpyHostToDevice, c->main_stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->main_stream));
+  return MVO_OK;
+}
+
+int mvo_group_track(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
+                    mvo_track_result* results) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  const int cn = c->grp_cn;
+  if (!images || !K || !results || stride < w * cn || w > c->cfg.max_width || h > c->cfg.max_height || w < 32 || h < 32) {
+    c->set_error("mvo_group_track: bad argument");
+    return MVO_ERR_INVALID;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const int B = c->cfg.batch;
+  c->stream = c->main_stream;
+  c->have_prev = false;   // the front-end chain (mvo_group_step) does not survive a tracking frame
+  int rc = track_prepare(c, w, h);
+  if (rc) return rc;
+  const int cap = c->trk_cap;
+  rc = ransac_prepare(c, std::max(c->rs.max_pts, 64), std::max(c->rs.cap_iters, 1));   // the RNG table lives there
+  if (rc) return rc;
+  rc = pnp_prepare(c, std::max(cap, c->pnp.max_pts), std::max(100, c->pnp.cap_iters));
+  if (rc) return rc;
+  PnpBufs& p = c->pnp;
+  StageTimer& tt = c->timers[ST_TOTAL];
+  cudaEventRecord(tt.beg, c->stream);
+  // ---- frames -> level 0 of the LK pyramid that becomes "next" ----
+  {
+    const int rowb = w * cn;
+    const uint8_t* src = images;
+    int spitch = stride;
+    long long sstride = (long long)h * stride;
+    if (!images_on_device) {
+      GroupSlot& sl = c->slots[0];
+      MVO_CUDA_TRY(c, sl.stage.alloc((size_t)B * h * rowb));
+      if (stride == rowb)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.stage.p, images, (size_t)B * h * rowb, cudaMemcpyHostToDevice, c->stream));
+      else
+        MVO_CUDA_TRY(c, cudaMemcpy2DAsync(sl.stage.p, rowb, images, stride, rowb, (size_t)B * h, cudaMemcpyHostToDevice, c->stream));
+      src = sl.stage.p;
+      spitch = rowb;
+      sstride = (long long)h * rowb;
+    }
+    int lk_pitch = 0;
+    long long lk_fs = 0;
+    uint8_t* lk0 = lk_level0(c, c->lk_cur, &lk_pitch, &lk_fs);
+    if (cn == 1) {
+      dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
+      unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, lk0, lk_pitch, lk_fs, nullptr, 0, 0, w, h);
+    } else {
+      dim3 grid((w + 4 * 256 - 1) / (4 * 256), h, B);
+      unpack_bgr_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, nullptr, 0, 0, lk0, lk_pitch, lk_fs, w, h);
+    }
+    c->launches++;
+  }
+  rc = lk_build_pyramid(c, c->lk_cur, nullptr, 0, 3);
+  if (rc) return rc;
+  const int gb = (B + 127) / 128;
+  const int k0 = c->trk_cur, k1 = k0 ^ 1;
+  if (c->trk_have_frame) {
+    rc = lk_run(c, c->lk_cur ^ 1, c->lk_cur, c->trk_xy[k0].p, c->trk_n[k0].p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
+    if (rc) return rc;
+    track_collect_kernel<<<B, 1024, 0, c->stream>>>(c->lk_pts_out.p, c->lk_status.p, c->lk_err.p, c->trk_obj[k0].p,
+                                                    c->trk_n[k0].p, cap, 30.0f, c->trk_xy[k1].p, c->trk_obj[k1].p,
+                                                    c->trk_n[k1].p, c->trk_src.p, p.img.p, p.obj.p, p.npts.p, p.max_pts);
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(p.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+    replicate_k_kernel<<<gb, 128, 0, c->stream>>>(p.K.p, B);
+    c->launches += 2;
+    rc = pnp_run(c, 100, 8.0, 0.99);   // src/tracker.cpp:309
+    if (rc) return rc;
+  }
+  gather_track_results_kernel<<<gb, 128, 0, c->stream>>>(c->trk_n[k0].p, c->trk_n[k1].p, p.result.p, p.pose_out.p,
+                                                         c->trk_have_frame ? 1 : 0, c->d_trk_res.p, B);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->h_trk_res.p, c->d_trk_res.p, (size_t)B * sizeof(mvo_track_result), cudaMemcpyDeviceToHost,
+                                  c->stream));
+  cudaEventRecord(tt.end, c->stream);
+  tt.used = true;
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  memcpy(results, c->h_trk_res.p, (size_t)B * sizeof(mvo_track_result));
+  if (c->trk_have_frame) c->trk_cur = k1;
+  c->lk_cur ^= 1;
+  c->trk_have_frame = true;
+  return MVO_OK;
+}
+
+int mvo_group_get_tracks(mvo_ctx* c, int stream, float* xy, int32_t* src_idx, int32_t* pnp_inliers, int cap, int* n_tracked,
+                         int* n_inliers) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  if (stream < 0 || stream >= c->cfg.batch || !c->h_trk_res.p || c->trk_cap <= 0) {
+    c->set_error("mvo_group_get_tracks: no tracking frame yet, or stream out of range");
+    return MVO_ERR_INVALID;
+  }
+  const mvo_track_result& r = c->h_trk_res.p[stream];
+  if (n_tracked) *n_tracked = r.n_tracked;
+  if (n_inliers) *n_inliers = r.n_pnp_inliers;
+  if (((xy || src_idx) && r.n_tracked > cap) || (pnp_inliers && r.n_pnp_inliers > cap)) {
+    c->set_error("mvo_group_get_tracks: caller buffers too small");
+    return MVO_ERR_CAPACITY;
+  }
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const size_t o = (size_t)stream * c->trk_cap;
+  if (xy && r.n_tracked > 0)
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(xy, c->trk_xy[c->trk_cur].p + o, (size_t)r.n_tracked * 8, cudaMemcpyDeviceToHost, c->main_stream));
+  if (src_idx && r.n_tracked > 0)
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(src_idx, c->trk_src.p + o, (size_t)r.n_tracked * 4, cudaMemcpyDeviceToHost, c->main_stream));
+  if (pnp_inliers && r.n_pnp_inliers > 0)
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(pnp_inliers, c->pnp.inl_idx.p + (size_t)stream * c->pnp.max_pts, (size_t)r.n_pnp_inliers * 4,
+                                    cudaMemcpyDeviceToHost, c->main_stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->main_stream));
   return MVO_OK;
 }
 

@@ -1267,7 +1267,9 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
   const int B = c->cfg.batch, cn = c->lk_cn;
   uint8_t* base = c->lk_pyr[which].p;
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (cn == 3) {
+  if (on_device == 3) {
+    // level 0 is in place already (all planes)
+  } else if (cn == 3) {
     // interleaved BGR -> staging -> three planes per stream
     const size_t fbytes = (size_t)c->lk_h * stride;
     const uint8_t* src = img;
@@ -1280,8 +1282,6 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
     lk_split3_kernel<<<grid, 256, 0, c->stream>>>(src, stride, (long long)fbytes, base, g.lv[0].pitch, g.frame_stride,
                                                   c->lk_w, c->lk_h);
     c->launches++;
-  } else if (on_device == 3) {
-    // nothing to copy
   } else if (on_device == 2) {
     // source is a batch of pitched device images with frame stride given by `stride` == pitch and
     // frame distance c->geom.frame_stride (ORB pyramid level 0)
@@ -1390,6 +1390,9 @@ extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next
   }
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if (n == 0) return MVO_OK;
+  // both ping-pong pyramids are rebuilt below: the group entry points must not take them for their previous frame
+  c->have_prev = false;
+  c->trk_have_frame = false;
   int rc = lk_prepare(c, w, h, std::max(n, c->lk_max_pts), channels);
   if (rc) return rc;
   rc = lk_build_pyramid(c, 0, prev, stride, 0);

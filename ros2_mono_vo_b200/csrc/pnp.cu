@@ -47,6 +47,10 @@ pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* 
   __shared__ int s_pos, s_it, s_i, s_idx[kPnpK];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int n = npts[b];
+  if (n < kPnpK) {   // no sample of distinct points exists (batched callers pass npts = 0 for streams without enough points)
+    for (int k = lane; k < iters * kPnpK; k += 32) subsets[(long long)b * iters * kPnpK + k] = 0;
+    return;
+  }
   if (lane == 0) {
     s_pos = 0;
     s_it = 0;
