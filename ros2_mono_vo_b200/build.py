@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs, "-lcudart"]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -7,6 +7,7 @@
 // Call sites it stands for: Tracker::update (/root/reference/src/tracker.cpp:274-333) and
 // Initializer::try_initializing (src/initializer.cpp:165-313).
 #include "context.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <string.h>
 #include <algorithm>
 
@@ -263,11 +264,18 @@ __global__ void gather_track_results_kernel(const int32_t* nprev, const int32_t*
 
 using namespace mvo;
 
-#define STAGE_BEG(c, s) cudaEventRecord((c)->timers[s].beg, (c)->stream)
+// every stage is also an NVTX range (domain-less, named like mvo_stage_ms' stages) around its enqueue calls, so a
+// timeline tool attributes the kernels of a step to ORB / kNN / LK / the model searches (tracing row)
+#define STAGE_BEG(c, s)                                   \
+  do {                                                    \
+    nvtxRangePushA(kStageNames[s]);                       \
+    cudaEventRecord((c)->timers[s].beg, (c)->stream);     \
+  } while (0)
 #define STAGE_END(c, s)                               \
   do {                                                \
     cudaEventRecord((c)->timers[s].end, (c)->stream); \
     (c)->timers[s].used = true;                       \
+    nvtxRangePop();                                   \
   } while (0)
 
 // layout of a slot's pinned output block for the configured outputs
