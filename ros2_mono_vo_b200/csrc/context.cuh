@@ -197,6 +197,7 @@ struct mvo_ctx {
   // ---------------- profiling / parity knobs (mvo_debug_set) ----------------
   int dbg_lk_impl = 2;     // 1: first-generation lk_track_kernel (in-tree cross-check), 2: lk_track2_kernel
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
+  int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel
 
   // ---------------- stage timing ----------------
   static constexpr int kNumStages = 10;

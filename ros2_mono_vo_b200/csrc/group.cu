@@ -949,6 +949,7 @@ int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   if (!c || !key) return MVO_ERR_INVALID;
   if (strcmp(key, "lk_impl") == 0) c->dbg_lk_impl = value;
   else if (strcmp(key, "knn_impl") == 0) c->dbg_knn_impl = value;
+  else if (strcmp(key, "h_refine_impl") == 0) c->dbg_h_refine_impl = value;
   else {
     c->set_error("mvo_debug_set: unknown key");
     return MVO_ERR_INVALID;

@@ -1077,6 +1077,508 @@ h_refine_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, co
   if (tid == 0) res[0] = s_cnt;
 }
 
+// ---- homography refinement, second generation ---------------------------------------------------------
+// Same algorithm and (element for element) the same arithmetic as h_refine_kernel above, re-organised for latency -- the
+// kernel is one CTA per stream and sits on the critical path of a single-stream frame:
+//   * the ordered inlier correspondences are compacted into shared memory once (every pass of the old kernel re-read
+//     idx[k] -> P1[idx[k]], P2[idx[k]] from global memory: two dependent L2 round trips per pass, 31 % of its time);
+//   * the serial pieces that ran on thread 0 with local-memory arrays (9 x 9 LU + inverse iteration for the DLT null
+//     vector, the 8 x 8 LU of every Levenberg-Marquardt step: 35 % of the time with 255 threads waiting) run on warp 0 with
+//     the matrix in shared memory: pivot search redundantly in every lane, row swap and elimination entries over lanes;
+//   * one pass per LM iteration: the residual at the trial point and -- speculatively -- the normal equations there are
+//     accumulated together (the old kernel made a second pass after accepting the step); the cross-warp sums are formed
+//     by warp 0 only, in the same warp order.
+constexpr int kRefCache = 2048;   // inlier correspondences kept in shared memory (32 KB); beyond that: global gather
+
+// LU with partial pivoting on an N x N matrix in shared memory by one warp; elementwise the operations of lu_solve<N>.
+// STORE_L keeps the multipliers in the lower triangle (smallest_eigvec_spd's factorisation); piv (registers, uniform).
+template <int N, bool STORE_L>
+__device__ __forceinline__ bool lu_factor_warp(double* A, double* b, int* piv, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double best = fabs(A[k * N + k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(A[i * N + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (!STORE_L && best == 0.0) return false;
+    piv[k] = p;
+    if (p != k) {
+      if (lane < N) {
+        const double t = A[k * N + lane];
+        A[k * N + lane] = A[p * N + lane];
+        A[p * N + lane] = t;
+      } else if (lane == N && b) {
+        const double t = b[k];
+        b[k] = b[p];
+        b[p] = t;
+      }
+      __syncwarp();
+    }
+    const double d = A[k * N + k];
+    const double inv = STORE_L ? (d != 0.0 ? 1.0 / d : 0.0) : 1.0 / d;
+    constexpr int kCols = N + 1;                   // columns k+1 .. N-1 of the matrix, column N = right-hand side
+    const int cols = kCols - (k + 1);
+    const int cnt = (N - 1 - k) * cols;
+    double fkeep = 0.0;
+    for (int e = lane; e < cnt; e += 32) {
+      const int i = k + 1 + e / cols, j = k + 1 + e % cols;
+      const double f = A[i * N + k] * inv;
+      if (j < N) {
+        if (STORE_L || f != 0.0) A[i * N + j] -= f * A[k * N + j];
+      } else if (b) {
+        if (f != 0.0) b[i] -= f * b[k];
+      }
+      fkeep = f;
+    }
+    (void)fkeep;
+    __syncwarp();
+    if (STORE_L) {
+      if (lane > k && lane < N) A[lane * N + k] = A[lane * N + k] * inv;
+      __syncwarp();
+    }
+  }
+  return true;
+}
+
+// solve A x = b (both in shared memory, destroyed; x returned in b): warp LU, then back substitution on lane 0
+template <int N>
+__device__ __forceinline__ bool lu_solve_warp(double* A, double* b, int lane) {
+  int piv[N];
+  const bool ok = lu_factor_warp<N, false>(A, b, piv, lane);
+  if (!ok) return false;
+  if (lane == 0) {
+    double x[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      double s2 = b[i];
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) s2 -= A[i * N + j] * x[j];
+      x[i] = s2 / A[i * N + i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[i] = x[i];
+  }
+  __syncwarp();
+  return true;
+}
+
+// smallest_eigvec_spd<N> (linalg.cuh) with the factorisation done by the warp; A in shared memory, x (N doubles) too
+template <int N>
+__device__ __forceinline__ void smallest_eigvec_spd_warp(double* A, double* xs, int lane) {
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) tr += A[i * N + i];
+  const double delta = 1e-15 * tr + 1e-300;
+  __syncwarp();
+  if (lane < N) A[lane * N + lane] += delta;
+  __syncwarp();
+  int piv[N];
+  lu_factor_warp<N, true>(A, nullptr, piv, lane);
+  if (lane == 0) {
+    double x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 1.0 / sqrt((double)N) * ((i & 1) ? 0.9 : 1.1);
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {   // row permutation + forward substitution (unit lower triangle)
+        // x[k] <-> x[piv[k]] with a run-time piv: select over the unrolled register file
+        const int pk = piv[k];
+        double xp = x[k];
+#pragma unroll
+        for (int q = k + 1; q < N; ++q)
+          if (q == pk) {
+            xp = x[q];
+            x[q] = x[k];
+          }
+        x[k] = xp;
+#pragma unroll
+        for (int j = 0; j < k; ++j) x[k] -= A[k * N + j] * x[j];
+      }
+#pragma unroll
+      for (int i = N - 1; i >= 0; --i) {
+        double sacc = x[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) sacc -= A[i * N + j] * x[j];
+        const double d = A[i * N + i];
+        x[i] = d != 0.0 ? sacc / d : sacc;
+      }
+      double nrm = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) nrm += x[i] * x[i];
+      nrm = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] *= nrm;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) xs[i] = x[i];
+  }
+  __syncwarp();
+}
+
+// warp tree (xor butterfly) per value, lane 0 of every warp -> s_part[warp][NV]; the caller synchronises
+template <int NV>
+__device__ __forceinline__ void warp_partials(double* v, double* s_part, int lane, int warp) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum_d(v[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_part[warp * NV + k] = v[k];
+}
+// every thread forms the block totals from the per-warp partials, warps in order (as block_sum)
+template <int NV>
+__device__ __forceinline__ void block_totals(double* v, const double* s_part) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kRefThreads / 32; ++w) t += s_part[w * NV + k];
+    v[k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kRefThreads)
+h_refine2_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2, const int32_t* __restrict__ npts,
+                 int max_pts, const float* __restrict__ thr2, double* __restrict__ best_model,
+                 uint8_t* __restrict__ mask, int32_t* __restrict__ result, int32_t* __restrict__ inl_idx) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kRefThreads / 32;
+  const int n = npts[b];
+  int32_t* res = result + b * 8;
+  if (res[0] <= 0) return;   // no model
+  const float2* P1 = p1 + (long long)b * max_pts;
+  const float2* P2 = p2 + (long long)b * max_pts;
+  uint8_t* mk = mask + (long long)b * max_pts;
+  int32_t* idx = inl_idx + (long long)b * max_pts;
+  __shared__ float4 s_pts[kRefCache];
+  __shared__ double s_part[kWarps * 47];
+  __shared__ double s_L[81];
+  __shared__ double s_A[64], s_Ap[64], s_d[8], s_vv[8], s_Dg[8], s_x[8], s_xd[8], s_v[8], s_ad[8], s_h0[9];
+  __shared__ double s_S, s_lam, s_lc, s_rinf;
+  __shared__ int s_warp[kWarps];
+  __shared__ int s_flag[2];
+  __shared__ float s_hf[9];
+  __shared__ int s_cnt;
+  // ---- ordered compaction of the inliers: indices to global memory, correspondences to shared memory ----
+  int base = 0;
+  for (int i0 = 0; i0 < n; i0 += kRefThreads) {
+    const int i = i0 + tid;
+    const int ok = (i < n) ? (mk[i] != 0) : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = base, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int cw = s_warp[w];
+      if (w < warp) off += cw;
+      tot += cw;
+    }
+    if (ok) {
+      const int k = off + __popc(bal & ((1u << lane) - 1));
+      idx[k] = i;
+      if (k < kRefCache) {
+        const float2 M = P1[i], m = P2[i];
+        s_pts[k] = make_float4(M.x, M.y, m.x, m.y);
+      }
+    }
+    base += tot;
+    __syncthreads();
+  }
+  const int ni = base;
+  if (ni < 4) return;
+  auto pt = [&](int k) -> float4 {
+    if (k < kRefCache) return s_pts[k];
+    const float2 M = P1[idx[k]], m = P2[idx[k]];
+    return make_float4(M.x, M.y, m.x, m.y);
+  };
+  // ---- DLT (HomographyEstimatorCallback::runKernel on the inliers) ----
+  double v4[4] = {0, 0, 0, 0};
+  for (int k = tid; k < ni; k += kRefThreads) {
+    const float4 q = pt(k);
+    v4[0] += q.z; v4[1] += q.w; v4[2] += q.x; v4[3] += q.y;
+  }
+  warp_partials<4>(v4, s_part, lane, warp);
+  __syncthreads();
+  block_totals<4>(v4, s_part);
+  __syncthreads();
+  const double cmx = v4[0] / ni, cmy = v4[1] / ni, cMx = v4[2] / ni, cMy = v4[3] / ni;
+  double d4[4] = {0, 0, 0, 0};
+  for (int k = tid; k < ni; k += kRefThreads) {
+    const float4 q = pt(k);
+    d4[0] += fabs(q.z - cmx); d4[1] += fabs(q.w - cmy); d4[2] += fabs(q.x - cMx); d4[3] += fabs(q.y - cMy);
+  }
+  warp_partials<4>(d4, s_part, lane, warp);
+  __syncthreads();
+  block_totals<4>(d4, s_part);
+  __syncthreads();
+  if (fabs(d4[0]) < DBL_EPSILON || fabs(d4[1]) < DBL_EPSILON || fabs(d4[2]) < DBL_EPSILON || fabs(d4[3]) < DBL_EPSILON) return;
+  const double smx = ni / d4[0], smy = ni / d4[1], sMx = ni / d4[2], sMy = ni / d4[3];
+  {
+    // LtL blocks: S = sum a a^T, Sx = sum x a a^T, Sy = sum y a a^T, Sr = sum (x^2+y^2) a a^T with a = (X, Y, 1)
+    double acc[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) acc[k] = 0;
+    for (int k = tid; k < ni; k += kRefThreads) {
+      const float4 q = pt(k);
+      const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
+      const double X = (q.x - cMx) * sMx, Y = (q.y - cMy) * sMy;
+      const double aa[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};
+      const double r = x * x + y * y;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        acc[j] += aa[j];
+        acc[6 + j] += x * aa[j];
+        acc[12 + j] += y * aa[j];
+        acc[18 + j] += r * aa[j];
+      }
+    }
+    warp_partials<24>(acc, s_part, lane, warp);
+    __syncthreads();
+    if (warp == 0) {
+      // lane k < 24 owns total k; the 9 x 9 normal matrix is scattered from them
+      double t = 0;
+      if (lane < 24)
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += s_part[w * 24 + lane];
+      for (int e = lane; e < 81; e += 32) s_L[e] = 0;
+      __syncwarp();
+      if (lane < 24) {
+        const int blk = lane / 6, s6 = lane % 6;
+        // symmetric 3 x 3 index pairs of packed entry s6: {0:(0,0), 1:(0,1), 2:(0,2), 3:(1,1), 4:(1,2), 5:(2,2)}
+        const int pi = s6 < 3 ? 0 : (s6 < 5 ? 1 : 2);
+        const int pj = s6 < 3 ? s6 : (s6 < 5 ? s6 - 2 : 2);
+#pragma unroll
+        for (int sw = 0; sw < 2; ++sw) {
+          const int i = sw ? pj : pi, j = sw ? pi : pj;
+          if (sw && pi == pj) break;
+          if (blk == 0) {
+            s_L[i * 9 + j] = t;
+            s_L[(3 + i) * 9 + 3 + j] = t;
+          } else if (blk == 1) {
+            s_L[i * 9 + 6 + j] = -t;
+            s_L[(6 + j) * 9 + i] = -t;
+          } else if (blk == 2) {
+            s_L[(3 + i) * 9 + 6 + j] = -t;
+            s_L[(6 + j) * 9 + 3 + i] = -t;
+          } else {
+            s_L[(6 + i) * 9 + 6 + j] = t;
+          }
+        }
+      }
+      __syncwarp();
+      smallest_eigvec_spd_warp<9>(s_L, s_h0, lane);   // the DLT null direction (inverse iteration)
+      if (lane == 0) {
+        double h0[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) h0[i] = s_h0[i];
+        const double inv_hn[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+        const double hn2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+        double t9[9], H[9];
+        mat3_mul(inv_hn, h0, t9);
+        mat3_mul(t9, hn2, H);
+        const double sc = 1. / H[8];
+        for (int i = 0; i < 8; ++i) s_x[i] = H[i] * sc;
+        s_lam = 1.0;
+        s_lc = 0.75;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- LM (cv::LMSolverImpl::run, maxIters 10, eps FLT_EPSILON) ----
+  // one pass: residual sum / max and the normal equations J^T J (upper triangle), J^T r at h
+  auto pass = [&](const double* h) {
+    double a47[47];
+#pragma unroll
+    for (int k = 0; k < 47; ++k) a47[k] = 0;
+    const double h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6], h7 = h[7];
+    for (int k = tid; k < ni; k += kRefThreads) {
+      const float4 q = pt(k);
+      const double Mx = q.x, My = q.y;
+      double ww = h6 * Mx + h7 * My + 1.;
+      ww = fabs(ww) > DBL_EPSILON ? 1. / ww : 0;
+      const double xi = (h0 * Mx + h1 * My + h2) * ww;
+      const double yi = (h3 * Mx + h4 * My + h5) * ww;
+      const double ex = xi - (double)q.z, ey = yi - (double)q.w;
+      const double jx[8] = {Mx * ww, My * ww, ww, 0, 0, 0, -Mx * ww * xi, -My * ww * xi};
+      const double jy[8] = {0, 0, 0, Mx * ww, My * ww, ww, -Mx * ww * yi, -My * ww * yi};
+      int o = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = i; j < 8; ++j) a47[o++] += jx[i] * jx[j] + jy[i] * jy[j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a47[36 + i] += jx[i] * ex + jy[i] * ey;
+      a47[44] += ex * ex + ey * ey;
+      a47[45] = fmax(a47[45], fmax(fabs(ex), fabs(ey)));
+    }
+#pragma unroll
+    for (int k = 0; k < 45; ++k) a47[k] = warp_sum_d(a47[k]);
+    double mx = a47[45];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 45; ++k) s_part[warp * 47 + k] = a47[k];
+      s_part[warp * 47 + 45] = mx;
+    }
+  };
+  // warp 0: block totals of a pass; lane k owns totals k and k + 32 (sum over the warps in order; entry 45 is a max)
+  auto totals = [&](double& t0, double& t1) {
+    t0 = 0;
+    t1 = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      t0 += s_part[w * 47 + lane];
+      if (lane + 32 < 45) t1 += s_part[w * 47 + lane + 32];
+      if (lane + 32 == 45) t1 = fmax(t1, s_part[w * 47 + 45]);
+    }
+  };
+  // scatter the totals of a pass into the normal matrix (full symmetric), J^T r, S, |r|_inf
+  auto commit = [&](double t0, double t1) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int e = lane + 32 * half;
+      const double t = half ? t1 : t0;
+      if (e < 36) {
+        int i = 0, o = e;
+        while (o >= 8 - i) {
+          o -= 8 - i;
+          ++i;
+        }
+        const int j = i + o;
+        s_A[i * 8 + j] = t;
+        s_A[j * 8 + i] = t;
+      } else if (e < 44) {
+        s_vv[e - 36] = t;
+      } else if (e == 44) {
+        s_S = t;
+      } else if (e == 45) {
+        s_rinf = t;
+      }
+    }
+  };
+  pass(s_x);
+  __syncthreads();
+  if (warp == 0) {
+    double t0, t1;
+    totals(t0, t1);
+    commit(t0, t1);
+    __syncwarp();
+    if (lane < 8) s_Dg[lane] = s_A[lane * 9];
+    __syncwarp();
+  }
+  for (int iter = 0;;) {
+    if (warp == 0) {
+      // solve (A + lam * D) d = v
+      const double lam = s_lam;
+      for (int e = lane; e < 64; e += 32) s_Ap[e] = s_A[e];
+      __syncwarp();
+      if (lane < 8) {
+        s_Ap[lane * 9] += lam * s_Dg[lane];      // one fused multiply-add, as in the first-generation kernel
+        s_d[lane] = s_vv[lane];
+      }
+      __syncwarp();
+      const bool ok = lu_solve_warp<8>(s_Ap, s_d, lane);
+      if (lane < 8) {
+        const double d = ok ? s_d[lane] : 0.0;
+        s_v[lane] = d;
+        s_xd[lane] = s_x[lane] - d;
+      }
+    }
+    __syncthreads();
+    pass(s_xd);
+    __syncthreads();
+    if (warp == 0) {
+      double t0, t1;
+      totals(t0, t1);
+      const double Sd = __shfl_sync(0xffffffffu, t1, 44 - 32), rinf_d = __shfl_sync(0xffffffffu, t1, 45 - 32);
+      if (lane < 8) {
+        double ad = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad += s_A[lane * 8 + j] * s_v[j];
+        s_ad[lane] = ad;
+      }
+      __syncwarp();
+      // dS = d . (2 v - A d);  R = (S - Sd) / dS   (every lane, redundantly: uniform control flow for the warp solves)
+      const double S = s_S;
+      double dS = 0, tdot = 0, dinf = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dS += s_v[i] * (2 * s_vv[i] - s_ad[i]);
+        tdot += s_v[i] * s_vv[i];
+        dinf = fmax(dinf, fabs(s_v[i]));
+      }
+      double lam = s_lam, lc = s_lc;
+      const double R = (S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+      if (R > 0.75) {
+        lam *= 0.5;
+        if (lam < lc) lam = 0;
+      } else if (R < 0.25) {
+        double nu = (Sd - S) / (fabs(tdot) > DBL_EPSILON ? tdot : 1) + 2;
+        nu = fmin(fmax(nu, 2.), 10.);
+        if (lam == 0) {
+          // lc = 1 / max |diag(A^-1)|
+          double maxval = DBL_EPSILON;
+          for (int c = 0; c < 8; ++c) {
+            __syncwarp();
+            for (int e = lane; e < 64; e += 32) s_Ap[e] = s_A[e];
+            if (lane < 8) s_d[lane] = (lane == c) ? 1.0 : 0.0;
+            __syncwarp();
+            if (lu_solve_warp<8>(s_Ap, s_d, lane)) maxval = fmax(maxval, fabs(s_d[c]));
+          }
+          lam = lc = 1. / maxval;
+          nu *= 0.5;
+        }
+        lam *= nu;
+      }
+      __syncwarp();
+      const bool accept = Sd < S;
+      if (accept) {
+        if (lane < 8) s_x[lane] = s_xd[lane];
+        commit(t0, t1);                      // the trial point's normal equations, S = Sd, |r|_inf
+      }
+      if (lane == 0) {
+        s_lam = lam;
+        s_lc = lc;
+        const double rinf_cur = accept ? rinf_d : s_rinf;
+        s_flag[0] = (iter + 1 < 10 && dinf >= (double)FLT_EPSILON && rinf_cur >= (double)FLT_EPSILON) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    ++iter;
+    if (!s_flag[0]) break;
+  }
+  // ---- final model + mask of the refined H ----
+  if (tid < 8) {
+    best_model[b * 9 + tid] = s_x[tid];
+    s_hf[tid] = (float)s_x[tid];
+  }
+  if (tid == 8) {
+    best_model[b * 9 + 8] = 1.0;
+    s_hf[8] = 1.f;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  const float t = thr2[b];
+  int c = 0;
+  for (int i = tid; i < n; i += kRefThreads) {
+    const int in = (h_error(s_hf, P1[i], P2[i]) <= t) ? 1 : 0;
+    mk[i] = (uint8_t)in;
+    c += in;
+  }
+  c = warp_sum(c);
+  if (lane == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (tid == 0) res[0] = s_cnt;
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------
 __global__ void normalize_points_kernel(const float2* __restrict__ p1, const float2* __restrict__ p2,
                                         const int32_t* __restrict__ npts, int max_pts, const double* __restrict__ K,
@@ -1245,8 +1747,12 @@ int ransac_find(mvo_ctx* c, int model, double conf) {
   if (model == MVO_MODEL_H) {
     rc = find_model<MVO_MODEL_H>(c, conf);
     if (rc) return rc;
-    h_refine_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.ln().thr2.p,
-                                                                r.ln().best_model.p, r.ln().mask.p, r.ln().result.p, r.ln().inl_idx.p);
+    if (c->dbg_h_refine_impl == 1)   // the first-generation kernel, kept as the in-tree cross-check
+      h_refine_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.ln().thr2.p,
+                                                                  r.ln().best_model.p, r.ln().mask.p, r.ln().result.p, r.ln().inl_idx.p);
+    else
+      h_refine2_kernel<<<c->cfg.batch, kRefThreads, 0, c->stream>>>(r.p1.p, r.p2.p, r.npts.p, r.max_pts, r.ln().thr2.p,
+                                                                   r.ln().best_model.p, r.ln().mask.p, r.ln().result.p, r.ln().inl_idx.p);
     c->launches++;
     MVO_CUDA_TRY(c, cudaGetLastError());
     return MVO_OK;
