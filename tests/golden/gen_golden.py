@@ -201,6 +201,27 @@ def gen_f_small():
     np.savez_compressed(os.path.join(HERE, "f_small.npz"), **out)
 
 
+def gen_c3():
+    """BASELINE configs[2] size against cv2 itself: 1920x1080, 5000 ORB features over 8 levels, LK on the keypoints,
+    keyframe matching 5000 x 5000 with Lowe ratio 0.7 (round-1 parity at this size was against the oracle only)."""
+    gen_orb("orb_c3.npz", 1080, 1920, 3, 5000, False)
+    f0, f1 = synth.synth_pair(1080, 1920, 3)
+    pts = lk_points(1080, 1920, f0, 5000, 3)
+    nxt, st, err = cv2.calcOpticalFlowPyrLK(f0, f1, pts, None)
+    np.savez_compressed(os.path.join(HERE, "lk_c3.npz"), c3_pts=pts, c3_next=nxt, c3_status=st.ravel(), c3_err=err.ravel(),
+                        c3_sha0=sha(f0), c3_sha1=sha(f1), c3_hw_seed=np.array([1080, 1920, 3]), cv2_version=cv2.__version__)
+    print("lk c3", len(pts), int(st.sum()))
+    orb = cv2.ORB_create(5000)
+    _, d0 = orb.detectAndCompute(f0, None)
+    _, d1 = orb.detectAndCompute(f1, None)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d0, d1, 2)
+    idx = np.array([[a.trainIdx, b.trainIdx] for a, b in m], np.int32)
+    dist = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    good = np.array([(a.queryIdx, a.trainIdx, a.distance) for a, b in m if a.distance < 0.7 * b.distance], np.float32)
+    np.savez_compressed(os.path.join(HERE, "knn_c3.npz"), d0=d0, d1=d1, idx=idx, dist=dist, good=good, cv2_version=cv2.__version__)
+    print("knn c3", len(m), len(good))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:            # e.g. `python gen_golden.py gen_lk_bgr`: regenerate single fixtures
@@ -216,3 +237,4 @@ if __name__ == "__main__":
     gen_orb("orb_c1.npz", 480, 640, 1, 1000, False)
     gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)
     gen_knn()
+    gen_c3()

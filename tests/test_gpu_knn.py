@@ -34,6 +34,18 @@ def test_knn_golden(ctx):
     assert (m["img_idx"] == 0).all()
 
 
+def test_knn_c3_vs_cv2_golden(ctx):
+    """configs[2] as worded: 5000 x 5000 keyframe matching with Lowe ratio 0.7, against cv2's own knnMatch output."""
+    g = load_golden("knn_c3.npz")
+    idx, dist = ctx.knn2(g["d0"], g["d1"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist.astype(np.float32), g["dist"])
+    m = ctx.knn_ratio(g["d0"], g["d1"], 0.7)
+    good = g["good"]
+    assert np.array_equal(m["query_idx"], good[:, 0].astype(np.int32))
+    assert np.array_equal(m["train_idx"], good[:, 1].astype(np.int32))
+    assert np.array_equal(m["distance"], good[:, 2])
+
+
 @pytest.mark.parametrize("nq,nt,bits", [(1000, 1000, 256), (2000, 2000, 256), (5000, 5000, 256), (777, 1313, 4),
                                         (33, 257, 2), (1, 2, 256), (3000, 255, 256)])
 def test_knn_vs_oracle(ctx, nq, nt, bits):

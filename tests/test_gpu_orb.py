@@ -37,7 +37,7 @@ def _compare(kps, desc, ref_oct, ref_x, ref_y, ref_fields, ref_desc):
         assert np.array_equal(np.asarray(ref_desc)[gi], desc[oi]), "descriptors differ"
 
 
-@pytest.mark.parametrize("name", ["orb_small.npz", "orb_c1.npz", "orb_c2.npz"])
+@pytest.mark.parametrize("name", ["orb_small.npz", "orb_c1.npz", "orb_c2.npz", "orb_c3.npz"])
 def test_orb_vs_cv2_golden(ctx_cache, name):
     g = load_golden(name)
     img = golden_image(g)

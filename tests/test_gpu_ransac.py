@@ -91,9 +91,13 @@ def test_ransac_vs_oracle(ctx, seed, planar, n, outl):
     Eo, meo, _ = ro.find_essential(p1, p2, K, 0.99, 1.0)
     assert np.array_equal(me, meo)
     R, t, mp, good = ctx.recover_pose(E, p1, p2, K, mask=me)
-    Ro, to, mpo, goodo = ro.recover_pose(Eo, p1, p2, K, mask=meo)
+    # recoverPose on the SAME essential matrix and mask: count and mask identical, pose within north_star's tolerances
+    Ro, to, mpo, goodo = ro.recover_pose(E, p1, p2, K, mask=me)
     assert rot_angle_deg(R, Ro) < ROT_TOL_DEG and dir_angle_deg(t, to) < T_TOL_DEG
-    assert abs(good - goodo) <= 1
+    assert good == goodo and np.array_equal(mp != 0, np.asarray(mpo).ravel() != 0)
+    # and on the oracle's own E (equal to the library's up to ~1e-6): same pose
+    Ro2, to2, _, _ = ro.recover_pose(Eo, p1, p2, K, mask=meo)
+    assert rot_angle_deg(R, Ro2) < ROT_TOL_DEG and dir_angle_deg(t, to2) < T_TOL_DEG
     if not planar and n >= 1000:
         # sanity against the ground-truth motion of the synthetic scene
         assert rot_angle_deg(R, Rgt) < 0.5 and dir_angle_deg(t, tgt) < 8.0

@@ -25,6 +25,16 @@ def test_knn2_orb_descriptors_and_ratio():
     assert np.array_equal(d, good[:, 2])
 
 
+def test_knn_c3_golden():
+    """configs[2]: 5000 x 5000 keyframe matching against cv2's knnMatch."""
+    g = load_golden("knn_c3.npz")
+    idx, dist = ko.knn2(g["d0"], g["d1"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist.astype(np.float32), g["dist"])
+    qi, ti, d = ko.find_matches(g["d0"], g["d1"], 0.7)
+    good = g["good"]
+    assert np.array_equal(qi, good[:, 0].astype(np.int32)) and np.array_equal(ti, good[:, 1].astype(np.int32))
+
+
 def test_knn_edge_cases():
     rng = np.random.default_rng(1)
     q = rng.integers(0, 256, (5, 32)).astype(np.uint8)

@@ -14,9 +14,9 @@ def _pair(g, tag):
     return f0, f1
 
 
-@pytest.mark.parametrize("tag", ["small", "c2"])
+@pytest.mark.parametrize("tag", ["small", "c2", "c3"])
 def test_lk_oracle_vs_cv2(tag):
-    g = load_golden("lk.npz")
+    g = load_golden("lk_c3.npz" if tag == "c3" else "lk.npz")
     f0, f1 = _pair(g, tag)
     nxt, st, err = lo.lk_track(f0, f1, g[f"{tag}_pts"])
     assert np.array_equal(st, g[f"{tag}_status"])

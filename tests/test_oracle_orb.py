@@ -6,7 +6,7 @@ from conftest import golden_image, kp_dict, load_golden, sha
 from oracle import orb_oracle as oo
 
 
-@pytest.mark.parametrize("name", ["orb_small.npz", "orb_c1.npz", "orb_c2.npz"])
+@pytest.mark.parametrize("name", ["orb_small.npz", "orb_c1.npz", "orb_c2.npz", "orb_c3.npz"])
 def test_oracle_orb_matches_cv2_golden(name):
     g = load_golden(name)
     img = golden_image(g)
