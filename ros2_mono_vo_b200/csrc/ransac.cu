@@ -109,7 +109,9 @@ __device__ __forceinline__ bool check_subset(const float2* s1, const float2* s2)
 
 // state per stream (8 ints): [0] draw offset into the global RNG table, [1] subsets produced so far, [2] flags
 // (2: RNG table exhausted, 4: no further subset can be drawn), [3] done (the adaptive loop has terminated inside
-// the evaluated range; later rounds are skipped), [4] hypotheses already solved + scored by earlier rounds
+// the evaluated range; later rounds are skipped), [4] hypotheses already solved + scored by earlier rounds, [5] the
+// adaptive loop's iteration bound after the last evaluated round (niters only ever shrinks, so no later round needs
+// subsets, models or scores beyond it; 0 = not known yet)
 template <int MODEL>
 __global__ void __launch_bounds__(256)
 ransac_attempt_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const float2* __restrict__ p1,
@@ -119,6 +121,7 @@ ransac_attempt_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const
   constexpr int K = MT<MODEL>::K;
   const int b = blockIdx.y;
   const int32_t* st = state + b * 8;
+  if (st[5] > 0) want_total = min(want_total, st[5]);
   if (st[3] || st[1] >= want_total) return;
   const int n = npts[b];
   const int draw_base = st[0];
@@ -166,6 +169,7 @@ ransac_chain_kernel(const uint32_t* __restrict__ rng_table, int rng_len, const i
   const int n = npts[b];
   int32_t* st = state + b * 8;
   if (st[3]) return;
+  if (st[5] > 0) want_total = min(want_total, st[5]);
   const int have = st[1];
   const int draw_base = st[0];
   if (have >= want_total) return;
@@ -557,7 +561,7 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
   const int nsub = min(min(min(state[b * 8 + 1], cap_iters), MAXIT), n_eval);
   __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
-  __shared__ int s_T;
+  __shared__ int s_T, s_bound;
   __shared__ unsigned long long s_win[2048 / 1024 + 1];
   __shared__ double s_m[9];
   __shared__ float s_mf[9];
@@ -565,6 +569,7 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
   if (tid == 0) {
     s_carry = 0;
     s_T = 0x7fffffff;   // "the loop did not stop inside the evaluated range"
+    s_bound = MAXIT;
     s_cnt = 0;
   }
   __syncthreads();
@@ -621,6 +626,7 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
         niters = update_iters(conf, (double)(n - cnt) / n, K, MAXIT);
       }
       if (it + 1 >= niters) atomicMin(&s_T, it + 1);
+      if (it == nsub - 1) s_bound = niters;   // the bound the sequential loop carries into iteration nsub
     }
   }
   __syncthreads();
@@ -633,6 +639,7 @@ ransac_select_kernel(const float2* __restrict__ p1, const float2* __restrict__ p
   if (tid == 0) {
     if (final_round) state[b * 8 + 3] = 1;
     state[b * 8 + 4] = nsub;   // hypotheses [0, nsub) are solved and scored
+    state[b * 8 + 5] = s_bound;
   }
   if (!final_round) return;   // the next round extends the range and selects again
   // winner = prefix max at iteration T-1
