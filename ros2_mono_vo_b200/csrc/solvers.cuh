@@ -22,17 +22,58 @@ __device__ inline int solve_h4(const float2* M, const float2* m, double* H) {
   }
   if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) return 0;
   smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
-  double L[8 * 9];
+  // Four correspondences determine H exactly (up to scale), so the null vector of OpenCV's 8 x 9 DLT system (its 9 x 9
+  // Jacobi eigen-decomposition) is the unique projective map P_i -> p_i; it is written down in closed form in the
+  // normalised coordinates: with the projective basis (a, b, c | q), P_q = sum lambda_i P_i and p_q = sum mu_i p_i
+  // (Cramer: lambda_a = det(P_q, P_b, P_c) ...), H0 ~ sum_i mu_i (prod_{j != i} lambda_j) p_i (P_j x P_k)^T.
+  // The basis triple is the best conditioned one (largest |det_src * det_dst|); everything stays in registers
+  // (the Gauss-Jordan null space on a local-memory 8 x 9 array was the longest kernel of the H search).
+  double X[4], Y[4], x[4], y[4];
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double x = (m[i].x - cmx) * smx, y = (m[i].y - cmy) * smy;
-    const double X = (M[i].x - cMx) * sMx, Y = (M[i].y - cMy) * sMy;
-    double* a = L + (2 * i) * 9;
-    a[0] = X; a[1] = Y; a[2] = 1; a[3] = 0; a[4] = 0; a[5] = 0; a[6] = -x * X; a[7] = -x * Y; a[8] = -x;
-    double* b = a + 9;
-    b[0] = 0; b[1] = 0; b[2] = 0; b[3] = X; b[4] = Y; b[5] = 1; b[6] = -y * X; b[7] = -y * Y; b[8] = -y;
+    x[i] = (m[i].x - cmx) * smx; y[i] = (m[i].y - cmy) * smy;
+    X[i] = (M[i].x - cMx) * sMx; Y[i] = (M[i].y - cMy) * sMy;
   }
-  double h0[9];
-  null_space<8, 9>(L, h0);
+  auto det3h = [](double ax, double ay, double bx, double by, double cx, double cy) {
+    return ax * (by - cy) - ay * (bx - cx) + (bx * cy - cx * by);
+  };
+  // determinant of the triple that leaves point t out, source and destination
+  double best = -1.0;
+  int tq = 3;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int a = t == 0 ? 1 : 0, b = t <= 1 ? 2 : 1, c = t <= 2 ? 3 : 2;
+    const double d = fabs(det3h(X[a], Y[a], X[b], Y[b], X[c], Y[c]) * det3h(x[a], y[a], x[b], y[b], x[c], y[c]));
+    if (d > best) {
+      best = d;
+      tq = t;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+    if (tq == t) {   // the left-out point becomes q = 3 (register swap, no dynamic indexing)
+      double s;
+      s = X[t]; X[t] = X[3]; X[3] = s;
+      s = Y[t]; Y[t] = Y[3]; Y[3] = s;
+      s = x[t]; x[t] = x[3]; x[3] = s;
+      s = y[t]; y[t] = y[3]; y[3] = s;
+    }
+  const double l0 = det3h(X[3], Y[3], X[1], Y[1], X[2], Y[2]), l1 = det3h(X[0], Y[0], X[3], Y[3], X[2], Y[2]),
+               l2 = det3h(X[0], Y[0], X[1], Y[1], X[3], Y[3]);
+  const double u0 = det3h(x[3], y[3], x[1], y[1], x[2], y[2]), u1 = det3h(x[0], y[0], x[3], y[3], x[2], y[2]),
+               u2 = det3h(x[0], y[0], x[1], y[1], x[3], y[3]);
+  const double w[3] = {u0 * (l1 * l2), u1 * (l0 * l2), u2 * (l0 * l1)};
+  double h0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    const double r[3] = {Y[j] - Y[k], X[k] - X[j], X[j] * Y[k] - X[k] * Y[j]};   // P_j x P_k
+    const double pw[3] = {w[i] * x[i], w[i] * y[i], w[i]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) h0[a * 3 + b] += pw[a] * r[b];
+  }
   const double inv_hn[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
   const double hn2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
   double t[9];

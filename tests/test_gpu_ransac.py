@@ -136,6 +136,18 @@ def test_hypothesis_sweep_matches_oracle_subsets(ctx):
                     t = 1.0 / ((K[0, 0] + K[1, 1]) / 2)
                     c = int((ro.e_errors(M, q1, q2) <= np.float32(t * t)).sum())
                 assert c == counts[h, m], (name, h, m)
+    # the 4-point homographies (closed form on the GPU) equal OpenCV's DLT + eigen-decomposition solution (oracle h_kernel,
+    # pinned to cv2.findHomography(4 points, 0) in tests/test_oracle_ransac.py) -- four points determine H exactly
+    idx, counts, models = ctx.score_hypotheses(0, p1, p2, 512, thr=1.0, K=K, want_models=True)
+    worst = 0.0
+    for h in range(512):
+        if counts[h, 0] < 0:
+            continue
+        Ho = ro.h_kernel(p1[idx[h]], p2[idx[h]])
+        if Ho is None:
+            continue
+        worst = max(worst, np.abs(models[h, 0].reshape(3, 3) - Ho).max() / np.abs(Ho).max())
+    assert worst < 1e-8, worst
     # a long sweep keeps following the stream across sampler launches
     idx, counts, _ = ctx.score_hypotheses(1, p1, p2, 4096, thr=1.0)
     ref = ro.sample_subsets("F", p1, p2, 4096)
