@@ -163,8 +163,11 @@ MVO_API int mvo_triangulate(mvo_ctx* ctx, const double P0[12], const double P1[1
 
 /* replaces cv::solvePnPRansac(points_3d, points_2d, K, d, rvec, tvec, false, iterations, reproj_err, confidence,
  * inliers): src/tracker.cpp:309 (the reference passes 100, 8.0, 0.99; SOLVEPNP_ITERATIVE; no extrinsic guess).
- * obj_xyz: n x 3 f32 (std::vector<cv::Point3f>), img_xy: n x 2 f32.  dist: n_dist distortion coefficients or NULL --
- * they must all be zero (rectified images).  inliers: capacity n indices of the winning hypothesis' inliers (may be
+ * obj_xyz: n x 3 f32 (std::vector<cv::Point3f>), img_xy: n x 2 f32.  dist: n_dist distortion coefficients
+ * (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]) or NULL.  Non-zero coefficients: the image points are undistorted on the
+ * device (cv::undistortPoints, as OpenCV's minimal solver does) and the search runs in the distortion-free camera, i.e.
+ * the 8 px threshold and the refinement are measured on undistorted pixels (OpenCV: on distorted ones); all-zero
+ * coefficients (rectified images) take the bit-compatible path.  n < 6: MVO_ERR_DEGENERATE.  inliers: capacity n indices of the winning hypothesis' inliers (may be
  * NULL), *n_inliers their count.  rvec / tvec: the Levenberg-Marquardt pose on those inliers.
  * MVO_ERR_DEGENERATE == OpenCV returning false (no model). */
 MVO_API int mvo_solve_pnp_ransac(mvo_ctx* ctx, const float* obj_xyz, const float* img_xy, int n, const double K[9],
@@ -209,6 +212,8 @@ MVO_API int mvo_group_step(mvo_ctx* ctx, const uint8_t* images, int w, int h, in
 /* Pipelined form of mvo_group_step: submit enqueues the upload (copy stream, double-buffered staging: pass PINNED host
  * frames) and the kernels of one step and returns at once; collect waits for the OLDEST submitted step and returns its
  * results.  Up to two steps may be in flight, so the H2D copy of step t+1 overlaps the kernels of step t.
+ * BUFFER LIFETIME: the upload is asynchronous -- host frames passed to mvo_group_submit must stay valid and unmodified
+ * until the mvo_group_collect of that step has returned (device frames: until then as well).
  * mvo_stage_ms reports the most recently enqueued step and is only meaningful when nothing else is in flight. */
 MVO_API int mvo_group_submit(mvo_ctx* ctx, const uint8_t* images, int w, int h, int stride, int images_on_device,
                              const double K[9]);

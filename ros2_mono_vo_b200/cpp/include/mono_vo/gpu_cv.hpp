@@ -31,8 +31,12 @@ inline cv::Mat mat3x3(const double * m)
   return r;
 }
 
+// first coordinate of a point vector, NULL when it is empty (&v[0] on an empty vector is undefined behaviour)
+inline const float * xy_ptr(const std::vector<cv::Point2f> & v) { return v.empty() ? nullptr : &v[0].x; }
+
 inline void mat_to_array(const cv::Mat & m, double * out, int n)
 {
+  if (m.empty() || m.rows * m.cols < n) throw std::runtime_error("gpu_cv: matrix is empty or too small");
   for (int i = 0; i < n; ++i) out[i] = m.at<double>(i / m.cols, i % m.cols);
 }
 
@@ -57,7 +61,7 @@ inline cv::Mat findHomography(
   double H[9];
   int n_in = 0;
   mask.assign(p1.size(), 0);
-  const int rc = mvo_find_homography(c, &p1[0].x, &p2[0].x, static_cast<int>(p1.size()), thr, H, mask.data(), &n_in);
+  const int rc = mvo_find_homography(c, xy_ptr(p1), xy_ptr(p2), static_cast<int>(p1.size()), thr, H, mask.data(), &n_in);
   if (rc == MVO_ERR_DEGENERATE) return cv::Mat();   // OpenCV returns an empty matrix when no model is found
   check(c, rc, "findHomography");
   return mat3x3(H);
@@ -71,7 +75,7 @@ inline cv::Mat findFundamentalMat(
   double F[9];
   int n_in = 0;
   mask.assign(p1.size(), 0);
-  const int rc = mvo_find_fundamental(c, &p1[0].x, &p2[0].x, static_cast<int>(p1.size()), thr, conf, F, mask.data(), &n_in);
+  const int rc = mvo_find_fundamental(c, xy_ptr(p1), xy_ptr(p2), static_cast<int>(p1.size()), thr, conf, F, mask.data(), &n_in);
   if (rc == MVO_ERR_DEGENERATE) return cv::Mat();
   check(c, rc, "findFundamentalMat");
   return mat3x3(F);
@@ -86,7 +90,7 @@ inline cv::Mat findEssentialMat(
   mat_to_array(K, k, 9);
   int n_in = 0;
   mask.assign(p1.size(), 0);
-  const int rc = mvo_find_essential(c, &p1[0].x, &p2[0].x, static_cast<int>(p1.size()), k, prob, threshold, E, mask.data(), &n_in);
+  const int rc = mvo_find_essential(c, xy_ptr(p1), xy_ptr(p2), static_cast<int>(p1.size()), k, prob, threshold, E, mask.data(), &n_in);
   if (rc == MVO_ERR_DEGENERATE) return cv::Mat();
   check(c, rc, "findEssentialMat");
   return mat3x3(E);
@@ -101,7 +105,7 @@ inline int recoverPose(
   mat_to_array(E, e, 9);
   mat_to_array(K, k, 9);
   int good = 0;
-  check(c, mvo_recover_pose(c, e, &p1[0].x, &p2[0].x, static_cast<int>(p1.size()), k, r, tt,
+  check(c, mvo_recover_pose(c, e, xy_ptr(p1), xy_ptr(p2), static_cast<int>(p1.size()), k, r, tt,
     mask.size() == p1.size() ? mask.data() : nullptr, &good), "recoverPose");
   R = mat3x3(r);
   t = cv::Mat(3, 1, CV_64F);
@@ -118,7 +122,7 @@ inline void triangulatePoints(
   mat_to_array(P0, p0, 12);
   mat_to_array(P1, p1, 12);
   points4d.assign(4 * pts0.size(), 0.f);
-  check(c, mvo_triangulate(c, p0, p1, &pts0[0].x, &pts1[0].x, static_cast<int>(pts0.size()), points4d.data()), "triangulatePoints");
+  check(c, mvo_triangulate(c, p0, p1, xy_ptr(pts0), xy_ptr(pts1), static_cast<int>(pts0.size()), points4d.data()), "triangulatePoints");
 }
 
 /// cv::solvePnPRansac(points_3d, points_2d, K, d, rvec, tvec, useExtrinsicGuess = false, iterationsCount, reprojectionError,

@@ -1274,8 +1274,9 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
     const size_t fbytes = (size_t)c->lk_h * stride;
     const uint8_t* src = img;
     if (!on_device) {
+      const size_t nbytes = fbytes * (B - 1) + (size_t)(c->lk_h - 1) * stride + (size_t)c->lk_w * 3;   // not past the last row
       MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * B));
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, fbytes * B, cudaMemcpyHostToDevice, c->stream));
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, nbytes, cudaMemcpyHostToDevice, c->stream));
       src = c->img_in.p;
     }
     dim3 grid((c->lk_w + 255) / 256, c->lk_h, B);

@@ -881,8 +881,10 @@ gray_rows_kernel(const uint8_t* __restrict__ src, int spitch, long long src_fram
 int upload_gray_rows(mvo_ctx* c, const uint8_t* host, int w, int h, int stride, int batch, uint8_t* dst, int dpitch,
                      long long dst_frame_stride) {
   const size_t fbytes = (size_t)h * stride;
-  MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * batch));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, host, fbytes * batch, cudaMemcpyHostToDevice, c->stream));
+  // the last row of the last frame ends after w bytes: a strided view (cv::Mat ROI) owns nothing behind it
+  const size_t nbytes = fbytes * (batch - 1) + (size_t)(h - 1) * stride + (size_t)w;
+  MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * batch + 16));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, host, nbytes, cudaMemcpyHostToDevice, c->stream));
   dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, batch);
   gray_rows_kernel<<<grid, 256, 0, c->stream>>>(c->img_in.p, stride, (long long)fbytes, dst, dpitch, dst_frame_stride, w, h);
   c->launches++;
@@ -905,8 +907,9 @@ int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int cha
   const size_t fbytes = (size_t)h * stride;
   const uint8_t* src = img;
   if (!on_device) {
+    const size_t nbytes = fbytes * (g.batch - 1) + (size_t)(h - 1) * stride + (size_t)w * 3;   // see upload_gray_rows
     MVO_CUDA_TRY(c, c->img_in.alloc(fbytes * g.batch));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, fbytes * g.batch, cudaMemcpyHostToDevice, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->img_in.p, img, nbytes, cudaMemcpyHostToDevice, c->stream));
     src = c->img_in.p;
   }
   dim3 grid((w + 255) / 256, h, g.batch);

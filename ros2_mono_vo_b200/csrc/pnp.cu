@@ -499,6 +499,36 @@ int pnp_prepare(mvo_ctx* c, int max_pts, int iters) {
 }
 
 // points in p.obj / p.img, counts in p.npts, K in p.K
+// cv::undistortPoints(img, K, dist, R = I, P = K) with its default criteria (5 fixed-point iterations): the pixel the
+// point would have in a distortion-free camera.  Coefficients (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]]).
+struct PnpDist {
+  double k[12];
+};
+__global__ void pnp_undistort_kernel(float2* __restrict__ img, const int32_t* __restrict__ npts, int max_pts,
+                                     const double* __restrict__ Kd, PnpDist d) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts[b]) return;
+  const double* K = Kd + b * 9;
+  const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+  float2 q = img[(long long)b * max_pts + i];
+  const double x0 = ((double)q.x - cx) / fx, y0 = ((double)q.y - cy) / fy;
+  double x = x0, y = y0;
+  const double* k = d.k;
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+    const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  q.x = (float)(x * fx + cx);
+  q.y = (float)(y * fy + cy);
+  img[(long long)b * max_pts + i] = q;
+}
+
 int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
   PnpBufs& p = c->pnp;
   RansacBufs& r = c->rs;
@@ -534,14 +564,26 @@ extern "C" int mvo_solve_pnp_ransac(mvo_ctx* c, const float* obj_xyz, const floa
     c->set_error("mvo_solve_pnp_ransac: bad argument");
     return MVO_ERR_INVALID;
   }
-  for (int i = 0; dist && i < n_dist; ++i)
-    if (dist[i] != 0.0) {
-      c->set_error("mvo_solve_pnp_ransac: non-zero distortion coefficients are not implemented (rectified images only)");
+  // distortion coefficients (the reference passes CameraInfo's d, src/tracker.cpp:309): the image points are undistorted
+  // on the device (cv::undistortPoints, what OpenCV's minimal solver does) and the whole search -- threshold, inlier
+  // list, refinement -- runs in the distortion-free camera.  All-zero coefficients take the untouched fast path.
+  PnpDist dk;
+  for (double& v : dk.k) v = 0.0;
+  bool distorted = false;
+  for (int i = 0; dist && i < n_dist; ++i) {
+    if (dist[i] == 0.0) continue;
+    if (i >= 12) {
+      c->set_error("mvo_solve_pnp_ransac: tilted-sensor distortion terms (tau_x, tau_y) are not implemented");
       return MVO_ERR_UNSUPPORTED;
     }
+    dk.k[i] = dist[i];
+    distorted = true;
+  }
   if (n < 6) {
-    c->set_error("mvo_solve_pnp_ransac: fewer than 6 correspondences (OpenCV switches to P3P / a direct solve)");
-    return n < 4 ? MVO_ERR_DEGENERATE : MVO_ERR_UNSUPPORTED;
+    // OpenCV switches to P3P (n == 4) / one EPnP solve on all points (n == 5); the reference cannot get here
+    // (Tracker::update goes LOST below min_tracked_points = 10 observations, src/tracker.cpp:293-297)
+    c->set_error("mvo_solve_pnp_ransac: fewer than 6 correspondences");
+    return MVO_ERR_DEGENERATE;
   }
   if (c->cfg.batch != 1) {
     c->set_error("the single-call geometry API needs a batch==1 context");
@@ -557,6 +599,10 @@ extern "C" int mvo_solve_pnp_ransac(mvo_ctx* c, const float* obj_xyz, const floa
   MVO_CUDA_TRY(c, cudaMemcpyAsync(p.img.p, img_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(p.npts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(p.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+  if (distorted) {
+    pnp_undistort_kernel<<<dim3((n + 255) / 256, 1), 256, 0, c->stream>>>(p.img.p, p.npts.p, p.max_pts, p.K.p, dk);
+    c->launches++;
+  }
   rc = pnp_run(c, iterations, reproj_err, confidence);
   if (rc) return rc;
   int res[8];

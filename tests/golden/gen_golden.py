@@ -149,6 +149,25 @@ def gen_pnp():
     np.savez_compressed(os.path.join(HERE, "pnp.npz"), **out)
 
 
+from gen_golden_common import distort_pixels  # noqa: E402
+
+
+PNP_DIST = np.array([-0.28, 0.07, 0.0008, -0.0005, -0.01])
+
+
+def gen_pnp_dist():
+    """cv::solvePnPRansac with CameraInfo-style distortion coefficients (the reference passes d_, src/tracker.cpp:309)."""
+    out = {"dist": PNP_DIST, "cv2_version": cv2.__version__}
+    for tag, n, seed, noise, outl in (("d1", 1500, 11, 0.5, 0.2), ("d2", 300, 12, 0.3, 0.1)):
+        obj, img, K, rv, tv = synth.pnp_scene(n, seed, noise, outl)
+        imgd = distort_pixels(img, K, PNP_DIST)
+        ok, r, t, inl = cv2.solvePnPRansac(obj, imgd, K, PNP_DIST, None, None, False, 100, 8.0, 0.99)
+        out.update({f"{tag}_args": np.array([n, seed, noise, outl]), f"{tag}_ok": ok, f"{tag}_rvec": r.ravel(), f"{tag}_tvec": t.ravel(),
+                    f"{tag}_inliers": inl.ravel().astype(np.int32), f"{tag}_rv_gt": rv, f"{tag}_tv_gt": tv})
+        print("pnp_dist", tag, ok, len(inl), np.abs(r.ravel() - rv).max(), np.abs(t.ravel() - tv).max())
+    np.savez_compressed(os.path.join(HERE, "pnp_dist.npz"), **out)
+
+
 def gen_ransac():
     """cv2 outputs at the reference's RANSAC call sites (src/initializer.cpp:82,87,228,236,125)."""
     K = synth.KITTI_K
@@ -238,3 +257,4 @@ if __name__ == "__main__":
     gen_orb("orb_c2.npz", 376, 1241, 2, 2000, False)
     gen_knn()
     gen_c3()
+    gen_pnp_dist()
