@@ -240,7 +240,9 @@ enum {
   MVO_OUT_TRACKS = 4,     /* LK next position / status / err of every keypoint of frame t-1       */
   MVO_OUT_MODELS = 8,     /* H, F, E and their inlier masks, the recoverPose mask                 */
   MVO_OUT_POINTS3D = 16,  /* triangulated homogeneous points                                      */
-  MVO_OUT_ALL = 31
+  MVO_OUT_CLOUD = 32,     /* the chirality-valid triangulated points, dehomogenised, in ROS axes, packed as the
+                             sensor_msgs/PointCloud2 payload (12 bytes per point)                   */
+  MVO_OUT_ALL = 63
 };
 typedef struct mvo_group_config {
   int32_t channels;   /* frames given to mvo_group_step / submit / track: 1 = gray8, 3 = BGR8 (the node feeds BGR8,
@@ -279,7 +281,11 @@ typedef struct mvo_stream_outputs {
   int64_t x4_stride;
   double H[9], F[9], E[9];
   int32_t flags;        /* bit0: FAST candidate list overflowed, bit1: keypoints truncated to the capacity */
-  int32_t reserved;
+  int32_t n_cloud;      /* points in cloud_xyz (== mvo_frame_result.n_triangulated)                        */
+  const float* cloud_xyz;   /* MVO_OUT_CLOUD: n_cloud x (x, y, z) f32 = PointCloud2.data of points3d_to_pointcloud_msg
+                               (src/utils.cpp:184-243) for the points with mask_pose set and z > 0 in both cameras,
+                               in the order of the tracks                                                   */
+  int32_t occupied_cells, total_cells;   /* keypoint distribution grid of frame t (see mvo_orb_occupancy)  */
 } mvo_stream_outputs;
 MVO_API int mvo_group_outputs(mvo_ctx* ctx, int stream, mvo_stream_outputs* out);
 
@@ -308,6 +314,26 @@ MVO_API int mvo_group_track(mvo_ctx* ctx, const uint8_t* images, int w, int h, i
  * (into the new list).  Any pointer may be NULL; cap = capacity of each array. */
 MVO_API int mvo_group_get_tracks(mvo_ctx* ctx, int stream, float* xy, int32_t* src_idx, int32_t* pnp_inliers, int cap,
                                  int* n_tracked, int* n_inliers);
+
+/* ------------------------------------------------------------------------------------------------
+ * by-products that save the reference's host loops.
+ *
+ * Keypoint-distribution grid == Initializer::good_keypoint_distribution (src/initializer.cpp:52-75): a grid of
+ * (rows / div) x (cols / div) cells, a cell is occupied when a keypoint has r = (int)(pt.y / div), c = (int)(pt.x / div)
+ * (flat index r * grid_cols + c, exactly the cv::Mat::at the reference performs; indices past the grid are ignored).
+ * The counts are a by-product of the kernel that writes the final keypoints (no extra pass over them).  div defaults
+ * to 50 (config/params.yaml: initializer.occupancy_grid_div); 0 switches the by-product off.  The reference's test is
+ * (double)occupied / total > kp_distribution_thresh.
+ * mvo_orb_occupancy: counts of the last mvo_orb_detect_and_compute call (stream 0) or of the group step most recently
+ * returned by mvo_group_step / mvo_group_collect. */
+MVO_API int mvo_set_occupancy_grid(mvo_ctx* ctx, int grid_div);
+MVO_API int mvo_orb_occupancy(mvo_ctx* ctx, int stream, int* occupied_cells, int* total_cells);
+/* points3d_to_pointcloud_msg's payload (src/utils.cpp:225-241) on the device: n points (x, y, z) f32 in the camera /
+ * OpenCV frame -> n x 12 bytes (ROS x = z, ROS y = -x, ROS z = -y), i.e. sensor_msgs::msg::PointCloud2::data with
+ * point_step 12, fields x / y / z FLOAT32 at offsets 0 / 4 / 8, height 1, width n, little endian, dense.
+ * points_on_device / out_on_device: the buffers are device pointers (MVO_MEM_DEVICE) instead of host memory. */
+MVO_API int mvo_pack_pointcloud(mvo_ctx* ctx, const float* points_xyz, int n, int points_on_device, uint8_t* out,
+                                int out_on_device);
 
 /* ------------------------------------------------------------------------------------------------
  * profiling / parity aids (not part of the reference-facing surface)

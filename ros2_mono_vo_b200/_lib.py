@@ -47,7 +47,8 @@ class MvoStreamOutputs(C.Structure):
                 ("mask_h", C.c_void_p), ("mask_f", C.c_void_p), ("mask_e", C.c_void_p), ("mask_pose", C.c_void_p),
                 ("X4", C.c_void_p), ("x4_stride", C.c_int64),
                 ("H", C.c_double * 9), ("F", C.c_double * 9), ("E", C.c_double * 9),
-                ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("n_cloud", C.c_int32), ("cloud_xyz", C.c_void_p),
+                ("occupied_cells", C.c_int32), ("total_cells", C.c_int32)]
 
 
 class MvoTrackResult(C.Structure):
@@ -55,7 +56,7 @@ class MvoTrackResult(C.Structure):
                 ("rvec", C.c_double * 3), ("tvec", C.c_double * 3)]
 
 
-MVO_OUT_KEYPOINTS, MVO_OUT_MATCHES, MVO_OUT_TRACKS, MVO_OUT_MODELS, MVO_OUT_POINTS3D, MVO_OUT_ALL = 1, 2, 4, 8, 16, 31
+MVO_OUT_KEYPOINTS, MVO_OUT_MATCHES, MVO_OUT_TRACKS, MVO_OUT_MODELS, MVO_OUT_POINTS3D, MVO_OUT_CLOUD, MVO_OUT_ALL = 1, 2, 4, 8, 16, 32, 63
 
 _u8p = C.POINTER(C.c_uint8)
 _f32p = C.POINTER(C.c_float)
@@ -104,6 +105,9 @@ SIGNATURES = {
     "mvo_group_set_tracks": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int]),
     "mvo_group_track": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "mvo_group_get_tracks": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _i32p, _i32p]),
+    "mvo_set_occupancy_grid": (C.c_int, [_vp, C.c_int]),
+    "mvo_orb_occupancy": (C.c_int, [_vp, C.c_int, _i32p, _i32p]),
+    "mvo_pack_pointcloud": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int]),
     "mvo_stage_ms": (C.c_int, [_vp, C.c_char_p, _f32p]),
     "mvo_stage_span_ms": (C.c_int, [_vp, C.c_char_p, _f32p, _f32p]),
     "mvo_debug_set": (C.c_int, [_vp, C.c_char_p, C.c_int]),

@@ -219,6 +219,8 @@ class Context:
                "mask_h": view(o.mask_h, np.uint8, (nt,)), "mask_f": view(o.mask_f, np.uint8, (nt,)),
                "mask_e": view(o.mask_e, np.uint8, (nt,)), "mask_pose": view(o.mask_pose, np.uint8, (nt,)),
                "H": np.array(o.H).reshape(3, 3), "F": np.array(o.F).reshape(3, 3), "E": np.array(o.E).reshape(3, 3)}
+        out["occupied_cells"], out["total_cells"] = int(o.occupied_cells), int(o.total_cells)
+        out["cloud_xyz"] = view(o.cloud_xyz, np.float32, (int(o.n_cloud), 3))
         if o.X4:
             full = view(o.X4, np.float32, (4, int(o.x4_stride)))
             out["X4"] = full[:, :nt].copy() if copy else full[:, :nt]
@@ -260,6 +262,24 @@ class Context:
         res = np.zeros(self.batch, RESULT_DTYPE)
         self._check(self.lib.mvo_group_collect(self.h, _ptr(res)))
         return res
+
+    # ---- SURVEY 8(f) #4 by-products -------------------------------------------------------------
+    def set_occupancy_grid(self, grid_div: int):
+        """Cell size of the keypoint-distribution grid (Initializer::good_keypoint_distribution); 0 = off."""
+        self._check(self.lib.mvo_set_occupancy_grid(self.h, int(grid_div)))
+
+    def orb_occupancy(self, stream: int = 0):
+        """(occupied cells, total cells) of the last orb_detect_and_compute / collected group step."""
+        a, b = C.c_int32(), C.c_int32()
+        self._check(self.lib.mvo_orb_occupancy(self.h, int(stream), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def pack_pointcloud(self, points_xyz) -> np.ndarray:
+        """points3d_to_pointcloud_msg's PointCloud2.data (n * 12 bytes, ROS axes) for n x 3 f32 points."""
+        pts = np.ascontiguousarray(points_xyz, np.float32).reshape(-1, 3)
+        out = np.zeros(len(pts) * 12, np.uint8)
+        self._check(self.lib.mvo_pack_pointcloud(self.h, _ptr(pts), len(pts), 0, _ptr(out), 0))
+        return out
 
     def group_reset(self):
         self._check(self.lib.mvo_group_reset(self.h))

@@ -23,6 +23,19 @@ static int ensure_stage(mvo_ctx* c, size_t bytes) {
   return MVO_OK;
 }
 
+namespace mvo {
+// points3d_to_pointcloud_msg's loop (src/utils.cpp:225-241): (x, y, z) camera / OpenCV axes -> ROS axes (z, -x, -y),
+// three floats per point; one thread per float of the output (coalesced 4-byte accesses on both sides)
+__global__ void __launch_bounds__(256) pack_cloud_kernel(const float* __restrict__ xyz, int n, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * n) return;
+  const int p = e / 3, k = e - 3 * p;
+  // out[0] = z, out[1] = -x, out[2] = -y
+  const float v = xyz[3 * p + (k == 0 ? 2 : k - 1)];
+  out[e] = k == 0 ? v : -v;
+}
+}  // namespace mvo
+
 extern "C" {
 
 const char* mvo_version(void) { return "monovo_b200 0.1 (sm_100a)"; }
@@ -136,6 +149,7 @@ void mvo_destroy(mvo_ctx* c) {
     sl.stage.release();
     sl.h_res.release();
     sl.h_flags.release();
+    sl.h_occ.release();
   }
   for (auto& ev : c->ev_fork)
     if (ev) cudaEventDestroy(ev);
@@ -146,7 +160,7 @@ void mvo_destroy(mvo_ctx* c) {
   c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->cand_sel.release(); c->sel_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();
   c->c2_count.release(); c->kps.release(); c->desc.release(); c->kp_valid.release(); c->kp_count.release();
-  c->flags.release(); c->h_stage.release(); c->prev_kps.release(); c->prev_desc.release();
+  c->flags.release(); c->occ.release(); c->cloud.release(); c->pack_tmp.release(); c->h_stage.release(); c->prev_kps.release(); c->prev_desc.release();
   c->prev_kp_count.release(); c->kp_xy.release(); c->prev_kp_xy.release(); c->d_results.release(); c->knn_q.release(); c->knn_t.release(); c->knn_best.release();
   c->knn_matches.release(); c->knn_nmatch.release(); c->knn_counts.release();
   c->lk_pyr[0].release(); c->lk_pyr[1].release(); c->lk_pts_in.release(); c->lk_pts_out.release();
@@ -194,11 +208,15 @@ int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int
   uint8_t* hs = c->h_stage.p;
   MVO_CUDA_TRY(c, cudaMemcpyAsync(hs, c->kp_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 16, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 32, c->occ.p, 8, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64, c->kps.p, kb, cudaMemcpyDeviceToHost, c->stream));
   if (desc) MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64 + kb, c->desc.p, db, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   int n = *reinterpret_cast<int*>(hs);
   const int flags = *reinterpret_cast<int*>(hs + 16);
+  c->occ_single[0] = reinterpret_cast<int*>(hs + 32)[0];
+  c->occ_single[1] = reinterpret_cast<int*>(hs + 32)[1];
+  c->occ_from_group = false;
   if (flags & 1) {
     c->set_error("FAST candidate list overflow");
     return MVO_ERR_CAPACITY;
@@ -338,6 +356,57 @@ int mvo_knn2(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int
       idx[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key & 0x3FFFFFu);
       dist[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key >> 22);
     }
+  return MVO_OK;
+}
+
+// ---- SURVEY 8(f) #4 -------------------------------------------------------------------------------
+int mvo_set_occupancy_grid(mvo_ctx* c, int grid_div) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  MVO_CHECK_ARG(c, grid_div >= 0, "mvo_set_occupancy_grid: negative cell size");
+  c->occupancy_div = grid_div;
+  if (c->geom_w > 0) orb_set_grid(c, c->geom_w, c->geom_h);
+  return MVO_OK;
+}
+
+int mvo_orb_occupancy(mvo_ctx* c, int stream, int* occupied_cells, int* total_cells) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_CHECK_ARG(c, occupied_cells && total_cells && stream >= 0 && stream < c->cfg.batch, "mvo_orb_occupancy: bad argument");
+  if (c->occ_from_group) {
+    MVO_CHECK_ARG(c, c->out_slot >= 0 && c->slots[c->out_slot].h_occ.p, "mvo_orb_occupancy: no finished group step");
+    *occupied_cells = c->slots[c->out_slot].h_occ.p[2 * stream];
+    *total_cells = c->slots[c->out_slot].h_occ.p[2 * stream + 1];
+  } else {
+    MVO_CHECK_ARG(c, stream == 0, "mvo_orb_occupancy: single-call contexts have one stream");
+    *occupied_cells = c->occ_single[0];
+    *total_cells = c->occ_single[1];
+  }
+  if (*occupied_cells < 0) {
+    c->set_error("the keypoint-distribution grid is switched off (mvo_set_occupancy_grid) or does not fit (rows x cols > 8192)");
+    return MVO_ERR_UNSUPPORTED;
+  }
+  return MVO_OK;
+}
+
+int mvo_pack_pointcloud(mvo_ctx* c, const float* points_xyz, int n, int points_on_device, uint8_t* out, int out_on_device) {
+  if (!c) return MVO_ERR_INVALID;
+  MVO_REQUIRE_IDLE(c);
+  MVO_CHECK_ARG(c, n >= 0 && (n == 0 || (points_xyz && out)), "mvo_pack_pointcloud: bad argument");
+  if (n == 0) return MVO_OK;
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  const size_t bytes = (size_t)n * 12;
+  MVO_CUDA_TRY(c, c->pack_tmp.alloc(2 * bytes));
+  const float* src = points_xyz;
+  if (!points_on_device) {
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(c->pack_tmp.p, points_xyz, bytes, cudaMemcpyHostToDevice, c->stream));
+    src = reinterpret_cast<const float*>(c->pack_tmp.p);
+  }
+  float* dst = out_on_device ? reinterpret_cast<float*>(out) : reinterpret_cast<float*>(c->pack_tmp.p + bytes);
+  pack_cloud_kernel<<<(3 * n + 255) / 256, 256, 0, c->stream>>>(src, n, dst);
+  c->launches++;
+  MVO_CUDA_TRY(c, cudaGetLastError());
+  if (!out_on_device) MVO_CUDA_TRY(c, cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, c->stream));
+  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return MVO_OK;
 }
 

@@ -33,6 +33,7 @@ struct OrbGeom {
   int kp_cap;               // final keypoint capacity per frame
   int nfeatures;
   int batch;
+  int grid_div, grid_rows, grid_cols;   // keypoint-distribution grid (src/initializer.cpp:57-61); grid_div 0 = off
 };
 
 // Candidate after FAST+NMS: packed position and score.

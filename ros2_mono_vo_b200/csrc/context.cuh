@@ -89,6 +89,7 @@ struct GroupSlot {
   mvo::DevBuf<uint8_t> stage;                 // batch * h * w staged host frames
   mvo::PinBuf<mvo_frame_result> h_res;        // pinned result records
   mvo::PinBuf<int32_t> h_flags;
+  mvo::PinBuf<int32_t> h_occ;           // batch * 2: occupied / total cells of the keypoint-distribution grid
   cudaEvent_t ev_up = nullptr, ev_free = nullptr, ev_done = nullptr;
   mvo::PinBuf<uint8_t> h_out;                 // full per-stream outputs (mvo_group_configure), sections of OutLayout
   int had_prev = 0;                           // the step enqueued in this slot had a previous frame
@@ -97,7 +98,7 @@ struct GroupSlot {
 // sections of a slot's pinned output block (byte offsets; every section holds batch * cap entries)
 struct OutLayout {
   size_t kps = 0, desc = 0, matches = 0, lk_xy = 0, lk_status = 0, lk_err = 0, mask[4] = {0, 0, 0, 0}, models = 0, x4 = 0,
-         prev_count = 0, total = 0;
+         cloud = 0, prev_count = 0, total = 0;
   int cap = 0, batch = 0;
   uint32_t mask_bits = 0;
 };
@@ -196,6 +197,12 @@ struct mvo_ctx {
 
   // ---------------- profiling / parity knobs (mvo_debug_set) ----------------
   int dbg_lk_impl = 2;     // 1: first-generation lk_track_kernel (in-tree cross-check), 2: lk_track2_kernel
+  int occupancy_div = 50;  // keypoint-distribution grid cell size (config/params.yaml: initializer.occupancy_grid_div)
+  mvo::DevBuf<int32_t> occ;            // batch * 2: occupied / total cells, written by orb_finalize_kernel
+  int occ_single[2] = {0, 0};          // ... of the last single-call detect
+  bool occ_from_group = false;         // mvo_orb_occupancy answers from the last collected group step
+  mvo::DevBuf<float> cloud;            // group step: batch * cap * 3 packed ROS-axis points (MVO_OUT_CLOUD)
+  mvo::DevBuf<uint8_t> pack_tmp;       // mvo_pack_pointcloud staging
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
   int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel
 
@@ -218,6 +225,7 @@ namespace mvo {
 
 // host-side module entry points (defined in the respective .cu files)
 int orb_prepare(mvo_ctx* c, int w, int h);
+void orb_set_grid(mvo_ctx* c, int w, int h);
 int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels, int on_device);
 int orb_run_detect(mvo_ctx* c, bool want_desc);
 int orb_run_levels_only(mvo_ctx* c);

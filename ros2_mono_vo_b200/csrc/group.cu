@@ -80,32 +80,60 @@ __global__ void make_proj_kernel(const double* __restrict__ K, const double* __r
   }
 }
 
-// chirality count of the triangulated points (src/initializer.cpp:134-157): z > 0 in both cameras
+// chirality count of the triangulated points (src/initializer.cpp:134-157): z > 0 in both cameras.  With `cloud` the
+// valid points are also compacted in track order and written as points3d_to_pointcloud_msg would pack them
+// (src/utils.cpp:225-241: ROS x = z, y = -x, z = -y; 12 bytes per point) -- MVO_OUT_CLOUD.
 __global__ void __launch_bounds__(256)
 tri_count_kernel(const float* __restrict__ X4, const uint8_t* __restrict__ mask, const double* __restrict__ pose,
-                 const int32_t* __restrict__ npts, int max_pts, int32_t* __restrict__ out) {
-  const int b = blockIdx.x, tid = threadIdx.x;
+                 const int32_t* __restrict__ npts, int max_pts, int32_t* __restrict__ out, float* __restrict__ cloud,
+                 int cloud_cap) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = npts[b];
   const double* R = pose + b * 12;
   const double* t = R + 9;
   const float* X = X4 + (long long)b * 4 * max_pts;
-  int c = 0;
-  for (int i = tid; i < n; i += 256) {
-    if (!mask[(long long)b * max_pts + i]) continue;
-    const float w = X[3LL * max_pts + i];
-    const float sc = w != 0.f ? 1.f / w : 1.f;        // convertPointsFromHomogeneous
-    const float x = X[i] * sc, y = X[1LL * max_pts + i] * sc, z = X[2LL * max_pts + i] * sc;
-    if (z <= 0) continue;
-    const double z2 = R[6] * (double)x + R[7] * (double)y + R[8] * (double)z + t[2];
-    if (z2 > 0) ++c;
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + tid;
+    bool ok = false;
+    float x = 0, y = 0, z = 0;
+    if (i < n && mask[(long long)b * max_pts + i]) {
+      const float w = X[3LL * max_pts + i];
+      const float sc = w != 0.f ? 1.f / w : 1.f;        // convertPointsFromHomogeneous
+      x = X[i] * sc;
+      y = X[1LL * max_pts + i] * sc;
+      z = X[2LL * max_pts + i] * sc;
+      if (z > 0) {
+        const double z2 = R[6] * (double)x + R[7] * (double)y + R[8] * (double)z + t[2];
+        ok = z2 > 0;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base, tot = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) {
+      if (w2 < warp) off += s_warp[w2];
+      tot += s_warp[w2];
+    }
+    if (ok && cloud) {
+      const int k = off + __popc(bal & ((1u << lane) - 1));
+      if (k < cloud_cap) {
+        float* o = cloud + ((long long)b * cloud_cap + k) * 3;
+        o[0] = z;
+        o[1] = -x;
+        o[2] = -y;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_base += tot;
+    __syncthreads();
   }
-  c = warp_sum(c);
-  __shared__ int s;
-  if (tid == 0) s = 0;
-  __syncthreads();
-  if ((tid & 31) == 0 && c) atomicAdd(&s, c);
-  __syncthreads();
-  if (tid == 0) out[b] = s;
+  if (tid == 0) out[b] = s_base;
 }
 
 __global__ void gather_results_kernel(const int32_t* kp_count, const int32_t* nmatch, const int32_t* ntracked,
@@ -309,6 +337,7 @@ static int out_prepare(mvo_ctx* c, int cap) {
       L.models = take(B * 27 * 8);
     }
     if (c->out_mask & MVO_OUT_POINTS3D) L.x4 = take(B * 4 * cap * 4);
+    if (c->out_mask & MVO_OUT_CLOUD) L.cloud = take(B * cap * 12);
     L.total = off;
   }
   for (auto& sl : c->slots) MVO_CUDA_TRY(c, sl.h_out.alloc(L.total));
@@ -365,6 +394,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     rc = out_prepare(c, cap);
     if (rc) return rc;
     if (om & MVO_OUT_MODELS) MVO_CUDA_TRY(c, c->e_mask_keep.alloc((size_t)B * r.max_pts));
+    if (om & MVO_OUT_CLOUD) MVO_CUDA_TRY(c, c->cloud.alloc((size_t)B * cap * 3));
   }
   uint8_t* const hout = c->slots[slot].h_out.p;
   c->slots[slot].had_prev = c->have_prev ? 1 : 0;
@@ -435,6 +465,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     MVO_CUDA_TRY(c, sl.h_res.alloc(B));
     MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
     MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, sl.h_occ.alloc(2 * B));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_occ.p, c->occ.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
     if (om && c->have_prev)
       MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.prev_count, c->prev_kp_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -533,7 +565,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       c->launches++;
       rc = pose_triangulate(c);
       if (rc) return rc;
-      tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.ln().mask.p, r.pose.p, r.npts.p, r.max_pts, ntri);
+      tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.ln().mask.p, r.pose.p, r.npts.p, r.max_pts, ntri,
+                                                 (om & MVO_OUT_CLOUD) ? c->cloud.p : nullptr, cap);
       c->launches++;
       STAGE_END(c, ST_TRI);
       cudaEventRecord(c->ev_join[1], c->stream);
@@ -567,6 +600,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       }
       if (om & MVO_OUT_POINTS3D)
         MVO_CUDA_TRY(c, copy_rows_d2h(hout + L.x4, r.X4.p, (size_t)cap * 4, (size_t)r.max_pts * 4, (size_t)B * 4, c->stream));
+      if (om & MVO_OUT_CLOUD)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.cloud, c->cloud.p, (size_t)B * cap * 12, cudaMemcpyDeviceToHost, c->stream));
       STAGE_END(c, ST_TOTAL);
       cudaEventRecord(c->ev_tail, c->stream);
       if (om & MVO_OUT_KEYPOINTS) cudaStreamWaitEvent(c->stream, c->ev_out_orb, 0);
@@ -603,6 +638,7 @@ static int group_finish(mvo_ctx* c, int slot, mvo_frame_result* results) {
   MVO_CUDA_TRY(c, cudaEventSynchronize(sl.ev_done));
   memcpy(results, sl.h_res.p, (size_t)B * sizeof(mvo_frame_result));
   c->out_slot = slot;
+  c->occ_from_group = true;
   int flags0 = 0, first = -1;
   for (int b = 0; b < B; ++b) {
     if (sl.h_flags.p[b] && first < 0) first = b;
@@ -700,6 +736,7 @@ int mvo_group_output_bytes(mvo_ctx* c, size_t* bytes) {
   if (om & MVO_OUT_TRACKS) n += B * cap * 13;
   if (om & MVO_OUT_MODELS) n += B * cap * 4 + B * 27 * 8;
   if (om & MVO_OUT_POINTS3D) n += B * cap * 16;
+  if (om & MVO_OUT_CLOUD) n += B * cap * 12;
   *bytes = n;
   return MVO_OK;
 }
@@ -719,6 +756,10 @@ int mvo_group_outputs(mvo_ctx* c, int stream, mvo_stream_outputs* out) {
   memset(out, 0, sizeof(*out));
   out->n_keypoints = r.n_keypoints;
   out->flags = sl.h_flags.p[stream];
+  if (sl.h_occ.p) {
+    out->occupied_cells = sl.h_occ.p[2 * stream];
+    out->total_cells = sl.h_occ.p[2 * stream + 1];
+  }
   if (!om || !h) return MVO_OK;
   if (om & MVO_OUT_KEYPOINTS) {
     out->keypoints = reinterpret_cast<const mvo_keypoint*>(h + L.kps) + b * cap;
@@ -747,6 +788,10 @@ int mvo_group_outputs(mvo_ctx* c, int stream, mvo_stream_outputs* out) {
   if (om & MVO_OUT_POINTS3D) {
     out->X4 = reinterpret_cast<const float*>(h + L.x4) + b * 4 * cap;
     out->x4_stride = (int64_t)cap;
+  }
+  if (om & MVO_OUT_CLOUD) {
+    out->cloud_xyz = reinterpret_cast<const float*>(h + L.cloud) + b * cap * 3;
+    out->n_cloud = r.n_triangulated;
   }
   return MVO_OK;
 }

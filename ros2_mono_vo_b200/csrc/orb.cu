@@ -45,6 +45,7 @@ constexpr int FS = 68;                   // score row stride
 #define MVO_ORB_MINB 6   // 40 registers, no spills, 6 CTAs / SM (5: 48 registers, 3 % slower; 7: spills)
 #endif
 constexpr int kLevelThreads = 256;
+constexpr int kGridMaxCells = 8192;      // occupancy bitmap of orb_finalize_kernel (1 KB of shared memory)
 constexpr int kFastCols = (TW + 8) / 4;  // 18 aligned 4-pixel groups cover x = -4 .. TW+3
 constexpr int kFastLanes = kLevelThreads / kFastCols;  // 14 row lanes
 constexpr int kHSegs = 3;                               // row segments of the horizontal resize pass
@@ -598,10 +599,15 @@ __global__ void __launch_bounds__(1024)
 orb_finalize_kernel(const __grid_constant__ OrbGeom g, const unsigned long long* __restrict__ key_sorted,
                     const float2* __restrict__ ra_sorted, const int32_t* __restrict__ c2_count,
                     mvo_keypoint* __restrict__ kps, float2* __restrict__ kp_xy, int32_t* __restrict__ kp_count,
-                    int32_t* __restrict__ flags) {
+                    int32_t* __restrict__ flags, int32_t* __restrict__ occ) {
   const int b = blockIdx.x;
   __shared__ int s_keep[kLevels], s_off[kLevels + 1];
+  __shared__ uint32_t s_grid[kGridMaxCells / 32];   // one bit per cell of the keypoint-distribution grid
+  __shared__ int s_occ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grid_cells = g.grid_rows * g.grid_cols;
+  for (int i = tid; i < kGridMaxCells / 32; i += blockDim.x) s_grid[i] = 0;
+  if (tid == 0) s_occ = 0;
   if (warp < kLevels) {
     const LevelGeom lv = g.lv[warp];
     const int m = c2_count[b * kLevels + warp];
@@ -647,6 +653,24 @@ orb_finalize_kernel(const __grid_constant__ OrbGeom g, const unsigned long long*
       kp.class_id = -1;
       kps[(long long)b * g.kp_cap + o] = kp;
       kp_xy[(long long)b * g.kp_cap + o] = make_float2(kp.x, kp.y);
+      if (g.grid_div > 0) {
+        // int r = obs.keypoint.pt.y / occupancy_grid_div_, c = obs.keypoint.pt.x / occupancy_grid_div_ (float / int)
+        const int r = (int)__fdiv_rn(kp.y, (float)g.grid_div), cc = (int)__fdiv_rn(kp.x, (float)g.grid_div);
+        const int cell = r * g.grid_cols + cc;     // grid.at<uchar>(r, c) of a continuous rows x cols Mat
+        if (cell >= 0 && cell < grid_cells) atomicOr(&s_grid[cell >> 5], 1u << (cell & 31));
+      }
+    }
+  }
+  if (occ) {
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < kGridMaxCells / 32; i += blockDim.x) cnt += __popc(s_grid[i]);
+    cnt = warp_sum(cnt);
+    if (lane == 0 && cnt) atomicAdd(&s_occ, cnt);
+    __syncthreads();
+    if (tid == 0) {
+      occ[b * 2] = g.grid_div > 0 ? s_occ : -1;
+      occ[b * 2 + 1] = grid_cells;
     }
   }
 }
@@ -735,6 +759,22 @@ orb_brief_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ 
 
 // ================================================================================================
 // host side
+// keypoint-distribution grid of Initializer::good_keypoint_distribution (src/initializer.cpp:57-58)
+void orb_set_grid(mvo_ctx* c, int w, int h) {
+  OrbGeom& g = c->geom;
+  const int div = c->occupancy_div;
+  g.grid_div = 0;
+  g.grid_rows = g.grid_cols = 0;
+  if (div > 0 && w > 0 && h > 0) {
+    const int rows = h / div, cols = w / div;
+    if (rows > 0 && cols > 0 && rows * cols <= kGridMaxCells) {
+      g.grid_div = div;
+      g.grid_rows = rows;
+      g.grid_cols = cols;
+    }
+  }
+}
+
 static int build_geometry(mvo_ctx* c, int w, int h, std::vector<uint32_t>& xt, std::vector<uint32_t>& yt) {
   OrbGeom& g = c->geom;
   const int n = c->cfg.nfeatures;
@@ -812,6 +852,7 @@ static int build_geometry(mvo_ctx* c, int w, int h, std::vector<uint32_t>& xt, s
   g.nfeatures = n;
   g.batch = c->cfg.batch;
   g.kp_cap = n + n / 4 + 64;
+  orb_set_grid(c, w, h);
   return MVO_OK;
 }
 
@@ -853,6 +894,7 @@ int orb_prepare(mvo_ctx* c, int w, int h) {
   MVO_CUDA_TRY(c, c->kp_valid.alloc(B * g.kp_cap));
   MVO_CUDA_TRY(c, c->kp_count.alloc(B));
   MVO_CUDA_TRY(c, c->flags.alloc(B));
+  MVO_CUDA_TRY(c, c->occ.alloc(B * 2));
   MVO_CUDA_TRY(c, cudaMemsetAsync(c->pyr.p, 0, B * g.frame_stride, c->stream));
   MVO_CUDA_TRY(c, cudaMemsetAsync(c->blur.p, 0, B * g.frame_stride, c->stream));
   c->geom_w = w;
@@ -1006,7 +1048,7 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
     c->launches++;
   }
   orb_finalize_kernel<<<g.batch, 1024, 0, c->stream>>>(g, c->c2_key_sorted.p, c->c2_ra_sorted.p, c->c2_count.p,
-                                                      c->kps.p, c->kp_xy.p, c->kp_count.p, c->flags.p);
+                                                      c->kps.p, c->kp_xy.p, c->kp_count.p, c->flags.p, c->occ.p);
   c->launches++;
   {
     // IC angle of the surviving keypoints, then (want_desc) their rBRIEF descriptors

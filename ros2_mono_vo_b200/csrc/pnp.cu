@@ -95,7 +95,10 @@ pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* 
 
 // One warp per hypothesis (epnp_solve_warp, pnp_math.cuh).
 constexpr int kEpnpWarps = 2;
-__global__ void __launch_bounds__(kEpnpWarps * 32)
+#ifndef MVO_EPNP_MINB
+#define MVO_EPNP_MINB 6   // 168 registers: 12 instead of 8 resident warps per SM (batched tracking step 4.35 -> 3.85 ms; 8 blocks / 128 registers loses again)
+#endif
+__global__ void __launch_bounds__(kEpnpWarps * 32, MVO_EPNP_MINB)
 pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, int max_pts,
                 const int32_t* __restrict__ subsets, int iters, double* __restrict__ models, int32_t* __restrict__ ok) {
   __shared__ double s_A[kEpnpWarps][144], s_V[kEpnpWarps][144];
