@@ -316,6 +316,18 @@ MVO_API int mvo_group_get_tracks(mvo_ctx* ctx, int stream, float* xy, int32_t* s
                                  int* n_tracked, int* n_inliers);
 
 /* ------------------------------------------------------------------------------------------------
+ * device-resident caches of the synchronous single-call path.  The reference gathers the same N x 32
+ * descriptor block before every match (src/frame.cpp:50-64, src/keyframe.cpp:78-92) and tracks every frame against the
+ * image that was the "next" image of the previous call (src/tracker.cpp:68-69, :331); both are recognised BY CONTENT
+ * (64-bit hash of the host buffer, so a modified or re-allocated buffer can never alias a stale device copy):
+ *   - descriptors returned by mvo_orb_detect_and_compute and blocks uploaded by mvo_knn_ratio / mvo_knn2 stay on the
+ *     device (4 most recently used blocks); a later match on the same content skips the upload;
+ *   - mvo_lk_track keeps both pyramids; an image whose pyramid is still resident is neither uploaded nor rebuilt.
+ * stats: descriptor hits, descriptor misses, pyramid hits, pyramid misses since mvo_create.
+ * mvo_debug_set("cache", 0) switches both caches off (A/B aid). */
+MVO_API int mvo_cache_stats(mvo_ctx* ctx, uint64_t stats[4]);
+
+/* ------------------------------------------------------------------------------------------------
  * by-products that save the reference's host loops.
  *
  * Keypoint-distribution grid == Initializer::good_keypoint_distribution (src/initializer.cpp:52-75): a grid of

@@ -263,6 +263,12 @@ class Context:
         self._check(self.lib.mvo_group_collect(self.h, _ptr(res)))
         return res
 
+    def cache_stats(self) -> dict:
+        """Hits / misses of the content-keyed device caches (descriptor blocks, LK pyramids) since creation."""
+        v = (C.c_uint64 * 4)()
+        self._check(self.lib.mvo_cache_stats(self.h, v))
+        return {"desc_hits": int(v[0]), "desc_misses": int(v[1]), "pyr_hits": int(v[2]), "pyr_misses": int(v[3])}
+
     # ---- SURVEY 8(f) #4 by-products -------------------------------------------------------------
     def set_occupancy_grid(self, grid_div: int):
         """Cell size of the keypoint-distribution grid (Initializer::good_keypoint_distribution); 0 = off."""

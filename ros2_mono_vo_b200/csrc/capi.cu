@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" entry points of libmonovo_b200.so (context, ORB, kNN).  See include/monovo_b200.h.
 #include "context.cuh"
+#include "host_hash.hpp"
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -181,6 +182,8 @@ int mvo_batch(const mvo_ctx* c) { return c ? c->cfg.batch : 0; }
 uint64_t mvo_launch_count(const mvo_ctx* c) { return c ? c->launches : 0; }
 int mvo_orb_num_levels(void) { return kLevels; }
 
+static int desc_cache_put_device(mvo_ctx* c, const uint8_t* host_copy, const uint8_t* dev, int n);
+
 // ------------------------------------------------------------------------------------------------
 int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels,
                                mvo_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
@@ -229,6 +232,8 @@ int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int
   memcpy(kps, hs + 64, (size_t)n * sizeof(mvo_keypoint));
   if (desc) memcpy(desc, hs + 64 + kb, (size_t)n * 32);
   *n_out = n;
+  // the descriptors stay on the device under their content hash: a find_matches on this block does not upload it again
+  if (desc) return desc_cache_put_device(c, desc, c->desc.p, n);
   return MVO_OK;
 }
 
@@ -298,20 +303,82 @@ int mvo_orb_get_fast(mvo_ctx* c, int level, uint32_t* xy, int32_t* score, int ca
 }
 
 // ------------------------------------------------------------------------------------------------
+// ---- descriptor cache: content-keyed device copies of N x 32 blocks (least recently used of kDescCache replaced) ----
+static DescCacheEntry* desc_cache_find(mvo_ctx* c, uint64_t hash, int n) {
+  for (auto& e : c->dcache)
+    if (e.hash == hash && e.n == n && hash) {
+      e.stamp = ++c->dcache_clock;
+      return &e;
+    }
+  return nullptr;
+}
+static DescCacheEntry* desc_cache_victim(mvo_ctx* c) {
+  DescCacheEntry* v = &c->dcache[0];
+  for (auto& e : c->dcache)
+    if (e.stamp < v->stamp) v = &e;
+  return v;
+}
+// the block produced by detect_and_compute stays on the device under the hash of the copy handed to the caller
+static int desc_cache_put_device(mvo_ctx* c, const uint8_t* host_copy, const uint8_t* dev, int n) {
+  if (!c->cache_enabled || n <= 0) return MVO_OK;
+  const uint64_t hash = content_hash(host_copy, (size_t)n * 32);
+  if (desc_cache_find(c, hash, n)) return MVO_OK;
+  DescCacheEntry* e = desc_cache_victim(c);
+  e->hash = 0;
+  MVO_CUDA_TRY(c, e->buf.alloc((size_t)n * 32));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(e->buf.p, dev, (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream));
+  e->hash = hash;
+  e->n = n;
+  e->stamp = ++c->dcache_clock;
+  return MVO_OK;
+}
+// device pointer of a host descriptor block: the cached copy when its content is known, else upload (and remember)
+static int desc_cache_get(mvo_ctx* c, const uint8_t* host, int n, const uint8_t** dev, mvo::DevBuf<uint8_t>& fallback) {
+  if (n <= 0) {
+    MVO_CUDA_TRY(c, fallback.alloc(32));
+    *dev = fallback.p;
+    return MVO_OK;
+  }
+  if (!c->cache_enabled) {
+    MVO_CUDA_TRY(c, fallback.alloc((size_t)n * 32));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(fallback.p, host, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    *dev = fallback.p;
+    return MVO_OK;
+  }
+  const uint64_t hash = content_hash(host, (size_t)n * 32);
+  if (DescCacheEntry* e = desc_cache_find(c, hash, n)) {
+    c->cache_stats[0]++;
+    *dev = e->buf.p;
+    return MVO_OK;
+  }
+  c->cache_stats[1]++;
+  DescCacheEntry* e = desc_cache_victim(c);
+  e->hash = 0;
+  MVO_CUDA_TRY(c, e->buf.alloc((size_t)n * 32));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(e->buf.p, host, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+  e->hash = hash;
+  e->n = n;
+  e->stamp = ++c->dcache_clock;
+  *dev = e->buf.p;
+  return MVO_OK;
+}
+
 static int knn_host(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, double ratio) {
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
-  MVO_CUDA_TRY(c, c->knn_q.alloc((size_t)std::max(nq, 1) * 32));
-  MVO_CUDA_TRY(c, c->knn_t.alloc((size_t)std::max(nt, 1) * 32));
   MVO_CUDA_TRY(c, c->knn_counts.alloc(2));
-  if (nq) MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
-  if (nt) MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
-  int rc = ensure_stage(c, 64);
+  const uint8_t *qd = nullptr, *td = nullptr;
+  int rc = desc_cache_get(c, q, nq, &qd, c->knn_q);
+  if (rc) return rc;
+  rc = desc_cache_get(c, t, nt, &td, c->knn_t);     // the query entry was just stamped: it is not the victim
+  if (rc) return rc;
+  rc = ensure_stage(c, 64);
+  if (rc) return rc;
   if (rc) return rc;
   int* hc = reinterpret_cast<int*>(c->h_stage.p);
   hc[0] = nq;
   hc[1] = nt;
   MVO_CUDA_TRY(c, cudaMemcpyAsync(c->knn_counts.p, hc, 8, cudaMemcpyHostToDevice, c->stream));
-  return knn_run(c, c->knn_q.p, c->knn_counts.p, std::max(nq, 1), std::max(nq, 1), c->knn_t.p, c->knn_counts.p + 1,
+  return knn_run(c, qd, c->knn_counts.p, std::max(nq, 1), std::max(nq, 1), td, c->knn_counts.p + 1,
                  std::max(nt, 1), std::max(nt, 1), ratio, 1);
 }
 
@@ -356,6 +423,13 @@ int mvo_knn2(mvo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int
       idx[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key & 0x3FFFFFu);
       dist[2 * i + k] = key == 0xFFFFFFFFu ? -1 : (int)(key >> 22);
     }
+  return MVO_OK;
+}
+
+// ---- cache statistics ------------------------------------------------------------------
+int mvo_cache_stats(mvo_ctx* c, uint64_t stats[4]) {
+  if (!c || !stats) return MVO_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) stats[i] = c->cache_stats[i];
   return MVO_OK;
 }
 

@@ -103,6 +103,15 @@ struct OutLayout {
   uint32_t mask_bits = 0;
 };
 
+// Device-resident copy of a descriptor block (N x 32 bytes) keyed by its content: FeatureProcessor::find_matches is
+// always called on blocks that were just produced by detect_and_compute or gathered again from the same observations
+// (src/frame.cpp:50-64, src/keyframe.cpp:78-92, src/tracker.cpp:190-201) -- they do not have to cross PCIe again.
+struct DescCacheEntry {
+  uint64_t hash = 0, stamp = 0;
+  int n = 0;
+  mvo::DevBuf<uint8_t> buf;
+};
+
 struct mvo_ctx {
   mvo_config cfg{};
   cudaStream_t stream = nullptr;     // the stream host code currently issues on (main stream, or an aux stream inside a fork)
@@ -203,6 +212,14 @@ struct mvo_ctx {
   bool occ_from_group = false;         // mvo_orb_occupancy answers from the last collected group step
   mvo::DevBuf<float> cloud;            // group step: batch * cap * 3 packed ROS-axis points (MVO_OUT_CLOUD)
   mvo::DevBuf<uint8_t> pack_tmp;       // mvo_pack_pointcloud staging
+  // ---- device-resident caches of the synchronous single-call path ----
+  static constexpr int kDescCache = 4;
+  DescCacheEntry dcache[kDescCache];
+  uint64_t dcache_clock = 0;
+  uint64_t lk_hash[2] = {0, 0};        // content hash of the image each LK pyramid slot was built from (0: none)
+  int lk_slot_prev = 0, lk_slot_next = 1;   // slots the last mvo_lk_track call used (mvo_lk_get_level's which = 0 / 1)
+  uint64_t cache_stats[4] = {0, 0, 0, 0};   // descriptor hits / misses, pyramid hits / misses
+  int cache_enabled = 1;               // mvo_debug_set("cache", 0) switches both caches off
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
   int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel
 

@@ -363,6 +363,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   const int B = c->cfg.batch;
   c->trk_have_frame = false;   // the tracking-frame chain (mvo_group_track) does not survive a front-end step
+  c->lk_hash[0] = c->lk_hash[1] = 0;   // ... nor does the single-call pyramid cache (the LK pyramids are rewritten)
   int rc = orb_prepare(c, w, h);
   if (rc) return rc;
   const OrbGeom& g = c->geom;
@@ -860,6 +861,7 @@ int mvo_group_track(mvo_ctx* c, const uint8_t* images, int w, int h, int stride,
   const int B = c->cfg.batch;
   c->stream = c->main_stream;
   c->have_prev = false;   // the front-end chain (mvo_group_step) does not survive a tracking frame
+  c->lk_hash[0] = c->lk_hash[1] = 0;
   int rc = track_prepare(c, w, h);
   if (rc) return rc;
   const int cap = c->trk_cap;
@@ -995,6 +997,11 @@ int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   if (strcmp(key, "lk_impl") == 0) c->dbg_lk_impl = value;
   else if (strcmp(key, "knn_impl") == 0) c->dbg_knn_impl = value;
   else if (strcmp(key, "h_refine_impl") == 0) c->dbg_h_refine_impl = value;
+  else if (strcmp(key, "cache") == 0) {
+    c->cache_enabled = value;
+    for (auto& e : c->dcache) e.hash = 0;
+    c->lk_hash[0] = c->lk_hash[1] = 0;
+  }
   else {
     c->set_error("mvo_debug_set: unknown key");
     return MVO_ERR_INVALID;

@@ -13,6 +13,7 @@
 //                      <= 30 Gauss-Newton iterations sampling J from a 32x32 smem region (texture-free
 //                      bilinear), re-staged only when the window leaves it.
 #include "context.cuh"
+#include "host_hash.hpp"
 #include <cuda.h>
 #include <algorithm>
 #include <stdlib.h>
@@ -1363,7 +1364,8 @@ extern "C" int mvo_lk_get_level(mvo_ctx* c, int which, int level, int plane, uin
   if (h) *h = lv.h;
   if (!out) return MVO_OK;
   if (out_stride < lv.w) return MVO_ERR_INVALID;
-  MVO_CUDA_TRY(c, cudaMemcpy2DAsync(out, out_stride, c->lk_pyr[which].p + (size_t)plane * g.frame_stride + lv.off, lv.pitch, lv.w,
+  const int slot = which == 0 ? c->lk_slot_prev : c->lk_slot_next;   // the pyramid cache may have swapped the slots
+  MVO_CUDA_TRY(c, cudaMemcpy2DAsync(out, out_stride, c->lk_pyr[slot].p + (size_t)plane * g.frame_stride + lv.off, lv.pitch, lv.w,
                                     lv.h, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return MVO_OK;
@@ -1391,18 +1393,43 @@ extern "C" int mvo_lk_track(mvo_ctx* c, const uint8_t* prev, const uint8_t* next
   }
   MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
   if (n == 0) return MVO_OK;
-  // both ping-pong pyramids are rebuilt below: the group entry points must not take them for their previous frame
+  // the ping-pong pyramids are (re)built below: the group entry points must not take them for their previous frame
   c->have_prev = false;
   c->trk_have_frame = false;
+  if (c->lk_w != w || c->lk_h != h || c->lk_cn != channels || c->lk_max_pts < n) c->lk_hash[0] = c->lk_hash[1] = 0;
   int rc = lk_prepare(c, w, h, std::max(n, c->lk_max_pts), channels);
   if (rc) return rc;
-  rc = lk_build_pyramid(c, 0, prev, stride, 0);
-  if (rc) return rc;
-  rc = lk_build_pyramid(c, 1, next, stride, 0);
-  if (rc) return rc;
+  // Pyramid cache: the tracker's "prev" image is the "next" image of its previous call
+  // (/root/reference/src/tracker.cpp:68-69, :331) in a fresh buffer, so a pyramid slot is recognised by the content
+  // hash of the image it was built from: a resident image is neither uploaded nor reduced again.
+  int sp = 0, sn = 1;
+  uint64_t hp = 0, hn = 0;
+  if (c->cache_enabled) {
+    hp = content_hash_rows(prev, h, (size_t)w * channels, (size_t)stride);
+    hn = content_hash_rows(next, h, (size_t)w * channels, (size_t)stride);
+    if (hp == c->lk_hash[1]) sp = 1, sn = 0;
+    else if (hp != c->lk_hash[0] && hn == c->lk_hash[0]) sp = 1, sn = 0;
+  }
+  const bool have_p = c->cache_enabled && c->lk_hash[sp] == hp, have_n = c->cache_enabled && c->lk_hash[sn] == hn && hn != hp;
+  c->cache_stats[2] += (have_p ? 1 : 0) + (have_n ? 1 : 0);
+  c->cache_stats[3] += (have_p ? 0 : 1) + (have_n ? 0 : 1);
+  if (!have_p) {
+    c->lk_hash[sp] = 0;
+    rc = lk_build_pyramid(c, sp, prev, stride, 0);
+    if (rc) return rc;
+    c->lk_hash[sp] = hp;
+  }
+  if (!have_n) {
+    c->lk_hash[sn] = 0;
+    rc = lk_build_pyramid(c, sn, next, stride, 0);
+    if (rc) return rc;
+    c->lk_hash[sn] = hn;
+  }
+  c->lk_slot_prev = sp;
+  c->lk_slot_next = sn;
   MVO_CUDA_TRY(c, cudaMemcpyAsync(c->lk_pts_in.p, prev_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(c->lk_npts.p, &n, 4, cudaMemcpyHostToDevice, c->stream));
-  rc = lk_run(c, 0, 1, c->lk_pts_in.p, c->lk_npts.p, c->lk_max_pts, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
+  rc = lk_run(c, sp, sn, c->lk_pts_in.p, c->lk_npts.p, c->lk_max_pts, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
   if (rc) return rc;
   MVO_CUDA_TRY(c, cudaMemcpyAsync(next_xy, c->lk_pts_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   MVO_CUDA_TRY(c, cudaMemcpyAsync(status, c->lk_status.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
