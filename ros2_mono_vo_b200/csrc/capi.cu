@@ -165,7 +165,7 @@ void mvo_destroy(mvo_ctx* c) {
   c->prev_kp_count.release(); c->kp_xy.release(); c->prev_kp_xy.release(); c->d_results.release(); c->knn_q.release(); c->knn_t.release(); c->knn_best.release();
   c->knn_matches.release(); c->knn_nmatch.release(); c->knn_counts.release();
   c->lk_pyr[0].release(); c->lk_pyr[1].release(); c->lk_pts_in.release(); c->lk_pts_out.release();
-  c->lk_status.release(); c->lk_err.release(); c->lk_npts.release();
+  c->lk_status.release(); c->lk_err.release(); c->lk_npts.release(); c->lk_work.release();
   c->rs.release();
   c->pnp.release();
   for (auto& t : c->timers) {

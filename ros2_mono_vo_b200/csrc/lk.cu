@@ -713,16 +713,20 @@ __device__ __noinline__ int3 lk_restage(LkWarpSmem2& sm, const CUtensorMap* map,
 #endif
 constexpr int kLk2Warps = MVO_LK2_WARPS;
 
+// PERSIST: the grid is a fixed number of resident CTAs and every warp draws points (work items: the points of all
+// streams, stream-major) from a global counter until none is left.  Points differ in their iteration counts and a CTA
+// stays resident until its slowest warp is done, so with one point per warp the achieved occupancy was 23 % of a
+// theoretical 31 %; drawing work keeps every warp slot busy to the end of the kernel.
+constexpr int kLk2MaxBatch = 1024;   // streams of a group the persistent form indexes (larger groups: one point per warp)
+template <bool PERSIST>
 __global__ void __launch_bounds__(kLk2Warps * 32, MVO_LK2_MINB)
 lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTmaps tm, const uint8_t* __restrict__ pyrI,
                  const uint8_t* __restrict__ pyrJ, const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev,
-                 int max_pts, float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+                 int max_pts, float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err,
+                 int* __restrict__ work_counter, int batch) {
   __shared__ LkWarpSmem2 sm_all[kLk2Warps];
-  const int b = blockIdx.y;
-  const int n = min(npts_dev[b], max_pts);
+  __shared__ int s_cum[PERSIST ? kLk2MaxBatch + 1 : 1];   // s_cum[b] = points of the streams before b
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * kLk2Warps + warp;
-  if (i >= n) return;
   LkWarpSmem2& sm = sm_all[warp];
   if (lane == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -730,10 +734,19 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  if (PERSIST) {
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int q = 0; q < batch; ++q) {
+        s_cum[q] = acc;
+        acc += min(npts_dev[q], max_pts);
+      }
+      s_cum[batch] = acc;
+    }
+    __syncthreads();
+  }
+  const int total_items = PERSIST ? s_cum[batch] : 0;
   uint32_t parI = 0, parJ = 0;
-  const float2 p0 = pts[(long long)b * max_pts + i];
-  float nx = 0.f, ny = 0.f, e = 0.f;
-  int st = 1;
   const float flt_scale = 1.f / (1 << 20);
   // the two runs of this lane: run -> (column c, row third rseg); lane 31 has no second run
   const int c0 = lane / 3, r0s = lane - 3 * c0;
@@ -743,6 +756,29 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
   const int qoff0 = (kRunLen * r0s) * kJW + c0, qoff1 = (kRunLen * r1s) * kJW + c1;
   uint32_t* const txl = sm.tx + lane;
   int32_t* const til = sm.ti + lane;
+  for (;;) {
+  int b, i;
+  if (PERSIST) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total_items) break;
+    int lo = 0, hi = batch;                 // largest b with s_cum[b] <= item
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_cum[mid] <= item) lo = mid;
+      else hi = mid;
+    }
+    b = lo;
+    i = item - s_cum[b];
+  } else {
+    b = blockIdx.y;
+    i = blockIdx.x * kLk2Warps + warp;
+    if (i >= min(npts_dev[b], max_pts)) return;
+  }
+  const float2 p0 = pts[(long long)b * max_pts + i];
+  float nx = 0.f, ny = 0.f, e = 0.f;
+  int st = 1;
 
   // template tile of a level: position and fast-path test depend on the input point only
   auto tmpl_pos = [&](int L, int& ix, int& iy, float& qx, float& qy) {
@@ -961,6 +997,9 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     status[o] = (uint8_t)st;
     err[o] = e;
   }
+  if (!PERSIST) break;
+  __syncwarp();
+  }   // work loop
 }
 
 // ---- multi-channel windows (the node feeds BGR8: /root/reference/src/mono_vo.cpp:94, src/tracker.cpp:68) -------
@@ -1338,8 +1377,19 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
         LkTmaps tm;
         memcpy(tm.m[0], c->lk_tmaps[prev_which][0], sizeof(tm.m[0]));
         memcpy(tm.m[1], c->lk_tmaps[next_which][1], sizeof(tm.m[1]));
-        lk_track2_kernel<<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
-            g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
+        const long long items = (long long)max_pts * c->cfg.batch;
+        if (c->dbg_lk_impl == 3 || items < 148LL * MVO_LK2_MINB * kLk2Warps * 4 || c->cfg.batch > kLk2MaxBatch) {
+          // few points (single stream): one point per warp fills the GPU better than a persistent grid
+          lk_track2_kernel<false><<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
+              g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
+              nullptr, c->cfg.batch);
+        } else {
+          MVO_CUDA_TRY(c, c->lk_work.alloc(1));
+          MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 4, c->stream));
+          lk_track2_kernel<true><<<dim3(148 * MVO_LK2_MINB, 1), kLk2Warps * 32, 0, c->stream>>>(
+              g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
+              c->lk_work.p, c->cfg.batch);
+        }
       }
     }
     c->launches++;
