@@ -29,8 +29,13 @@ mvo_ctx* context(int min_width, int min_height, int nfeatures) {
   State& s = state();
   std::lock_guard<std::mutex> lock(s.mu);
   const int want_n = nfeatures > 0 ? nfeatures : (s.nfeatures > 0 ? s.nfeatures : 1000);
-  const int want_w = std::max({min_width, s.w, 64}), want_h = std::max({min_height, s.h, 64});
-  if (s.ctx && want_w == s.w && want_h == s.h && want_n == s.nfeatures) return s.ctx;
+  // max_width / max_height are limits the library checks image sizes against, not allocation sizes: the ABI's maximum,
+  // so a larger image never replaces the context (and with it the cached pyramids / descriptor blocks).  Only a
+  // different ORB feature count (a second cv::ORB::create(n) with another n) builds a new one.
+  (void)min_width;
+  (void)min_height;
+  const int want_w = 16384, want_h = 16384;
+  if (s.ctx && want_n == s.nfeatures) return s.ctx;
   if (s.ctx) {
     s.launches_retired += mvo_launch_count(s.ctx);
     mvo_destroy(s.ctx);

@@ -19,7 +19,7 @@
 #include <rclcpp/logging.hpp>
 #endif
 
-struct mvo_ctx;
+#include "monovo_b200.h"   // mvo_ctx, mvo_keypoint (the scratch members below)
 
 namespace mono_vo
 {
@@ -50,7 +50,7 @@ public:
 
   /// The stream context (for the geometry / LK entry points in mono_vo/gpu_cv.hpp); created on first use.
   mvo_ctx * context(int width, int height) const;
-  /// The current context (sized for the images seen so far); for call sites that have no image at hand.
+  /// The same context; for call sites that have no image at hand.
   mvo_ctx * context() const;
 
 private:
@@ -58,5 +58,9 @@ private:
   rclcpp::Logger logger_;
   mutable mvo_ctx * ctx_ = nullptr;
   mutable int ctx_w_ = 0, ctx_h_ = 0;
+  // capacity-sized staging of detect / detect_and_compute (methods are const like the reference's: mutable scratch;
+  // like the reference's cv::Ptr<cv::ORB>, one FeatureProcessor is used from one thread)
+  mutable std::vector<mvo_keypoint> kp_scratch_;
+  mutable std::vector<unsigned char> desc_scratch_;
 };
 }  // namespace mono_vo

@@ -30,13 +30,16 @@ FeatureProcessor::~FeatureProcessor()
 
 mvo_ctx * FeatureProcessor::context(int width, int height) const
 {
-  if (ctx_ && width <= ctx_w_ && height <= ctx_h_) return ctx_;
-  if (ctx_) mvo_destroy(ctx_);
-  ctx_ = nullptr;
+  (void)width;
+  (void)height;
+  if (ctx_) return ctx_;
+  // One context for the life of the node.  max_width / max_height are only the limits the library checks image
+  // sizes against (its buffers are sized for the images that actually arrive), so they are set to the ABI's maximum:
+  // a larger image never destroys and re-creates the context (and with it the cached pyramids / descriptor blocks).
   mvo_config cfg{};
   cfg.device = 0;
-  cfg.max_width = std::max(width, ctx_w_);
-  cfg.max_height = std::max(height, ctx_h_);
+  cfg.max_width = 16384;
+  cfg.max_height = 16384;
   cfg.nfeatures = num_features_;
   cfg.batch = 1;
   if (mvo_create(&ctx_, &cfg) != MVO_OK) fail(nullptr, "FeatureProcessor: mvo_create");
@@ -47,7 +50,7 @@ mvo_ctx * FeatureProcessor::context(int width, int height) const
 
 mvo_ctx * FeatureProcessor::context() const
 {
-  return context(std::max(ctx_w_, 64), std::max(ctx_h_, 64));
+  return context(0, 0);
 }
 
 std::vector<cv::KeyPoint> FeatureProcessor::detect(const cv::Mat & image) const
@@ -55,7 +58,8 @@ std::vector<cv::KeyPoint> FeatureProcessor::detect(const cv::Mat & image) const
   std::vector<cv::KeyPoint> keypoints;
   mvo_ctx * c = context(image.cols, image.rows);
   const int cap = num_features_ + num_features_ / 4 + 64;
-  std::vector<mvo_keypoint> kps(cap);
+  std::vector<mvo_keypoint> & kps = kp_scratch_;      // capacity-sized scratch lives with the object, not per call
+  kps.resize(cap);
   int n = 0;
   if (mvo_orb_detect_and_compute(c, image.data, image.cols, image.rows, static_cast<int>(image.step),
       image.channels(), kps.data(), nullptr, cap, &n) != MVO_OK) fail(c, "FeatureProcessor::detect");
@@ -72,11 +76,12 @@ void FeatureProcessor::detect_and_compute(
 {
   mvo_ctx * c = context(image.cols, image.rows);
   const int cap = num_features_ + num_features_ / 4 + 64;
-  std::vector<mvo_keypoint> kps(cap);
-  cv::Mat desc(cap, 32, CV_8UC1);
+  std::vector<mvo_keypoint> & kps = kp_scratch_;
+  kps.resize(cap);
+  desc_scratch_.resize(static_cast<size_t>(cap) * 32);
   int n = 0;
   if (mvo_orb_detect_and_compute(c, image.data, image.cols, image.rows, static_cast<int>(image.step),
-      image.channels(), kps.data(), desc.data, cap, &n) != MVO_OK) fail(c, "FeatureProcessor::detect_and_compute");
+      image.channels(), kps.data(), desc_scratch_.data(), cap, &n) != MVO_OK) fail(c, "FeatureProcessor::detect_and_compute");
   keypoints.clear();
   keypoints.reserve(n);
   for (int i = 0; i < n; ++i) {
@@ -84,7 +89,15 @@ void FeatureProcessor::detect_and_compute(
     keypoints.emplace_back(cv::Point2f(k.x, k.y), k.size, k.angle, k.response, k.octave, k.class_id);
   }
   descriptors.create(n, 32, CV_8UC1);
-  for (int i = 0; i < n; ++i) std::copy(desc.ptr<unsigned char>(i), desc.ptr<unsigned char>(i) + 32, descriptors.ptr<unsigned char>(i));
+  if (n > 0) {
+    if (static_cast<size_t>(descriptors.step) == 32) {     // a fresh n x 32 CV_8UC1 Mat is dense: one copy
+      std::copy(desc_scratch_.begin(), desc_scratch_.begin() + static_cast<size_t>(n) * 32, descriptors.ptr<unsigned char>(0));
+    } else {
+      for (int i = 0; i < n; ++i)
+        std::copy(desc_scratch_.begin() + static_cast<size_t>(i) * 32, desc_scratch_.begin() + static_cast<size_t>(i + 1) * 32,
+                  descriptors.ptr<unsigned char>(i));
+    }
+  }
 }
 
 std::vector<cv::DMatch> FeatureProcessor::find_matches(
