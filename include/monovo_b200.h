@@ -353,7 +353,8 @@ MVO_API int mvo_pack_pointcloud(mvo_ctx* ctx, const float* points_xyz, int n, in
  *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels.
  * mvo_debug_time: re-runs one stage of the group pipeline `reps` times on the state left by the last mvo_group_step
  *                (at least two steps must have run) and returns the average device time per run in ms, measured with
- *                CUDA events on the context stream.  what = "lk_track" | "knn" | "orb" | "orb_dense" | "lk_pyramid".
+ *                CUDA events on the context stream.  what = "lk_track" | "knn" | "orb" | "orb_levels" (the eight fused
+ *                level kernels as a step launches them) | "orb_dense" (pyramid + blur only) | "lk_pyramid".
  */
 MVO_API int mvo_debug_set(mvo_ctx* ctx, const char* key, int value);
 MVO_API int mvo_debug_time(mvo_ctx* ctx, const char* what, int reps, float* ms);

@@ -98,6 +98,9 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
     for (int k = 0; k < 4; ++k)
       keep(cudaStreamCreateWithPriority(&c->aux_stream[k], cudaStreamNonBlocking, k == 2 ? prio_lo : prio_hi));
     keep(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    keep(cudaStreamCreateWithPriority(&c->lk_stream, cudaStreamNonBlocking, prio_lo));
+    keep(cudaEventCreateWithFlags(&c->ev_unpack, cudaEventDisableTiming));
+    keep(cudaEventCreateWithFlags(&c->ev_lk_done, cudaEventDisableTiming));
     keep(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
     for (auto& sl : c->slots) {
       keep(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
@@ -157,6 +160,12 @@ void mvo_destroy(mvo_ctx* c) {
   for (auto& ev : c->ev_join)
     if (ev) cudaEventDestroy(ev);
   if (c->ev_tail) cudaEventDestroy(c->ev_tail);
+  if (c->lk_stream) {
+    cudaStreamSynchronize(c->lk_stream);
+    cudaStreamDestroy(c->lk_stream);
+  }
+  if (c->ev_unpack) cudaEventDestroy(c->ev_unpack);
+  if (c->ev_lk_done) cudaEventDestroy(c->ev_lk_done);
   c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
   c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->cand_sel.release(); c->sel_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();

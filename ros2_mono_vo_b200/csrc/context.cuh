@@ -119,6 +119,9 @@ struct mvo_ctx {
   cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // group step: F, E(+pose), kNN, H + tail
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_tail = nullptr;       // all model searches + the result gather of the latest enqueued step are done
+  cudaStream_t lk_stream = nullptr;    // group step: LK pyramid + tracker + correspondence list (runs beside ORB)
+  cudaEvent_t ev_unpack = nullptr;     // main stream: level 0 of the new frame's ORB and LK pyramids is written
+  cudaEvent_t ev_lk_done = nullptr;    // LK stream: the tracker of the latest enqueued step has read both pyramids
   bool own_stream = false;
   static constexpr int kSlots = 2;
   cudaStream_t copy_stream = nullptr;  // H2D of staged frames
@@ -247,6 +250,7 @@ int orb_prepare(mvo_ctx* c, int w, int h);
 void orb_set_grid(mvo_ctx* c, int w, int h);
 int orb_upload(mvo_ctx* c, const uint8_t* img, int w, int h, int stride, int channels, int on_device);
 int orb_run_detect(mvo_ctx* c, bool want_desc);
+int orb_run_levels_fast(mvo_ctx* c);
 int orb_run_levels_only(mvo_ctx* c);
 int orb_run_brief_given(mvo_ctx* c, int n);
 

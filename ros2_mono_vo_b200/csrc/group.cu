@@ -444,7 +444,9 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     int lk_pitch = 0;
     long long lk_fs = 0;
     uint8_t* lk0 = lk_level0(c, c->lk_cur, &lk_pitch, &lk_fs);
-    // the LK pyramid about to be overwritten was read by the LK track of two steps ago and by nothing since
+    // The LK pyramid slot about to be overwritten is the "previous" pyramid of the last enqueued step's tracker, which
+    // runs on its own stream; the keypoint-position buffer ORB is about to fill is that tracker's input as well.
+    cudaStreamWaitEvent(c->main_stream, c->ev_lk_done, 0);
     if (cn == 1) {
       dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
       unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride,
@@ -456,93 +458,61 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     }
     c->launches++;
     if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
+    cudaEventRecord(c->ev_unpack, c->main_stream);
   }
-  // the keypoint / descriptor buffers ORB is about to fill were the previous step's "prev" set: its kNN must be done
-  cudaStreamWaitEvent(c->main_stream, c->ev_join[2], 0);
-  rc = orb_run_detect(c, true);
-  if (rc) return rc;
-  {
-    GroupSlot& sl = c->slots[slot];
-    MVO_CUDA_TRY(c, sl.h_res.alloc(B));
-    MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-    MVO_CUDA_TRY(c, sl.h_occ.alloc(2 * B));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_occ.p, c->occ.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (om && c->have_prev)
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.prev_count, c->prev_kp_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-  }
-  STAGE_END(c, ST_ORB);
-  cudaEventRecord(c->ev_fork[0], c->main_stream);
-  if (om & MVO_OUT_KEYPOINTS) {
-    // keypoints + descriptors of the new frame leave on the output stream while the step goes on
-    cudaEventRecord(c->ev_o_orb, c->main_stream);
-    cudaStreamWaitEvent(c->out_stream, c->ev_o_orb, 0);
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.kps, c->kps.p, (size_t)B * cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost,
-                                    c->out_stream));
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.desc, c->desc.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, c->out_stream));
-    cudaEventRecord(c->ev_out_orb, c->out_stream);
-  }
-
   const int cur = c->lk_cur, prev = cur ^ 1;
-  if (c->have_prev) {
-    // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
-    Fork f(c, c->aux_stream[2], 0, c->ev_fork[0]);
-    cudaStreamWaitEvent(c->stream, c->ev_tail, 0);   // the previous step's gather still reads the match counters
-    STAGE_BEG(c, ST_KNN);
-    rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
-    if (rc) return rc;
-    STAGE_END(c, ST_KNN);
-    cudaEventRecord(c->ev_join[2], c->stream);
-  }
-  // ---- LK pyramid of the new frame (level 0 = ORB level 0, device to device) ----
-  STAGE_BEG(c, ST_LK);
-  rc = lk_build_pyramid(c, cur, nullptr, 0, 3);   // level 0 was written by the unpack kernel
-  if (rc) return rc;
-  if (c->have_prev) {
-    cudaStreamWaitEvent(c->main_stream, c->ev_out_lk, 0);   // the previous step's track outputs have left the LK buffers
-    rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
-    if (rc) return rc;
-    // the correspondence buffers feed the model searches of the previous step until its tail is done; from here on
-    // this step's ORB + LK have overlapped them (software pipelining across the two steps in flight)
-    cudaStreamWaitEvent(c->main_stream, c->ev_tail, 0);
-    lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
-                                                 c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
-    c->launches++;
-    if (om & MVO_OUT_TRACKS) {
-      cudaEventRecord(c->ev_o_lk, c->main_stream);
-      cudaStreamWaitEvent(c->out_stream, c->ev_o_lk, 0);
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_xy, c->lk_pts_out.p, (size_t)B * cap * 8, cudaMemcpyDeviceToHost, c->out_stream));
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_status, c->lk_status.p, (size_t)B * cap, cudaMemcpyDeviceToHost, c->out_stream));
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_err, c->lk_err.p, (size_t)B * cap * 4, cudaMemcpyDeviceToHost, c->out_stream));
-      cudaEventRecord(c->ev_out_lk, c->out_stream);
-    }
-  }
-  STAGE_END(c, ST_LK);
-
+  // ---- LK pyramid of the new frame + tracker: needs the unpacked frame and the PREVIOUS frame's keypoints only, so it
+  // runs beside ORB(t) on its own stream -- for a single stream ORB -> LK -> searches was the critical path, now it is
+  // max(ORB, LK -> searches); in a group the small pyramid levels of ORB fill the tracker's tail and vice versa ----
+  int32_t *res_h = nullptr, *res_f = nullptr, *ntri = nullptr;
+  const int gb = (B + 127) / 128;
   if (c->have_prev) {
     // counts kept per stage
     MVO_CUDA_TRY(c, c->knn_counts.alloc((size_t)4 * B));
-    int32_t* res_h = c->knn_counts.p;
-    int32_t* res_f = res_h + B;
-    int32_t* ntri = res_f + B;
-    const int gb = (B + 127) / 128;
-    MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
-    fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.lane[0].thr2.p, 1.0f, r.K.p, B);   // + replicate K to every stream
-    c->launches++;
-    cudaEventRecord(c->ev_fork[1], c->main_stream);
-    {
-      // ---- F RANSAC (thr 1.0, conf 0.99), lane 1 ----
-      Fork f(c, c->aux_stream[0], 1, c->ev_fork[1]);
-      STAGE_BEG(c, ST_F);
-      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.ln().thr2.p, 1.0f, nullptr, B);
-      c->launches++;
-      rc = ransac_find(c, MVO_MODEL_F, 0.99);
+    res_h = c->knn_counts.p;
+    res_f = res_h + B;
+    ntri = res_f + B;
+  }
+  {
+    Fork f(c, c->lk_stream, 0, c->ev_unpack);
+    STAGE_BEG(c, ST_LK);
+    rc = lk_build_pyramid(c, cur, nullptr, 0, 3);   // level 0 was written by the unpack kernel
+    if (rc) return rc;
+    if (c->have_prev) {
+      cudaStreamWaitEvent(c->stream, c->ev_out_lk, 0);   // the previous step's track outputs have left the LK buffers
+      rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
       if (rc) return rc;
-      copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_f, B);
+      // the correspondence buffers feed the model searches of the previous step until its tail is done; from here on
+      // this step's ORB + LK have overlapped them (software pipelining across the two steps in flight)
+      cudaStreamWaitEvent(c->stream, c->ev_tail, 0);
+      lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
+                                                   c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
       c->launches++;
-      STAGE_END(c, ST_F);
-      cudaEventRecord(c->ev_join[0], c->stream);
+      if (om & MVO_OUT_TRACKS) {
+        cudaEventRecord(c->ev_o_lk, c->stream);
+        cudaStreamWaitEvent(c->out_stream, c->ev_o_lk, 0);
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_xy, c->lk_pts_out.p, (size_t)B * cap * 8, cudaMemcpyDeviceToHost, c->out_stream));
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_status, c->lk_status.p, (size_t)B * cap, cudaMemcpyDeviceToHost, c->out_stream));
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.lk_err, c->lk_err.p, (size_t)B * cap * 4, cudaMemcpyDeviceToHost, c->out_stream));
+        cudaEventRecord(c->ev_out_lk, c->out_stream);
+      }
     }
+    cudaEventRecord(c->ev_lk_done, c->stream);
+    STAGE_END(c, ST_LK);
+    if (c->have_prev) {
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.lane[0].thr2.p, 1.0f, r.K.p, B);   // + replicate K to every stream
+      c->launches++;
+      cudaEventRecord(c->ev_fork[1], c->stream);
+    }
+  }
+
+  // (the tracker is enqueued before ORB so that it starts as soon as the frame is unpacked, not after the host has
+  // issued the ORB launches)
+  // The model searches depend on the tracker only.  The essential-matrix chain is the longest dependency chain of a frame
+  // (5-point solver -> recoverPose -> triangulation), the homography chain the second longest: they are issued before
+  // the ~20 ORB launches so that a single stream does not wait for the host to get to them (F, the shortest, after ORB).
+  if (c->have_prev) {
     {
       // ---- E RANSAC (K, conf 0.99, thr 1.0) -> recoverPose -> triangulate + chirality, lane 2 ----
       Fork f(c, c->aux_stream[1], 2, c->ev_fork[1]);
@@ -573,7 +543,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       cudaEventRecord(c->ev_join[1], c->stream);
     }
     {
-      // ---- H RANSAC (thr 1.0), lane 0, then the join of all searches and the result gather: tail stream ----
+      // ---- H RANSAC (thr 1.0), lane 0, on the tail stream (the join of all searches follows there, further down) ----
       Fork f(c, c->aux_stream[3], 0, c->ev_fork[1]);
       STAGE_BEG(c, ST_H);
       rc = ransac_find(c, MVO_MODEL_H, 0.995);
@@ -581,6 +551,61 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_h, B);
       c->launches++;
       STAGE_END(c, ST_H);
+    }
+  }
+  // the keypoint / descriptor buffers ORB is about to fill were the previous step's "prev" set: its kNN must be done
+  cudaStreamWaitEvent(c->main_stream, c->ev_join[2], 0);
+  rc = orb_run_detect(c, true);
+  if (rc) return rc;
+  {
+    GroupSlot& sl = c->slots[slot];
+    MVO_CUDA_TRY(c, sl.h_res.alloc(B));
+    MVO_CUDA_TRY(c, sl.h_flags.alloc(B));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_flags.p, c->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, sl.h_occ.alloc(2 * B));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.h_occ.p, c->occ.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (om && c->have_prev)
+      MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.prev_count, c->prev_kp_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  STAGE_END(c, ST_ORB);
+  cudaEventRecord(c->ev_fork[0], c->main_stream);
+  if (om & MVO_OUT_KEYPOINTS) {
+    // keypoints + descriptors of the new frame leave on the output stream while the step goes on
+    cudaEventRecord(c->ev_o_orb, c->main_stream);
+    cudaStreamWaitEvent(c->out_stream, c->ev_o_orb, 0);
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.kps, c->kps.p, (size_t)B * cap * sizeof(mvo_keypoint), cudaMemcpyDeviceToHost,
+                                    c->out_stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hout + L.desc, c->desc.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, c->out_stream));
+    cudaEventRecord(c->ev_out_orb, c->out_stream);
+  }
+
+  if (c->have_prev) {
+    // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
+    Fork f(c, c->aux_stream[2], 0, c->ev_fork[0]);
+    cudaStreamWaitEvent(c->stream, c->ev_tail, 0);   // the previous step's gather still reads the match counters
+    STAGE_BEG(c, ST_KNN);
+    rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
+    if (rc) return rc;
+    STAGE_END(c, ST_KNN);
+    cudaEventRecord(c->ev_join[2], c->stream);
+  }
+  if (c->have_prev) {
+    {
+      // ---- F RANSAC (thr 1.0, conf 0.99), lane 1 ----
+      Fork f(c, c->aux_stream[0], 1, c->ev_fork[1]);
+      STAGE_BEG(c, ST_F);
+      fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.ln().thr2.p, 1.0f, nullptr, B);
+      c->launches++;
+      rc = ransac_find(c, MVO_MODEL_F, 0.99);
+      if (rc) return rc;
+      copy_i32_strided_kernel<<<gb, 128, 0, c->stream>>>(r.ln().result.p, 8, res_f, B);
+      c->launches++;
+      STAGE_END(c, ST_F);
+      cudaEventRecord(c->ev_join[0], c->stream);
+    }
+    {
+      // ---- the join of all searches and the result gather: tail stream (after the H search enqueued above) ----
+      Fork f(c, c->aux_stream[3], 0, c->ev_fork[1]);
       for (int k = 0; k < 3; ++k) cudaStreamWaitEvent(c->stream, c->ev_join[k], 0);
       gather_results_kernel<<<gb, 128, 0, c->stream>>>(c->kp_count.p, c->knn_nmatch.p, r.npts.p, res_h, res_f,
                                                        r.lane[2].result.p, ntri, r.pose.p, 1, c->d_results.p, B);
@@ -611,6 +636,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     }
   } else {
     Fork f(c, c->aux_stream[3], 0, c->ev_fork[0]);
+    cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0);   // the step is done when its LK pyramid is built, too
     gather_results_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(c->kp_count.p, nullptr, nullptr, nullptr, nullptr,
                                                                  nullptr, nullptr, nullptr, 0, c->d_results.p, B);
     c->launches++;
@@ -1037,6 +1063,8 @@ int mvo_debug_time(mvo_ctx* c, const char* what, int reps, float* ms) {
       rc = orb_run_detect(c, true);
     else if (strcmp(what, "orb_dense") == 0)
       rc = orb_run_levels_only(c);
+    else if (strcmp(what, "orb_levels") == 0)
+      rc = orb_run_levels_fast(c);
     else {
       c->set_error("mvo_debug_time: unknown stage");
       return MVO_ERR_INVALID;

@@ -1017,6 +1017,13 @@ int orb_run_levels_only(mvo_ctx* c) {
   return launch_levels(c, 0);
 }
 
+// the eight fused level kernels exactly as orb_run_detect launches them (pyramid + FAST + NMS + blur), nothing after
+int orb_run_levels_fast(mvo_ctx* c) {
+  int rc = clear_counters(c);
+  if (rc) return rc;
+  return launch_levels(c, 1);
+}
+
 int orb_run_detect(mvo_ctx* c, bool want_desc) {
   const OrbGeom& g = c->geom;
   int rc = clear_counters(c);
