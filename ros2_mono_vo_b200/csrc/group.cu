@@ -1023,6 +1023,7 @@ int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   if (strcmp(key, "lk_impl") == 0) c->dbg_lk_impl = value;
   else if (strcmp(key, "knn_impl") == 0) c->dbg_knn_impl = value;
   else if (strcmp(key, "h_refine_impl") == 0) c->dbg_h_refine_impl = value;
+  else if (strcmp(key, "e5_roots_impl") == 0) c->dbg_e5_roots_impl = value;
   else if (strcmp(key, "cache") == 0) {
     c->cache_enabled = value;
     for (auto& e : c->dcache) e.hash = 0;

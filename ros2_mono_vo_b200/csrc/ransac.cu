@@ -394,10 +394,166 @@ __device__ inline double bracket_root(const double (&q)[11], double lo, double h
   return x;
 }
 
+// All ten roots of the degree-10 determinant polynomial at once: Ehrlich-Aberth iteration (simultaneous Newton steps
+// with the other roots deflated implicitly: w_k -= N_k / (1 - N_k sum_{j != k} 1 / (w_k - w_j)), N = p / p'), one lane per
+// root inside the 16-lane group of a hypothesis, started from Bini's initial guesses (the upper convex hull of
+// (k, log |c_k|) gives the root moduli: the roots of these polynomials spread over four orders of magnitude).  About ten
+// iterations of ~1000 dependent cycles replace the derivative-level bracketing below (10 levels x up to 100 safeguarded
+// Newton / bisection steps: 148 us for the 32 hypotheses of a first round, the longest kernel on a single stream's
+// critical path).  Like cv::solvePoly in the reference's findEssentialMat, it finds the complex roots and keeps those with
+// |Im z| <= 1e-10; they are polished by Newton steps on the real polynomial and handed out in ascending order, as the
+// bracketing path does.  Returns false (uniform inside the 16-lane group) when the iteration did not converge or the
+// polynomial is degenerate: the caller then runs the bracketing path.
+__device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16, double& myroot, int& ncrit) {
+  const unsigned full = 0xffffffffu;
+  // `usable` is uniform inside the 16-lane group but not across the warp's two groups: no early return before the
+  // warp-wide shuffles below, an unusable group just idles through the iteration
+  bool usable = true;
+#pragma unroll
+  for (int k = 0; k <= 10; ++k) usable = usable && isfinite(c[k]);
+  usable = usable && (c[10] != 0.0) && (c[0] != 0.0);
+  // ---- initial guesses: lane k holds log |c_k| (lanes 0 .. 10), the hull walk runs redundantly in every lane ----
+  const double mylog = (l16 <= 10 && usable && c[l16 <= 10 ? l16 : 0] != 0.0) ? log(fabs(c[l16 <= 10 ? l16 : 0])) : -1e300;
+  double lg[11];
+#pragma unroll
+  for (int k = 0; k <= 10; ++k) lg[k] = __shfl_sync(full, mylog, k, 16);
+  double wr = 0.0, wi = 0.0;
+  {
+    int k0 = 0, seg = 0;
+    double rad = 1.0;
+    int seg_lo = 0, seg_hi = 10, seg_id = 0;
+#pragma unroll 1
+    while (k0 < 10) {
+      int best = k0 + 1;
+      double bs = -1e300;
+#pragma unroll 1
+      for (int j = k0 + 1; j <= 10; ++j) {
+        const double sl = (lg[j] - lg[k0]) / (double)(j - k0);
+        if (sl >= bs) {
+          bs = sl;
+          best = j;
+        }
+      }
+      if (l16 >= k0 && l16 < best) {
+        rad = exp(-bs);                 // |c_k0 / c_best|^(1 / (best - k0))
+        seg_lo = k0;
+        seg_hi = best;
+        seg_id = seg;
+      }
+      k0 = best;
+      ++seg;
+    }
+    if (!(rad > 1e-150 && rad < 1e150)) usable = false;
+    const double ang = 2.0 * (double)(l16 - seg_lo) / (double)(seg_hi - seg_lo) + 0.2 * (double)seg_id + 0.223;
+    double sn, cs;
+    sincospi(ang, &sn, &cs);
+    wr = rad * cs;
+    wi = rad * sn;
+  }
+  {
+    // a group is usable only if all of its lanes are
+    const unsigned ub = __ballot_sync(full, usable);
+    const int half = (threadIdx.x >> 4) & 1;
+    usable = ((ub >> (16 * half)) & 0xffffu) == 0xffffu;
+  }
+  const bool act = l16 < 10 && usable;
+  bool conv = !act;
+  bool done = false;
+#pragma unroll 1
+  for (int it = 0; it < 48; ++it) {
+    // p(w), p'(w): Horner with real coefficients
+    double pr = c[10], pi = 0.0, dr = 0.0, di = 0.0;
+#pragma unroll
+    for (int k = 9; k >= 0; --k) {
+      const double tr = dr * wr - di * wi + pr;
+      di = dr * wi + di * wr + pi;
+      dr = tr;
+      const double t = pr * wr - pi * wi + c[k];
+      pi = pr * wi + pi * wr;
+      pr = t;
+    }
+    // S = sum_{j != k} 1 / (w - w_j)
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const double er = wr - __shfl_sync(full, wr, j, 16), ei = wi - __shfl_sync(full, wi, j, 16);
+      const double m = er * er + ei * ei;
+      if (j != l16 && m > 0.0) {
+        const double im = 1.0 / m;
+        sr += er * im;
+        si -= ei * im;
+      }
+    }
+    if (!conv) {
+      const double dm = dr * dr + di * di;
+      double nr = 0.0, ni = 0.0;                 // N = p / p'
+      if (dm > 0.0) {
+        const double im = 1.0 / dm;
+        nr = (pr * dr + pi * di) * im;
+        ni = (pi * dr - pr * di) * im;
+      }
+      // corr = N / (1 - N S)
+      const double qr = 1.0 - (nr * sr - ni * si), qi = -(nr * si + ni * sr);
+      const double qm = qr * qr + qi * qi;
+      double cr = nr, ci = ni;
+      if (qm > 0.0) {
+        const double im = 1.0 / qm;
+        cr = (nr * qr + ni * qi) * im;
+        ci = (ni * qr - nr * qi) * im;
+      }
+      wr -= cr;
+      wi -= ci;
+      conv = (cr * cr + ci * ci <= 1e-26 * (wr * wr + wi * wi)) || (pr == 0.0 && pi == 0.0);
+    }
+    const bool bad = act && !(isfinite(wr) && isfinite(wi));
+    const unsigned cb = __ballot_sync(full, conv), bb = __ballot_sync(full, bad);
+    if (bb) break;                                               // (warp-uniform: both groups fall back)
+    if (cb == full) {
+      done = true;
+      break;
+    }
+  }
+  if (!done) return false;
+  // classify, polish on the real polynomial, ascending order
+  double z = wr;
+  bool real = act && fabs(wi) <= 1e-10;
+  if (real) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      double dv;
+      const double v = poly_eval10(c, z, dv);
+      if (dv == 0.0 || !isfinite(v)) break;
+      const double zn = z - v / dv;
+      if (!isfinite(zn) || zn == z) break;
+      z = zn;
+    }
+  }
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const double zj = __shfl_sync(full, z, j, 16);
+    const bool rj = __shfl_sync(full, (int)real, j, 16) != 0;
+    if (rj && (zj < z || (zj == z && j < l16))) ++rank;
+  }
+  const unsigned rb = __ballot_sync(full, real);
+  const int half = (threadIdx.x >> 4) & 1;
+  ncrit = __popc((rb >> (16 * half)) & 0xffffu);
+  double out = 0.0;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const double zj = __shfl_sync(full, z, j, 16);
+    const int rkj = __shfl_sync(full, rank, j, 16);
+    const bool rj = __shfl_sync(full, (int)real, j, 16) != 0;
+    if (rj && rkj == l16) out = zj;
+  }
+  myroot = out;
+  return usable;
+}
+
 constexpr int kRootsThreads = 128;   // 8 hypotheses per block, 16 lanes each
 __global__ void __launch_bounds__(kRootsThreads)
 e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1, const double* __restrict__ scratch,
-                double* __restrict__ models, int32_t* __restrict__ nmodels) {
+                double* __restrict__ models, int32_t* __restrict__ nmodels, int impl) {
   const int b = blockIdx.y;
   if (state[b * 8 + 3]) return;
   const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15;
@@ -420,8 +576,28 @@ e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1
   bound = 2.0 * bound + 1e-300;
   double myroot = 0.0;
   int ncrit = 0;
+  // all roots at once (Ehrlich-Aberth iteration); the derivative-level bracketing only where that did not converge
+  bool have = false;
+  if (impl != 1) {
+    double r2 = 0.0;
+    int n2 = 0;
+    const bool ok = aberth_real_roots(c, l16, r2, n2) && deg == 10;
+    // group-uniform result; the bracketing loop below is warp-level code, so it runs when either group needs it
+    if (ok) {
+      myroot = r2;
+      ncrit = n2;
+      have = true;
+    }
+  }
+  const bool need_levels = __any_sync(full, !have);
+  double root_keep = myroot;
+  int ncrit_keep = ncrit;
+  if (need_levels) {
+    myroot = 0.0;
+    ncrit = 0;
+  }
 #pragma unroll 1
-  for (int lvl = 9; lvl >= 0; --lvl) {
+  for (int lvl = need_levels ? 9 : -1; lvl >= 0; --lvl) {
     const bool lvl_on = (deg > 0) && (lvl <= deg - 1);
     const int qd = deg - lvl;
     double q[11];
@@ -464,6 +640,10 @@ e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1
       myroot = (l16 < nn) ? r : 0.0;
       ncrit = nn;
     }
+  }
+  if (have) {          // this group's Ehrlich-Aberth result stands (the other group of the warp needed the bracketing)
+    myroot = root_keep;
+    ncrit = ncrit_keep;
   }
   // lanes 0 .. ncrit-1 hold the real roots of det B(z): one essential matrix each
   bool valid = false;
@@ -1700,7 +1880,7 @@ static void solve_score(mvo_ctx* c, int h0, int h1) {
                                                r.ln().e5_scratch.p);
     dim3 gr((count + kRootsThreads / 16 - 1) / (kRootsThreads / 16), B);
     e5_roots_kernel<<<gr, kRootsThreads, 0, c->stream>>>(r.ln().state.p, r.cap_iters, h0, h1, r.ln().e5_scratch.p, r.ln().models.p,
-                                                         r.ln().nmodels.p);
+                                                         r.ln().nmodels.p, c->dbg_e5_roots_impl);
     c->launches++;
   } else {
     ransac_solve_kernel<MODEL><<<gs, tpb, 0, c->stream>>>(r.p1.p, r.p2.p, r.q1.p, r.q2.p, r.max_pts, r.ln().subsets.p,
