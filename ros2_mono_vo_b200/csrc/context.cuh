@@ -226,7 +226,7 @@ struct mvo_ctx {
   uint64_t cache_stats[4] = {0, 0, 0, 0};   // descriptor hits / misses, pyramid hits / misses
   int cache_enabled = 1;               // mvo_debug_set("cache", 0) switches both caches off
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
-  int dbg_e5_roots_impl = 1;   // 1: derivative-level bracketing only, 2: Ehrlich-Aberth iteration first (default once verified on the GPU)
+  int dbg_e5_roots_impl = 2;   // 1: derivative-level bracketing only (cross-check), 2: Ehrlich-Aberth iteration first, bracketing where it is not trusted
   int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel
 
   // ---------------- stage timing ----------------

@@ -404,7 +404,12 @@ __device__ inline double bracket_root(const double (&q)[11], double lo, double h
 // |Im z| <= 1e-10; they are polished by Newton steps on the real polynomial and handed out in ascending order, as the
 // bracketing path does.  Returns false (uniform inside the 16-lane group) when the iteration did not converge or the
 // polynomial is degenerate: the caller then runs the bracketing path.
+#ifdef MVO_DK_DEBUG
+#define g_dbg_h dbg_h
+__device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16, double& myroot, int& ncrit, int dbg_h) {
+#else
 __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16, double& myroot, int& ncrit) {
+#endif
   const unsigned full = 0xffffffffu;
   // `usable` is uniform inside the 16-lane group but not across the warp's two groups: no early return before the
   // warp-wide shuffles below, an unusable group just idles through the iteration
@@ -459,10 +464,14 @@ __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16
   const bool act = l16 < 10 && usable;
   bool conv = !act;
   bool done = false;
+  int nres = 0;
+  double err2 = 0.0;
 #pragma unroll 1
   for (int it = 0; it < 48; ++it) {
     // p(w), p'(w): Horner with real coefficients
     double pr = c[10], pi = 0.0, dr = 0.0, di = 0.0;
+    const double aw = sqrt(wr * wr + wi * wi);
+    double ab = fabs(c[10]);                    // sum |c_k| |w|^k: the rounding-error scale of the Horner value
 #pragma unroll
     for (int k = 9; k >= 0; --k) {
       const double tr = dr * wr - di * wi + pr;
@@ -471,7 +480,15 @@ __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16
       const double t = pr * wr - pi * wi + c[k];
       pi = pr * wi + pi * wr;
       pr = t;
+      ab = ab * aw + fabs(c[k]);
     }
+    // a root is final when its correction is below 1e-13 |w| (simple roots: the cubic convergence gets there one or two
+    // steps after the residual does) or when |p(w)| has been down at the rounding level of its own evaluation for
+    // three steps (clustered roots never satisfy a step-size test: their corrections jitter at eps^(1/m))
+    nres = (pr * pr + pi * pi <= 1e-29 * ab * ab) ? nres + 1 : 0;
+    if (nres >= 3) conv = true;
+    // first-order bound on what the evaluation noise lets this root be known to: 4e-15 sum|c_k||w|^k / |p'(w)|
+    if (!conv || nres >= 3) err2 = (1.6e-29 * ab * ab) / fmax(dr * dr + di * di, 1e-300);
     // S = sum_{j != k} 1 / (w - w_j)
     double sr = 0.0, si = 0.0;
 #pragma unroll
@@ -512,8 +529,27 @@ __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16
       done = true;
       break;
     }
+#ifdef MVO_DK_DEBUG
+    if (it == 47) printf("noconv lane %d usable %d conv %d w = %g %g cb %08x\n", threadIdx.x & 31, (int)usable, (int)conv, wr, wi, cb);
+#endif
   }
+#ifdef MVO_DK_DEBUG
+  if ((threadIdx.x & 31) == 0) printf("aberth done=%d\n", (int)done);
+#endif
   if (!done) return false;
+  // A pair of close real roots is a cluster the iteration resolves only to ~sqrt(eps): it ends as m +- i e with a small
+  // e > 1e-10 and both roots would be lost.  Such a group (an imaginary part that is neither zero nor clearly non-zero)
+  // is left to the bracketing path, which separates the pair by its sign changes.
+  // A root inside a tight cluster (|p'| tiny: the roots of some samples all lie within a few per cent of each other) is
+  // not known to better than err = noise / |p'|; a group with such a root goes to the bracketing path as well.
+  {
+    const double w2 = wr * wr + wi * wi;
+    const bool vague = act && err2 > 1e-10 * w2;
+    const bool suspicious = vague || (act && fabs(wi) > 1e-10 && fabs(wi) <= fmax(1e-6 * fmax(1.0, fabs(wr)), 16.0 * sqrt(err2)));
+    const unsigned sb = __ballot_sync(full, suspicious);
+    const int half0 = (threadIdx.x >> 4) & 1;
+    if ((sb >> (16 * half0)) & 0xffffu) usable = false;
+  }
   // classify, polish on the real polynomial, ascending order
   double z = wr;
   bool real = act && fabs(wi) <= 1e-10;
@@ -546,6 +582,11 @@ __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16
     const bool rj = __shfl_sync(full, (int)real, j, 16) != 0;
     if (rj && rkj == l16) out = zj;
   }
+#ifdef MVO_DK_DEBUG
+  if (g_dbg_h == 423 && l16 < 11)
+    printf("h423 lane %d c=%g w=(%.12g, %.3g) z=%.12g real=%d rank=%d usable=%d ncrit=%d out=%.12g\n", l16, c[l16], wr, wi, z, (int)real, rank,
+           (int)usable, ncrit, out);
+#endif
   myroot = out;
   return usable;
 }
@@ -581,7 +622,12 @@ e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1
   if (impl != 1) {
     double r2 = 0.0;
     int n2 = 0;
+#ifdef MVO_DK_DEBUG
+    const bool ok = aberth_real_roots(c, l16, r2, n2, live ? h : -1) && deg == 10;
+    if (h == 423 && live && l16 == 0) printf("h423 ok=%d deg=%d n2=%d\n", (int)ok, deg, n2);
+#else
     const bool ok = aberth_real_roots(c, l16, r2, n2) && deg == 10;
+#endif
     // group-uniform result; the bracketing loop below is warp-level code, so it runs when either group needs it
     if (ok) {
       myroot = r2;
