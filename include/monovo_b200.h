@@ -350,13 +350,20 @@ MVO_API int mvo_pack_pointcloud(mvo_ctx* ctx, const float* points_xyz, int n, in
 /* ------------------------------------------------------------------------------------------------
  * profiling / parity aids (not part of the reference-facing surface)
  * mvo_debug_set: "lk_impl" = 1 | 2 selects the first- / second-generation gray LK kernel (identical results; the old
- *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels.
+ *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels, "h_refine_impl" / "e5_roots_impl"
+ *                = 1 for the first-generation homography refinement / the bracketing root finder, "cache" = 0 and
+ *                "graph" = 0 to switch the content caches / the CUDA-graph step off.
  * mvo_debug_time: re-runs one stage of the group pipeline `reps` times on the state left by the last mvo_group_step
  *                (at least two steps must have run) and returns the average device time per run in ms, measured with
  *                CUDA events on the context stream.  what = "lk_track" | "knn" | "orb" | "orb_levels" (the eight fused
  *                level kernels as a step launches them) | "orb_dense" (pyramid + blur only) | "lk_pyramid".
  */
 MVO_API int mvo_debug_set(mvo_ctx* ctx, const char* key, int value);
+/* CUDA-graph form of the synchronous mvo_group_step (groups whose frames are <= 4 MB, host frames): the step is captured
+ * once per buffer parity and replayed with one launch -- the ~85 launches of a step, not the GPU, bound a single stream.
+ * stats: graphs captured, steps replayed from a graph, captures abandoned (the plain step ran instead).
+ * mvo_debug_set("graph", 0) switches the graph form off (mvo_stage_ms needs plain steps). */
+MVO_API int mvo_graph_stats(mvo_ctx* ctx, uint64_t stats[3]);
 MVO_API int mvo_debug_time(mvo_ctx* ctx, const char* what, int reps, float* ms);
 
 #ifdef __cplusplus

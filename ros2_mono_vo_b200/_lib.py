@@ -106,6 +106,7 @@ SIGNATURES = {
     "mvo_group_track": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "mvo_group_get_tracks": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _i32p, _i32p]),
     "mvo_cache_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "mvo_graph_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "mvo_set_occupancy_grid": (C.c_int, [_vp, C.c_int]),
     "mvo_orb_occupancy": (C.c_int, [_vp, C.c_int, _i32p, _i32p]),
     "mvo_pack_pointcloud": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int]),

@@ -269,6 +269,12 @@ class Context:
         self._check(self.lib.mvo_cache_stats(self.h, v))
         return {"desc_hits": int(v[0]), "desc_misses": int(v[1]), "pyr_hits": int(v[2]), "pyr_misses": int(v[3])}
 
+    def graph_stats(self) -> dict:
+        """CUDA-graph form of the synchronous group step: graphs captured, steps replayed, captures abandoned."""
+        v = (C.c_uint64 * 3)()
+        self._check(self.lib.mvo_graph_stats(self.h, v))
+        return {"captures": int(v[0]), "replays": int(v[1]), "fallbacks": int(v[2])}
+
     # ---- SURVEY 8(f) #4 by-products -------------------------------------------------------------
     def set_occupancy_grid(self, grid_div: int):
         """Cell size of the keypoint-distribution grid (Initializer::good_keypoint_distribution); 0 = off."""

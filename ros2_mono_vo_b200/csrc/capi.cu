@@ -101,6 +101,7 @@ int mvo_create(mvo_ctx** out, const mvo_config* cfg) {
     keep(cudaStreamCreateWithPriority(&c->lk_stream, cudaStreamNonBlocking, prio_lo));
     keep(cudaEventCreateWithFlags(&c->ev_unpack, cudaEventDisableTiming));
     keep(cudaEventCreateWithFlags(&c->ev_lk_done, cudaEventDisableTiming));
+    keep(cudaEventCreateWithFlags(&c->ev_graph_done, cudaEventDisableTiming));
     keep(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
     for (auto& sl : c->slots) {
       keep(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
@@ -166,6 +167,9 @@ void mvo_destroy(mvo_ctx* c) {
   }
   if (c->ev_unpack) cudaEventDestroy(c->ev_unpack);
   if (c->ev_lk_done) cudaEventDestroy(c->ev_lk_done);
+  if (c->ev_graph_done) cudaEventDestroy(c->ev_graph_done);
+  for (auto& gph : c->step_graph)
+    if (gph.exec) cudaGraphExecDestroy(gph.exec);
   c->img_in.release(); c->pyr.release(); c->blur.release(); c->xtab.release(); c->ytab.release();
   c->cand_xy.release(); c->cand_score.release(); c->cand_count.release(); c->cand_sel.release(); c->sel_count.release(); c->hist.release();
   c->c2_key.release(); c->c2_key_sorted.release(); c->c2_ra.release(); c->c2_ra_sorted.release();

@@ -48,6 +48,12 @@ struct OrbGeom {
     }                                                                             \
   } while (0)
 
+// bumped by every real (re)allocation: a captured CUDA graph holds raw pointers and is re-captured when it changes
+inline unsigned long long& alloc_epoch() {
+  static unsigned long long e = 0;
+  return e;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -68,6 +74,7 @@ struct DevBuf {
     n = 0;
     cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
     if (e == cudaSuccess) n = count;
+    ++alloc_epoch();
     return e;
   }
   void release() {
@@ -97,6 +104,7 @@ struct PinBuf {
     n = 0;
     cudaError_t e = cudaMallocHost((void**)&p, (count ? count : 1) * sizeof(T));
     if (e == cudaSuccess) n = count;
+    ++alloc_epoch();
     return e;
   }
   void release() {

@@ -217,6 +217,20 @@ struct mvo_ctx {
   bool occ_from_group = false;         // mvo_orb_occupancy answers from the last collected group step
   mvo::DevBuf<float> cloud;            // group step: batch * cap * 3 packed ROS-axis points (MVO_OUT_CLOUD)
   mvo::DevBuf<uint8_t> pack_tmp;       // mvo_pack_pointcloud staging
+  // ---- CUDA-graph form of the synchronous group step (small groups: the host's ~85 launches per step, not the GPU,
+  // bound a single stream).  One executable graph per buffer parity (the keypoint / descriptor / pyramid buffers swap
+  // every frame), re-captured when the geometry, the output mask, a knob or any allocation changes. ----
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long epoch = 0, key = 0;
+    int launches = 0;
+  };
+  StepGraph step_graph[2];
+  bool capturing = false;             // group_enqueue is being recorded into a graph: no waits on events of earlier steps
+  int graph_enabled = 1;              // mvo_debug_set("graph", 0) switches the graph form off (per-stage timers need that)
+  int steps_since_change = 0;         // plain steps since the last (re)allocation: the graph is captured after two
+  cudaEvent_t ev_graph_done = nullptr;
+  uint64_t graph_stats[3] = {0, 0, 0};   // captures, replays, capture fall-backs
   // ---- device-resident caches of the synchronous single-call path ----
   static constexpr int kDescCache = 4;
   DescCacheEntry dcache[kDescCache];

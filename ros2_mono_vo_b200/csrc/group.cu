@@ -294,16 +294,24 @@ using namespace mvo;
 
 // every stage is also an NVTX range (domain-less, named like mvo_stage_ms' stages) around its enqueue calls, so a
 // timeline tool attributes the kernels of a step to ORB / kNN / LK / the model searches (tracing row)
-#define STAGE_BEG(c, s)                                   \
-  do {                                                    \
-    nvtxRangePushA(kStageNames[s]);                       \
-    cudaEventRecord((c)->timers[s].beg, (c)->stream);     \
+#define STAGE_BEG(c, s)                                                          \
+  do {                                                                           \
+    nvtxRangePushA(kStageNames[s]);                                              \
+    if (!(c)->capturing) cudaEventRecord((c)->timers[s].beg, (c)->stream);       \
   } while (0)
-#define STAGE_END(c, s)                               \
-  do {                                                \
-    cudaEventRecord((c)->timers[s].end, (c)->stream); \
-    (c)->timers[s].used = true;                       \
-    nvtxRangePop();                                   \
+#define STAGE_END(c, s)                                                          \
+  do {                                                                           \
+    if (!(c)->capturing) {                                                       \
+      cudaEventRecord((c)->timers[s].end, (c)->stream);                          \
+      (c)->timers[s].used = true;                                                \
+    }                                                                            \
+    nvtxRangePop();                                                              \
+  } while (0)
+// wait on an event recorded by an EARLIER step: meaningless (and not allowed) while a step is captured into a graph --
+// the graph form only runs synchronous steps, every earlier step is complete
+#define WAIT_PREV_STEP(c, st, ev)                          \
+  do {                                                     \
+    if (!(c)->capturing) cudaStreamWaitEvent(st, ev, 0);   \
   } while (0)
 
 // layout of a slot's pinned output block for the configured outputs
@@ -425,7 +433,11 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     int spitch = stride;
     long long sstride = (long long)h * stride;
     const int rowb = w * cn;     // bytes of one frame row
-    if (!images_on_device) {
+    if (!images_on_device && c->capturing) {
+      src = c->slots[slot].stage.p;      // filled by mvo_group_step right before the graph launch
+      spitch = rowb;
+      sstride = (long long)h * rowb;
+    } else if (!images_on_device) {
       GroupSlot& sl = c->slots[slot];
       MVO_CUDA_TRY(c, sl.stage.alloc((size_t)B * h * rowb));
       cudaStreamWaitEvent(c->copy_stream, sl.ev_free, 0);
@@ -446,7 +458,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     uint8_t* lk0 = lk_level0(c, c->lk_cur, &lk_pitch, &lk_fs);
     // The LK pyramid slot about to be overwritten is the "previous" pyramid of the last enqueued step's tracker, which
     // runs on its own stream; the keypoint-position buffer ORB is about to fill is that tracker's input as well.
-    cudaStreamWaitEvent(c->main_stream, c->ev_lk_done, 0);
+    WAIT_PREV_STEP(c, c->main_stream, c->ev_lk_done);
     if (cn == 1) {
       dim3 grid((w + 16 * 256 - 1) / (16 * 256), h, B);
       unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch, g.frame_stride,
@@ -457,7 +469,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
                                                             g.frame_stride, lk0, lk_pitch, lk_fs, w, h);
     }
     c->launches++;
-    if (!images_on_device) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
+    if (!images_on_device && !c->capturing) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
     cudaEventRecord(c->ev_unpack, c->main_stream);
   }
   const int cur = c->lk_cur, prev = cur ^ 1;
@@ -479,12 +491,12 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     rc = lk_build_pyramid(c, cur, nullptr, 0, 3);   // level 0 was written by the unpack kernel
     if (rc) return rc;
     if (c->have_prev) {
-      cudaStreamWaitEvent(c->stream, c->ev_out_lk, 0);   // the previous step's track outputs have left the LK buffers
+      WAIT_PREV_STEP(c, c->stream, c->ev_out_lk);   // the previous step's track outputs have left the LK buffers
       rc = lk_run(c, prev, cur, c->prev_kp_xy.p, c->prev_kp_count.p, cap, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p);
       if (rc) return rc;
       // the correspondence buffers feed the model searches of the previous step until its tail is done; from here on
       // this step's ORB + LK have overlapped them (software pipelining across the two steps in flight)
-      cudaStreamWaitEvent(c->stream, c->ev_tail, 0);
+      WAIT_PREV_STEP(c, c->stream, c->ev_tail);
       lk_collect_kernel<<<B, 1024, 0, c->stream>>>(c->prev_kp_xy.p, c->lk_pts_out.p, c->lk_status.p, c->lk_err.p,
                                                    c->prev_kp_count.p, cap, 30.0f, r.p1.p, r.p2.p, r.npts.p);
       c->launches++;
@@ -500,7 +512,8 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     cudaEventRecord(c->ev_lk_done, c->stream);
     STAGE_END(c, ST_LK);
     if (c->have_prev) {
-      MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
+      if (!c->capturing)   // (graph form: K was copied before the graph launch)
+        MVO_CUDA_TRY(c, cudaMemcpyAsync(r.K.p, K, 72, cudaMemcpyHostToDevice, c->stream));
       fill_params_kernel<<<gb, 128, 0, c->stream>>>(r.lane[0].thr2.p, 1.0f, r.K.p, B);   // + replicate K to every stream
       c->launches++;
       cudaEventRecord(c->ev_fork[1], c->stream);
@@ -554,7 +567,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
     }
   }
   // the keypoint / descriptor buffers ORB is about to fill were the previous step's "prev" set: its kNN must be done
-  cudaStreamWaitEvent(c->main_stream, c->ev_join[2], 0);
+  WAIT_PREV_STEP(c, c->main_stream, c->ev_join[2]);
   rc = orb_run_detect(c, true);
   if (rc) return rc;
   {
@@ -582,7 +595,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
   if (c->have_prev) {
     // ---- kNN + ratio: query = previous descriptors, train = new descriptors (src/tracker.cpp:190-191) ----
     Fork f(c, c->aux_stream[2], 0, c->ev_fork[0]);
-    cudaStreamWaitEvent(c->stream, c->ev_tail, 0);   // the previous step's gather still reads the match counters
+    WAIT_PREV_STEP(c, c->stream, c->ev_tail);   // the previous step's gather still reads the match counters
     STAGE_BEG(c, ST_KNN);
     rc = knn_run(c, c->prev_desc.p, c->prev_kp_count.p, cap, cap, c->desc.p, c->kp_count.p, cap, cap, 0.7, B);
     if (rc) return rc;
@@ -681,6 +694,146 @@ static int group_finish(mvo_ctx* c, int slot, mvo_frame_result* results) {
   return MVO_OK;
 }
 
+// ---- CUDA-graph form of the synchronous step -----------------------------------------------------------------------
+// What a graph is valid for: everything the enqueue code reads besides device memory contents.
+static unsigned long long step_graph_key(const mvo_ctx* c, int w, int h) {
+  unsigned long long k = 1469598103934665603ull;
+  auto mix = [&k](unsigned long long v) { k = (k ^ v) * 1099511628211ull; };
+  mix((unsigned long long)w); mix((unsigned long long)h); mix((unsigned long long)c->grp_cn); mix(c->out_mask);
+  mix((unsigned long long)c->occupancy_div); mix((unsigned long long)c->dbg_lk_impl); mix((unsigned long long)c->dbg_knn_impl);
+  mix((unsigned long long)c->dbg_h_refine_impl); mix((unsigned long long)c->dbg_e5_roots_impl);
+  // which physical buffers are "current" and "previous" right now (they swap every frame)
+  mix((unsigned long long)(uintptr_t)c->kps.p); mix((unsigned long long)(uintptr_t)c->prev_kps.p);
+  mix((unsigned long long)(uintptr_t)c->desc.p); mix((unsigned long long)(uintptr_t)c->kp_xy.p);
+  mix((unsigned long long)(uintptr_t)c->kp_count.p); mix((unsigned long long)c->lk_cur);
+  mix((unsigned long long)(uintptr_t)c->main_stream);
+  return k;
+}
+// After a capture the cross-step events were last "recorded" inside the capture; give them a real (already complete)
+// record so that a later plain step can wait on them.  All streams are idle here (synchronous steps only).
+static void rearm_events(mvo_ctx* c, int slot) {
+  cudaEventRecord(c->ev_tail, c->aux_stream[3]);
+  cudaEventRecord(c->ev_lk_done, c->lk_stream);
+  cudaEventRecord(c->ev_unpack, c->main_stream);
+  cudaEventRecord(c->ev_fork[0], c->main_stream);
+  cudaEventRecord(c->ev_fork[1], c->lk_stream);
+  cudaEventRecord(c->ev_join[0], c->aux_stream[0]);
+  cudaEventRecord(c->ev_join[1], c->aux_stream[1]);
+  cudaEventRecord(c->ev_join[2], c->aux_stream[2]);
+  cudaEventRecord(c->ev_o_orb, c->main_stream);
+  cudaEventRecord(c->ev_o_lk, c->lk_stream);
+  cudaEventRecord(c->ev_out_orb, c->out_stream);
+  cudaEventRecord(c->ev_out_lk, c->out_stream);
+  cudaEventRecord(c->slots[slot].ev_done, c->aux_stream[3]);
+}
+
+// Small groups on host frames: the host's ~85 launches per step (0.35 - 0.45 ms), not the GPU's critical path (0.42 ms for
+// one 1241 x 376 stream), bound the synchronous step.  The step is therefore captured once per buffer parity into a CUDA
+// graph (every stream of the fork / join schedule above becomes a branch) and replayed with one launch; the frames and K
+// are copied by plain asynchronous copies in front of the graph, so no node ever needs new parameters.
+static int group_step_graph(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, const double* K,
+                            mvo_frame_result* results, bool* used) {
+  *used = false;
+  const int B = c->cfg.batch, cn = c->grp_cn;
+  const size_t rowb = (size_t)w * cn, bytes = (size_t)B * h * rowb;
+  if (!c->graph_enabled || !c->have_prev || bytes > (4u << 20) || c->steps_since_change < 1) return MVO_OK;
+  GroupSlot& sl = c->slots[0];
+  if (!sl.stage.p || sl.stage.n < bytes || !c->rs.K.p) return MVO_OK;
+  const int parity = c->lk_cur & 1;
+  mvo_ctx::StepGraph& gph = c->step_graph[parity];
+  const unsigned long long key = step_graph_key(c, w, h);
+  MVO_CUDA_TRY(c, cudaSetDevice(c->cfg.device));
+  // inputs of the step: plain copies in front of the graph (all earlier work is complete: synchronous steps)
+  if ((size_t)stride == rowb)
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(sl.stage.p, images, bytes, cudaMemcpyHostToDevice, c->main_stream));
+  else
+    MVO_CUDA_TRY(c, cudaMemcpy2DAsync(sl.stage.p, rowb, images, stride, rowb, (size_t)B * h, cudaMemcpyHostToDevice, c->main_stream));
+  MVO_CUDA_TRY(c, cudaMemcpyAsync(c->rs.K.p, K, 72, cudaMemcpyHostToDevice, c->main_stream));
+  if (!gph.exec || gph.key != key || gph.epoch != alloc_epoch()) {
+    if (gph.exec) {
+      cudaGraphExecDestroy(gph.exec);
+      gph.exec = nullptr;
+    }
+    const unsigned long long epoch0 = alloc_epoch();
+    const unsigned long long l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    MVO_CUDA_TRY(c, cudaStreamBeginCapture(c->main_stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    int rc = group_enqueue(c, images, w, h, stride, 0, K, 0);
+    if (rc == MVO_OK) cudaStreamWaitEvent(c->main_stream, sl.ev_done, 0);   // join the tail (and through it every branch)
+    c->capturing = false;
+    const cudaError_t e = cudaStreamEndCapture(c->main_stream, &graph);
+    if (rc != MVO_OK || e != cudaSuccess || !graph || alloc_epoch() != epoch0) {
+      // (an allocation inside the capture, or a capture error: fall back to the plain step for this frame)
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      rearm_events(c, 0);
+      c->steps_since_change = 0;
+      c->graph_stats[2]++;
+      if (rc != MVO_OK) return rc;
+      // group_enqueue already advanced the bookkeeping (buffer swap): undo it, the plain path redoes the step
+      std::swap(c->kps, c->prev_kps);
+      std::swap(c->kp_xy, c->prev_kp_xy);
+      std::swap(c->desc, c->prev_desc);
+      std::swap(c->kp_count, c->prev_kp_count);
+      c->lk_cur ^= 1;
+      c->launches = l0;
+      return MVO_OK;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&gph.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    rearm_events(c, 0);
+    if (ei != cudaSuccess) {
+      gph.exec = nullptr;
+      cudaGetLastError();
+      std::swap(c->kps, c->prev_kps);
+      std::swap(c->kp_xy, c->prev_kp_xy);
+      std::swap(c->desc, c->prev_desc);
+      std::swap(c->kp_count, c->prev_kp_count);
+      c->lk_cur ^= 1;
+      c->launches = l0;
+      return MVO_OK;
+    }
+    gph.key = key;
+    gph.epoch = epoch0;
+    gph.launches = (int)(c->launches - l0);
+    c->graph_stats[0]++;
+  } else {
+    // replay: the host-side bookkeeping group_enqueue does at its end
+    c->trk_have_frame = false;
+    c->lk_hash[0] = c->lk_hash[1] = 0;
+    for (auto& t : c->timers) t.used = false;
+    c->slots[0].had_prev = 1;
+    std::swap(c->kps, c->prev_kps);
+    std::swap(c->kp_xy, c->prev_kp_xy);
+    std::swap(c->desc, c->prev_desc);
+    std::swap(c->kp_count, c->prev_kp_count);
+    c->lk_cur ^= 1;
+    c->have_prev = true;
+    c->launches += (unsigned long long)gph.launches;
+    c->graph_stats[1]++;
+  }
+  MVO_CUDA_TRY(c, cudaGraphLaunch(gph.exec, c->main_stream));
+  MVO_CUDA_TRY(c, cudaEventRecord(c->ev_graph_done, c->main_stream));
+  MVO_CUDA_TRY(c, cudaEventSynchronize(c->ev_graph_done));
+  *used = true;
+  // results as group_finish hands them out (the slot's ev_done belongs to the graph: completion is ev_graph_done)
+  memcpy(results, sl.h_res.p, (size_t)B * sizeof(mvo_frame_result));
+  c->out_slot = 0;
+  c->occ_from_group = true;
+  int flags0 = 0, first = -1;
+  for (int b = 0; b < B; ++b) {
+    if (sl.h_flags.p[b] && first < 0) first = b;
+    flags0 |= sl.h_flags.p[b];
+  }
+  if (flags0 & 3) {
+    c->set_error(std::string(flags0 & 1 ? "FAST candidate list overflow" : "keypoint capacity exceeded") + " (first on stream " +
+                 std::to_string(first) + ")");
+    return MVO_ERR_CAPACITY;
+  }
+  return MVO_OK;
+}
+
 int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K,
                    mvo_frame_result* results) {
   if (!c) return MVO_ERR_INVALID;
@@ -692,9 +845,17 @@ int mvo_group_step(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, 
     c->set_error("mvo_group_step: submitted steps are still in flight (mvo_group_collect them first)");
     return MVO_ERR_INVALID;
   }
+  if (!images_on_device && images && K && stride >= w * c->grp_cn && w == c->geom_w && h == c->geom_h) {
+    bool used = false;
+    const int rcg = group_step_graph(c, images, w, h, stride, K, results, &used);
+    if (rcg != MVO_OK || used) return rcg;
+  }
+  const unsigned long long e0 = alloc_epoch();
   int rc = group_enqueue(c, images, w, h, stride, images_on_device, K, 0);
   if (rc) return rc;
-  return group_finish(c, 0, results);
+  rc = group_finish(c, 0, results);
+  c->steps_since_change = (alloc_epoch() == e0) ? c->steps_since_change + 1 : 0;
+  return rc;
 }
 
 int mvo_group_submit(mvo_ctx* c, const uint8_t* images, int w, int h, int stride, int images_on_device, const double* K) {
@@ -1018,12 +1179,19 @@ int mvo_stage_span_ms(mvo_ctx* c, const char* stage, float* beg_ms, float* end_m
   return MVO_ERR_INVALID;
 }
 
+int mvo_graph_stats(mvo_ctx* c, uint64_t stats[3]) {
+  if (!c || !stats) return MVO_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) stats[i] = c->graph_stats[i];
+  return MVO_OK;
+}
+
 int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   if (!c || !key) return MVO_ERR_INVALID;
   if (strcmp(key, "lk_impl") == 0) c->dbg_lk_impl = value;
   else if (strcmp(key, "knn_impl") == 0) c->dbg_knn_impl = value;
   else if (strcmp(key, "h_refine_impl") == 0) c->dbg_h_refine_impl = value;
   else if (strcmp(key, "e5_roots_impl") == 0) c->dbg_e5_roots_impl = value;
+  else if (strcmp(key, "graph") == 0) c->graph_enabled = value;
   else if (strcmp(key, "cache") == 0) {
     c->cache_enabled = value;
     for (auto& e : c->dcache) e.hash = 0;

@@ -1028,11 +1028,13 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
   const OrbGeom& g = c->geom;
   int rc = clear_counters(c);
   if (rc) return rc;
-  cudaEventRecord(c->timers[9].beg, c->stream);   // "orb_dense": the eight fused level kernels
+  if (!c->capturing) cudaEventRecord(c->timers[9].beg, c->stream);   // "orb_dense": the eight fused level kernels
   rc = launch_levels(c, 1);
   if (rc) return rc;
-  cudaEventRecord(c->timers[9].end, c->stream);
-  c->timers[9].used = true;
+  if (!c->capturing) {
+    cudaEventRecord(c->timers[9].end, c->stream);
+    c->timers[9].used = true;
+  }
   int max_cap = 0;
   for (int l = 0; l < kLevels; ++l) max_cap = std::max(max_cap, g.lv[l].cand_cap);
   {

@@ -1,0 +1,82 @@
+"""GPU: the CUDA-graph form of the synchronous group step (small groups on host frames) gives exactly the plain step's
+results and outputs, survives resets / interleaved single calls, and falls back where it does not apply."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("h,w,n,batch,bgr", [(376, 1241, 2000, 1, False), (240, 320, 300, 3, False), (240, 320, 300, 2, True)])
+def test_graph_step_equals_plain_step(h, w, n, batch, bgr):
+    from ros2_mono_vo_b200 import Context, _lib
+    nframes = 9
+    seqs = [synth.synth_sequence(h, w, s, nframes) for s in range(batch)]
+    K = seqs[0][1]
+
+    def frames(t):
+        f = np.stack([seqs[s][0][t] for s in range(batch)])
+        return np.ascontiguousarray(np.stack([f, 255 - f, f // 2 + 10], -1)) if bgr else f
+
+    outs = {}
+    for graph in (1, 0):
+        c = Context(w, h, nfeatures=n, batch=batch)
+        c.group_configure(channels=3 if bgr else 1, outputs=_lib.MVO_OUT_ALL)
+        c.debug_set("graph", graph)
+        rec = []
+        for t in range(nframes):
+            res = c.group_step(frames(t), K)
+            rec.append((res.copy(), [c.group_outputs(s) for s in range(batch)]))
+            if t == 5:   # a reset in the middle: the next step starts from feature extraction again
+                c.group_reset()
+        l = c.launch_count
+        gs = c.graph_stats()
+        if graph:
+            assert gs["captures"] >= 2 and gs["replays"] >= 1 and gs["fallbacks"] == 0, gs
+        else:
+            assert gs == {"captures": 0, "replays": 0, "fallbacks": 0}
+        outs[graph] = (rec, l)
+        c.close()
+    (ra, la), (rb, lb) = outs[1], outs[0]
+    assert la == lb                                     # the graph form accounts for the same kernels
+    for t, ((resa, oa), (resb, ob)) in enumerate(zip(ra, rb)):
+        assert resa.tobytes() == resb.tobytes(), t
+        for s in range(batch):
+            for k, v in oa[s].items():
+                w_ = ob[s][k]
+                if isinstance(v, np.ndarray):
+                    assert w_ is not None and v.tobytes() == w_.tobytes(), (t, s, k)
+                else:
+                    assert v == w_ or (v is None and w_ is None), (t, s, k)
+
+
+def test_graph_survives_single_calls_and_pipelined_steps():
+    from ros2_mono_vo_b200 import Context
+    h, w, n = 240, 320, 300
+    frames, K = synth.synth_sequence(h, w, 2, 10)
+    c = Context(w, h, nfeatures=n, batch=1)
+    ref = Context(w, h, nfeatures=n, batch=1)
+    ref.debug_set("graph", 0)
+
+    def both(fn):
+        a, b = fn(c), fn(ref)
+        return a, b
+    for t in range(5):
+        a, b = both(lambda x: x.group_step(frames[t][None], K))
+        assert a.tobytes() == b.tobytes()
+    # a synchronous single call in between (rebuilds LK pyramids, forgets the previous frame)
+    both(lambda x: x.lk_track(frames[1], frames[2], np.array([[50.0, 60.0]], np.float32)))
+    for t in range(5, 8):
+        a, b = both(lambda x: x.group_step(frames[t][None], K))
+        assert a.tobytes() == b.tobytes(), t
+    # pipelined steps, then synchronous ones again
+    for x in (c, ref):
+        x.group_submit(frames[8][None].copy(), K)
+    a, b = both(lambda x: x.group_collect())
+    assert a.tobytes() == b.tobytes()
+    for t in (9, 8, 7, 6):
+        a, b = both(lambda x: x.group_step(frames[t][None], K))
+        assert a.tobytes() == b.tobytes(), t
+    c.close()
+    ref.close()

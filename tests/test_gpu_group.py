@@ -54,7 +54,8 @@ def test_group_step_equals_single_calls(h, w, n, batch):
                     assert int(res[s][key]) == val, (t, s, key, int(res[s][key]), val)
             prev[s] = (imgs[s], kps, desc)
         ms = grp.stage_ms()
-        assert ms["total"] > 0 and ms["orb"] > 0
+        if t <= 1:      # plain launches; later steps of a small group replay a CUDA graph (no per-stage events)
+            assert ms["total"] > 0 and ms["orb"] > 0
     # the first stream against the oracle where that is cheap: keypoint and match counts
     okp, odesc = oo.orb_detect_and_compute(seqs[0][0][nframes - 1], n)
     okp0, odesc0 = oo.orb_detect_and_compute(seqs[0][0][nframes - 2], n)
