@@ -591,6 +591,9 @@ __device__ __forceinline__ bool aberth_real_roots(const double (&c)[11], int l16
   return usable;
 }
 
+#ifdef MVO_DK_DEBUG
+__device__ unsigned g_e5_stats[2];
+#endif
 constexpr int kRootsThreads = 128;   // 8 hypotheses per block, 16 lanes each
 __global__ void __launch_bounds__(kRootsThreads)
 e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1, const double* __restrict__ scratch,
@@ -634,6 +637,9 @@ e5_roots_kernel(const int32_t* __restrict__ state, int cap_iters, int h0, int h1
       ncrit = n2;
       have = true;
     }
+#ifdef MVO_DK_DEBUG
+    if (live && l16 == 0) atomicAdd(&g_e5_stats[ok ? 0 : 1], 1u);
+#endif
   }
   const bool need_levels = __any_sync(full, !have);
   double root_keep = myroot;
@@ -1971,6 +1977,14 @@ static int find_model(mvo_ctx* c, double conf) {
   solve_score<MODEL>(c, 0, MAXIT);
   select_pass<MODEL>(c, MAXIT, conf);
   MVO_CUDA_TRY(c, cudaGetLastError());
+#ifdef MVO_DK_DEBUG
+  if (MODEL == MVO_MODEL_E) {
+    unsigned hs[2];
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpyFromSymbol(hs, g_e5_stats, 8);
+    fprintf(stderr, "e5 roots: aberth %u, bracketing %u\n", hs[0], hs[1]);
+  }
+#endif
   return MVO_OK;
 }
 
