@@ -526,4 +526,140 @@ MVO_HD int real_roots(const double* c, double* roots) {
   return ncrit;
 }
 
+#ifdef __CUDACC__
+// ---- warp-cooperative versions (matrix in shared memory) --------------------------------------------------------------
+// LU with partial pivoting on an N x N matrix in shared memory by one warp; elementwise the operations of lu_solve<N>.
+// STORE_L keeps the multipliers in the lower triangle (smallest_eigvec_spd's factorisation); piv (registers, uniform).
+template <int N, bool STORE_L>
+__device__ __forceinline__ bool lu_factor_warp(double* A, double* b, int* piv, int lane) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double best = fabs(A[k * N + k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) {
+      const double v = fabs(A[i * N + k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    if (!STORE_L && best == 0.0) return false;
+    piv[k] = p;
+    if (p != k) {
+      if (lane < N) {
+        const double t = A[k * N + lane];
+        A[k * N + lane] = A[p * N + lane];
+        A[p * N + lane] = t;
+      } else if (lane == N && b) {
+        const double t = b[k];
+        b[k] = b[p];
+        b[p] = t;
+      }
+      __syncwarp();
+    }
+    const double d = A[k * N + k];
+    const double inv = STORE_L ? (d != 0.0 ? 1.0 / d : 0.0) : 1.0 / d;
+    constexpr int kCols = N + 1;                   // columns k+1 .. N-1 of the matrix, column N = right-hand side
+    const int cols = kCols - (k + 1);
+    const int cnt = (N - 1 - k) * cols;
+    double fkeep = 0.0;
+    for (int e = lane; e < cnt; e += 32) {
+      const int i = k + 1 + e / cols, j = k + 1 + e % cols;
+      const double f = A[i * N + k] * inv;
+      if (j < N) {
+        if (STORE_L || f != 0.0) A[i * N + j] -= f * A[k * N + j];
+      } else if (b) {
+        if (f != 0.0) b[i] -= f * b[k];
+      }
+      fkeep = f;
+    }
+    (void)fkeep;
+    __syncwarp();
+    if (STORE_L) {
+      if (lane > k && lane < N) A[lane * N + k] = A[lane * N + k] * inv;
+      __syncwarp();
+    }
+  }
+  return true;
+}
+
+// solve A x = b (both in shared memory, destroyed; x returned in b): warp LU, then back substitution on lane 0
+template <int N>
+__device__ __forceinline__ bool lu_solve_warp(double* A, double* b, int lane) {
+  int piv[N];
+  const bool ok = lu_factor_warp<N, false>(A, b, piv, lane);
+  if (!ok) return false;
+  if (lane == 0) {
+    double x[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      double s2 = b[i];
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) s2 -= A[i * N + j] * x[j];
+      x[i] = s2 / A[i * N + i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[i] = x[i];
+  }
+  __syncwarp();
+  return true;
+}
+
+// smallest_eigvec_spd<N> (linalg.cuh) with the factorisation done by the warp; A in shared memory, x (N doubles) too
+template <int N, int ITERS = 4>
+__device__ __forceinline__ void smallest_eigvec_spd_warp(double* A, double* xs, int lane) {
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) tr += A[i * N + i];
+  const double delta = 1e-15 * tr + 1e-300;
+  __syncwarp();
+  if (lane < N) A[lane * N + lane] += delta;
+  __syncwarp();
+  int piv[N];
+  lu_factor_warp<N, true>(A, nullptr, piv, lane);
+  if (lane == 0) {
+    double x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 1.0 / sqrt((double)N) * ((i & 1) ? 0.9 : 1.1);
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {   // row permutation + forward substitution (unit lower triangle)
+        // x[k] <-> x[piv[k]] with a run-time piv: select over the unrolled register file
+        const int pk = piv[k];
+        double xp = x[k];
+#pragma unroll
+        for (int q = k + 1; q < N; ++q)
+          if (q == pk) {
+            xp = x[q];
+            x[q] = x[k];
+          }
+        x[k] = xp;
+#pragma unroll
+        for (int j = 0; j < k; ++j) x[k] -= A[k * N + j] * x[j];
+      }
+#pragma unroll
+      for (int i = N - 1; i >= 0; --i) {
+        double sacc = x[i];
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) sacc -= A[i * N + j] * x[j];
+        const double d = A[i * N + i];
+        x[i] = d != 0.0 ? sacc / d : sacc;
+      }
+      double nrm = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) nrm += x[i] * x[i];
+      nrm = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] *= nrm;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) xs[i] = x[i];
+  }
+  __syncwarp();
+}
+
+#endif  // __CUDACC__
+
 }  // namespace mvo
