@@ -214,22 +214,36 @@ int mvo_orb_detect_and_compute(mvo_ctx* c, const uint8_t* img, int w, int h, int
     c->set_error("mvo_orb_detect_and_compute needs a batch==1 context (use mvo_group_step for groups)");
     return MVO_ERR_INVALID;
   }
-  rc = orb_upload(c, img, w, h, stride, channels, 0);
-  if (rc) return rc;
-  rc = orb_run_detect(c, desc != nullptr);
-  if (rc) return rc;
-  const size_t kb = (size_t)g.kp_cap * sizeof(mvo_keypoint), db = (size_t)g.kp_cap * 32;
-  rc = ensure_stage(c, kb + db + 64);
-  if (rc) return rc;
-  uint8_t* hs = c->h_stage.p;
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs, c->kp_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 16, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 32, c->occ.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64, c->kps.p, kb, cudaMemcpyDeviceToHost, c->stream));
-  if (desc) MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64 + kb, c->desc.p, db, cudaMemcpyDeviceToHost, c->stream));
-  MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  int n = *reinterpret_cast<int*>(hs);
-  const int flags = *reinterpret_cast<int*>(hs + 16);
+  size_t kb = 0, db = 0;
+  uint8_t* hs = nullptr;
+  int n = 0, flags = 0;
+  for (;;) {
+    rc = orb_upload(c, img, w, h, stride, channels, 0);
+    if (rc) return rc;
+    rc = orb_run_detect(c, desc != nullptr);
+    if (rc) return rc;
+    kb = (size_t)g.kp_cap * sizeof(mvo_keypoint);
+    db = (size_t)g.kp_cap * 32;
+    rc = ensure_stage(c, kb + db + 64);
+    if (rc) return rc;
+    hs = c->h_stage.p;
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hs, c->kp_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 16, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 32, c->occ.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64, c->kps.p, kb, cudaMemcpyDeviceToHost, c->stream));
+    if (desc) MVO_CUDA_TRY(c, cudaMemcpyAsync(hs + 64 + kb, c->desc.p, db, cudaMemcpyDeviceToHost, c->stream));
+    MVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    n = *reinterpret_cast<int*>(hs);
+    flags = *reinterpret_cast<int*>(hs + 16);
+    if (!(flags & 1) || c->cand_scale >= 16) break;
+    // FAST candidate list overflow (frames that are mostly noise: ~10 % of the pixels are corners): cv::ORB still
+    // returns features there, so the list capacity is doubled and the frame is run again instead of failing
+    c->cand_scale *= 2;
+    c->geom_w = c->geom_h = -1;                  // rebuild the geometry with the larger lists
+    c->have_prev = false;
+    rc = orb_prepare(c, w, h);
+    if (rc) return rc;
+  }
   c->occ_single[0] = reinterpret_cast<int*>(hs + 32)[0];
   c->occ_single[1] = reinterpret_cast<int*>(hs + 32)[1];
   c->occ_from_group = false;

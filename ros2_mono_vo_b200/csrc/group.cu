@@ -827,8 +827,14 @@ static int group_step_graph(mvo_ctx* c, const uint8_t* images, int w, int h, int
     flags0 |= sl.h_flags.p[b];
   }
   if (flags0 & 3) {
-    c->set_error(std::string(flags0 & 1 ? "FAST candidate list overflow" : "keypoint capacity exceeded") + " (first on stream " +
-                 std::to_string(first) + ")");
+    if ((flags0 & 1) && c->cand_scale < 16) {
+      // the candidate lists are doubled for the steps that follow (the geometry is rebuilt, the previous frame forgotten)
+      c->cand_scale *= 2;
+      c->geom_w = c->geom_h = -1;
+      c->have_prev = false;
+    }
+    c->set_error(std::string(flags0 & 1 ? "FAST candidate list overflow (capacity doubled for the next step)" : "keypoint capacity exceeded") +
+                 " (first on stream " + std::to_string(first) + ")");
     return MVO_ERR_CAPACITY;
   }
   return MVO_OK;

@@ -806,7 +806,9 @@ static int build_geometry(mvo_ctx* c, int w, int h, std::vector<uint32_t>& xt, s
     lv.quota = quotas[l];
     lv.off = off;
     off += (long long)lv.pitch * align_up((size_t)lv.h, 8);
-    lv.cand_cap = std::max(4096, (lv.w * lv.h) / 16);
+    // FAST + NMS candidates per level and frame: 1 / 16 of the pixels covers natural images many times over; a frame of
+    // pure sensor noise has ~10 % corners -- the detect call then doubles cand_scale and runs again (capi.cu)
+    lv.cand_cap = std::max(4096, (int)std::min<long long>((long long)(lv.w * lv.h) / 16 * c->cand_scale, (long long)lv.w * lv.h / 2 + 4096));
     lv.cand_off = cand_off;
     cand_off += lv.cand_cap;
     lv.xtab_off = xoff;

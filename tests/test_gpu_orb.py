@@ -83,6 +83,25 @@ def test_orb_vs_oracle_seeded(ctx_cache, h, w, n, seed):
     assert np.array_equal(desc, odesc)
 
 
+def test_orb_noise_frame_grows_the_candidate_lists():
+    """A frame of pure noise has ~10 % FAST corners after NMS, more than the default candidate capacity (1 / 16 of the
+    pixels): the detect call doubles the lists and runs again instead of failing; the result is still cv::ORB's."""
+    from ros2_mono_vo_b200 import Context
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (240, 320)).astype(np.uint8)
+    ctx = Context(320, 240, nfeatures=500)
+    kps, desc = ctx.orb_detect_and_compute(img)
+    okp, odesc = oo.orb_detect_and_compute(img, 500)
+    assert len(kps) == len(okp) > 300
+    assert np.array_equal(kps, okp) and np.array_equal(desc, odesc)
+    # and the context keeps working on ordinary frames afterwards
+    img2 = synth.synth_frame(240, 320, 5)
+    k2, d2 = ctx.orb_detect_and_compute(img2)
+    o2, od2 = oo.orb_detect_and_compute(img2, 500)
+    assert np.array_equal(k2, o2) and np.array_equal(d2, od2)
+    ctx.close()
+
+
 def test_orb_bgr_input(ctx_cache):
     img = synth.synth_frame(240, 320, 31)
     rng = np.random.default_rng(3)
