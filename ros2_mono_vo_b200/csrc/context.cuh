@@ -211,6 +211,7 @@ struct mvo_ctx {
   int dbg_lk_impl = 2;     // 1: first-generation lk_track_kernel (in-tree cross-check), 2: lk_track2_kernel (persistent
                            // warps for large point sets), 3: lk_track2_kernel with one point per warp always
   mvo::DevBuf<int32_t> lk_work;   // work counter of the persistent LK kernel
+  int dbg_lk_ctas_per_sm = 5;     // resident CTAs per SM of the persistent LK kernel (5 = all the shared memory of an SM)
   int cand_scale = 1;      // FAST candidate list capacity in units of (level pixels / 16); doubled after an overflow
   int occupancy_div = 50;  // keypoint-distribution grid cell size (config/params.yaml: initializer.occupancy_grid_div)
   mvo::DevBuf<int32_t> occ;            // batch * 2: occupied / total cells, written by orb_finalize_kernel

@@ -718,15 +718,60 @@ constexpr int kLk2Warps = MVO_LK2_WARPS;
 // stays resident until its slowest warp is done, so with one point per warp the achieved occupancy was 23 % of a
 // theoretical 31 %; drawing work keeps every warp slot busy to the end of the kernel.
 constexpr int kLk2MaxBatch = 1024;   // streams of a group the persistent form indexes (larger groups: one point per warp)
-template <bool PERSIST>
-__global__ void __launch_bounds__(kLk2Warps * 32, MVO_LK2_MINB)
+// CN = 3 (BGR8, what the node feeds: /root/reference/src/mono_vo.cpp:94): OpenCV's window then spans the three colour
+// planes -- every sum of the gray algorithm (the 2 x 2 normal matrix, the mismatch vector of each iteration, the L1 error)
+// runs over 21 x 21 x 3 values and nothing else changes.  A TEAM of three warps tracks one point, one warp per plane with
+// exactly the gray code path (its own TMA tiles, template, quads); at the three reduction points the warps exchange their
+// exact integer partial sums through shared memory behind a named barrier, so all three take the same decisions and
+// iterate in lock step.  (The first-generation lk_track_cn_kernel keeps all three planes in one warp: 23 KB of shared
+// memory per warp, 8 resident warps per SM, 3.5 ms per 32 x 2000 points; it stays as the cross-check, lk_impl = 1.)
+constexpr int kLk2WarpsCn = 3;   // CN = 3: one team per CTA (static shared memory stays below 48 KB)
+// (five CTAs per SM = 128 registers.  Six would cap the kernel at 96 registers; ptxas then spills 72 bytes and that build
+// returned wrong positions for points with border levels on the B200 -- the cause was not found, the same source is
+// correct at 128 and 170 registers, and tests/test_gpu_lk.py compares this kernel with the first-generation one on
+// border-heavy point sets so that a regression of that kind is seen.)
+#ifndef MVO_LK_T_MINB
+#define MVO_LK_T_MINB 5
+#endif
+template <bool PERSIST, int CN>
+__global__ void __launch_bounds__((CN == 1 ? kLk2Warps : kLk2WarpsCn) * 32, CN == 1 ? MVO_LK2_MINB : MVO_LK_T_MINB)
 lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTmaps tm, const uint8_t* __restrict__ pyrI,
                  const uint8_t* __restrict__ pyrJ, const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev,
                  int max_pts, float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err,
                  int* __restrict__ work_counter, int batch) {
-  __shared__ LkWarpSmem2 sm_all[kLk2Warps];
+  constexpr int NW = CN == 1 ? kLk2Warps : kLk2WarpsCn;
+  static_assert(CN == 1 || (CN == 3 && NW % CN == 0 && PERSIST), "teams of CN warps, persistent form only");
+  __shared__ LkWarpSmem2 sm_all[NW];
   __shared__ int s_cum[PERSIST ? kLk2MaxBatch + 1 : 1];   // s_cum[b] = points of the streams before b
+  __shared__ long long s_team[CN == 1 ? 1 : NW / CN][2][CN][3];   // team exchange: [team][slot parity][plane][value]
+  __shared__ int s_item[CN == 1 ? 1 : NW / CN][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = CN == 1 ? 0 : warp / CN, ch = CN == 1 ? 0 : warp - team * CN;
+  uint32_t tpar = 0, fpar = 0;
+  auto team_barrier = [&]() {
+    if (CN > 1) {
+      __syncwarp();   // (bar.sync is an aligned barrier: the warp must arrive converged)
+      asm volatile("barrier.sync %0, %1;" ::"r"(1 + team), "r"(32 * CN) : "memory");
+    }
+  };
+  // exact integer sums over the planes of the team (identity for gray); every warp of the team gets the same totals
+  auto team_sum3 = [&](long long& v0, long long& v1, long long& v2) {
+    if (CN == 1) return;
+    if (lane == 0) {
+      s_team[team][tpar][ch][0] = v0;
+      s_team[team][tpar][ch][1] = v1;
+      s_team[team][tpar][ch][2] = v2;
+    }
+    team_barrier();
+    v0 = v1 = v2 = 0;
+#pragma unroll
+    for (int q = 0; q < CN; ++q) {
+      v0 += s_team[team][tpar][q][0];
+      v1 += s_team[team][tpar][q][1];
+      v2 += s_team[team][tpar][q][2];
+    }
+    tpar ^= 1;   // two slots: a warp can only reach its next-but-one exchange after everybody has read this one
+  };
   LkWarpSmem2& sm = sm_all[warp];
   if (lane == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -760,8 +805,17 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
   int b, i;
   if (PERSIST) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    if (CN == 1) {
+      if (lane == 0) item = atomicAdd(work_counter, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    } else {
+      // two slots: a point can end without a single exchange (every level out of range), so the drawing warp may be
+      // back here before a team mate has read the previous item
+      if (ch == 0 && lane == 0) s_item[team][fpar] = atomicAdd(work_counter, 1);
+      team_barrier();
+      item = s_item[team][fpar];
+      fpar ^= 1;
+    }
     if (item >= total_items) break;
     int lo = 0, hi = batch;                 // largest b with s_cum[b] <= item
     while (hi - lo > 1) {
@@ -777,6 +831,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     if (i >= min(npts_dev[b], max_pts)) return;
   }
   const float2 p0 = pts[(long long)b * max_pts + i];
+  const int plane = b * CN + ch;         // planar pyramids: plane (b * CN + ch); also the z coordinate of the tensor maps
   float nx = 0.f, ny = 0.f, e = 0.f;
   int st = 1;
 
@@ -798,13 +853,13 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     int ix, iy;
     float qx, qy;
     ireq = tmpl_pos(g.nlevels - 1, ix, iy, qx, qy) == 2;
-    if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][g.nlevels - 1], (ix - 1) & ~15, iy - 1, b, &sm.bar[0], kTileHI);
+    if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][g.nlevels - 1], (ix - 1) & ~15, iy - 1, plane, &sm.bar[0], kTileHI);
   }
 
   for (int L = g.nlevels - 1; L >= 0; --L) {
     const LkLevel lv = g.lv[L];
-    const uint8_t* I = pyrI + (long long)b * g.frame_stride + lv.off;
-    const uint8_t* J = pyrJ + (long long)b * g.frame_stride + lv.off;
+    const uint8_t* I = pyrI + (long long)plane * g.frame_stride + lv.off;
+    const uint8_t* J = pyrJ + (long long)plane * g.frame_stride + lv.off;
     const int w = lv.w, h = lv.h, pitch = lv.pitch;
     if (L == g.nlevels - 1) {
       const float s = 1.f / (float)(1 << L);
@@ -838,7 +893,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
         jy0 = ty0;
         jpend = true;
         __syncwarp();   // every lane is done with the previous level's J tile and quads
-        if (lane == 0) tma_tile(sm.rawJ, &tm.m[1][L], jx0 & ~15, jy0, b, &sm.bar[1], kTileHJ);
+        if (lane == 0) tma_tile(sm.rawJ, &tm.m[1][L], jx0 & ~15, jy0, plane, &sm.bar[1], kTileHJ);
       }
     }
     int w00, w01, w10, w11;
@@ -848,7 +903,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     if (kind == 2) {
       if (!ireq) {   // (a level above was out of range: nothing was prefetched)
         __syncwarp();
-        if (lane == 0) tma_tile(sm.rawI, &tm.m[0][L], (ix - 1) & ~15, iy - 1, b, &sm.bar[0], kTileHI);
+        if (lane == 0) tma_tile(sm.rawI, &tm.m[0][L], (ix - 1) & ~15, iy - 1, plane, &sm.bar[0], kTileHI);
       }
       mbar_wait(&sm.bar[0], parI);
       parI ^= 1;
@@ -877,7 +932,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
       float nqx, nqy;
       ireq = tmpl_pos(L - 1, nix, niy, nqx, nqy) == 2;
       __syncwarp();
-      if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][L - 1], (nix - 1) & ~15, niy - 1, b, &sm.bar[0], kTileHI);
+      if (ireq && lane == 0) tma_tile(sm.rawI, &tm.m[0][L - 1], (nix - 1) & ~15, niy - 1, plane, &sm.bar[0], kTileHI);
     }
     uint32_t txy[2 * kRunLen];
 #pragma unroll
@@ -898,9 +953,12 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
       sA12 += gx * gy;
       sA22 += gy * gy;
     }
-    const float A11 = __fmul_rn((float)warp_sum_wide(sA11), flt_scale);
-    const float A12 = __fmul_rn((float)warp_sum_wide(sA12), flt_scale);
-    const float A22 = __fmul_rn((float)warp_sum_wide(sA22), flt_scale);
+    long long tA11 = warp_sum_wide(sA11), tA12 = warp_sum_wide(sA12), tA22 = warp_sum_wide(sA22);
+    team_sum3(tA11, tA12, tA22);
+
+    const float A11 = __fmul_rn((float)tA11, flt_scale);
+    const float A12 = __fmul_rn((float)tA12, flt_scale);
+    const float A22 = __fmul_rn((float)tA22, flt_scale);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dA = __fsub_rn(A11, A22);
     const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -913,7 +971,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     // (re)stage the J region so that it covers the window at integer position (inx, iny)
     auto cover = [&](int inx, int iny) {
       if (jpend || inx < jx0 || inx - jx0 > kJSlackX || iny < jy0 || iny - jy0 > kJSlackY) {
-        const int3 r = lk_restage(sm, &tm.m[1][L], J, inx, iny, w, h, pitch, lane, b, jpend, jx0, jy0, parJ);
+        const int3 r = lk_restage(sm, &tm.m[1][L], J, inx, iny, w, h, pitch, lane, plane, jpend, jx0, jy0, parJ);
         jx0 = r.x;
         jy0 = r.y;
         parJ = (uint32_t)r.z;
@@ -943,8 +1001,10 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
         sb1 += da * (int)(short)(txy[k] & 0xffffu) + db * (int)(short)(txy[kRunLen + k] & 0xffffu);
         sb2 += da * ((int)txy[k] >> 16) + db * ((int)txy[kRunLen + k] >> 16);
       }
-      const float b1 = __fmul_rn((float)warp_sum_wide(sb1), flt_scale);
-      const float b2 = __fmul_rn((float)warp_sum_wide(sb2), flt_scale);
+      long long tb1 = warp_sum_wide(sb1), tb2 = warp_sum_wide(sb2), tb3 = 0;
+      team_sum3(tb1, tb2, tb3);
+      const float b1 = __fmul_rn((float)tb1, flt_scale);
+      const float b2 = __fmul_rn((float)tb2, flt_scale);
       const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       cx = __fadd_rn(cx, dx);
@@ -981,8 +1041,9 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
           const int eb = abs((dp2a_hi_su(Vb, qb, dp2a_lo_su(Vt, qb, 1 << 8)) >> 9) - LK2_TI(kRunLen + k));
           se += has1 ? eb : 0;
         }
-        se = __reduce_add_sync(0xffffffffu, se);
-        e = __fdiv_rn((float)se, (float)(32 * LKW * LKW));
+        long long te = __reduce_add_sync(0xffffffffu, se), te1 = 0, te2 = 0;
+        team_sum3(te, te1, te2);
+        e = __fdiv_rn((float)(int)te, (float)(32 * LKW * CN * LKW));
       }
     }
     if (jpend) {   // a requested tile nobody consumed (degenerate level, window left the image): drain it
@@ -991,7 +1052,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
     }
 #undef LK2_TI
   }
-  if (lane == 0) {
+  if (lane == 0 && ch == 0) {
     const long long o = (long long)b * max_pts + i;
     out_pts[o] = make_float2(nx, ny);
     status[o] = (uint8_t)st;
@@ -1363,10 +1424,22 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
   LkGeom g;
   lk_geometry(c->lk_w, c->lk_h, g);
   if (max_pts > 0) {
-    if (c->lk_cn == 3) {
+    if (c->lk_cn == 3 && (c->dbg_lk_impl == 1 || c->cfg.batch > kLk2MaxBatch)) {
       dim3 grid((max_pts + kLkWarpsCn - 1) / kLkWarpsCn, c->cfg.batch);
       lk_track_cn_kernel<3><<<grid, kLkWarpsCn * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p,
                                                                     pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
+    } else if (c->lk_cn == 3) {
+      // BGR8: teams of three warps (one per colour plane) on the second-generation kernel, persistent form
+      LkTmaps tm;
+      memcpy(tm.m[0], c->lk_tmaps[prev_which][0], sizeof(tm.m[0]));
+      memcpy(tm.m[1], c->lk_tmaps[next_which][1], sizeof(tm.m[1]));
+      const long long items = (long long)max_pts * c->cfg.batch;
+      const int ctas = (int)std::min<long long>(148LL * MVO_LK_T_MINB, std::max<long long>(items, 1));
+      MVO_CUDA_TRY(c, c->lk_work.alloc(1));
+      MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 4, c->stream));
+      lk_track2_kernel<true, 3><<<dim3(ctas, 1), kLk2WarpsCn * 32, 0, c->stream>>>(
+          g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
+          c->lk_work.p, c->cfg.batch);
     } else {
       dim3 grid((max_pts + kLkWarps - 1) / kLkWarps, c->cfg.batch);
       // mvo_debug_set("lk_impl", 1): the first-generation kernel (kept as the in-tree cross-check; identical results)
@@ -1380,13 +1453,14 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
         const long long items = (long long)max_pts * c->cfg.batch;
         if (c->dbg_lk_impl == 3 || items < 148LL * MVO_LK2_MINB * kLk2Warps * 4 || c->cfg.batch > kLk2MaxBatch) {
           // few points (single stream): one point per warp fills the GPU better than a persistent grid
-          lk_track2_kernel<false><<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
+          lk_track2_kernel<false, 1><<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
               g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
               nullptr, c->cfg.batch);
         } else {
           MVO_CUDA_TRY(c, c->lk_work.alloc(1));
           MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 4, c->stream));
-          lk_track2_kernel<true><<<dim3(148 * MVO_LK2_MINB, 1), kLk2Warps * 32, 0, c->stream>>>(
+          const int per_sm = std::min(std::max(c->dbg_lk_ctas_per_sm, 1), MVO_LK2_MINB);
+          lk_track2_kernel<true, 1><<<dim3(148 * per_sm, 1), kLk2Warps * 32, 0, c->stream>>>(
               g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
               c->lk_work.p, c->cfg.batch);
         }

@@ -94,6 +94,34 @@ def test_lk_bgr_vs_cv2_golden(ctx, tag):
     assert np.abs(n3[mm] - o3[mm]).max() < POS_TOL
 
 
+@pytest.mark.parametrize("h,w,seed", [(240, 320, 12), (480, 640, 5), (121, 203, 9)])
+def test_lk_bgr_team_kernel_matches_first_generation(ctx, h, w, seed):
+    """The three-warp-team BGR8 kernel against the one-warp-per-point kernel (lk_impl = 1): identical outputs, on a point
+    set that is dense along the image borders (border template / border J region on one to four levels) and includes
+    points whose windows leave the image."""
+    f0, f1 = synth.synth_pair_bgr(h, w, seed)
+    rng = np.random.default_rng(seed)
+    inner = rng.uniform([0, 0], [w - 1, h - 1], (1500, 2))
+    edge = np.concatenate([np.stack([rng.uniform(-3, 45, 400), rng.uniform(0, h, 400)], 1),
+                           np.stack([rng.uniform(w - 45, w + 3, 400), rng.uniform(0, h, 400)], 1),
+                           np.stack([rng.uniform(0, w, 400), rng.uniform(-3, 45, 400)], 1),
+                           np.stack([rng.uniform(0, w, 400), rng.uniform(h - 45, h + 3, 400)], 1)])
+    grid = np.stack(np.meshgrid(np.arange(20, w - 19, 40.0), np.arange(20, h - 19, 40.0)), -1).reshape(-1, 2)
+    pts = np.concatenate([inner, edge, grid]).astype(np.float32)
+    for frames in ((f0, f1), (np.repeat(f0[:, :, :1], 3, 2), np.repeat(f1[:, :, :1], 3, 2))):
+        ctx.debug_set("cache", 0)
+        try:
+            new = ctx.lk_track(*frames, pts)
+            ctx.debug_set("lk_impl", 1)
+            old = ctx.lk_track(*frames, pts)
+        finally:
+            ctx.debug_set("lk_impl", 0)
+            ctx.debug_set("cache", 1)
+        assert np.array_equal(new[1], old[1])
+        assert np.array_equal(new[0], old[0], equal_nan=True)
+        assert np.array_equal(new[2], old[2])
+
+
 def test_lk_outside_and_nan_points(ctx):
     """Points outside the image and a NaN coordinate (values from cv2 4.13.0 on the same pair: status 0 1 0 0 1 1; OpenCV
     floors a NaN to INT_MIN, i.e. out of range on every level, and still returns the propagated coordinates)."""
