@@ -204,6 +204,78 @@ def sequence_depth(h: int, w: int, stream: int) -> np.ndarray:
     return 6.0 + 20.0 * _smooth_field(h, w, rng)
 
 
+def _sample_bilinear(f: np.ndarray, xs: np.ndarray, ys: np.ndarray) -> np.ndarray:
+    """f (float, h x w) at fractional positions, reflect-101 outside."""
+    h, w = f.shape
+    x0 = np.floor(xs).astype(int)
+    y0 = np.floor(ys).astype(int)
+    ax, ay = xs - x0, ys - y0
+
+    def refl(i, n):
+        i = np.abs(i)
+        i = np.where(i >= n, 2 * (n - 1) - i, i)
+        return np.clip(i, 0, n - 1)
+
+    x0r, x1r = refl(x0, w), refl(x0 + 1, w)
+    y0r, y1r = refl(y0, h), refl(y0 + 1, h)
+    return (f[y0r, x0r] * (1 - ax) + f[y0r, x1r] * ax) * (1 - ay) + (f[y1r, x0r] * (1 - ax) + f[y1r, x1r] * ax) * ay
+
+
+def room_planes(stream: int) -> np.ndarray:
+    """Walls of a seeded convex room around camera 0 (rows n_x, n_y, n_z, d with n.X = d, camera axes: x right, y down,
+    z forward): a road 1.65 below the camera, a ceiling, two side walls and a front wall, each slightly slanted.  From
+    any point inside a convex room every ray meets exactly one wall first and nothing is ever occluded."""
+    rng = np.random.default_rng(1000 * stream + 31)
+    j = lambda a: rng.uniform(-a, a)
+    return np.array([[j(0.03), 1.0, j(0.02), 1.65],
+                     [j(0.03), -1.0, j(0.03), rng.uniform(4.0, 6.0)],
+                     [-1.0, j(0.05), j(0.08), rng.uniform(5.0, 8.0)],
+                     [1.0, j(0.05), j(0.08), rng.uniform(5.0, 8.0)],
+                     [j(0.15), j(0.05), 1.0, rng.uniform(28.0, 34.0)]])
+
+
+def render_rigid(base: np.ndarray, planes: np.ndarray, K: np.ndarray, R_wc: np.ndarray, C: np.ndarray):
+    """Exact view of the room `planes`, textured by camera 0's frame `base` (a wall point has the colour of the pixel of
+    camera 0 it projects to), from the camera with orientation R_wc (camera -> world = camera 0) at position C: ray /
+    wall intersection in closed form per pixel, one bilinear sample of `base`.  The scene is rigid for any motion,
+    rotation included (synth_sequence's is rigid to first order only).  Returns the u8 frame and the depth map."""
+    h, w = base.shape
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    D = np.tensordot(R_wc @ np.linalg.inv(K), np.stack([xx, yy, np.ones_like(xx)]), 1)     # ray directions (world)
+    s = np.full((h, w), np.inf)
+    for n0, n1, n2, d in planes:
+        den = n0 * D[0] + n1 * D[1] + n2 * D[2]
+        num = d - (n0 * C[0] + n1 * C[1] + n2 * C[2])
+        si = np.where(den > 1e-12, num / np.where(den > 1e-12, den, 1.0), np.inf)
+        s = np.minimum(s, np.where(si > 0, si, np.inf))
+    X = C[:, None, None] + s * D
+    q = np.tensordot(K, X, 1)
+    out = _sample_bilinear(base.astype(np.float64), q[0] / q[2], q[1] / q[2])
+    depth = np.tensordot(R_wc.T, X - C[:, None, None], 1)[2]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8), depth
+
+
+def synth_rigid_sequence(h: int, w: int, stream: int, nframes: int):
+    """A seeded camera moving (forward translation, a little sideways drift and a slow yaw / pitch / roll) through an
+    exactly rigid scene: every frame is render_rigid of the same textured room (depths 6 .. 33).
+    Returns frames, K, R_wc (nframes x 3 x 3), C (nframes x 3): X_world = R_wc[k] X_cam_k + C[k], world = camera 0."""
+    rng = np.random.default_rng(1000 * stream + 29)
+    base = synth_frame(h, w, 1000 * stream)
+    K = sequence_camera(h, w)
+    planes = room_planes(stream)
+    frames, Rs, Cs = [base], [np.eye(3)], [np.zeros(3)]
+    C = np.zeros(3)
+    rv = np.zeros(3)
+    for _ in range(1, nframes):
+        rv = rv + np.array([rng.uniform(-0.0005, 0.0005), rng.uniform(0.001, 0.003), rng.uniform(-0.0003, 0.0003)])
+        R = rodrigues(rv)
+        C = C + R @ np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.02, 0.02), rng.uniform(0.4, 0.6)])
+        frames.append(render_rigid(base, planes, K, R, C)[0])
+        Rs.append(R)
+        Cs.append(C.copy())
+    return frames, K, np.stack(Rs), np.stack(Cs)
+
+
 def rodrigues(rvec) -> np.ndarray:
     rvec = np.asarray(rvec, dtype=np.float64)
     th = np.linalg.norm(rvec)
