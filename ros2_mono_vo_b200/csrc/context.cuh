@@ -243,6 +243,7 @@ struct mvo_ctx {
   int cache_enabled = 1;               // mvo_debug_set("cache", 0) switches both caches off
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
   int dbg_e5_roots_impl = 2;   // 1: derivative-level bracketing only (cross-check), 2: Ehrlich-Aberth iteration first, bracketing where it is not trusted
+  int dbg_pnp_epnp_impl = 1;   // 12 x 12 Jacobi of pnp_epnp_kernel: 0 round 1 (cross-check), 1 one element pair per lane + short scalar chain
   int dbg_pnp_refine_impl = 2; // 1: first-generation initial pose of pnp_refine_kernel (cross-check), 2: block sums + warp LU
   int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel
 

@@ -217,6 +217,35 @@ MVO_HD void smallest_eigvec_spd(double* A, double* x) {
   }
 }
 
+// Rotation parameters of one Jacobi step from (a_pp, a_qq, a_pq).  FAST = false: the expressions of jacobi_eig (theta, t,
+// c, s: three divisions and two square roots in a row).  FAST = true: the same rotation without theta and t.  With
+// d = a_qq - a_pp, x = d^2 + 4 a_pq^2 and g = 1 / sqrt(x):  c^2 = (1 + |d| g) / 2,  s = sgn(theta) a_pq g / c -- two
+// reciprocal square roots and a handful of multiply-adds on the critical path of every rotation; c and s agree with the
+// slow form to a few ulp.
+template <bool FAST>
+MVO_HD __forceinline__ void jacobi_cs(double app, double aqq, double apq, double& c, double& s) {
+  if (FAST) {
+    const double d = aqq - app;
+#ifdef __CUDA_ARCH__
+    const double g = rsqrt(fma(d, d, 4.0 * apq * apq));
+    const double z = fma(0.5 * fabs(d), g, 0.5);
+    const double q = rsqrt(z);                       // 1 / c
+#else
+    const double g = 1.0 / sqrt(d * d + 4.0 * apq * apq);
+    const double z = 0.5 * fabs(d) * g + 0.5;
+    const double q = 1.0 / sqrt(z);
+#endif
+    const double ag = (d >= 0.0 ? apq : -apq) * g;   // sgn(d) a_pq g = sgn(theta) |a_pq| g   (d = 0: theta = +-0 counts as >= 0 ...
+    c = z * q;
+    s = (d == 0.0 ? fabs(apq) * g : ag) * q;         // ... so t = +1 there whatever the sign of a_pq)
+  } else {
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    c = 1.0 / sqrt(t * t + 1.0);
+    s = t * c;
+  }
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix.  A is destroyed (diagonal = eigenvalues),
 // V (row-major, columns = eigenvectors).
 template <int N>
@@ -321,9 +350,72 @@ __device__ void jacobi_eig_warp(double* A, double* V, int lane) {
 }
 #endif
 
+#ifdef __CUDACC__
+// jacobi_eig_warp without divergence and with one barrier less per rotation.  A rotation (p, q) is 32 independent plane
+// rotations of element pairs plus the 2 x 2 block: the column update A <- A J touches (A[k][p], A[k][q]), the row update
+// A <- J^T A touches (A[p][k], A[q][k]) -- outside the block (k != p, q) they do not see each other's results -- and V
+// <- V J touches (V[k][p], V[k][q]).  That is 10 + 10 + 12 pairs: one per lane, every lane running the same
+// instructions on its own two addresses (jacobi_eig_warp ran three divergent branches one after the other: 520 of its
+// 890 cycles per rotation).  The four entries of the block are computed redundantly by every lane from the broadcast
+// values, column update first, and stored by lane 0.  Same rotation order and element-wise expressions as jacobi_eig.
+// (A form with the rows in registers and shuffles instead of shared memory needs the (p, q) loops unrolled -- 66 bodies,
+// 38 K instructions against a 32 KB instruction cache -- and ran at half the speed of the shared-memory form.)
+template <int N, bool FAST_CS>
+__device__ void jacobi_eig_warp3(double* A, double* V, int lane) {
+  static_assert(3 * N - 4 == 32, "one pair per lane: 2 (N - 2) pairs of A and N of V");
+  for (int i = lane; i < N * N; i += 32) V[i] = (i / N == i % N) ? 1.0 : 0.0;
+  __syncwarp();
+  const int role = lane < N - 2 ? 0 : (lane < 2 * (N - 2) ? 1 : 2);      // column pair, row pair, eigenvector pair
+  const int l = lane - (role == 0 ? 0 : (role == 1 ? N - 2 : 2 * (N - 2)));
+#pragma unroll 1
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+      diag += A[i * N + i] * A[i * N + i];
+#pragma unroll 1
+      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+    }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll 1
+    for (int p = 0; p < N - 1; ++p)
+#pragma unroll 1
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p * N + q];
+        if (apq == 0.0) continue;   // warp-uniform
+        const double app = A[p * N + p], aqq = A[q * N + q], aqp = A[q * N + p];
+        double c, s;
+        jacobi_cs<FAST_CS>(app, aqq, apq, c, s);
+        // this lane's pair
+        int k = l;
+        if (role != 2) {            // the l-th index that is neither p nor q
+          k += (k >= p);
+          k += (k >= q);
+        }
+        double* M = role == 2 ? V : A;
+        const int ia = role == 1 ? p * N + k : k * N + p, ib = role == 1 ? q * N + k : k * N + q;
+        __syncwarp();   // every lane has read the block
+        const double x = M[ia], y = M[ib];
+        M[ia] = c * x - s * y;
+        M[ib] = s * x + c * y;
+        // the block: rows p and q of A J, then J^T on them
+        const double ppc = c * app - s * apq, pqc = s * app + c * apq;
+        const double qpc = c * aqp - s * aqq, qqc = s * aqp + c * aqq;
+        if (lane == 0) {
+          A[p * N + p] = c * ppc - s * qpc;
+          A[q * N + p] = s * ppc + c * qpc;
+          A[p * N + q] = c * pqc - s * qqc;
+          A[q * N + q] = s * pqc + c * qqc;
+        }
+        __syncwarp();
+      }
+  }
+}
+#endif
+
 // The same cyclic Jacobi, fully unrolled for small N: every index is a compile-time constant after unrolling, so A and
 // V live in registers instead of local memory (the per-point 4 x 4 triangulation problems run this 256 K times a step).
-template <int N>
+template <int N, bool FAST_CS = false>
 MVO_HD __forceinline__ void jacobi_eig_reg(double* A, double* V) {
 #pragma unroll
   for (int i = 0; i < N; ++i)
@@ -345,9 +437,8 @@ MVO_HD __forceinline__ void jacobi_eig_reg(double* A, double* V) {
       for (int q = p + 1; q < N; ++q) {
         const double apq = A[p * N + q];
         if (apq != 0.0) {
-          const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
-          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+          double c, s;
+          jacobi_cs<FAST_CS>(A[p * N + p], A[q * N + q], apq, c, s);
 #pragma unroll
           for (int k = 0; k < N; ++k) {
             const double akp = A[k * N + p], akq = A[k * N + q];

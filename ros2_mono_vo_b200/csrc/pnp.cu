@@ -36,61 +36,68 @@ __global__ void pnp_normalize_kernel(const float2* __restrict__ img, const int32
   xn[(long long)b * max_pts + i] = make_double2((double)x, (double)y);
 }
 
-// the registrator's getSubset without a subset check: distinct indices, a repeated draw is redrawn.  The walk over
-// the RNG stream is sequential by nature (one thread); the stream itself is staged through shared memory in chunks by
-// the whole warp, so the walker pays shared-memory instead of global-memory latency per draw.
-constexpr int kPnpRngChunk = 1024;
-__global__ void __launch_bounds__(32)
+// the registrator's getSubset without a subset check: distinct indices, a repeated draw is redrawn.  The walk over the
+// RNG stream is sequential -- sample k starts where sample k - 1 stopped -- but where a sample that starts at a given
+// offset stops does not depend on anything else, so every offset of a 1024-draw window simulates "the sample that would
+// start here" in parallel (thread per offset), one thread then follows the chain offset -> next offset from the current
+// position (one shared-memory load per sample instead of ~40 dependent instructions per draw: 52 -> 6 us), and the
+// threads the chain visited write their samples out.
+constexpr int kPnpSampleThreads = 1024;
+__global__ void __launch_bounds__(kPnpSampleThreads)
 pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* __restrict__ npts, int iters,
                   int32_t* __restrict__ subsets) {
-  __shared__ uint32_t s_rng[kPnpRngChunk];
-  __shared__ int s_pos, s_it, s_i, s_idx[kPnpK];
-  const int b = blockIdx.x, lane = threadIdx.x;
+  __shared__ int s_next[kPnpSampleThreads], s_slot[kPnpSampleThreads];
+  __shared__ int s_pos, s_it;
+  const int b = blockIdx.x, t = threadIdx.x;
   const int n = npts[b];
+  int32_t* out = subsets + (long long)b * iters * kPnpK;
   if (n < kPnpK) {   // no sample of distinct points exists (batched callers pass npts = 0 for streams without enough points)
-    for (int k = lane; k < iters * kPnpK; k += 32) subsets[(long long)b * iters * kPnpK + k] = 0;
+    for (int k = t; k < iters * kPnpK; k += kPnpSampleThreads) out[k] = 0;
     return;
   }
-  if (lane == 0) {
+  if (t == 0) {
     s_pos = 0;
     s_it = 0;
-    s_i = 0;
   }
-  __syncwarp();
-  for (int base = 0; base < rng_len; base += kPnpRngChunk) {
-    if (s_it >= iters) break;
-    const int len = min(kPnpRngChunk, rng_len - base);
-    for (int k = lane; k < len; k += 32) s_rng[k] = rng[base + k];
-    __syncwarp();
-    if (lane == 0) {
-      int pos = s_pos, it = s_it, i = s_i;
-      int idx[kPnpK];
-      for (int j = 0; j < kPnpK; ++j) idx[j] = s_idx[j];
-      while (it < iters && pos < base + len) {
-        const int v = (int)(s_rng[pos++ - base] % (uint32_t)n);
-        bool dup = false;
-        for (int j = 0; j < kPnpK; ++j) dup = dup || (j < i && idx[j] == v);
-        if (dup) continue;
+  __syncthreads();
+  for (;;) {
+    const int base = s_pos, it0 = s_it;
+    if (it0 >= iters || base >= rng_len) break;
+    int idx[kPnpK];
+    int o = base + t, i = 0;
+    while (i < kPnpK && o < rng_len) {
+      const int v = (int)(rng[o++] % (uint32_t)n);
+      bool dup = false;
 #pragma unroll
-        for (int j = 0; j < kPnpK; ++j)
-          if (j == i) idx[j] = v;
-        if (++i == kPnpK) {
-          for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = idx[j];
-          ++it;
-          i = 0;
-        }
-      }
-      s_pos = pos;
-      s_it = it;
-      s_i = i;
-      for (int j = 0; j < kPnpK; ++j) s_idx[j] = idx[j];
+      for (int j = 0; j < kPnpK; ++j) dup = dup || (j < i && idx[j] == v);
+      if (dup) continue;
+#pragma unroll
+      for (int j = 0; j < kPnpK; ++j)
+        if (j == i) idx[j] = v;
+      ++i;
     }
-    __syncwarp();
+    s_next[t] = i == kPnpK ? o - base : -1;   // (relative; a sample that starts near the end of the window may stop outside)
+    s_slot[t] = -1;
+    __syncthreads();
+    if (t == 0) {
+      int cur = 0, it = it0;
+      while (it < iters && cur < kPnpSampleThreads && s_next[cur] >= 0) {
+        s_slot[cur] = it++;
+        cur = s_next[cur];
+      }
+      // the stream ran out inside a sample (cannot happen with the table sizes in use): stop, the rest is marked below
+      s_pos = (cur < kPnpSampleThreads && it < iters) ? rng_len : base + cur;
+      s_it = it;
+    }
+    __syncthreads();
+    const int slot = s_slot[t];
+    if (slot >= 0) {
+#pragma unroll
+      for (int j = 0; j < kPnpK; ++j) out[slot * kPnpK + j] = idx[j];
+    }
+    __syncthreads();
   }
-  // the stream ran out (cannot happen with the table sizes in use): the remaining subsets are marked unusable
-  if (lane == 0)
-    for (int it = s_it; it < iters; ++it)
-      for (int j = 0; j < kPnpK; ++j) subsets[((long long)b * iters + it) * kPnpK + j] = 0;
+  for (int k = s_it * kPnpK + t; k < iters * kPnpK; k += kPnpSampleThreads) out[k] = 0;   // unusable samples
 }
 
 // One warp per hypothesis (epnp_solve_warp, pnp_math.cuh).
@@ -98,6 +105,7 @@ constexpr int kEpnpWarps = 2;
 #ifndef MVO_EPNP_MINB
 #define MVO_EPNP_MINB 6   // 168 registers: 12 instead of 8 resident warps per SM (batched tracking step 4.35 -> 3.85 ms; 8 blocks / 128 registers loses again)
 #endif
+template <int IMPL>
 __global__ void __launch_bounds__(kEpnpWarps * 32, MVO_EPNP_MINB)
 pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, int max_pts,
                 const int32_t* __restrict__ subsets, int iters, double* __restrict__ models, int32_t* __restrict__ ok) {
@@ -117,7 +125,7 @@ pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, i
     us[i][1] = u.y;
   }
   double R[9], t[3];
-  const bool good = epnp_solve_warp<kPnpK>(pw, us, s_A[warp], s_V[warp], lane, R, t);
+  const bool good = epnp_solve_warp<kPnpK, IMPL>(pw, us, s_A[warp], s_V[warp], lane, R, t);
   if (lane == 0) {
     double* m = models + ((long long)b * iters + it) * 12;
     for (int q = 0; q < 9; ++q) m[q] = R[q];
@@ -663,9 +671,13 @@ int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
   const float thr2 = (float)(reproj_err * reproj_err);
   dim3 gn((p.max_pts + 255) / 256, B);
   pnp_normalize_kernel<<<gn, 256, 0, c->stream>>>(p.img.p, p.npts.p, p.max_pts, p.K.p, p.xn.p);
-  pnp_sample_kernel<<<B, 32, 0, c->stream>>>(r.rng.p, r.rng_len, p.npts.p, iters, p.subsets.p);
+  pnp_sample_kernel<<<B, kPnpSampleThreads, 0, c->stream>>>(r.rng.p, r.rng_len, p.npts.p, iters, p.subsets.p);
   dim3 ge((iters + kEpnpWarps - 1) / kEpnpWarps, B);
-  pnp_epnp_kernel<<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
+  // mvo_debug_set("pnp_epnp_impl", 0): the round-1 form of the 12 x 12 eigen-decomposition (cross-check)
+  if (c->dbg_pnp_epnp_impl == 0)
+    pnp_epnp_kernel<0><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
+  else
+    pnp_epnp_kernel<1><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
   dim3 gs(iters, B);
   pnp_score_kernel<<<gs, 256, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.ok.p, iters,
                                              thr2, p.counts.p);

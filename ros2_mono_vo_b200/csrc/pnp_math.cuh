@@ -109,7 +109,7 @@ MVO_HD void ls_solve(const double* A, const double* b, double* x) {
     Atb[i] = s;
   }
   PNP_DBG("ls%d AtA %.6g %.6g %.6g %.6g Atb %.6g %.6g %.6g\n", N, AtA[0], AtA[1], AtA[N+1], AtA[N*N-1], Atb[0], Atb[1], Atb[N-1]);
-  jacobi_eig_reg<N>(AtA, V);   // N <= 5: fully unrolled, AtA and V stay in registers
+  jacobi_eig_reg<N, true>(AtA, V);   // N <= 5: fully unrolled, AtA and V stay in registers; short scalar chain per rotation
   PNP_DBG("ls%d eig %.6g %.6g %.6g V0 %.6g %.6g %.6g\n", N, AtA[0], AtA[N+1], AtA[N*N-1], V[0], V[1], V[2]);
   double lmax = 0;
   for (int i = 0; i < N; ++i) lmax = fmax(lmax, AtA[i * N + i]);
@@ -125,13 +125,14 @@ MVO_HD void ls_solve(const double* A, const double* b, double* x) {
 }
 
 // closest rotation to a 3x3 matrix: R = U V^T of its SVD (polar factor), through the eigenvectors of A^T A
+template <bool FAST_CS = false>
 MVO_HD void polar_rotation(const double* A, double* R) {
   double AtA[9], V[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) AtA[i * 3 + j] = A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j];
-  jacobi_eig<3>(AtA, V);
+  jacobi_eig_reg<3, FAST_CS>(AtA, V);
   // U_e = A v_e / sigma_e for the two largest singular values, the third completes a right-handed pair of frames
   int order[3] = {0, 1, 2};
 #pragma unroll
@@ -383,53 +384,43 @@ template <int N>
 MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const double (*v)[12], const double (*alphas)[4],
                         const double (*pw)[3], const double (*us)[2], double* R, double* t) {
   double betas[4] = {0, 0, 0, 0};
-  if (mode == 0) {
-    double A[24], x[4];
-    const int cols[4] = {0, 1, 3, 6};
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) A[i * 4 + j] = L[i * 10 + cols[j]];
-    ls_solve<6, 4>(A, rho, x);
-    if (x[0] < 0) {
-      betas[0] = sqrt(-x[0]);
-      betas[1] = -x[1] / betas[0];
-      betas[2] = -x[2] / betas[0];
-      betas[3] = -x[3] / betas[0];
-    } else {
-      betas[0] = sqrt(x[0]);
-      betas[1] = x[1] / betas[0];
-      betas[2] = x[2] / betas[0];
-      betas[3] = x[3] / betas[0];
-    }
-  } else if (mode == 1) {
-    double A[18], x[3];
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) A[i * 3 + j] = L[i * 10 + j];
-    ls_solve<6, 3>(A, rho, x);
-    if (x[0] < 0) {
-      betas[0] = sqrt(-x[0]);
-      betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
-    } else {
-      betas[0] = sqrt(x[0]);
-      betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
-    }
-    if (x[1] < 0) betas[0] = -betas[0];
-  } else {
+  {
+    // The three approximations solve 6 x 4, 6 x 3 and 6 x 5 systems (columns {0, 1, 3, 6}, {0, 1, 2}, {0 .. 4} of L).  The
+    // three lanes of a warp run them side by side, so all three are written as one 6 x 5 problem with zero columns at
+    // the end: a zero column is an exact zero eigenvalue that no rotation touches (a_pq == 0 is skipped) and the
+    // back-substitution drops, so x equals the smaller problem's solution bit for bit and the lanes do not diverge.
     double A[30], x[5];
+    const int ncols = mode == 0 ? 4 : (mode == 1 ? 3 : 5);
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int j = 0; j < 5; ++j) A[i * 5 + j] = L[i * 10 + j];
+      for (int j = 0; j < 5; ++j) {
+        const int col = mode == 0 ? (j == 2 ? 3 : (j == 3 ? 6 : j)) : j;
+        A[i * 5 + j] = j < ncols ? L[i * 10 + col] : 0.0;
+      }
     ls_solve<6, 5>(A, rho, x);
-    if (x[0] < 0) {
-      betas[0] = sqrt(-x[0]);
-      betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+    if (mode == 0) {
+      if (x[0] < 0) {
+        betas[0] = sqrt(-x[0]);
+        betas[1] = -x[1] / betas[0];
+        betas[2] = -x[2] / betas[0];
+        betas[3] = -x[3] / betas[0];
+      } else {
+        betas[0] = sqrt(x[0]);
+        betas[1] = x[1] / betas[0];
+        betas[2] = x[2] / betas[0];
+        betas[3] = x[3] / betas[0];
+      }
     } else {
-      betas[0] = sqrt(x[0]);
-      betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
+      if (x[0] < 0) {
+        betas[0] = sqrt(-x[0]);
+        betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+      } else {
+        betas[0] = sqrt(x[0]);
+        betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
+      }
+      if (x[1] < 0) betas[0] = -betas[0];
+      if (mode == 2) betas[2] = x[3] / betas[0];
     }
-    if (x[1] < 0) betas[0] = -betas[0];
-    betas[2] = x[3] / betas[0];
   }
   PNP_DBG("mode %d betas0 %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
   // five Gauss-Newton steps on the six distance constraints
@@ -483,7 +474,7 @@ MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const doub
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int k = 0; k < 3; ++k) ABt[3 * j + k] += (pcs[i][j] - pc0[j]) * (pw[i][k] - pw0[k]);
-  polar_rotation(ABt, R);
+  polar_rotation<true>(ABt, R);
   if (det3(R) < 0) {
     R[6] = -R[6];
     R[7] = -R[7];
@@ -544,9 +535,14 @@ MVO_HD bool epnp_solve(const double (*pw)[3], const double (*us)[2], double* Rou
 // (jacobi_eig_warp: same rotation order and expressions as jacobi_eig); the three beta approximations run on lanes
 // 0, 1, 2 side by side and the winner is picked with OpenCV's rule.  sA / sV: 144 doubles of shared memory each.
 // The result is returned in every lane.
-template <int N>
+// IMPL 0: jacobi_eig_warp (round 1, kept as the cross-check); 1: jacobi_eig_warp3 (one element pair per lane, no
+// divergence, short scalar chain for the rotation parameters).
+template <int N, int IMPL>
 __device__ bool epnp_solve_warp(const double (*pw)[3], const double (*us)[2], double* sA, double* sV, int lane, double* Rout,
                                 double* tout) {
+#ifdef MVO_EPNP_CLOCK
+  const long long c0 = clock64();
+#endif
   double cws[4][3], alphas[N][4];
   {
     double MtM[144];
@@ -554,12 +550,25 @@ __device__ bool epnp_solve_warp(const double (*pw)[3], const double (*us)[2], do
     for (int q = lane; q < 144; q += 32) sA[q] = MtM[q];   // identical in every lane
   }
   __syncwarp();
-  jacobi_eig_warp<12>(sA, sV, lane);
+#ifdef MVO_EPNP_CLOCK
+  const long long c1 = clock64();
+#endif
+  if (IMPL == 0) jacobi_eig_warp<12>(sA, sV, lane);
+  else jacobi_eig_warp3<12, true>(sA, sV, lane);
   __syncwarp();
+#ifdef MVO_EPNP_CLOCK
+  const long long c2 = clock64();
+#endif
   double v[4][12], L[60], rho[6];
   epnp_basis(sA, sV, cws, v, L, rho);
+#ifdef MVO_EPNP_CLOCK
+  const long long c3 = clock64();
+#endif
   const int mode = lane < 3 ? lane : 0;
   const double err = epnp_mode<N>(mode, L, rho, v, alphas, pw, us, Rout, tout);
+#ifdef MVO_EPNP_CLOCK
+  if (lane == 0) printf("cycles: build %lld jacobi %lld basis %lld modes %lld\n", c1 - c0, c2 - c1, c3 - c2, clock64() - c3);
+#endif
   // OpenCV keeps candidate 0 unless a later one is strictly better (NaN errors never win)
   const double e0 = __shfl_sync(0xffffffffu, err, 0), e1 = __shfl_sync(0xffffffffu, err, 1), e2 = __shfl_sync(0xffffffffu, err, 2);
   int win = 0;

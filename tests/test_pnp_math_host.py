@@ -24,22 +24,22 @@ def _build():
     return EXE
 
 
-def _run(exe, obj, xn, device):
+def _run(exe, obj, xn, device, impl=1):
     inp = "5\n" + "\n".join(" ".join(repr(float(v)) for v in list(o) + list(x)) for o, x in zip(obj, xn)) + "\n"
-    r = subprocess.run([exe] + (["--device"] if device else []), input=inp, capture_output=True, text=True, timeout=120)
+    r = subprocess.run([exe] + (["--device", str(impl)] if device else []), input=inp, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     tok = r.stdout.split()
     return int(tok[0]), np.array(tok[1:], np.float64)
 
 
-def _check(device):
+def _check(device, impl=1):
     exe = _build()
     obj, img, K, _, _ = synth.pnp_scene(2000, 1, 0.5, 0.05)
     tight = 0
     for s in po.sample_subsets(2000, 12):
         o = obj[s].astype(np.float64)
         xn = po.normalize(img[s], K).astype(np.float32).astype(np.float64)
-        ok, v = _run(exe, o, xn, device)
+        ok, v = _run(exe, o, xn, device, impl)
         R, t = po.epnp(o, xn)
         assert ok == 1
         dR, dt = np.abs(v[:9].reshape(3, 3) - R).max(), np.abs(v[9:12] - t).max()
@@ -59,5 +59,8 @@ def test_pnp_math_host_vs_oracle():
 
 
 @pytest.mark.gpu
-def test_pnp_math_device_vs_oracle():
-    _check(device=True)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_pnp_math_device_vs_oracle(impl):
+    """impl: the two forms of the warp's 12 x 12 eigen-decomposition (round 1; one element pair per lane + short scalar
+    chain for the rotation parameters)."""
+    _check(device=True, impl=impl)
