@@ -360,7 +360,7 @@ __device__ void jacobi_eig_warp(double* A, double* V, int lane) {
 // values, column update first, and stored by lane 0.  Same rotation order and element-wise expressions as jacobi_eig.
 // (A form with the rows in registers and shuffles instead of shared memory needs the (p, q) loops unrolled -- 66 bodies,
 // 38 K instructions against a 32 KB instruction cache -- and ran at half the speed of the shared-memory form.)
-template <int N, bool FAST_CS>
+template <int N, bool FAST_CS, bool SKIP_TINY = FAST_CS>
 __device__ void jacobi_eig_warp3(double* A, double* V, int lane) {
   static_assert(3 * N - 4 == 32, "one pair per lane: 2 (N - 2) pairs of A and N of V");
   for (int i = lane; i < N * N; i += 32) V[i] = (i / N == i % N) ? 1.0 : 0.0;
@@ -384,9 +384,13 @@ __device__ void jacobi_eig_warp3(double* A, double* V, int lane) {
         const double apq = A[p * N + q];
         if (apq == 0.0) continue;   // warp-uniform
         const double app = A[p * N + p], aqq = A[q * N + q], aqp = A[q * N + p];
-        double c, s;
-        jacobi_cs<FAST_CS>(app, aqq, apq, c, s);
-        // this lane's pair
+        if (SKIP_TINY && sweep >= 3) {
+          // an off-diagonal entry below the rounding level of both diagonal entries: the rotation would change neither
+          // eigenvalue and turn the eigenvectors by < 1e-15 -- most of the last sweeps (which only confirm convergence)
+          const double gq = 128.0 * fabs(apq);
+          if (fabs(app) + gq == fabs(app) && fabs(aqq) + gq == fabs(aqq)) continue;   // warp-uniform
+        }
+        // this lane's pair (loaded ahead of the scalar chain: its latency hides behind the two rsqrt)
         int k = l;
         if (role != 2) {            // the l-th index that is neither p nor q
           k += (k >= p);
@@ -394,8 +398,10 @@ __device__ void jacobi_eig_warp3(double* A, double* V, int lane) {
         }
         double* M = role == 2 ? V : A;
         const int ia = role == 1 ? p * N + k : k * N + p, ib = role == 1 ? q * N + k : k * N + q;
-        __syncwarp();   // every lane has read the block
         const double x = M[ia], y = M[ib];
+        double c, s;
+        jacobi_cs<FAST_CS>(app, aqq, apq, c, s);
+        __syncwarp();   // every lane has read the block
         M[ia] = c * x - s * y;
         M[ib] = s * x + c * y;
         // the block: rows p and q of A J, then J^T on them

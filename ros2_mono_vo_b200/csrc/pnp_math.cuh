@@ -124,6 +124,63 @@ MVO_HD void ls_solve(const double* A, const double* b, double* x) {
   }
 }
 
+// least squares  min |A x - b|  of a full-rank M x N system by Householder QR -- what OpenCV's EPnP runs for its
+// Gauss-Newton steps (modules/calib3d/src/epnp.cpp, qr_solve: column scaling by the largest entry, reflector
+// v = a + sign(a_kk) |a| e_k).  A and b are destroyed.  Returns false for a zero column or a diagonal of R that spans more
+// than nine orders of magnitude (the caller falls back to the minimum-norm solver).  Fully unrolled: everything stays in registers; 3 N + N slow operations against the ~40 Jacobi
+// rotations of ls_solve.
+template <int M, int N>
+MVO_HD __forceinline__ bool qr_solve(double* A, double* b, double* x) {
+  double A1[N], A2[N];
+  double dmin = 1e300, dmax = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double eta = 0;
+#pragma unroll
+    for (int i = k; i < M; ++i) eta = fmax(eta, fabs(A[i * N + k]));
+    if (eta == 0) return false;
+    const double inv_eta = 1.0 / eta;
+    double sum = 0;
+#pragma unroll
+    for (int i = k; i < M; ++i) {
+      A[i * N + k] *= inv_eta;
+      sum += A[i * N + k] * A[i * N + k];
+    }
+    double sigma = sqrt(sum);
+    if (A[k * N + k] < 0) sigma = -sigma;
+    A[k * N + k] += sigma;
+    A1[k] = sigma * A[k * N + k];
+    A2[k] = -eta * sigma;
+    dmin = fmin(dmin, fabs(A2[k]));
+    dmax = fmax(dmax, fabs(A2[k]));
+    const double inv_a1 = 1.0 / A1[k];
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) {
+      double d = 0;
+#pragma unroll
+      for (int i = k; i < M; ++i) d += A[i * N + k] * A[i * N + j];
+      const double tau = d * inv_a1;
+#pragma unroll
+      for (int i = k; i < M; ++i) A[i * N + j] -= tau * A[i * N + k];
+    }
+    // the same reflector on b
+    double d = 0;
+#pragma unroll
+    for (int i = k; i < M; ++i) d += A[i * N + k] * b[i];
+    const double tau = d * inv_a1;
+#pragma unroll
+    for (int i = k; i < M; ++i) b[i] -= tau * A[i * N + k];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double d = 0;
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) d += A[i * N + j] * x[j];
+    x[i] = (b[i] - d) / A2[i];
+  }
+  return dmin > 1e-9 * dmax;   // (|r_kk| of an unpivoted QR: a crude rank test -- a doubtful system goes to the minimum-norm solver)
+}
+
 // closest rotation to a 3x3 matrix: R = U V^T of its SVD (polar factor), through the eigenvectors of A^T A
 template <bool FAST_CS = false>
 MVO_HD void polar_rotation(const double* A, double* R) {
@@ -384,6 +441,9 @@ template <int N>
 MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const double (*v)[12], const double (*alphas)[4],
                         const double (*pw)[3], const double (*us)[2], double* R, double* t) {
   double betas[4] = {0, 0, 0, 0};
+#if defined(MVO_EPNP_CLOCK) && defined(__CUDA_ARCH__)
+  const long long m0 = clock64();
+#endif
   {
     // The three approximations solve 6 x 4, 6 x 3 and 6 x 5 systems (columns {0, 1, 3, 6}, {0, 1, 2}, {0 .. 4} of L).  The
     // three lanes of a warp run them side by side, so all three are written as one 6 x 5 problem with zero columns at
@@ -397,7 +457,32 @@ MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const doub
         const int col = mode == 0 ? (j == 2 ? 3 : (j == 3 ? 6 : j)) : j;
         A[i * 5 + j] = j < ncols ? L[i * 10 + col] : 0.0;
       }
-    ls_solve<6, 5>(A, rho, x);
+    // Full-rank systems (the rule) are solved by Householder QR, each lane its own size; cvSolve(CV_SVD) in OpenCV, i.e.
+    // the same least-squares solution.  Rank-deficient ones take the minimum-norm path, uniformly.
+    bool solved;
+    {
+      double Aq[30], bq[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) bq[q] = rho[q];
+      if (mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Aq[i * 4 + j] = A[i * 5 + j];
+        solved = qr_solve<6, 4>(Aq, bq, x);
+      } else if (mode == 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Aq[i * 3 + j] = A[i * 5 + j];
+        solved = qr_solve<6, 3>(Aq, bq, x);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 30; ++q) Aq[q] = A[q];
+        solved = qr_solve<6, 5>(Aq, bq, x);
+      }
+    }
+    if (!solved) ls_solve<6, 5>(A, rho, x);
     if (mode == 0) {
       if (x[0] < 0) {
         betas[0] = sqrt(-x[0]);
@@ -423,6 +508,9 @@ MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const doub
     }
   }
   PNP_DBG("mode %d betas0 %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
+#if defined(MVO_EPNP_CLOCK) && defined(__CUDA_ARCH__)
+  const long long m1 = clock64();
+#endif
   // five Gauss-Newton steps on the six distance constraints
   for (int it = 0; it < 5; ++it) {
     double A[24], bb[6], x[4];
@@ -436,12 +524,22 @@ MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const doub
       bb[i] = rho[i] - (l[0] * b0 * b0 + l[1] * b0 * b1 + l[2] * b1 * b1 + l[3] * b0 * b2 + l[4] * b1 * b2 +
                         l[5] * b2 * b2 + l[6] * b0 * b3 + l[7] * b1 * b3 + l[8] * b2 * b3 + l[9] * b3 * b3);
     }
-    ls_solve<6, 4>(A, bb, x);
+    {
+      double Aq[24], bq[6];
+#pragma unroll
+      for (int q = 0; q < 24; ++q) Aq[q] = A[q];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) bq[q] = bb[q];
+      if (!qr_solve<6, 4>(Aq, bq, x)) ls_solve<6, 4>(A, bb, x);   // (OpenCV leaves x untouched when its QR meets a zero column)
+    }
     PNP_DBG("  gn %d betas %.6g %.6g %.6g %.6g x %.6g %.6g %.6g %.6g bb %.6g %.6g A0 %.6g %.6g %.6g %.6g Lsum %.10g\n", it, betas[0], betas[1], betas[2], betas[3], x[0], x[1], x[2], x[3], bb[0], bb[5], A[0], A[1], A[2], A[3], L[0]+L[11]+L[22]+L[33]+L[44]+L[55]+L[59]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) betas[q] += x[q];
   }
   PNP_DBG("mode %d betas %.10g %.10g %.10g %.10g\n", mode, betas[0], betas[1], betas[2], betas[3]);
+#if defined(MVO_EPNP_CLOCK) && defined(__CUDA_ARCH__)
+  const long long m2 = clock64();
+#endif
   // control points in the camera frame, sign, absolute orientation
   double ccs[4][3];
 #pragma unroll
@@ -474,7 +572,13 @@ MVO_HD double epnp_mode(int mode, const double* L, const double* rho, const doub
     for (int j = 0; j < 3; ++j)
 #pragma unroll
       for (int k = 0; k < 3; ++k) ABt[3 * j + k] += (pcs[i][j] - pc0[j]) * (pw[i][k] - pw0[k]);
+#if defined(MVO_EPNP_CLOCK) && defined(__CUDA_ARCH__)
+  const long long m3 = clock64();
+#endif
   polar_rotation<true>(ABt, R);
+#if defined(MVO_EPNP_CLOCK) && defined(__CUDA_ARCH__)
+  if (threadIdx.x == 0 && R[0] != 123.0) printf("mode cycles: init %lld gn %lld cc %lld polar %lld\n", m1 - m0, m2 - m1, m3 - m2, clock64() - m3);
+#endif
   if (det3(R) < 0) {
     R[6] = -R[6];
     R[7] = -R[7];
