@@ -351,8 +351,10 @@ MVO_API int mvo_pack_pointcloud(mvo_ctx* ctx, const float* points_xyz, int n, in
  * profiling / parity aids (not part of the reference-facing surface)
  * mvo_debug_set: "lk_impl" = 1 | 2 selects the first- / second-generation gray LK kernel (identical results; the old
  *                one is the in-tree cross-check), "knn_impl" likewise for the matching kernels, "h_refine_impl" / "e5_roots_impl"
- *                = 1 for the first-generation homography refinement / the bracketing root finder, "cache" = 0 and
- *                "graph" = 0 to switch the content caches / the CUDA-graph step off.
+ *                = 1 for the first-generation homography refinement / the bracketing root finder, "pnp_epnp_impl" = 0 /
+ *                "pnp_refine_impl" = 1 for the round-1 EPnP eigen-solver / refinement start, "pnp_rounds" = 1 to evaluate all
+ *                hypotheses of a batched solvePnPRansac in one round, "cache" = 0 and "graph" = 0 to switch the content
+ *                caches / the CUDA-graph step off.
  * mvo_debug_time: re-runs one stage of the group pipeline `reps` times on the state left by the last mvo_group_step
  *                (at least two steps must have run) and returns the average device time per run in ms, measured with
  *                CUDA events on the context stream.  what = "lk_track" | "knn" | "orb" | "orb_levels" (the eight fused

@@ -73,6 +73,7 @@ struct PnpBufs {
   mvo::DevBuf<int32_t> subsets;       // batch * iters * 5
   mvo::DevBuf<double> models;         // batch * iters * 12 : R (9) | t (3)
   mvo::DevBuf<int32_t> ok, counts;    // batch * iters
+  mvo::DevBuf<int32_t> bound;         // batch : hypotheses the adaptive loop can still reach after the first round
   mvo::DevBuf<double> best_model;     // batch * 12
   mvo::DevBuf<int32_t> result;        // batch * 8 : inliers, iterations run, winning iteration (-1: none)
   mvo::DevBuf<double> pose_out;       // batch * 8 : rvec, tvec, planar flag
@@ -243,6 +244,7 @@ struct mvo_ctx {
   int cache_enabled = 1;               // mvo_debug_set("cache", 0) switches both caches off
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
   int dbg_e5_roots_impl = 2;   // 1: derivative-level bracketing only (cross-check), 2: Ehrlich-Aberth iteration first, bracketing where it is not trusted
+  int dbg_pnp_rounds = 0;      // 1: batched solvePnPRansac evaluates all hypotheses in one round (cross-check)
   int dbg_pnp_epnp_impl = 1;   // 12 x 12 Jacobi of pnp_epnp_kernel: 0 round 1 (cross-check), 1 one element pair per lane + short scalar chain
   int dbg_pnp_refine_impl = 2; // 1: first-generation initial pose of pnp_refine_kernel (cross-check), 2: block sums + warp LU
   int dbg_h_refine_impl = 2;   // 1: first-generation h_refine_kernel (cross-check), 2: h_refine2_kernel

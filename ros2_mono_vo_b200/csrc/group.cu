@@ -1199,6 +1199,7 @@ int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   else if (strcmp(key, "e5_roots_impl") == 0) c->dbg_e5_roots_impl = value;
   else if (strcmp(key, "pnp_refine_impl") == 0) c->dbg_pnp_refine_impl = value;
   else if (strcmp(key, "pnp_epnp_impl") == 0) c->dbg_pnp_epnp_impl = value;
+  else if (strcmp(key, "pnp_rounds") == 0) c->dbg_pnp_rounds = value;
   else if (strcmp(key, "graph") == 0) c->graph_enabled = value;
   else if (strcmp(key, "lk_ctas_per_sm") == 0) c->dbg_lk_ctas_per_sm = value;
   else if (strcmp(key, "cache") == 0) {

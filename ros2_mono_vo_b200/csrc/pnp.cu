@@ -102,17 +102,20 @@ pnp_sample_kernel(const uint32_t* __restrict__ rng, int rng_len, const int32_t* 
 
 // One warp per hypothesis (epnp_solve_warp, pnp_math.cuh).
 constexpr int kEpnpWarps = 2;
+constexpr int kPnpFirstRound = 32;   // hypotheses of the first round of a batched call
 #ifndef MVO_EPNP_MINB
 #define MVO_EPNP_MINB 6   // 168 registers: 12 instead of 8 resident warps per SM (batched tracking step 4.35 -> 3.85 ms; 8 blocks / 128 registers loses again)
 #endif
 template <int IMPL>
 __global__ void __launch_bounds__(kEpnpWarps * 32, MVO_EPNP_MINB)
 pnp_epnp_kernel(const float* __restrict__ obj, const double2* __restrict__ xn, int max_pts,
-                const int32_t* __restrict__ subsets, int iters, double* __restrict__ models, int32_t* __restrict__ ok) {
+                const int32_t* __restrict__ subsets, int iters, int it_begin, int it_end, const int32_t* __restrict__ bound,
+                double* __restrict__ models, int32_t* __restrict__ ok) {
   __shared__ double s_A[kEpnpWarps][144], s_V[kEpnpWarps][144];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int it = blockIdx.x * kEpnpWarps + warp;
-  if (it >= iters) return;
+  const int it = it_begin + blockIdx.x * kEpnpWarps + warp;
+  if (it >= it_end) return;
+  if (bound && it >= bound[b]) return;   // second round: the sequential loop of this stream stops before this hypothesis
   double pw[kPnpK][3], us[kPnpK][2];
   const int32_t* s = subsets + ((long long)b * iters + it) * kPnpK;
   for (int i = 0; i < kPnpK; ++i) {
@@ -148,8 +151,10 @@ __device__ __forceinline__ float pnp_err(const double* m, const double* K, float
 __global__ void __launch_bounds__(256)
 pnp_score_kernel(const float* __restrict__ obj, const float2* __restrict__ img, const int32_t* __restrict__ npts,
                  int max_pts, const double* __restrict__ K, const double* __restrict__ models,
-                 const int32_t* __restrict__ ok, int iters, float thr2, int32_t* __restrict__ counts) {
-  const int b = blockIdx.y, it = blockIdx.x;
+                 const int32_t* __restrict__ ok, int iters, int it_begin, const int32_t* __restrict__ bound, float thr2,
+                 int32_t* __restrict__ counts) {
+  const int b = blockIdx.y, it = it_begin + blockIdx.x;
+  if (bound && it >= bound[b]) return;
   const long long h = (long long)b * iters + it;
   if (!ok[h]) {
     if (threadIdx.x == 0) counts[h] = -1;
@@ -185,6 +190,24 @@ __device__ int pnp_update_iters(double p, double ep, int model_points, int max_i
   num = log(num);
   denom = log(denom);
   return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
+// Hypotheses the sequential loop can still reach after the first `first` ones (the loop of pnp_select_kernel, stopped
+// there): RANSACUpdateNumIters only ever lowers the bound, so everything at or beyond it is never looked at.
+__global__ void pnp_bound_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ npts, int iters, int first,
+                                 double conf, int batch, int32_t* __restrict__ bound) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int n = npts[b];
+  int niters = iters, best_count = 0;
+  for (int it = 0; it < niters && it < first; ++it) {
+    const int c = counts[(long long)b * iters + it];
+    if (c > max(best_count, kPnpK - 1)) {
+      best_count = c;
+      niters = pnp_update_iters(conf, (double)(n - c) / n, kPnpK, niters);
+    }
+  }
+  bound[b] = niters;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -623,6 +646,7 @@ int pnp_prepare(mvo_ctx* c, int max_pts, int iters) {
     MVO_CUDA_TRY(c, p.models.alloc(n * 12));
     MVO_CUDA_TRY(c, p.ok.alloc(n));
     MVO_CUDA_TRY(c, p.counts.alloc(n));
+    MVO_CUDA_TRY(c, p.bound.alloc(B));
     p.cap_iters = iters;
   }
   MVO_CUDA_TRY(c, p.npts.alloc(B));
@@ -672,15 +696,32 @@ int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
   dim3 gn((p.max_pts + 255) / 256, B);
   pnp_normalize_kernel<<<gn, 256, 0, c->stream>>>(p.img.p, p.npts.p, p.max_pts, p.K.p, p.xn.p);
   pnp_sample_kernel<<<B, kPnpSampleThreads, 0, c->stream>>>(r.rng.p, r.rng_len, p.npts.p, iters, p.subsets.p);
-  dim3 ge((iters + kEpnpWarps - 1) / kEpnpWarps, B);
-  // mvo_debug_set("pnp_epnp_impl", 0): the round-1 form of the 12 x 12 eigen-decomposition (cross-check)
-  if (c->dbg_pnp_epnp_impl == 0)
-    pnp_epnp_kernel<0><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
-  else
-    pnp_epnp_kernel<1><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, p.models.p, p.ok.p);
-  dim3 gs(iters, B);
-  pnp_score_kernel<<<gs, 256, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.ok.p, iters,
-                                             thr2, p.counts.p);
+  // Batched calls evaluate the hypotheses in two rounds: the adaptive loop usually stops after a dozen of the (up to)
+  // `iters` hypotheses, so the first kPnpFirstRound are solved and scored, a one-thread-per-stream replay of the loop
+  // gives each stream's bound, and the second launch exits at once for everything beyond it (32 streams x 100
+  // hypotheses: 586 -> ~200 us of EPnP).  A single stream runs all of them side by side anyway: one round.
+  const bool two_rounds = B >= 4 && iters > kPnpFirstRound && c->dbg_pnp_rounds != 1;
+  const int first = two_rounds ? kPnpFirstRound : iters;
+  for (int round = 0; round < (two_rounds ? 2 : 1); ++round) {
+    const int it0 = round == 0 ? 0 : first, it1 = round == 0 ? first : iters;
+    const int32_t* bound = round == 0 ? nullptr : p.bound.p;
+    dim3 ge((it1 - it0 + kEpnpWarps - 1) / kEpnpWarps, B);
+    // mvo_debug_set("pnp_epnp_impl", 0): the round-1 form of the 12 x 12 eigen-decomposition (cross-check)
+    if (c->dbg_pnp_epnp_impl == 0)
+      pnp_epnp_kernel<0><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, it0, it1, bound,
+                                                                p.models.p, p.ok.p);
+    else
+      pnp_epnp_kernel<1><<<ge, kEpnpWarps * 32, 0, c->stream>>>(p.obj.p, p.xn.p, p.max_pts, p.subsets.p, iters, it0, it1, bound,
+                                                                p.models.p, p.ok.p);
+    dim3 gs(it1 - it0, B);
+    pnp_score_kernel<<<gs, 256, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.ok.p, iters, it0,
+                                               bound, thr2, p.counts.p);
+    c->launches += 2;
+    if (two_rounds && round == 0) {
+      pnp_bound_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(p.counts.p, p.npts.p, iters, first, conf, B, p.bound.p);
+      c->launches++;
+    }
+  }
   pnp_select_kernel<<<B, 1024, 0, c->stream>>>(p.obj.p, p.img.p, p.npts.p, p.max_pts, p.K.p, p.models.p, p.counts.p,
                                               iters, thr2, conf, p.mask.p, p.inl_idx.p, p.best_model.p, p.result.p);
   {
@@ -694,7 +735,7 @@ int pnp_run(mvo_ctx* c, int iters, double reproj_err, double conf) {
                                                                            p.best_model.p, p.result.p, p.pose_out.p,
                                                                            c->dbg_pnp_refine_impl, cache);
   }
-  c->launches += 6;
+  c->launches += 4;
   MVO_CUDA_TRY(c, cudaGetLastError());
   return MVO_OK;
 }
