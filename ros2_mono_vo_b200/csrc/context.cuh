@@ -211,7 +211,8 @@ struct mvo_ctx {
   // ---------------- profiling / parity knobs (mvo_debug_set) ----------------
   int dbg_lk_impl = 2;     // 1: first-generation lk_track_kernel (in-tree cross-check), 2: lk_track2_kernel (persistent
                            // warps for large point sets), 3: lk_track2_kernel with one point per warp always
-  mvo::DevBuf<int32_t> lk_work;   // work counter of the persistent LK kernel
+  mvo::DevBuf<int32_t> lk_work;   // work counters of the persistent LK kernels (two: BGR8 runs a team and a gray launch)
+  mvo::DevBuf<int32_t> lk_colour[2];   // per pyramid buffer and stream: nonzero = the BGR8 frame has pixels with differing channels
   int dbg_lk_ctas_per_sm = 5;     // resident CTAs per SM of the persistent LK kernel (5 = all the shared memory of an SM)
   int cand_scale = 1;      // FAST candidate list capacity in units of (level pixels / 16); doubled after an overflow
   int occupancy_div = 50;  // keypoint-distribution grid cell size (config/params.yaml: initializer.occupancy_grid_div)
@@ -244,6 +245,7 @@ struct mvo_ctx {
   int cache_enabled = 1;               // mvo_debug_set("cache", 0) switches both caches off
   int dbg_knn_impl = 0;    // kNN kernel choice (0 = default)
   int dbg_e5_roots_impl = 2;   // 1: derivative-level bracketing only (cross-check), 2: Ehrlich-Aberth iteration first, bracketing where it is not trusted
+  int dbg_lk_bgr_gray = 1;     // 0: BGR8 streams with identical planes go through the three-warp teams as well (cross-check)
   int dbg_pnp_rounds = 0;      // 1: batched solvePnPRansac evaluates all hypotheses in one round (cross-check)
   int dbg_pnp_epnp_impl = 1;   // 12 x 12 Jacobi of pnp_epnp_kernel: 0 round 1 (cross-check), 1 one element pair per lane + short scalar chain
   int dbg_pnp_refine_impl = 2; // 1: first-generation initial pose of pnp_refine_kernel (cross-check), 2: block sums + warp LU

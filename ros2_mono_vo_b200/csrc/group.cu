@@ -191,7 +191,7 @@ __global__ void copy_i32_strided_kernel(const int32_t* src, int stride, int32_t*
 __global__ void __launch_bounds__(256)
 unpack_bgr_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long src_frame_stride, uint8_t* __restrict__ gray,
                          int gpitch, long long gray_frame_stride, uint8_t* __restrict__ planes, int ppitch,
-                         long long plane_stride, int w, int h) {
+                         long long plane_stride, int w, int h, int32_t* __restrict__ colour) {
   const int y = blockIdx.y, b = blockIdx.z;
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x >= w) return;
@@ -213,6 +213,8 @@ unpack_bgr_frames_kernel(const uint8_t* __restrict__ src, int spitch, long long 
   *reinterpret_cast<uint32_t*>(d) = p0;
   *reinterpret_cast<uint32_t*>(d + plane_stride) = p1;
   *reinterpret_cast<uint32_t*>(d + 2 * plane_stride) = p2;
+  // some pixel with differing channels: the stream is not a gray camera behind a BGR8 conversion (lk_track2_kernel, MUL = 3)
+  if (((p0 ^ p1) | (p1 ^ p2)) && __ldcg(colour + b) == 0) atomicOr(colour + b, 1);
 }
 
 __global__ void replicate_k_kernel(double* K, int batch) {
@@ -465,8 +467,10 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
                                                         lk0, lk_pitch, lk_fs, w, h);
     } else {
       dim3 grid((w + 4 * 256 - 1) / (4 * 256), h, B);
+      MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_colour[c->lk_cur].p, 0, sizeof(int32_t) * B, c->stream));
       unpack_bgr_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, c->pyr.p + l0.off, l0.pitch,
-                                                            g.frame_stride, lk0, lk_pitch, lk_fs, w, h);
+                                                            g.frame_stride, lk0, lk_pitch, lk_fs, w, h,
+                                                            c->lk_colour[c->lk_cur].p);
     }
     c->launches++;
     if (!images_on_device && !c->capturing) cudaEventRecord(c->slots[slot].ev_free, c->main_stream);
@@ -1090,7 +1094,9 @@ int mvo_group_track(mvo_ctx* c, const uint8_t* images, int w, int h, int stride,
       unpack_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, lk0, lk_pitch, lk_fs, nullptr, 0, 0, w, h);
     } else {
       dim3 grid((w + 4 * 256 - 1) / (4 * 256), h, B);
-      unpack_bgr_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, nullptr, 0, 0, lk0, lk_pitch, lk_fs, w, h);
+      MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_colour[c->lk_cur].p, 0, sizeof(int32_t) * B, c->stream));
+      unpack_bgr_frames_kernel<<<grid, 256, 0, c->stream>>>(src, spitch, sstride, nullptr, 0, 0, lk0, lk_pitch, lk_fs, w, h,
+                                                            c->lk_colour[c->lk_cur].p);
     }
     c->launches++;
   }
@@ -1200,6 +1206,7 @@ int mvo_debug_set(mvo_ctx* c, const char* key, int value) {
   else if (strcmp(key, "pnp_refine_impl") == 0) c->dbg_pnp_refine_impl = value;
   else if (strcmp(key, "pnp_epnp_impl") == 0) c->dbg_pnp_epnp_impl = value;
   else if (strcmp(key, "pnp_rounds") == 0) c->dbg_pnp_rounds = value;
+  else if (strcmp(key, "lk_bgr_gray") == 0) c->dbg_lk_bgr_gray = value;
   else if (strcmp(key, "graph") == 0) c->graph_enabled = value;
   else if (strcmp(key, "lk_ctas_per_sm") == 0) c->dbg_lk_ctas_per_sm = value;
   else if (strcmp(key, "cache") == 0) {

@@ -733,12 +733,23 @@ constexpr int kLk2WarpsCn = 3;   // CN = 3: one team per CTA (static shared memo
 #ifndef MVO_LK_T_MINB
 #define MVO_LK_T_MINB 5
 #endif
-template <bool PERSIST, int CN>
+// MUL = 3 (with CN = 1): a BGR8 stream whose three planes are identical in both frames -- a gray camera behind the node's
+// BGR8 conversion (/root/reference/src/mono_vo.cpp:94), which is what a KITTI gray sequence becomes.  Every sum over the
+// three planes is then exactly three times the sum over one: the gray code path runs on plane 0 (plane index 3 b) and
+// multiplies its exact integer sums by three where the team kernel would have added three equal partial sums -- the same
+// integers, so the same floats afterwards.  colour_a / colour_b (per stream, nonzero = some pixel of that frame has
+// differing channels; written by the kernels that split BGR8 frames into planes) select the streams of a launch:
+// want_colour = 1 the team kernel's, 0 the MUL = 3 kernel's; null = every stream.
+template <bool PERSIST, int CN, int MUL = 1>
 __global__ void __launch_bounds__((CN == 1 ? kLk2Warps : kLk2WarpsCn) * 32, CN == 1 ? MVO_LK2_MINB : MVO_LK_T_MINB)
 lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTmaps tm, const uint8_t* __restrict__ pyrI,
                  const uint8_t* __restrict__ pyrJ, const float2* __restrict__ pts, const int32_t* __restrict__ npts_dev,
                  int max_pts, float2* __restrict__ out_pts, uint8_t* __restrict__ status, float* __restrict__ err,
-                 int* __restrict__ work_counter, int batch) {
+                 int* __restrict__ work_counter, int batch, const int32_t* __restrict__ colour_a,
+                 const int32_t* __restrict__ colour_b, int want_colour) {
+  static_assert(MUL == 1 || (MUL == 3 && CN == 1), "MUL = 3: the gray path on identical BGR planes");
+  constexpr int PLANES = CN * MUL;   // planes per stream in the pyramid buffers
+  auto selected = [&](int q) { return !colour_a || (((colour_a[q] | colour_b[q]) != 0) == (want_colour != 0)); };
   constexpr int NW = CN == 1 ? kLk2Warps : kLk2WarpsCn;
   static_assert(CN == 1 || (CN == 3 && NW % CN == 0 && PERSIST), "teams of CN warps, persistent form only");
   __shared__ LkWarpSmem2 sm_all[NW];
@@ -756,7 +767,14 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
   };
   // exact integer sums over the planes of the team (identity for gray); every warp of the team gets the same totals
   auto team_sum3 = [&](long long& v0, long long& v1, long long& v2) {
-    if (CN == 1) return;
+    if (CN == 1) {
+      if (MUL != 1) {
+        v0 *= MUL;
+        v1 *= MUL;
+        v2 *= MUL;
+      }
+      return;
+    }
     if (lane == 0) {
       s_team[team][tpar][ch][0] = v0;
       s_team[team][tpar][ch][1] = v1;
@@ -784,7 +802,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
       int acc = 0;
       for (int q = 0; q < batch; ++q) {
         s_cum[q] = acc;
-        acc += min(npts_dev[q], max_pts);
+        acc += selected(q) ? min(npts_dev[q], max_pts) : 0;
       }
       s_cum[batch] = acc;
     }
@@ -828,10 +846,10 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
   } else {
     b = blockIdx.y;
     i = blockIdx.x * kLk2Warps + warp;
-    if (i >= min(npts_dev[b], max_pts)) return;
+    if (i >= min(npts_dev[b], max_pts) || !selected(b)) return;
   }
   const float2 p0 = pts[(long long)b * max_pts + i];
-  const int plane = b * CN + ch;         // planar pyramids: plane (b * CN + ch); also the z coordinate of the tensor maps
+  const int plane = b * PLANES + ch;     // planar pyramids: plane (b * PLANES + ch); also the z coordinate of the tensor maps
   float nx = 0.f, ny = 0.f, e = 0.f;
   int st = 1;
 
@@ -1043,7 +1061,7 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
         }
         long long te = __reduce_add_sync(0xffffffffu, se), te1 = 0, te2 = 0;
         team_sum3(te, te1, te2);
-        e = __fdiv_rn((float)(int)te, (float)(32 * LKW * CN * LKW));
+        e = __fdiv_rn((float)(int)te, (float)(32 * LKW * PLANES * LKW));
       }
     }
     if (jpend) {   // a requested tile nobody consumed (degenerate level, window left the image): drain it
@@ -1258,14 +1276,17 @@ lk_track_cn_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__
 }
 
 // interleaved BGR rows -> three planes (level 0 of planes b*3 + ch)
+// colour[b] becomes nonzero when some pixel of stream b has differing channels (lk_track2_kernel's MUL = 3 path)
 __global__ void lk_split3_kernel(const uint8_t* __restrict__ src, int stride, long long in_frame_stride,
-                                 uint8_t* __restrict__ dst, int pitch, long long frame_stride, int w, int h) {
+                                 uint8_t* __restrict__ dst, int pitch, long long frame_stride, int w, int h,
+                                 int32_t* __restrict__ colour) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= w) return;
   const uint8_t* p = src + (long long)b * in_frame_stride + (long long)y * stride + 3 * x;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) dst[((long long)b * 3 + ch) * frame_stride + (long long)y * pitch + x] = p[ch];
+  if (((p[0] ^ p[1]) | (p[1] ^ p[2])) && __ldcg(colour + b) == 0) atomicOr(colour + b, 1);
 }
 
 // ================================================================================================
@@ -1344,6 +1365,8 @@ int lk_prepare(mvo_ctx* c, int w, int h, int max_pts, int cn) {
   MVO_CUDA_TRY(c, c->lk_status.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_err.alloc(B * (size_t)max_pts));
   MVO_CUDA_TRY(c, c->lk_npts.alloc(B));
+  for (int k = 0; k < 2; ++k) MVO_CUDA_TRY(c, c->lk_colour[k].alloc(B));
+  MVO_CUDA_TRY(c, c->lk_work.alloc(2));
   c->lk_w = w;
   c->lk_h = h;
   c->lk_max_pts = max_pts;
@@ -1381,8 +1404,9 @@ int lk_build_pyramid(mvo_ctx* c, int which, const uint8_t* img, int stride, int 
       src = c->img_in.p;
     }
     dim3 grid((c->lk_w + 255) / 256, c->lk_h, B);
+    MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_colour[which].p, 0, sizeof(int32_t) * B, c->stream));
     lk_split3_kernel<<<grid, 256, 0, c->stream>>>(src, stride, (long long)fbytes, base, g.lv[0].pitch, g.frame_stride,
-                                                  c->lk_w, c->lk_h);
+                                                  c->lk_w, c->lk_h, c->lk_colour[which].p);
     c->launches++;
   } else if (on_device == 2) {
     // source is a batch of pitched device images with frame stride given by `stride` == pitch and
@@ -1429,17 +1453,32 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
       lk_track_cn_kernel<3><<<grid, kLkWarpsCn * 32, 0, c->stream>>>(g, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p,
                                                                     pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev);
     } else if (c->lk_cn == 3) {
-      // BGR8: teams of three warps (one per colour plane) on the second-generation kernel, persistent form
+      // BGR8: teams of three warps (one per colour plane) on the second-generation kernel, persistent form, for the
+      // streams with real colour; the streams whose planes are identical in both frames (a gray camera behind the
+      // node's BGR8 conversion) take the gray path with tripled sums (mvo_debug_set("lk_bgr_gray", 0): all to the teams)
       LkTmaps tm;
       memcpy(tm.m[0], c->lk_tmaps[prev_which][0], sizeof(tm.m[0]));
       memcpy(tm.m[1], c->lk_tmaps[next_which][1], sizeof(tm.m[1]));
       const long long items = (long long)max_pts * c->cfg.batch;
+      const bool split = c->dbg_lk_bgr_gray != 0;
+      const int32_t* ca = split ? c->lk_colour[prev_which].p : nullptr;
+      const int32_t* cb = split ? c->lk_colour[next_which].p : nullptr;
+      MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 8, c->stream));
       const int ctas = (int)std::min<long long>(148LL * MVO_LK_T_MINB, std::max<long long>(items, 1));
-      MVO_CUDA_TRY(c, c->lk_work.alloc(1));
-      MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 4, c->stream));
       lk_track2_kernel<true, 3><<<dim3(ctas, 1), kLk2WarpsCn * 32, 0, c->stream>>>(
           g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
-          c->lk_work.p, c->cfg.batch);
+          c->lk_work.p, c->cfg.batch, ca, cb, 1);
+      if (split) {
+        if (items < 148LL * MVO_LK2_MINB * kLk2Warps * 4)
+          lk_track2_kernel<false, 1, 3><<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
+              g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
+              nullptr, c->cfg.batch, ca, cb, 0);
+        else
+          lk_track2_kernel<true, 1, 3><<<dim3(148 * MVO_LK2_MINB, 1), kLk2Warps * 32, 0, c->stream>>>(
+              g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
+              c->lk_work.p + 1, c->cfg.batch, ca, cb, 0);
+        c->launches++;
+      }
     } else {
       dim3 grid((max_pts + kLkWarps - 1) / kLkWarps, c->cfg.batch);
       // mvo_debug_set("lk_impl", 1): the first-generation kernel (kept as the in-tree cross-check; identical results)
@@ -1455,14 +1494,13 @@ int lk_run(mvo_ctx* c, int prev_which, int next_which, const float2* pts_dev, co
           // few points (single stream): one point per warp fills the GPU better than a persistent grid
           lk_track2_kernel<false, 1><<<dim3((max_pts + kLk2Warps - 1) / kLk2Warps, c->cfg.batch), kLk2Warps * 32, 0, c->stream>>>(
               g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
-              nullptr, c->cfg.batch);
+              nullptr, c->cfg.batch, nullptr, nullptr, 0);
         } else {
-          MVO_CUDA_TRY(c, c->lk_work.alloc(1));
           MVO_CUDA_TRY(c, cudaMemsetAsync(c->lk_work.p, 0, 4, c->stream));
           const int per_sm = std::min(std::max(c->dbg_lk_ctas_per_sm, 1), MVO_LK2_MINB);
           lk_track2_kernel<true, 1><<<dim3(148 * per_sm, 1), kLk2Warps * 32, 0, c->stream>>>(
               g, tm, c->lk_pyr[prev_which].p, c->lk_pyr[next_which].p, pts_dev, npts_dev, max_pts, out_dev, status_dev, err_dev,
-              c->lk_work.p, c->cfg.batch);
+              c->lk_work.p, c->cfg.batch, nullptr, nullptr, 0);
         }
       }
     }

@@ -122,6 +122,56 @@ def test_lk_bgr_team_kernel_matches_first_generation(ctx, h, w, seed):
         assert np.array_equal(new[2], old[2])
 
 
+def test_lk_bgr_gray_streams_take_the_gray_path_with_identical_results():
+    """A BGR8 group in which some streams are gray cameras behind a BGR8 conversion (identical planes, what cv_bridge
+    makes of a mono8 KITTI frame: /root/reference/src/mono_vo.cpp:94) and some have real colour: the identical-plane
+    streams are tracked on one plane with tripled sums, the others by the three-warp teams, and every output equals the
+    all-teams run (lk_bgr_gray = 0) and the one-warp-per-point kernel (lk_impl = 1).  Frame pairs where only one of the
+    two frames is gray must not take the gray path.  Persistent kernels (34 streams x 400 points)."""
+    from ros2_mono_vo_b200 import Context, _lib
+    h, w, B, n = 240, 320, 34, 400
+    frames = []
+    for t in range(3):
+        fs = []
+        for s in range(B):
+            g0, g1 = synth.synth_pair(h, w, 100 + s)
+            c0, c1 = synth.synth_pair_bgr(h, w, 100 + s)
+            gray3 = [np.repeat(g[:, :, None], 3, 2) for g in (g0, g1, g0)]
+            col = [c0, c1, c0]
+            if s % 3 == 0:
+                f = gray3[t]                      # gray camera throughout
+            elif s % 3 == 1:
+                f = col[t]                        # colour throughout
+            else:
+                f = gray3[t] if t != 1 else col[t]   # gray, colour, gray: both pairs are mixed
+            fs.append(f)
+        frames.append(np.stack(fs))
+    K = synth.sequence_camera(h, w)
+    outs = {}
+    for mode in ("default", "teams", "first"):
+        c = Context(w, h, nfeatures=n, batch=B)
+        c.group_configure(channels=3, outputs=_lib.MVO_OUT_TRACKS)
+        if mode == "teams":
+            c.debug_set("lk_bgr_gray", 0)
+        if mode == "first":
+            c.debug_set("lk_impl", 1)
+        got = []
+        for t in range(3):
+            res = c.group_step(frames[t], K)
+            if t:
+                got.append([{k: v.copy() for k, v in c.group_outputs(s).items() if k.startswith("track") or k.startswith("lk")} for s in range(B)])
+                assert (res["n_tracked"] > 50).all()
+        outs[mode] = got
+        c.close()
+    keys = outs["default"][0][0].keys()
+    assert len(keys) >= 2
+    for mode in ("teams", "first"):
+        for t in range(2):
+            for s in range(B):
+                for k in keys:
+                    assert np.array_equal(outs["default"][t][s][k], outs[mode][t][s][k], equal_nan=True), (mode, t, s, k)
+
+
 def test_lk_outside_and_nan_points(ctx):
     """Points outside the image and a NaN coordinate (values from cv2 4.13.0 on the same pair: status 0 1 0 0 1 1; OpenCV
     floors a NaN to INT_MIN, i.e. out of range on every level, and still returns the propagated coordinates)."""
