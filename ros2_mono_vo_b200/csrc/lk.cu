@@ -729,7 +729,8 @@ constexpr int kLk2WarpsCn = 3;   // CN = 3: one team per CTA (static shared memo
 // (five CTAs per SM = 128 registers.  Six would cap the kernel at 96 registers; ptxas then spills 72 bytes and that build
 // returned wrong positions for points with border levels on the B200 -- the cause was not found, the same source is
 // correct at 128 and 170 registers, and tests/test_gpu_lk.py compares this kernel with the first-generation one on
-// border-heavy point sets so that a regression of that kind is seen.)
+// border-heavy point sets so that a regression of that kind is seen.  Six CTAs at 112 registers without spills
+// (__maxnreg__) are correct as well and no faster: 2.43 against 2.38 ms -- the kernel is issue-bound like the gray one.)
 #ifndef MVO_LK_T_MINB
 #define MVO_LK_T_MINB 5
 #endif
