@@ -517,6 +517,15 @@ lk_track_kernel(const __grid_constant__ LkGeom g, const uint8_t* __restrict__ py
 //   * Code size is part of the design: the first unrolled version of this kernel (47 KB) thrashed the 32 KB instruction
 //     cache (ncu r02b: 95.7 % hit rate, GPC instruction fetch at 72 % of peak); the two runs of the setup share one body.
 constexpr int kJW = 29;                 // quad columns == pitch in words
+// The border / restaging helpers of the second-generation tracker are inlined.  They used to be out of line (code size);
+// with thirteen arguments (some passed on the stack) and 50 - 70 bytes of registers saved around the calls, two builds
+// of the kernel -- the BGR8 team form at 96 registers, and the gray form once two more 64-bit sums were live across the
+// calls -- returned wrong positions for points with border levels while every build without those saves was correct
+// (same source at 128 registers; this inlined form).  Inlined, the kernel needs no spills at 96 registers and is 6 %
+// faster (0.647 -> 0.607 ms per 32 x 2000 points).
+#ifndef MVO_LK_OUTLINE
+#define MVO_LK_OUTLINE __forceinline__
+#endif
 constexpr int kJH = 28;                 // quad rows
 constexpr int kJSlackX = kJW - LKW;     // 8: inx - jx0 in [0, 8]
 constexpr int kJSlackY = kJH - LKW;     // 7
@@ -616,7 +625,7 @@ __device__ __forceinline__ void lk_build_quads(uint32_t* jq, const uint32_t* raw
 }
 
 // J region that touches the image border: lane = pixel column, reflecting row / column walk straight from global memory
-__device__ __noinline__ void lk_stage_j2_border(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
+__device__ MVO_LK_OUTLINE void lk_stage_j2_border(uint32_t* jq, const uint8_t* __restrict__ J, int jx0, int jy0, int w, int h,
                                                 int pitch, int lane) {
   const uint8_t* p = J + safe_reflect(jx0 + lane, w);
   uint32_t pprev = 0;
@@ -637,7 +646,7 @@ __device__ __noinline__ void lk_stage_j2_border(uint32_t* jq, const uint8_t* __r
 
 // Border windows: the first kernel's row walk writes the template in pixel order (it handles reflected image rows /
 // columns and zeroed derivatives outside the image); out of line, rare.
-__device__ __noinline__ void lk_setup_border(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch, int lane,
+__device__ MVO_LK_OUTLINE void lk_setup_border(const uint8_t* __restrict__ I, int ix, int iy, int w, int h, int pitch, int lane,
                                              int w00, int w01, int w10, int w11, uint2* pt_out) {
   lk_setup_patch<false>(I, ix, iy, w, h, pitch, lane, w00, w01, w10, w11, pt_out);
 }
@@ -679,7 +688,7 @@ __device__ __forceinline__ void lk_setup_run(const uint32_t* __restrict__ raw, i
 
 // Out of line (code size): wait for the requested tile and / or fetch a new one so that the quads cover the window at
 // (inx, iny).  Returns the region origin and the parity of the J barrier.
-__device__ __noinline__ int3 lk_restage(LkWarpSmem2& sm, const CUtensorMap* map, const uint8_t* __restrict__ J, int inx,
+__device__ MVO_LK_OUTLINE int3 lk_restage(LkWarpSmem2& sm, const CUtensorMap* map, const uint8_t* __restrict__ J, int inx,
                                         int iny, int w, int h, int pitch, int lane, int b, bool jpend, int jx0, int jy0,
                                         uint32_t parJ) {
   bool have_tile = jpend;   // a tile is in flight (it covers the start position of the level by construction)
@@ -726,11 +735,10 @@ constexpr int kLk2MaxBatch = 1024;   // streams of a group the persistent form i
 // iterate in lock step.  (The first-generation lk_track_cn_kernel keeps all three planes in one warp: 23 KB of shared
 // memory per warp, 8 resident warps per SM, 3.5 ms per 32 x 2000 points; it stays as the cross-check, lk_impl = 1.)
 constexpr int kLk2WarpsCn = 3;   // CN = 3: one team per CTA (static shared memory stays below 48 KB)
-// (five CTAs per SM = 128 registers.  Six would cap the kernel at 96 registers; ptxas then spills 72 bytes and that build
-// returned wrong positions for points with border levels on the B200 -- the cause was not found, the same source is
-// correct at 128 and 170 registers, and tests/test_gpu_lk.py compares this kernel with the first-generation one on
-// border-heavy point sets so that a regression of that kind is seen.  Six CTAs at 112 registers without spills
-// (__maxnreg__) are correct as well and no faster: 2.43 against 2.38 ms -- the kernel is issue-bound like the gray one.)
+// (five CTAs per SM = 128 registers.  Six CTAs at 112 registers (__maxnreg__) are no faster: 2.43 against 2.38 ms -- the
+// kernel is issue-bound like the gray one.  A 96-register build with the helpers out of line returned wrong positions at
+// border points, see MVO_LK_OUTLINE; tests/test_gpu_lk.py compares this kernel with the first-generation one on
+// border-heavy point sets so that a regression of that kind is seen.)
 #ifndef MVO_LK_T_MINB
 #define MVO_LK_T_MINB 5
 #endif
@@ -964,15 +972,22 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
 #else
 #define LK2_TI(k) til[(k) * 32]
 #endif
-    int sA11 = 0, sA12 = 0, sA22 = 0;
+    // The mismatch vector of an iteration is sum (J - I) g = sum J g - sum I g over the window, in exact integers: the
+    // second sum does not change while the level iterates, so it is taken once here and the iteration loop neither
+    // loads the template intensities nor subtracts them (two of its ten instructions per sample).
+    int sA11 = 0, sA12 = 0, sA22 = 0, sI1 = 0, sI2 = 0;
 #pragma unroll
     for (int k = 0; k < 2 * kRunLen; ++k) {
       const int gx = (int)(short)(txy[k] & 0xffffu), gy = (int)txy[k] >> 16;
       sA11 += gx * gx;
       sA12 += gx * gy;
       sA22 += gy * gy;
+      const int ti = LK2_TI(k);   // |I|, |J| <= 255 * 32 and |g| <= 16 * 255 (Scharr of u8): a lane's 14 products stay below 2^29
+      sI1 += ti * gx;
+      sI2 += ti * gy;
     }
     long long tA11 = warp_sum_wide(sA11), tA12 = warp_sum_wide(sA12), tA22 = warp_sum_wide(sA22);
+    const long long tI1 = warp_sum_wide(sI1), tI2 = warp_sum_wide(sI2);
     team_sum3(tA11, tA12, tA22);
 
     const float A11 = __fmul_rn((float)tA11, flt_scale);
@@ -1015,12 +1030,12 @@ lk_track2_kernel(const __grid_constant__ LkGeom g, const __grid_constant__ LkTma
 #pragma unroll
       for (int k = 0; k < kRunLen; ++k) {
         const uint32_t qa = q0[k * kJW], qb = q1[k * kJW];
-        const int da = (dp2a_hi_su(Vb, qa, dp2a_lo_su(Vt, qa, 1 << 8)) >> 9) - LK2_TI(k);
-        const int db = (dp2a_hi_su(Vb, qb, dp2a_lo_su(Vt, qb, 1 << 8)) >> 9) - LK2_TI(kRunLen + k);
-        sb1 += da * (int)(short)(txy[k] & 0xffffu) + db * (int)(short)(txy[kRunLen + k] & 0xffffu);
-        sb2 += da * ((int)txy[k] >> 16) + db * ((int)txy[kRunLen + k] >> 16);
+        const int ja = dp2a_hi_su(Vb, qa, dp2a_lo_su(Vt, qa, 1 << 8)) >> 9;
+        const int jb = dp2a_hi_su(Vb, qb, dp2a_lo_su(Vt, qb, 1 << 8)) >> 9;
+        sb1 += ja * (int)(short)(txy[k] & 0xffffu) + jb * (int)(short)(txy[kRunLen + k] & 0xffffu);
+        sb2 += ja * ((int)txy[k] >> 16) + jb * ((int)txy[kRunLen + k] >> 16);
       }
-      long long tb1 = warp_sum_wide(sb1), tb2 = warp_sum_wide(sb2), tb3 = 0;
+      long long tb1 = warp_sum_wide(sb1) - tI1, tb2 = warp_sum_wide(sb2) - tI2, tb3 = 0;
       team_sum3(tb1, tb2, tb3);
       const float b1 = __fmul_rn((float)tb1, flt_scale);
       const float b2 = __fmul_rn((float)tb2, flt_scale);
