@@ -11,6 +11,10 @@
 #include "linalg.cuh"
 #include <algorithm>
 
+#ifndef MVO_TRI_FAST_CS
+#define MVO_TRI_FAST_CS true   // rotation parameters of the 4 x 4 Jacobi by the two-rsqrt chain (linalg.cuh: jacobi_cs)
+#endif
+
 namespace mvo {
 
 __device__ __forceinline__ void triangulate_one(const double* P0, const double* P1, double x0, double y0, double x1,
@@ -32,7 +36,7 @@ __device__ __forceinline__ void triangulate_one(const double* P0, const double* 
       S[i * 4 + j] = s;
       S[j * 4 + i] = s;
     }
-  jacobi_eig_reg<4>(S, V);
+  jacobi_eig_reg<4, MVO_TRI_FAST_CS>(S, V);
   // eigenvector of the smallest eigenvalue, selected without dynamic indexing (keeps V in registers)
   double lmin = S[0];
 #pragma unroll
