@@ -572,24 +572,27 @@ orb_rank_kernel(const __grid_constant__ OrbGeom g, const unsigned long long* __r
   const int level = blockIdx.y, b = blockIdx.z;
   const LevelGeom lv = g.lv[level];
   const int m = c2_count[b * kLevels + level];
-  if (blockIdx.x * kRankThreads >= m) return;
   const long long base = (long long)b * g.cand_total + lv.cand_off;
   __shared__ unsigned long long s_key[kRankThreads];
-  const int i = blockIdx.x * kRankThreads + threadIdx.x;
-  const unsigned long long mine = (i < m) ? key[base + i] : ~0ull;
-  int rank = 0;
-  for (int j0 = 0; j0 < m; j0 += kRankThreads) {
-    const int j = j0 + threadIdx.x;
-    __syncthreads();
-    s_key[threadIdx.x] = (j < m) ? key[base + j] : ~0ull;
-    __syncthreads();
-    const int lim = min(kRankThreads, m - j0);
+  // the grid covers 2 n_0 candidates plus slack (a level keeps ~2 n_l, ties can add a few): block-stride beyond that.
+  // (It used to cover the whole candidate capacity: 114 CTAs per level and stream of which 4 had work.)
+  for (int blk = blockIdx.x; blk * kRankThreads < m; blk += gridDim.x) {
+    const int i = blk * kRankThreads + threadIdx.x;
+    const unsigned long long mine = (i < m) ? key[base + i] : ~0ull;
+    int rank = 0;
+    for (int j0 = 0; j0 < m; j0 += kRankThreads) {
+      const int j = j0 + threadIdx.x;
+      __syncthreads();
+      s_key[threadIdx.x] = (j < m) ? key[base + j] : ~0ull;
+      __syncthreads();
+      const int lim = min(kRankThreads, m - j0);
 #pragma unroll 8
-    for (int t = 0; t < lim; ++t) rank += (s_key[t] < mine) ? 1 : 0;
-  }
-  if (i < m) {
-    key_sorted[base + rank] = mine;
-    ra_sorted[base + rank] = ra[base + i];
+      for (int t = 0; t < lim; ++t) rank += (s_key[t] < mine) ? 1 : 0;
+    }
+    if (i < m) {
+      key_sorted[base + rank] = mine;
+      ra_sorted[base + rank] = ra[base + i];
+    }
   }
 }
 
@@ -1053,7 +1056,8 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
     c->launches++;
   }
   {
-    dim3 grid((max_cap + kRankThreads - 1) / kRankThreads, kLevels, g.batch);
+    const int want = 2 * g.lv[0].quota + g.lv[0].quota / 4 + 64;
+    dim3 grid(std::min((want + kRankThreads - 1) / kRankThreads, (max_cap + kRankThreads - 1) / kRankThreads), kLevels, g.batch);
     orb_rank_kernel<<<grid, kRankThreads, 0, c->stream>>>(g, c->c2_key.p, c->c2_ra.p, c->c2_count.p,
                                                          c->c2_key_sorted.p, c->c2_ra_sorted.p);
     c->launches++;
