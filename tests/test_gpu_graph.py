@@ -8,7 +8,8 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("h,w,n,batch,bgr", [(376, 1241, 2000, 1, False), (240, 320, 300, 3, False), (240, 320, 300, 2, True)])
+@pytest.mark.parametrize("h,w,n,batch,bgr", [(376, 1241, 2000, 1, False), (240, 320, 300, 3, False), (240, 320, 300, 2, True),
+                                             (240, 320, 300, 2, "gray3")])
 def test_graph_step_equals_plain_step(h, w, n, batch, bgr):
     from ros2_mono_vo_b200 import Context, _lib
     nframes = 9
@@ -17,6 +18,8 @@ def test_graph_step_equals_plain_step(h, w, n, batch, bgr):
 
     def frames(t):
         f = np.stack([seqs[s][0][t] for s in range(batch)])
+        if bgr == "gray3":   # a gray camera behind a BGR8 conversion: the tracker's identical-plane path inside the graph
+            return np.ascontiguousarray(np.stack([f, f, f], -1))
         return np.ascontiguousarray(np.stack([f, 255 - f, f // 2 + 10], -1)) if bgr else f
 
     outs = {}
