@@ -504,6 +504,10 @@ orb_select_kernel(const __grid_constant__ OrbGeom g, const uint32_t* __restrict_
 }
 
 constexpr int kHarrisWarps = 8;
+#ifndef MVO_HARRIS_PER_WARP
+#define MVO_HARRIS_PER_WARP 4
+#endif
+constexpr int kHarrisPerWarp = MVO_HARRIS_PER_WARP;   // candidates of level 0 per warp (software-pipelined loop)
 
 __global__ void __launch_bounds__(kHarrisWarps * 32)
 orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ sel_xy,
@@ -513,25 +517,49 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
   const int tid = threadIdx.x;
   const int count = sel_count[b * kLevels + level];
   const int warp = tid >> 5, lane = tid & 31;
+  if (blockIdx.x == 0 && tid == 0) c2_count[b * kLevels + level] = count;
   if (blockIdx.x * kHarrisWarps >= count) return;
   const int pitch = g.lv[level].pitch, cand_off = g.lv[level].cand_off;
   const uint8_t* img = pyr + (long long)b * g.frame_stride + g.lv[level].off;
-  // grid-stride over this level's selected candidates: the grid is sized for 2 n_0 plus slack, ties may exceed it
-  for (int ci = blockIdx.x * kHarrisWarps + warp; ci < count; ci += gridDim.x * kHarrisWarps) {
-  const uint32_t xy = sel_xy[(long long)b * g.cand_total + cand_off + ci];
+  // Grid-stride over this level's selected candidates, about four per warp, software-pipelined: the 16 neighbourhood
+  // bytes of the next candidate are requested before the current one is reduced (one candidate per warp and launch
+  // wave left the kernel waiting on its gathers: 14 waves of one L2 round trip each).
+  // Harris 7x7 block of Sobel-3 gradients: 49 positions over the 32 lanes (2 rounds); per position the 8 neighbours.
+  const int stride_c = gridDim.x * kHarrisWarps;
+  const long long sel_base = (long long)b * g.cand_total + cand_off;
+  auto fetch = [&](int ci, uint32_t& xy, int (&px)[16]) {
+    xy = sel_xy[sel_base + ci];
+    const int x = xy & 0xffff, y = xy >> 16;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int p = lane + 32 * r;
+      if (p < 49) {
+        const int dy = p / 7 - 3, dx = p - (p / 7) * 7 - 3;
+        const uint8_t* q = img + (long long)(y + dy) * pitch + x + dx;
+        px[8 * r + 0] = q[-pitch - 1]; px[8 * r + 1] = q[-pitch]; px[8 * r + 2] = q[-pitch + 1];
+        px[8 * r + 3] = q[-1];         px[8 * r + 4] = q[1];
+        px[8 * r + 5] = q[pitch - 1];  px[8 * r + 6] = q[pitch];  px[8 * r + 7] = q[pitch + 1];
+      }
+    }
+  };
+  int ci = blockIdx.x * kHarrisWarps + warp;
+  uint32_t xy = 0, xy_n = 0;
+  int px[16], pn[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) px[q] = pn[q] = 0;
+  if (ci < count) fetch(ci, xy, px);
+  for (; ci < count; ci += stride_c) {
+  const int ci_n = ci + stride_c;
+  if (ci_n < count) fetch(ci_n, xy_n, pn);
   const int x = xy & 0xffff, y = xy >> 16;
-
-  // Harris 7x7 block of Sobel-3 gradients: 49 positions over the 32 lanes (2 rounds)
   int sa = 0, sb = 0, sc = 0;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int p = lane + 32 * r;
     if (p < 49) {
-      const int dy = p / 7 - 3, dx = p - (p / 7) * 7 - 3;
-      const uint8_t* q = img + (long long)(y + dy) * pitch + x + dx;
-      const int a00 = q[-pitch - 1], a01 = q[-pitch], a02 = q[-pitch + 1];
-      const int a10 = q[-1], a12 = q[1];
-      const int a20 = q[pitch - 1], a21 = q[pitch], a22 = q[pitch + 1];
+      const int a00 = px[8 * r + 0], a01 = px[8 * r + 1], a02 = px[8 * r + 2];
+      const int a10 = px[8 * r + 3], a12 = px[8 * r + 4];
+      const int a20 = px[8 * r + 5], a21 = px[8 * r + 6], a22 = px[8 * r + 7];
       const int ix = (a12 - a10) * 2 + (a02 - a00) + (a22 - a20);
       const int iy = (a21 - a01) * 2 + (a20 - a00) + (a22 - a02);
       sa += ix * ix;
@@ -552,13 +580,16 @@ orb_harris_angle_kernel(const __grid_constant__ OrbGeom g, const uint8_t* __rest
     const float apb = __fadd_rn(fa, fb);
     const float t2 = __fmul_rn(__fmul_rn(k, apb), apb);
     const float resp = __fmul_rn(__fsub_rn(t1, t2), s4);
-    const int pos = atomicAdd(c2_count + b * kLevels + level, 1);
-    const long long o = (long long)b * g.cand_total + cand_off + pos;
+    // (the candidate's own index is dense and unique already: no counter to contend for)
+    const long long o = (long long)b * g.cand_total + cand_off + ci;
     // ascending key == (response desc, y asc, x asc); -0.f canonicalised so that ties compare equal
     const uint32_t ro = ~float_orderable(__fadd_rn(resp, 0.f));
     c2_key[o] = ((unsigned long long)ro << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
     c2_ra[o] = make_float2(resp, 0.f);   // the angle is computed for the survivors only (orb_brief_kernel)
   }
+  xy = xy_n;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) px[q] = pn[q];
   }  // candidate loop
 }
 
@@ -1048,8 +1079,8 @@ int orb_run_detect(mvo_ctx* c, bool want_desc) {
                                                           c->cand_sel.p, c->sel_count.p);
     c->launches++;
     // warp per selected candidate; level 0 keeps ~2 n_0 (+ ties): size the grid for that, grid-stride beyond
-    const int want = 2 * g.lv[0].quota + g.lv[0].quota / 4 + 64;
-    dim3 grid(std::min((want + kHarrisWarps - 1) / kHarrisWarps, (max_cap + kHarrisWarps - 1) / kHarrisWarps), kLevels,
+    const int want = (2 * g.lv[0].quota + g.lv[0].quota / 4 + 64 + kHarrisPerWarp - 1) / kHarrisPerWarp;
+    dim3 grid(std::max(1, std::min((want + kHarrisWarps - 1) / kHarrisWarps, (max_cap + kHarrisWarps - 1) / kHarrisWarps)), kLevels,
               g.batch);
     orb_harris_angle_kernel<<<grid, kHarrisWarps * 32, 0, c->stream>>>(g, c->pyr.p, c->cand_sel.p, c->sel_count.p,
                                                                       c->c2_key.p, c->c2_ra.p, c->c2_count.p);
