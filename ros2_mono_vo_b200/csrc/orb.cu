@@ -505,7 +505,7 @@ orb_select_kernel(const __grid_constant__ OrbGeom g, const uint32_t* __restrict_
 
 constexpr int kHarrisWarps = 8;
 #ifndef MVO_HARRIS_PER_WARP
-#define MVO_HARRIS_PER_WARP 4
+#define MVO_HARRIS_PER_WARP 8
 #endif
 constexpr int kHarrisPerWarp = MVO_HARRIS_PER_WARP;   // candidates of level 0 per warp (software-pipelined loop)
 
