@@ -5,12 +5,15 @@
 // (SURVEY.md 8f "next #1").  Contract: oracle/pnp_oracle.py, pinned to cv2 4.13.0.
 //
 //   pnp_normalize_kernel   image points -> K-normalised coordinates rounded to float (undistortPoints on float input)
-//   pnp_sample_kernel      the registrator's 5-point samples from the OpenCV MWC stream (no subset check)
+//   pnp_sample_kernel      the registrator's 5-point samples from the OpenCV MWC stream (no subset check): every offset
+//                          of the stream simulates the sample that would start there, one thread follows the chain
 //   pnp_epnp_kernel        warp per hypothesis (FP64): EPnP -- PCA control points with cv::SVD's signs (one-sided
-//                          Jacobi, replayed exactly), 12x12 M^T M eigenvectors by a warp-cooperative cyclic Jacobi, the
-//                          three beta approximations + 5 Gauss-Newton steps + absolute orientation on three lanes,
-//                          best reprojection error
+//                          Jacobi, replayed exactly), 12x12 M^T M eigenvectors by a warp-cooperative cyclic Jacobi (one
+//                          element pair per lane), the three beta approximations (QR) + 5 Gauss-Newton steps (QR) +
+//                          absolute orientation on three lanes, best reprojection error
 //   pnp_score_kernel       CTA per hypothesis: float squared reprojection error <= thr^2, warp-reduced counts
+//   pnp_bound_kernel       batched calls: hypotheses the adaptive loop can still reach after the first 32 of a stream
+//                          (the second epnp / score launch skips the rest)
 //   pnp_select_kernel      replays the sequential adaptive loop (strict '>' update, shrinking niters), writes the
 //                          inlier mask and the ordered inlier list of the winner
 //   pnp_refine_kernel      solvePnP(inliers, ITERATIVE): DLT initialisation + Levenberg-Marquardt as CvLevMarq runs it
