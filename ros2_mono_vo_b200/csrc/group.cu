@@ -83,7 +83,8 @@ __global__ void make_proj_kernel(const double* __restrict__ K, const double* __r
 // chirality count of the triangulated points (src/initializer.cpp:134-157): z > 0 in both cameras.  With `cloud` the
 // valid points are also compacted in track order and written as points3d_to_pointcloud_msg would pack them
 // (src/utils.cpp:225-241: ROS x = z, y = -x, z = -y; 12 bytes per point) -- MVO_OUT_CLOUD.
-__global__ void __launch_bounds__(256)
+constexpr int kTriCountThreads = 1024;   // one CTA per stream walks its ~1700 tracks in chunks: two chunks instead of seven
+__global__ void __launch_bounds__(kTriCountThreads)
 tri_count_kernel(const float* __restrict__ X4, const uint8_t* __restrict__ mask, const double* __restrict__ pose,
                  const int32_t* __restrict__ npts, int max_pts, int32_t* __restrict__ out, float* __restrict__ cloud,
                  int cloud_cap) {
@@ -92,11 +93,11 @@ tri_count_kernel(const float* __restrict__ X4, const uint8_t* __restrict__ mask,
   const double* R = pose + b * 12;
   const double* t = R + 9;
   const float* X = X4 + (long long)b * 4 * max_pts;
-  __shared__ int s_warp[8];
+  __shared__ int s_warp[kTriCountThreads / 32];
   __shared__ int s_base;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += 256) {
+  for (int i0 = 0; i0 < n; i0 += kTriCountThreads) {
     const int i = i0 + tid;
     bool ok = false;
     float x = 0, y = 0, z = 0;
@@ -116,7 +117,7 @@ tri_count_kernel(const float* __restrict__ X4, const uint8_t* __restrict__ mask,
     __syncthreads();
     int off = s_base, tot = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < 8; ++w2) {
+    for (int w2 = 0; w2 < kTriCountThreads / 32; ++w2) {
       if (w2 < warp) off += s_warp[w2];
       tot += s_warp[w2];
     }
@@ -553,7 +554,7 @@ static int group_enqueue(mvo_ctx* c, const uint8_t* images, int w, int h, int st
       c->launches++;
       rc = pose_triangulate(c);
       if (rc) return rc;
-      tri_count_kernel<<<B, 256, 0, c->stream>>>(r.X4.p, r.ln().mask.p, r.pose.p, r.npts.p, r.max_pts, ntri,
+      tri_count_kernel<<<B, kTriCountThreads, 0, c->stream>>>(r.X4.p, r.ln().mask.p, r.pose.p, r.npts.p, r.max_pts, ntri,
                                                  (om & MVO_OUT_CLOUD) ? c->cloud.p : nullptr, cap);
       c->launches++;
       STAGE_END(c, ST_TRI);
