@@ -5,6 +5,7 @@
 //   stdout: R (9) t (3) of epnp_solve<5>, then rvec of rotation_to_rvec, then R again from rvec_to_rotation
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <cuda_runtime.h>
 #include "../../ros2_mono_vo_b200/csrc/pnp_math.cuh"
 
@@ -29,6 +30,17 @@ __global__ void epnp_device(const double* in, double* out) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--cs") {
+    // rotation parameters of a Jacobi step, both forms (linalg.cuh: jacobi_cs): stdin "app aqq apq" per line
+    double app, aqq, apq;
+    while (scanf("%lf %lf %lf", &app, &aqq, &apq) == 3) {
+      double c0, s0, c1, s1;
+      mvo::jacobi_cs<false>(app, aqq, apq, c0, s0);
+      mvo::jacobi_cs<true>(app, aqq, apq, c1, s1);
+      printf("%.17g %.17g %.17g %.17g\n", c0, s0, c1, s1);
+    }
+    return 0;
+  }
   int n = 0;
   if (scanf("%d", &n) != 1 || n != mvo::kPnpK) return 2;
   double pw[mvo::kPnpK][3], us[mvo::kPnpK][2];

@@ -64,3 +64,29 @@ def test_pnp_math_device_vs_oracle(impl):
     """impl: the two forms of the warp's 12 x 12 eigen-decomposition (round 1; one element pair per lane + short scalar
     chain for the rotation parameters)."""
     _check(device=True, impl=impl)
+
+
+def test_jacobi_rotation_parameters_fast_form_equals_the_textbook_form():
+    """linalg.cuh jacobi_cs<true> (no theta, no t: two reciprocal square roots) against jacobi_cs<false> (the expressions
+    of jacobi_eig) and against the defining properties: c^2 + s^2 = 1 and the rotation annihilates a_pq.  Host build."""
+    exe = _build()
+    rng = np.random.default_rng(5)
+    rows = []
+    for scale in (1e-12, 1e-3, 1.0, 1e6):
+        for _ in range(200):
+            app, aqq = rng.normal(size=2) * scale
+            apq = rng.normal() * scale * 10.0 ** rng.uniform(-12, 1)
+            rows.append((app, aqq, apq))
+    rows += [(1.0, 1.0, 0.5), (1.0, 1.0, -0.5), (2.0, 2.0, 1e-30), (0.0, 0.0, 1.0), (3.0, -3.0, 1e-300)]   # d == 0, tiny a_pq
+    inp = "\n".join("%r %r %r" % tuple(float(v) for v in r) for r in rows) + "\n"
+    r = subprocess.run([exe, "--cs"], input=inp, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = np.array([[float(v) for v in l.split()] for l in r.stdout.splitlines()])
+    assert out.shape == (len(rows), 4)
+    c0, s0, c1, s1 = out.T
+    assert np.abs(c1 - c0).max() < 4e-16 and np.abs(s1 - s0).max() < 4e-16
+    assert np.abs(c1 * c1 + s1 * s1 - 1).max() < 1e-15
+    app, aqq, apq = np.array(rows).T
+    # off-diagonal entry after the rotation: (c^2 - s^2) a_pq + c s (a_pp - a_qq), relative to the entries involved
+    resid = (c1 * c1 - s1 * s1) * apq + c1 * s1 * (app - aqq)
+    assert (np.abs(resid) <= 4e-16 * (np.abs(apq) + np.abs(app - aqq))).all()
